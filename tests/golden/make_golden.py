@@ -1,0 +1,302 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference).
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+Every file stores the seeded inputs (or the seeds that regenerate them through
+`hy2dl_b200.synthetic`), and the reference's outputs and autograd gradients in fp32 on the host
+CPU.  `tests/test_oracle_golden.py` pins `oracle/hy2dl_oracle.py` to these; the `-m gpu` tests
+compare the CUDA path with them as well.
+"""
+import os
+import sys
+
+import numpy as np
+import pandas as pd
+import torch
+
+REF = "/root/reference/Hy2DL"
+for sub in ("modelzoo", "aux_functions", "datasetzoo"):
+    sys.path.append(os.path.join(REF, sub))
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+
+from basedataset import BaseDataset  # noqa: E402  (reference)
+from cudalstm import CudaLSTM  # noqa: E402
+from functions_training import nse_basin_averaged, weighted_rmse  # noqa: E402
+from hbv import HBV  # noqa: E402
+from hybrid import Hybrid  # noqa: E402
+from shm import SHM  # noqa: E402
+from uh_routing import UH_routing  # noqa: E402
+
+from hy2dl_b200.synthetic import lstm_weights, make_basins  # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def t(a):
+    return torch.tensor(np.asarray(a), dtype=torch.float32)
+
+
+def load_weights(model, w):
+    model.load_state_dict({k: t(v) for k, v in w.items()})
+
+
+def batch_from_basins(data, B, T, n_last, seed):
+    """Draw B windows (basin b, random end) from the synthetic basins; returns numpy arrays."""
+    rng = np.random.default_rng(seed)
+    nb, nr, _ = data.x_d.shape
+    xd_mean = data.x_d.reshape(-1, data.x_d.shape[2]).mean(0)
+    xd_std = data.x_d.reshape(-1, data.x_d.shape[2]).std(0)
+    xs_mean, xs_std = data.x_s.mean(0), data.x_s.std(0, ddof=1)
+    xl, xc, yo, sd = [], [], [], []
+    for _ in range(B):
+        b = int(rng.integers(nb))
+        i = int(rng.integers(T - 1, nr))
+        dyn = (data.x_d[b, i - T + 1:i + 1] - xd_mean) / xd_std
+        sta = np.broadcast_to((data.x_s[b] - xs_mean) / xs_std, (T, data.x_s.shape[1]))
+        xl.append(np.concatenate([dyn, sta], axis=1))
+        if data.x_conc is not None:
+            xc.append(data.x_conc[b, i - T + 1:i + 1])
+        yo.append(data.y_obs[b, i - n_last + 1:i + 1])
+        sd.append(np.full((n_last, 1), np.nanstd(data.y_obs[b]), dtype=np.float32))
+    out = dict(x_lstm=np.stack(xl).astype(np.float32), y_obs=np.stack(yo).astype(np.float32),
+               basin_std=np.stack(sd).astype(np.float32))
+    if xc:
+        out["x_conceptual"] = np.stack(xc).astype(np.float32)
+    return out
+
+
+def grads_of(model):
+    return {"grad." + k: p.grad.detach().numpy().copy() for k, p in model.named_parameters()}
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB, {len(arrays)} arrays")
+
+
+# ------------------------------------------------------------------------------------------------
+def case_cudalstm(name, shape, B, T, H, wseed, store_full_grads):
+    data = make_basins(shape, n_basins=6, n_rows=T + 40, seed=42)
+    batch = batch_from_basins(data, B, T, 1, seed=7)
+    batch["y_obs"][0, 0, 0] = np.nan  # exercise the loss mask
+    I = batch["x_lstm"].shape[2]
+    hp = {"input_size_lstm": I, "hidden_size": H, "no_of_layers": 1, "drop_out_rate": 0.0}
+    model = CudaLSTM(hp)
+    load_weights(model, lstm_weights(I, H, 1, seed=wseed))
+    y = model(t(batch["x_lstm"]))["y_hat"]
+    loss = nse_basin_averaged(y_sim=y, y_obs=t(batch["y_obs"]), per_basin_target_std=t(batch["basin_std"]))
+    loss.backward()
+    g = grads_of(model)
+    if not store_full_grads:  # keep the fixture small for H = 256: strided slices + norms
+        g = {k: (v if v.size <= 4096 else v[::16, ::8].copy()) for k, v in g.items()} | {
+            k + ".norm": np.float64(np.linalg.norm(v.astype(np.float64))) for k, v in g.items()}
+    save(name, meta=np.array([B, T, I, H, wseed]), y_hat=y.detach().numpy(), loss=loss.detach().numpy(),
+         **batch, **g)
+
+
+def case_hybrid(name, shape, model_cls, model_key, B, T, n_last, H, m, dynamic, wseed, loss_kind, routing=True):
+    data = make_basins(shape, n_basins=6, n_rows=T + 60, seed=42 if shape == "gb" else 111111)
+    batch = batch_from_basins(data, B, T, n_last, seed=11)
+    I = batch["x_lstm"].shape[2]
+    hp = {"input_size_lstm": I, "hidden_size": H, "no_of_layers": 1, "seq_length": T, "predict_last_n": n_last,
+          "n_conceptual_models": m, "conceptual_dynamic_parameterization": list(dynamic)}
+    model = Hybrid(hp, conceptual_model=model_cls, routing_model=UH_routing if routing else None)
+    n_out = model.linear.out_features
+    load_weights(model, lstm_weights(I, H, n_out, seed=wseed))
+    pred = model(x_lstm=t(batch["x_lstm"]), x_conceptual=t(batch["x_conceptual"]))
+    if loss_kind == "nse":
+        loss = nse_basin_averaged(y_sim=pred["y_hat"], y_obs=t(batch["y_obs"]),
+                                  per_basin_target_std=t(batch["basin_std"]))
+    else:
+        loss = weighted_rmse(y_sim=pred["y_hat"], y_obs=t(batch["y_obs"]))
+    loss.backward()
+    out = {"y_hat": pred["y_hat"].detach().numpy(), "loss": loss.detach().numpy()}
+    for k, v in pred["internal_states"].items():
+        out["state." + k] = v.detach().numpy()
+    for k, v in pred["final_states"].items():
+        out["final." + k] = v.detach().numpy()
+    for k, v in pred["parameters"].items():
+        out["param." + k] = v.detach().numpy()
+    g = grads_of(model)
+    g = {k: v for k, v in g.items()}
+    save(name, meta=np.array([B, T, n_last, I, H, m, wseed, int(routing)]),
+         dynamic=np.array(list(dynamic)), model=np.array(model_key), loss_kind=np.array(loss_kind),
+         **batch, **out, **g)
+
+
+def case_direct(name, model_cls, ranges_of, B, T, m, ncols, dynamic_all=True, drop=()):
+    """Bucket model alone: random in-range parameters as leaves, gradient of a random linear functional."""
+    rng = np.random.default_rng(5)
+    data = make_basins("us" if ncols == 4 else "gb", n_basins=B, n_rows=T, seed=3)
+    xc = data.x_conc[:, :T]
+    model = model_cls(n_models=m)
+    pars, store = {}, {}
+    for k, (lo, hi) in ranges_of(model).items():
+        if k in drop:
+            continue
+        u = rng.uniform(0.02, 0.98, (B, T if dynamic_all else 1, m)).astype(np.float32)
+        leaf = torch.tensor(lo + u * (hi - lo), dtype=torch.float32, requires_grad=True)
+        store[k] = leaf
+        pars[k] = leaf if dynamic_all else leaf.expand(-1, T, -1)
+    init = {k: torch.tensor(rng.uniform(0.0, 30.0, (B, m)).astype(np.float32), requires_grad=True)
+            for k in model._initial_states}
+    wq = t(rng.normal(0, 1, (B, T, 1)))
+    ws = {k: t(rng.normal(0, 0.1, (B, T, m))) for k in model._initial_states}
+    pred = model(x_conceptual=t(xc), parameters=pars, initial_states=init)
+    fun = (pred["y_hat"] * wq).sum() + sum((pred["internal_states"][k] * ws[k]).sum() for k in ws)
+    fun.backward()
+    out = {"x_conceptual": xc, "wq": wq.numpy(), "y_hat": pred["y_hat"].detach().numpy()}
+    for k in store:
+        out["param." + k] = store[k].detach().numpy()
+        out["grad.param." + k] = store[k].grad.numpy()
+    for k in init:
+        out["init." + k] = init[k].detach().numpy()
+        out["grad.init." + k] = init[k].grad.numpy()
+        out["ws." + k] = ws[k].numpy()
+        out["state." + k] = pred["internal_states"][k].detach().numpy()
+    save(name, meta=np.array([B, T, m, ncols, int(dynamic_all)]), **out)
+
+
+def case_uh():
+    rng = np.random.default_rng(9)
+    B, T = 6, 80
+    a = torch.tensor(rng.uniform(0.05, 2.85, B).astype(np.float32), requires_grad=True)
+    b = torch.tensor(rng.uniform(0.1, 6.4, B).astype(np.float32), requires_grad=True)
+    q = torch.tensor(rng.gamma(1.0, 1.0, (B, T, 1)).astype(np.float32), requires_grad=True)
+    w = t(rng.normal(0, 1, (B, T, 1)))
+    model = UH_routing()
+    y = model(discharge=q, parameters={"alpha": a.reshape(B, 1, 1).expand(B, T, 1),
+                                       "beta": b.reshape(B, 1, 1).expand(B, T, 1)})
+    (y * w).sum().backward()
+    uh = model._gamma_routing(alpha=a.detach(), beta=b.detach(), uh_len=15)[:, :, 0].numpy()
+    save("uh_direct", alpha=a.detach().numpy(), beta=b.detach().numpy(), q=q.detach().numpy(), w=w.numpy(),
+         y=y.detach().numpy(), uh=uh, grad_alpha=a.grad.numpy(), grad_beta=b.grad.numpy(), grad_q=q.grad.numpy())
+
+
+def case_losses():
+    rng = np.random.default_rng(13)
+    B, T = 16, 37
+    ys = torch.tensor(rng.gamma(1.0, 1.0, (B, T, 1)).astype(np.float32), requires_grad=True)
+    yo = rng.gamma(1.0, 1.0, (B, T, 1)).astype(np.float32)
+    yo[rng.random((B, T, 1)) < 0.1] = np.nan
+    yo[3] = np.nan  # a sample with no valid target at all
+    sd = np.repeat(rng.uniform(0.2, 3.0, (B, 1, 1)).astype(np.float32), T, axis=1)
+    l1 = nse_basin_averaged(y_sim=ys, y_obs=t(yo), per_basin_target_std=t(sd))
+    (g1,) = torch.autograd.grad(l1, ys)
+    l2 = weighted_rmse(y_sim=ys, y_obs=t(yo))
+    (g2,) = torch.autograd.grad(l2, ys)
+    save("losses", y_sim=ys.detach().numpy(), y_obs=yo, basin_std=sd, nse=l1.detach().numpy(), grad_nse=g1.numpy(),
+         wrmse=l2.detach().numpy(), grad_wrmse=g2.numpy())
+
+
+class _ArrayDataset(BaseDataset):
+    """Reference BaseDataset fed from in-memory arrays instead of CSV files."""
+    arrays = None
+    dyn_names = None
+    conc_names = None
+    stat_names = None
+
+    def _read_attributes(self):
+        a = type(self).arrays
+        return pd.DataFrame(a.x_s, index=[str(i) for i in range(a.x_s.shape[0])], columns=type(self).stat_names)
+
+    def _read_data(self, catch_id):
+        a = type(self).arrays
+        b = int(catch_id)
+        idx = pd.date_range("1990-01-01", periods=a.x_d.shape[1], freq="D")
+        df = pd.DataFrame(a.x_d[b], index=idx, columns=type(self).dyn_names)
+        df["q"] = a.y_obs[b, :, 0]
+        return df
+
+
+def case_sampler():
+    import tempfile
+    nb, nr, L, n_last = 4, 160, 30, 5
+    a = make_basins("gb", n_basins=nb, n_rows=nr, seed=21, nan_frac=0.15)
+    a.x_d[1, 50:53, 2] = np.nan  # NaN inputs invalidate every window touching them
+    a.y_obs[2, 100:120] = np.nan  # a stretch with all-NaN targets
+    _ArrayDataset.arrays = a
+    _ArrayDataset.dyn_names = ["precipitation", "peti", "temperature"]
+    _ArrayDataset.stat_names = [f"s{i}" for i in range(a.x_s.shape[1])]
+    day0 = pd.Timestamp("1990-01-01")
+    with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
+        f.write("\n".join(str(i) for i in range(nb)))
+    ds = _ArrayDataset(dynamic_input=_ArrayDataset.dyn_names, target=["q"], sequence_length=L,
+                       time_period=[str(day0 + pd.Timedelta(days=L - n_last))[:10],
+                                    str(day0 + pd.Timedelta(days=nr - 1))[:10]],
+                       path_data="", path_entities=f.name, predict_last_n=n_last,
+                       static_input=_ArrayDataset.stat_names, conceptual_input=_ArrayDataset.dyn_names,
+                       check_NaN=True)
+    os.unlink(f.name)
+    ds.calculate_basin_std()
+    ds.calculate_global_statistics()
+    ds.standardize_data(standardize_output=False)
+    ve = np.array([(int(b), i) for b, i in ds.valid_entities], dtype=np.int64)
+    pick = np.random.default_rng(2).choice(len(ds), 12, replace=False)
+    samples = [ds[int(k)] for k in pick]
+    save("sampler", meta=np.array([nb, nr, L, n_last]), x_d=a.x_d, x_s=a.x_s, y_obs=a.y_obs,
+         valid_entities=ve, pick=pick,
+         x_lstm=np.stack([s["x_lstm"].numpy() for s in samples]),
+         x_conceptual=np.stack([s["x_conceptual"].numpy() for s in samples]),
+         y_win=np.stack([s["y_obs"].numpy() for s in samples]),
+         basin_std=np.stack([s["basin_std"].numpy() for s in samples]),
+         scaler_x_d_mean=ds.scaler["x_d_mean"].numpy(), scaler_x_d_std=ds.scaler["x_d_std"].numpy(),
+         scaler_x_s_mean=ds.scaler["x_s_mean"].numpy(), scaler_x_s_std=ds.scaler["x_s_std"].numpy(),
+         scaler_y_mean=ds.scaler["y_mean"].numpy(), scaler_y_std=ds.scaler["y_std"].numpy(),
+         std_per_basin=np.array([ds.basin_std[str(i)].item() for i in range(nb)], dtype=np.float32))
+
+
+def case_train_steps():
+    """Three notebook-style updates (zero_grad, fwd, loss, bwd, clip 1, Adam 1e-3) on the hybrid SHM."""
+    B, T, n_last, H = 8, 60, 30, 16
+    data = make_basins("gb", n_basins=6, n_rows=T + 60, seed=42)
+    I = 25
+    hp = {"input_size_lstm": I, "hidden_size": H, "no_of_layers": 1, "seq_length": T, "predict_last_n": n_last,
+          "n_conceptual_models": 2, "conceptual_dynamic_parameterization": ["dd", "kf", "beta"]}
+    model = Hybrid(hp, conceptual_model=SHM, routing_model=UH_routing)
+    load_weights(model, lstm_weights(I, H, model.linear.out_features, seed=31))
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    losses, norms, batches = [], [], []
+    for step in range(3):
+        batch = batch_from_basins(data, B, T, n_last, seed=100 + step)
+        batches.append(batch)
+        opt.zero_grad()
+        pred = model(x_lstm=t(batch["x_lstm"]), x_conceptual=t(batch["x_conceptual"]))
+        loss = nse_basin_averaged(y_sim=pred["y_hat"], y_obs=t(batch["y_obs"]),
+                                  per_basin_target_std=t(batch["basin_std"]))
+        loss.backward()
+        norms.append(float(torch.nn.utils.clip_grad_norm_(model.parameters(), 1)))
+        opt.step()
+        losses.append(loss.item())
+    out = {f"step{s}.{k}": v for s, b in enumerate(batches) for k, v in b.items()}
+    out.update({"final." + k: v.detach().numpy() for k, v in model.state_dict().items()})
+    save("train_steps", meta=np.array([B, T, n_last, I, H, 2, 31]), losses=np.array(losses), norms=np.array(norms),
+         **out)
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    case_cudalstm("cudalstm_c1", "gb", B=4, T=365, H=64, wseed=1, store_full_grads=True)
+    case_cudalstm("cudalstm_c3", "us_lstm", B=2, T=120, H=256, wseed=2, store_full_grads=False)
+    case_hybrid("hybrid_shm_c2", "gb", SHM, "shm", B=4, T=365, n_last=182, H=64, m=1,
+                dynamic=["dd", "f_thr", "sumax", "beta", "perc", "kf", "ki", "kb"], wseed=3, loss_kind="nse")
+    case_hybrid("hybrid_shm_mixed", "us", SHM, "shm", B=3, T=90, n_last=40, H=16, m=3,
+                dynamic=["dd", "beta", "ki"], wseed=4, loss_kind="wrmse")
+    case_hybrid("hybrid_hbv_c4", "us", HBV, "hbv", B=3, T=140, n_last=70, H=32, m=16,
+                dynamic=["BETA", "BETAET"], wseed=5, loss_kind="wrmse")
+    case_hybrid("hybrid_hbv_norouting", "gb", HBV, "hbv", B=3, T=80, n_last=30, H=16, m=2,
+                dynamic=["TT", "FC", "K1", "CFMAX"], wseed=6, loss_kind="nse", routing=False)
+    case_direct("shm_direct", SHM, lambda mdl: mdl.parameter_ranges, B=6, T=120, m=2, ncols=3)
+    case_direct("shm_direct_static4", SHM, lambda mdl: mdl.parameter_ranges, B=5, T=60, m=1, ncols=4,
+                dynamic_all=False)
+    case_direct("hbv_direct", HBV, lambda mdl: mdl.parameter_ranges, B=6, T=120, m=2, ncols=4)
+    case_direct("hbv_direct_nobetaet", HBV, lambda mdl: mdl.parameter_ranges, B=5, T=60, m=1, ncols=3,
+                dynamic_all=False, drop=("BETAET",))
+    case_uh()
+    case_losses()
+    case_sampler()
+    case_train_steps()

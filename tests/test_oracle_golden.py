@@ -1,0 +1,169 @@
+"""Pin the oracle (oracle/hy2dl_oracle.py) to the golden vectors produced by the unmodified reference.
+
+fp32 oracle vs reference fp32: same op order, so agreement is at rounding level (rtol 2e-5 stated).
+fp64 oracle vs reference fp32: the reference's own fp32 rounding noise through T recurrent steps
+bounds this (rtol 2e-4 stated, looser on purpose: it measures the *reference's* error).
+"""
+import numpy as np
+import pytest
+import torch
+
+from _util import O, PARAM_KEYS, assert_close, golden, oracle_hybrid, tt, weights
+
+F32 = dict(rtol=2e-5, atol=1e-7)
+F64 = dict(rtol=3e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, F32), (torch.float64, F64)])
+@pytest.mark.parametrize("name", ["cudalstm_c1", "cudalstm_c3"])
+def test_cudalstm(name, dtype, tol):
+    g = golden(name)
+    B, T, I, H, wseed = [int(v) for v in g["meta"]]
+    w = weights(I, H, 1, wseed, dtype)
+    y = O.cudalstm_forward(w, tt(g["x_lstm"], dtype))
+    loss = O.nse_basin_averaged(y, tt(g["y_obs"], dtype), tt(g["basin_std"], dtype))
+    loss.backward()
+    assert_close(y.detach(), g["y_hat"], what="y_hat", **tol)
+    assert_close(loss.detach(), g["loss"], what="loss", **tol)
+    for k in PARAM_KEYS:
+        ref = g["grad." + k]
+        got = w[k].grad.numpy()
+        if ref.shape != got.shape:
+            assert_close(np.linalg.norm(got.astype(np.float64)), g["grad." + k + ".norm"], what=k + ".norm", **tol)
+            got = got[::16, ::8]
+        assert_close(got, ref, what="grad " + k, **tol)
+
+
+def test_cudalstm_library_path_matches_cell_loop():
+    g = golden("cudalstm_c1")
+    B, T, I, H, wseed = [int(v) for v in g["meta"]]
+    w = weights(I, H, 1, wseed, grad=False)
+    a = O.cudalstm_forward(w, tt(g["x_lstm"]), library=True)
+    assert_close(a, g["y_hat"], what="library y_hat", **F32)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, F32), (torch.float64, F64)])
+@pytest.mark.parametrize("name", ["hybrid_shm_c2", "hybrid_shm_mixed", "hybrid_hbv_c4", "hybrid_hbv_norouting"])
+def test_hybrid(name, dtype, tol):
+    g = golden(name)
+    w, pred, loss = oracle_hybrid(g, dtype)
+    assert_close(pred["y_hat"].detach(), g["y_hat"], what="y_hat", **tol)
+    assert_close(loss.detach(), g["loss"], what="loss", **tol)
+    for k, v in pred["internal_states"].items():
+        assert_close(v.detach(), g["state." + k], what="state " + k, **tol)
+    for k, v in pred["final_states"].items():
+        assert_close(v.detach(), g["final." + k], what="final " + k, **tol)
+    for k, v in pred["parameters"].items():
+        assert_close(v.detach(), g["param." + k], what="param " + k, **tol)
+    for k in PARAM_KEYS:
+        assert_close(w[k].grad, g["grad." + k], what="grad " + k, **tol)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, F32), (torch.float64, F64)])
+@pytest.mark.parametrize("name", ["shm_direct", "shm_direct_static4", "hbv_direct", "hbv_direct_nobetaet"])
+def test_bucket_direct(name, dtype, tol):
+    g = golden(name)
+    B, T, m, ncols, dyn = [int(v) for v in g["meta"]]
+    model = "shm" if name.startswith("shm") else "hbv"
+    ranges, states, _ = O.MODEL_TABLE[model]
+    leaves = {k: tt(g["param." + k], dtype, True) for k in ranges if "param." + k in g}
+    pars = {k: (v if dyn else v.expand(-1, T, -1)) for k, v in leaves.items()}
+    init = {k: tt(g["init." + k], dtype, True) for k in states}
+    pred = O.RUNNERS[model](tt(g["x_conceptual"], dtype), pars, m, init=init)
+    fun = (pred["y_hat"] * tt(g["wq"], dtype)).sum()
+    for k in states:
+        fun = fun + (pred["internal_states"][k] * tt(g["ws." + k], dtype)).sum()
+    fun.backward()
+    assert_close(pred["y_hat"].detach(), g["y_hat"], what="y_hat", **tol)
+    for k in states:
+        assert_close(pred["internal_states"][k].detach(), g["state." + k], what="state " + k, **tol)
+        assert_close(init[k].grad, g["grad.init." + k], what="grad init " + k, **tol)
+    for k, v in leaves.items():
+        assert_close(v.grad, g["grad.param." + k], what="grad param " + k, **tol)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, F32), (torch.float64, F64)])
+def test_uh(dtype, tol):
+    g = golden("uh_direct")
+    a, b, q = tt(g["alpha"], dtype, True), tt(g["beta"], dtype, True), tt(g["q"], dtype, True)
+    y = O.uh_route(q, a, b)
+    (y * tt(g["w"], dtype)).sum().backward()
+    assert_close(O.uh_weights(a.detach(), b.detach()), g["uh"], what="uh", **tol)
+    assert_close(y.detach(), g["y"], what="y", **tol)
+    assert_close(q.grad, g["grad_q"], what="grad q", **tol)
+    assert_close(a.grad, g["grad_alpha"], what="grad alpha", rtol=max(tol["rtol"], 2e-4), atol=1e-6)
+    assert_close(b.grad, g["grad_beta"], what="grad beta", rtol=max(tol["rtol"], 2e-4), atol=1e-6)
+
+
+def test_uh_weights_match_scipy_gamma():
+    from scipy.stats import gamma
+    a = np.array([0.3, 1.0, 2.5])
+    b = np.array([0.7, 2.0, 6.0])
+    x = np.arange(15) + 0.5
+    pdf = np.stack([gamma.pdf(x, a=ai, scale=bi) for ai, bi in zip(a, b)], axis=1)
+    ref = pdf / pdf.sum(0)
+    got = O.uh_weights(torch.tensor(a), torch.tensor(b)).numpy()
+    assert_close(got, ref, rtol=1e-10, what="gamma pdf")
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, F32), (torch.float64, F64)])
+def test_losses(dtype, tol):
+    g = golden("losses")
+    ys = tt(g["y_sim"], dtype, True)
+    l1 = O.nse_basin_averaged(ys, tt(g["y_obs"], dtype), tt(g["basin_std"], dtype))
+    (g1,) = torch.autograd.grad(l1, ys)
+    l2 = O.weighted_rmse(ys, tt(g["y_obs"], dtype))
+    (g2,) = torch.autograd.grad(l2, ys)
+    assert_close(l1.detach(), g["nse"], what="nse", **tol)
+    assert_close(g1, g["grad_nse"], what="grad nse", **tol)
+    assert_close(l2.detach(), g["wrmse"], what="wrmse", **tol)
+    assert_close(g2, g["grad_wrmse"], what="grad wrmse", **tol)
+
+
+def test_sampler_flags_and_gather():
+    g = golden("sampler")
+    nb, nr, L, n_last = [int(v) for v in g["meta"]]
+    # validity flags: the reference's time window starts at row 0 of the synthetic arrays
+    ve = []
+    for b in range(nb):
+        ok = O.valid_window_flags(g["x_d"][b], g["y_obs"][b], L, n_last)
+        if np.isnan(g["x_s"][b]).any():
+            ok[:] = False
+        ve += [(b, int(i)) for i in np.nonzero(ok.numpy())[0]]
+    assert np.array_equal(np.array(ve, dtype=np.int64), g["valid_entities"])
+    # standardisation + gather
+    x_d = (torch.tensor(g["x_d"]) - torch.tensor(g["scaler_x_d_mean"])) / torch.tensor(g["scaler_x_d_std"])
+    x_s = (torch.tensor(g["x_s"]) - torch.tensor(g["scaler_x_s_mean"])) / torch.tensor(g["scaler_x_s_std"])
+    row0 = torch.arange(nb) * nr
+    sel = g["valid_entities"][g["pick"]]
+    out = O.window_gather(x_d.reshape(nb * nr, -1), x_s, torch.tensor(g["y_obs"]).reshape(nb * nr, 1),
+                          torch.tensor(g["x_d"]).reshape(nb * nr, -1), torch.tensor(g["std_per_basin"]), row0,
+                          torch.tensor(sel[:, 0]), torch.tensor(sel[:, 1]), L, n_last)
+    assert_close(out["x_lstm"], g["x_lstm"], rtol=1e-6, what="x_lstm")
+    assert_close(out["x_conceptual"], g["x_conceptual"], rtol=0, what="x_conceptual")
+    assert_close(out["y_obs"], g["y_win"], rtol=0, what="y window")
+    assert_close(out["basin_std"], g["basin_std"], rtol=0, what="basin_std")
+
+
+def test_train_steps():
+    """Three clip+Adam updates reproduce the reference's final weights (rtol 1e-5 on fp32 weights)."""
+    g = golden("train_steps")
+    B, T, n_last, I, H, m, wseed = [int(v) for v in g["meta"]]
+    n_out = 8 * m + 2
+    w = weights(I, H, n_out, wseed)
+    keys = list(PARAM_KEYS)
+    ea = [torch.zeros_like(w[k]) for k in keys]
+    es = [torch.zeros_like(w[k]) for k in keys]
+    for step in range(3):
+        for k in keys:
+            w[k].grad = None
+        pred = O.hybrid_forward(w, tt(g[f"step{step}.x_lstm"]), tt(g[f"step{step}.x_conceptual"]), model="shm",
+                                n_models=m, dynamic=["dd", "kf", "beta"], warmup=T - n_last)
+        loss = O.nse_basin_averaged(pred["y_hat"], tt(g[f"step{step}.y_obs"]), tt(g[f"step{step}.basin_std"]))
+        loss.backward()
+        assert_close(loss.detach(), g["losses"][step], rtol=2e-5, what=f"loss {step}")
+        with torch.no_grad():
+            norm = O.clip_and_adam([w[k] for k in keys], [w[k].grad for k in keys], ea, es, step + 1)
+        assert_close(norm, g["norms"][step], rtol=2e-5, what=f"norm {step}")
+    for k in keys:
+        assert_close(w[k].detach(), g["final." + k], rtol=1e-5, what="final " + k)
