@@ -1,0 +1,67 @@
+// extern "C" entry points of the LSTM kernels: argument checks + precision dispatch.
+#include "common.cuh"
+
+namespace hy2dl {
+int lstm_fp32_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H, const float* w_ih,
+                  const float* w_hh, const float* b_ih, const float* b_hh, float* h_seq, float* c_seq, float* gates,
+                  float* h_last, void* ws, int64_t ws_bytes, cudaStream_t s);
+int lstm_fp32_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const float* gates, const float* c_seq,
+                  const float* dh_seq, int64_t dh_t0, const float* dh_last, float* dG, cudaStream_t s);
+int lstm_fp32_wgrad(const float* dG, const float* h_seq, const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
+                    int64_t H, float* dw_ih, float* dw_hh, float* db, void* ws, int64_t ws_bytes, cudaStream_t s);
+int64_t lstm_fp32_workspace(int kind, int64_t B, int64_t T, int64_t I, int64_t H);
+
+static int check_lstm_shape(const char* who, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H) {
+  HY_REQUIRE(B > 0 && T > 0, HY2DL_ERR_SHAPE, "%s: empty batch or sequence (B=%lld T=%lld)", who, (long long)B, (long long)T);
+  HY_REQUIRE(H == 64 || H == 128 || H == 256, HY2DL_ERR_SHAPE, "%s: hidden_size=%lld not supported (64, 128, 256)", who, (long long)H);
+  HY_REQUIRE(I > 0 && I <= 64 && IP == round_up(I, 8), HY2DL_ERR_SHAPE,
+             "%s: input_size=%lld (<= 64) with IP=%lld (must be I rounded up to 8)", who, (long long)I, (long long)IP);
+  return HY2DL_OK;
+}
+}  // namespace hy2dl
+using namespace hy2dl;
+
+extern "C" int64_t hy2dl_workspace_bytes(int kind, int64_t B, int64_t T, int64_t I, int64_t H, int64_t C) {
+  (void)C;
+  if (kind == HY2DL_WS_LSTM_FWD || kind == HY2DL_WS_LSTM_BWD || kind == HY2DL_WS_LSTM_WGRAD)
+    return lstm_fp32_workspace(kind, B, T, I, H);
+  hy2dl::set_error("hy2dl_workspace_bytes: unknown kind %d", kind);
+  return -1;
+}
+
+extern "C" int hy2dl_lstm_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H,
+                              const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* h_seq,
+                              float* c_seq, float* gates, float* h_last, void* ws, int64_t ws_bytes, int precision,
+                              hy2dl_stream_t stream) {
+  int rc = check_lstm_shape("hy2dl_lstm_fwd", B, T, I, IP, H);
+  if (rc) return rc;
+  HY_PTR(xT); HY_PTR(w_ih); HY_PTR(w_hh); HY_PTR(b_ih); HY_PTR(b_hh);
+  HY_PTR_OPT(h_seq); HY_PTR_OPT(c_seq); HY_PTR_OPT(gates); HY_PTR_OPT(h_last);
+  HY_REQUIRE(h_seq || h_last, HY2DL_ERR_ALIGN, "hy2dl_lstm_fwd: both h_seq and h_last are null");
+  HY_REQUIRE(precision == HY2DL_PREC_FP32, HY2DL_ERR_SHAPE, "hy2dl_lstm_fwd: precision %d not built", precision);
+  return lstm_fp32_fwd(xT, B, T, I, IP, H, w_ih, w_hh, b_ih, b_hh, h_seq, c_seq, gates, h_last, ws, ws_bytes,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int hy2dl_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const float* gates,
+                              const float* c_seq, const float* dh_seq, int64_t dh_t0, const float* dh_last, float* dG,
+                              void* ws, int64_t ws_bytes, int precision, hy2dl_stream_t stream) {
+  (void)ws; (void)ws_bytes;
+  int rc = check_lstm_shape("hy2dl_lstm_bwd", B, T, 8, 8, H);
+  if (rc) return rc;
+  HY_PTR(w_hh); HY_PTR(gates); HY_PTR(c_seq); HY_PTR(dG); HY_PTR_OPT(dh_seq); HY_PTR_OPT(dh_last);
+  HY_REQUIRE(dh_seq || dh_last, HY2DL_ERR_ALIGN, "hy2dl_lstm_bwd: no external gradient given");
+  HY_REQUIRE(dh_t0 >= 0 && dh_t0 <= T, HY2DL_ERR_SHAPE, "hy2dl_lstm_bwd: dh_t0=%lld out of range", (long long)dh_t0);
+  HY_REQUIRE(precision == HY2DL_PREC_FP32, HY2DL_ERR_SHAPE, "hy2dl_lstm_bwd: precision %d not built", precision);
+  return lstm_fp32_bwd(B, T, H, w_hh, gates, c_seq, dh_seq, dh_t0, dh_last, dG, (cudaStream_t)stream);
+}
+
+extern "C" int hy2dl_lstm_wgrad(const float* dG, const float* h_seq, const float* xT, int64_t B, int64_t T, int64_t I,
+                                int64_t IP, int64_t H, float* dw_ih, float* dw_hh, float* db, void* ws,
+                                int64_t ws_bytes, int precision, hy2dl_stream_t stream) {
+  int rc = check_lstm_shape("hy2dl_lstm_wgrad", B, T, I, IP, H);
+  if (rc) return rc;
+  HY_PTR(dG); HY_PTR(h_seq); HY_PTR(xT); HY_PTR(dw_ih); HY_PTR(dw_hh); HY_PTR(db);
+  HY_REQUIRE(precision == HY2DL_PREC_FP32, HY2DL_ERR_SHAPE, "hy2dl_lstm_wgrad: precision %d not built", precision);
+  return lstm_fp32_wgrad(dG, h_seq, xT, B, T, I, IP, H, dw_ih, dw_hh, db, ws, ws_bytes, (cudaStream_t)stream);
+}

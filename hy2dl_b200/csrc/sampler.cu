@@ -1,0 +1,114 @@
+// K5: GPU-resident sliding-window sampler (datasetzoo/basedataset.py:168-195 + default collate).
+// The whole data set lives in HBM as concatenated per-basin series; one launch turns a batch of
+// (basin, end index) pairs into the time-major native layouts the LSTM / conceptual kernels read,
+// so no per-sample host work and no [B,T,I] host->device copy is left on the training path.
+#include "common.cuh"
+
+namespace hy2dl {
+
+struct GatherArgs {
+  const float *x_d, *x_s, *x_conc, *y_obs, *basin_std;
+  const int64_t *row0, *basin, *end;
+  int64_t B, L, n_last, nd, ns, nc, IP;
+  float *xT, *forc, *y_win, *std_win;
+};
+
+// grid: (ceil(B/32), L). Each block handles one time step of 32 samples; threads sweep the IP
+// columns of xT so that the [B][IP] slab of a step is written as one contiguous run.
+__global__ void __launch_bounds__(256) window_gather_kernel(GatherArgs a) {
+  const int64_t t = blockIdx.y;
+  const int64_t b0 = (int64_t)blockIdx.x * 32;
+  __shared__ int64_t s_row[32], s_basin[32];
+  if (threadIdx.x < 32) {
+    const int64_t b = b0 + threadIdx.x;
+    if (b < a.B) {
+      const int64_t bs = a.basin[b];
+      s_basin[threadIdx.x] = bs;
+      s_row[threadIdx.x] = a.row0[bs] + a.end[b] - (a.L - 1) + t;   // resident row of step t
+    }
+  }
+  __syncthreads();
+  const int64_t nb = min((int64_t)32, a.B - b0);
+  const int64_t I = a.nd + a.ns;
+  for (int64_t e = threadIdx.x; e < nb * a.IP; e += blockDim.x) {
+    const int64_t lb = e / a.IP, c = e - lb * a.IP;
+    float v = 0.f;
+    if (c < a.nd) v = __ldg(a.x_d + s_row[lb] * a.nd + c);
+    else if (c < I) v = __ldg(a.x_s + s_basin[lb] * a.ns + (c - a.nd));
+    a.xT[(t * a.B + b0) * a.IP + e] = v;
+  }
+  if (a.forc) {
+    for (int64_t e = threadIdx.x; e < nb * 3; e += blockDim.x) {
+      const int64_t c = e / nb, lb = e - c * nb;
+      const float* r = a.x_conc + s_row[lb] * a.nc;
+      float v;
+      if (c < 2) v = __ldg(r + c);
+      else v = (a.nc == 4) ? (__ldg(r + 2) + __ldg(r + 3)) / 2.f : __ldg(r + 2);
+      a.forc[(t * 3 + c) * a.B + b0 + lb] = v;
+    }
+  }
+  const int64_t tl = t - (a.L - a.n_last);
+  if (tl >= 0 && threadIdx.x < nb) {
+    const int lb = threadIdx.x;
+    a.y_win[tl * a.B + b0 + lb] = __ldg(a.y_obs + s_row[lb]);
+    a.std_win[tl * a.B + b0 + lb] = __ldg(a.basin_std + s_basin[lb]);
+  }
+}
+
+// [B][T][I] -> [T][B][IP] (zero padded).  Tile transpose through shared memory: reads are
+// contiguous along (t, i) of one sample, writes contiguous along (b, i) of one step.
+__global__ void __launch_bounds__(256) pack_x_kernel(const float* __restrict__ x, int64_t B, int64_t T, int64_t I,
+                                                      int64_t IP, float* __restrict__ xT) {
+  extern __shared__ float tile[];  // [8 samples][8 steps * I]
+  const int64_t b0 = (int64_t)blockIdx.x * 8, t0 = (int64_t)blockIdx.y * 8;
+  const int64_t nb = min((int64_t)8, B - b0), nt = min((int64_t)8, T - t0);
+  const int64_t run = nt * I;
+  for (int64_t e = threadIdx.x; e < nb * run; e += blockDim.x) {
+    const int64_t lb = e / run, r = e - lb * run;
+    tile[lb * 8 * I + r] = __ldg(x + ((b0 + lb) * T + t0) * I + r);
+  }
+  __syncthreads();
+  for (int64_t e = threadIdx.x; e < nt * nb * IP; e += blockDim.x) {
+    const int64_t lt = e / (nb * IP), r = e - lt * nb * IP;
+    const int64_t lb = r / IP, c = r - lb * IP;
+    xT[((t0 + lt) * B + b0) * IP + r] = c < I ? tile[lb * 8 * I + lt * I + c] : 0.f;
+  }
+}
+
+}  // namespace hy2dl
+using namespace hy2dl;
+
+extern "C" int hy2dl_window_gather(const float* x_d, const float* x_s, const float* x_conc, const float* y_obs,
+                                   const float* basin_std, const int64_t* row0, const int64_t* basin,
+                                   const int64_t* end, int64_t B, int64_t L, int64_t n_last, int64_t nd, int64_t ns,
+                                   int64_t nc, int64_t IP, float* xT, float* forc, float* y_win, float* std_win,
+                                   hy2dl_stream_t stream) {
+  HY_REQUIRE(B > 0 && L > 0 && n_last > 0 && n_last <= L && nd > 0 && ns >= 0, HY2DL_ERR_SHAPE,
+             "hy2dl_window_gather: bad sizes B=%lld L=%lld n_last=%lld nd=%lld ns=%lld", (long long)B, (long long)L,
+             (long long)n_last, (long long)nd, (long long)ns);
+  HY_REQUIRE(IP >= nd + ns && IP % 4 == 0, HY2DL_ERR_SHAPE, "hy2dl_window_gather: IP=%lld must be >= nd+ns and a multiple of 4", (long long)IP);
+  HY_REQUIRE(forc == nullptr || nc == 3 || nc == 4, HY2DL_ERR_SHAPE, "hy2dl_window_gather: nc must be 3 or 4");
+  HY_REQUIRE(L <= 65535, HY2DL_ERR_SHAPE, "hy2dl_window_gather: L=%lld exceeds 65535", (long long)L);
+  HY_NONNULL(x_d); HY_NONNULL(y_obs); HY_NONNULL(basin_std); HY_NONNULL(row0); HY_NONNULL(basin); HY_NONNULL(end);
+  HY_PTR(xT); HY_NONNULL(y_win); HY_NONNULL(std_win);
+  HY_REQUIRE(ns == 0 || x_s != nullptr, HY2DL_ERR_ALIGN, "hy2dl_window_gather: x_s is null but ns > 0");
+  HY_REQUIRE(forc == nullptr || x_conc != nullptr, HY2DL_ERR_ALIGN, "hy2dl_window_gather: x_conc is null");
+  GatherArgs a{x_d, x_s, x_conc, y_obs, basin_std, row0, basin, end, B, L, n_last, nd, ns, nc, IP, xT, forc, y_win, std_win};
+  dim3 grid((unsigned)cdiv(B, 32), (unsigned)L);
+  window_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  HY_LAUNCH_CHECK();
+  return HY2DL_OK;
+}
+
+extern "C" int hy2dl_pack_x(const float* x, int64_t B, int64_t T, int64_t I, int64_t IP, float* xT, hy2dl_stream_t stream) {
+  HY_REQUIRE(B > 0 && T > 0 && I > 0 && IP >= I && IP % 4 == 0, HY2DL_ERR_SHAPE,
+             "hy2dl_pack_x: bad sizes B=%lld T=%lld I=%lld IP=%lld", (long long)B, (long long)T, (long long)I, (long long)IP);
+  HY_REQUIRE(I <= 1024, HY2DL_ERR_SHAPE, "hy2dl_pack_x: I=%lld exceeds 1024", (long long)I);
+  HY_NONNULL(x); HY_PTR(xT);
+  dim3 grid((unsigned)cdiv(B, 8), (unsigned)cdiv(T, 8));
+  HY_REQUIRE(grid.y <= 65535, HY2DL_ERR_SHAPE, "hy2dl_pack_x: T=%lld too long", (long long)T);
+  const size_t smem = (size_t)(8 * 8 * I) * sizeof(float);
+  pack_x_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, B, T, I, IP, xT);
+  HY_LAUNCH_CHECK();
+  return HY2DL_OK;
+}

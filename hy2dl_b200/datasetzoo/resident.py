@@ -1,0 +1,169 @@
+"""GPU-resident sliding-window sampler.
+
+The reference keeps every basin as CPU tensors and builds each sample in Python
+(datasetzoo/basedataset.py:168-195), then collates 256 of them and copies the batch to the device
+every step -- measured at ~11 k sequences/s, the real bottleneck of the reference on any GPU
+(SURVEY.md section 6).  Here the standardised series of all basins live in HBM once (~70 MB for
+CAMELS-GB) and one kernel launch (csrc/sampler.cu) gathers a batch of (basin, end index) windows
+directly into the time-major layouts the LSTM and bucket kernels read.
+
+Validity rules and statistics follow basedataset.py:216-267 (basin std, global scaler) and
+:311-334 (window validity).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Iterator, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .._lib import call, ptr, stream
+from ..ops import round_up
+
+
+def valid_window_flags(x: np.ndarray, y: np.ndarray, seq_length: int, predict_last_n: int,
+                       attributes: Optional[np.ndarray] = None, check_nan: bool = True) -> np.ndarray:
+    """bool [N]: row i can end a sample (basedataset.py:311-334), vectorised with prefix sums."""
+    n = x.shape[0]
+    ok = np.zeros(n, dtype=bool)
+    if n < seq_length:
+        return ok
+    ok[seq_length - 1:] = True
+    if not check_nan:
+        return ok
+    if attributes is not None and np.isnan(attributes).any():
+        return np.zeros(n, dtype=bool)
+    bad_x = np.concatenate([[0], np.cumsum(np.isnan(x).any(axis=1))])
+    good_y = np.concatenate([[0], np.cumsum(~np.isnan(y).all(axis=1) if y.ndim > 1 else ~np.isnan(y))])
+    i = np.arange(seq_length - 1, n)
+    ok[i] &= (bad_x[i + 1] - bad_x[i + 1 - seq_length]) == 0
+    ok[i] &= (good_y[i + 1] - good_y[i + 1 - predict_last_n]) > 0
+    return ok
+
+
+@dataclass
+class Batch:
+    """One gathered batch in native layouts (include/hy2dl_b200.h)."""
+    xT: torch.Tensor                 # [L, B, IP]
+    forc: Optional[torch.Tensor]     # [L, 3, B]
+    y_obs: torch.Tensor              # [n_last, B]
+    basin_std: torch.Tensor          # [n_last, B]
+    basin: torch.Tensor              # [B] int64 basin index
+    end: torch.Tensor                # [B] int64 end row within the basin
+    input_size: int
+
+    def as_reference(self) -> Dict[str, torch.Tensor]:
+        """The reference's sample dict ([B, T, ...] tensors), for API-level comparisons."""
+        d = {"x_lstm": self.xT[:, :, :self.input_size].permute(1, 0, 2).contiguous(),
+             "y_obs": self.y_obs.t().unsqueeze(2).contiguous(),
+             "basin_std": self.basin_std.t().unsqueeze(2).contiguous()}
+        if self.forc is not None:
+            d["x_conceptual"] = self.forc.permute(2, 0, 1).contiguous()
+        return d
+
+
+class ResidentDataset:
+    """x_d [nb, nr, nd], x_s [nb, ns] or None, x_conc [nb, nr, nc] or None, y_obs [nb, nr, 1] (numpy)."""
+
+    def __init__(self, x_d: np.ndarray, y_obs: np.ndarray, sequence_length: int, predict_last_n: int = 1,
+                 x_s: Optional[np.ndarray] = None, x_conc: Optional[np.ndarray] = None, device="cuda",
+                 check_nan: bool = True, basins: Optional[Sequence[int]] = None):
+        if basins is not None:  # data-parallel shard: this rank's basins only
+            basins = np.asarray(basins)
+            x_d, y_obs = x_d[basins], y_obs[basins]
+            x_s = None if x_s is None else x_s[basins]
+            x_conc = None if x_conc is None else x_conc[basins]
+        self.sequence_length, self.predict_last_n = sequence_length, predict_last_n
+        self.nb, self.nr, self.nd = x_d.shape
+        self.ns = 0 if x_s is None else x_s.shape[1]
+        self.nc = 0 if x_conc is None else x_conc.shape[2]
+        self.input_size = self.nd + self.ns
+        self.IP = round_up(self.input_size, 8)
+        self.device = torch.device(device)
+        self._x_d, self._x_s, self._x_conc, self._y = x_d, x_s, x_conc, y_obs
+        inputs = x_d if x_conc is None else np.concatenate([x_d, x_conc], axis=2)
+        ve = []
+        for b in range(self.nb):
+            ok = valid_window_flags(inputs[b], y_obs[b], sequence_length, predict_last_n,
+                                    None if x_s is None else x_s[b], check_nan)
+            idx = np.nonzero(ok)[0]
+            ve.append(np.stack([np.full_like(idx, b), idx], axis=1))
+        self.valid_entities = np.concatenate(ve, axis=0).astype(np.int64)
+        self.scaler: Dict[str, np.ndarray] = {}
+        self.basin_std = np.zeros(self.nb, dtype=np.float32)
+        self._resident = False
+
+    def __len__(self) -> int:
+        return len(self.valid_entities)
+
+    # ---- statistics (training period only; basedataset.py:216-267) ------------------------------
+    def calculate_basin_std(self):
+        self.basin_std = np.array([np.nanstd(self._y[b]) for b in range(self.nb)], dtype=np.float32)
+
+    def calculate_global_statistics(self):
+        gx = self._x_d.reshape(-1, self.nd)
+        self.scaler["x_d_mean"] = np.nanmean(gx, axis=0).astype(np.float32)
+        self.scaler["x_d_std"] = np.nanstd(gx, axis=0).astype(np.float32)
+        gy = self._y.reshape(-1, self._y.shape[2])
+        self.scaler["y_mean"] = np.nanmean(gy, axis=0).astype(np.float32)
+        self.scaler["y_std"] = np.nanstd(gy, axis=0).astype(np.float32)
+        if self._x_s is not None:
+            self.scaler["x_s_mean"] = self._x_s.mean(axis=0).astype(np.float32)
+            self.scaler["x_s_std"] = self._x_s.std(axis=0, ddof=1).astype(np.float32)
+
+    def standardize_data(self, standardize_output: bool = True):
+        """Standardise and move everything to the GPU (call once, after the statistics)."""
+        x_d = (self._x_d - self.scaler["x_d_mean"]) / self.scaler["x_d_std"]
+        y = self._y
+        if standardize_output:
+            y = (y - self.scaler["y_mean"]) / self.scaler["y_std"]
+        x_s = None if self._x_s is None else (self._x_s - self.scaler["x_s_mean"]) / self.scaler["x_s_std"]
+        self._upload(x_d, x_s, self._x_conc, y)
+
+    def to_device_raw(self):
+        """Upload without standardisation (e.g. validation sets that reuse a training scaler first)."""
+        self._upload(self._x_d, self._x_s, self._x_conc, self._y)
+
+    def _upload(self, x_d, x_s, x_conc, y):
+        dev = self.device
+        f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+        self.d_x_d = f32(x_d.reshape(self.nb * self.nr, self.nd))
+        self.d_y = f32(y.reshape(self.nb * self.nr))
+        self.d_x_s = None if x_s is None else f32(x_s)
+        self.d_x_conc = None if x_conc is None else f32(x_conc.reshape(self.nb * self.nr, self.nc))
+        self.d_std = f32(self.basin_std)
+        self.d_row0 = (torch.arange(self.nb, dtype=torch.int64) * self.nr).to(dev)
+        self.d_valid = torch.as_tensor(self.valid_entities).to(dev)
+        self._resident = True
+
+    # ---- gather ---------------------------------------------------------------------------------
+    def gather(self, sample_ids: torch.Tensor) -> Batch:
+        """sample_ids: int64 device tensor of indices into valid_entities."""
+        if not self._resident:
+            raise RuntimeError("call standardize_data() or to_device_raw() first")
+        sel = self.d_valid.index_select(0, sample_ids)
+        return self.gather_pairs(sel[:, 0].contiguous(), sel[:, 1].contiguous())
+
+    def gather_pairs(self, basin: torch.Tensor, end: torch.Tensor) -> Batch:
+        _lib.require_cuda(self.d_x_d, "resident series")
+        B, L, n_last, dev = basin.numel(), self.sequence_length, self.predict_last_n, self.device
+        xT = torch.empty(L, B, self.IP, dtype=torch.float32, device=dev)
+        forc = torch.empty(L, 3, B, dtype=torch.float32, device=dev) if self.nc else None
+        y_win = torch.empty(n_last, B, dtype=torch.float32, device=dev)
+        std_win = torch.empty(n_last, B, dtype=torch.float32, device=dev)
+        call("hy2dl_window_gather", ptr(self.d_x_d), ptr(self.d_x_s), ptr(self.d_x_conc), ptr(self.d_y),
+             ptr(self.d_std), ptr(self.d_row0), ptr(basin), ptr(end), B, L, n_last, self.nd, self.ns, self.nc, self.IP,
+             ptr(xT), ptr(forc), ptr(y_win), ptr(std_win), stream())
+        return Batch(xT, forc, y_win, std_win, basin, end, self.input_size)
+
+    def epoch(self, batch_size: int, generator: Optional[torch.Generator] = None, drop_last: bool = True,
+              shuffle: bool = True) -> Iterator[Batch]:
+        """Shuffled pass over all valid windows (DataLoader(shuffle=True, drop_last=True) semantics)."""
+        n = len(self)
+        order = (torch.randperm(n, device=self.device, generator=generator) if shuffle
+                 else torch.arange(n, device=self.device))
+        stop = n - n % batch_size if drop_last else n
+        for i in range(0, stop, batch_size):
+            yield self.gather(order[i:i + batch_size])

@@ -1,0 +1,370 @@
+"""torch.autograd.Function wrappers around the C-ABI kernels.
+
+Tensors that travel between these functions are in the library's native time-major layouts
+(include/hy2dl_b200.h); the model classes in hy2dl_b200.modelzoo turn them into the reference's
+[batch, time, feature] views at the API boundary.  PyTorch is used for memory, streams and the
+autograd graph only -- every arithmetic step on the path is one of our kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ParMap, call, ptr, require_cuda, stream
+
+PRECISIONS = {"fp32": _lib.PREC_FP32, "tf32x3": _lib.PREC_TF32X3, "bf16": _lib.PREC_BF16}
+
+
+def round_up(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+def _ws(kind: int, B: int, T: int, I: int, H: int, device) -> torch.Tensor:
+    n = _lib.load().hy2dl_workspace_bytes(kind, B, T, I, H, 0)
+    if n < 0:
+        raise RuntimeError(_lib.last_error())
+    return torch.empty(max(int(n), 16), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------------------------------
+# layout packing (no gradient w.r.t. inputs: the reference never asks for dL/dx either)
+# --------------------------------------------------------------------------------------------------
+def pack_x(x: torch.Tensor) -> torch.Tensor:
+    """[B,T,I] -> native [T,B,IP]."""
+    require_cuda(x, "x_lstm")
+    x = x.detach().contiguous()
+    B, T, I = x.shape
+    IP = round_up(I, 8)
+    xT = torch.empty(T, B, IP, dtype=torch.float32, device=x.device)
+    call("hy2dl_pack_x", ptr(x), B, T, I, IP, ptr(xT), stream())
+    return xT
+
+
+def pack_forcing(xc: torch.Tensor) -> torch.Tensor:
+    """[B,T,3|4] -> native [T,3,B] (P, PET, Tmean)."""
+    require_cuda(xc, "x_conceptual")
+    xc = xc.detach().contiguous()
+    B, T, nc = xc.shape
+    forc = torch.empty(T, 3, B, dtype=torch.float32, device=xc.device)
+    call("hy2dl_pack_forcing", ptr(xc), B, T, nc, ptr(forc), stream())
+    return forc
+
+
+# --------------------------------------------------------------------------------------------------
+# LSTM
+# --------------------------------------------------------------------------------------------------
+class LstmFunction(torch.autograd.Function):
+    """h_seq [T,B,H] and h_last [B,H] from xT [T,B,IP]; one layer, h0 = c0 = 0.
+
+    `dh_t0`: the caller promises that the gradient flowing into h_seq is zero (and may be
+    uninitialised memory) for steps t < dh_t0 -- the hybrid head only feeds steps >= warm-up.
+    """
+
+    @staticmethod
+    def forward(ctx, xT, w_ih, w_hh, b_ih, b_hh, I: int, dh_t0: int, want_seq: bool, precision: int):
+        for n, t in (("xT", xT), ("weight_ih", w_ih), ("weight_hh", w_hh), ("bias_ih", b_ih), ("bias_hh", b_hh)):
+            require_cuda(t, n)
+        T, B, IP = xT.shape
+        H = w_hh.shape[1]
+        dev = xT.device
+        need_grad = any(ctx.needs_input_grad[1:5])
+        w_ih, w_hh, b_ih, b_hh = (t.detach().contiguous() for t in (w_ih, w_hh, b_ih, b_hh))
+        h_seq = torch.empty(T, B, H, dtype=torch.float32, device=dev) if (want_seq or need_grad) else None
+        h_last = torch.empty(B, H, dtype=torch.float32, device=dev)
+        c_seq = torch.empty(T, B, H, dtype=torch.float32, device=dev) if need_grad else None
+        gates = torch.empty(T, B, 4, H, dtype=torch.float32, device=dev) if need_grad else None
+        ws = _ws(_lib.WS_LSTM_FWD, B, T, I, H, dev)
+        call("hy2dl_lstm_fwd", ptr(xT), B, T, I, IP, H, ptr(w_ih), ptr(w_hh), ptr(b_ih), ptr(b_hh), ptr(h_seq),
+             ptr(c_seq), ptr(gates), ptr(h_last), ptr(ws), ws.numel(), precision, stream())
+        ctx.save_for_backward(xT, w_hh, h_seq, c_seq, gates)
+        ctx.meta = (B, T, I, IP, H, dh_t0, precision, want_seq)
+        if not want_seq:
+            none = torch.empty(0, device=dev)
+            ctx.mark_non_differentiable(none)
+            return none, h_last
+        return h_seq, h_last
+
+    @staticmethod
+    def backward(ctx, dh_seq, dh_last):
+        xT, w_hh, h_seq, c_seq, gates = ctx.saved_tensors
+        B, T, I, IP, H, dh_t0, precision, want_seq = ctx.meta
+        dev = xT.device
+        if not want_seq or dh_seq is None or dh_seq.numel() == 0:
+            dh_seq = None
+        else:
+            dh_seq = dh_seq.contiguous()
+        if dh_last is not None:
+            dh_last = dh_last.contiguous()
+        if dh_seq is None and dh_last is None:
+            return (None,) * 9
+        ws_b = _ws(_lib.WS_LSTM_BWD, B, T, I, H, dev)
+        # dG overwrites the gate tape in place (the kernel reads each element before writing it)
+        dG = gates
+        call("hy2dl_lstm_bwd", B, T, H, ptr(w_hh), ptr(gates), ptr(c_seq), ptr(dh_seq), dh_t0, ptr(dh_last), ptr(dG),
+             ptr(ws_b), ws_b.numel(), precision, stream())
+        dw_ih = torch.empty(4 * H, I, dtype=torch.float32, device=dev)
+        dw_hh = torch.empty(4 * H, H, dtype=torch.float32, device=dev)
+        db = torch.empty(4 * H, dtype=torch.float32, device=dev)
+        ws_w = _ws(_lib.WS_LSTM_WGRAD, B, T, I, H, dev)
+        call("hy2dl_lstm_wgrad", ptr(dG), ptr(h_seq), ptr(xT), B, T, I, IP, H, ptr(dw_ih), ptr(dw_hh), ptr(db),
+             ptr(ws_w), ws_w.numel(), precision, stream())
+        return None, dw_ih, dw_hh, db, db.clone(), None, None, None, None
+
+
+def lstm(xT, w_ih, w_hh, b_ih, b_hh, input_size: int, dh_t0: int = 0, want_seq: bool = True,
+         precision: str = "fp32") -> Tuple[torch.Tensor, torch.Tensor]:
+    return LstmFunction.apply(xT, w_ih, w_hh, b_ih, b_hh, input_size, dh_t0, want_seq, PRECISIONS[precision])
+
+
+# --------------------------------------------------------------------------------------------------
+# head + parameter mapping
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class ParLayout:
+    """Where each conceptual / routing parameter's plane lives inside the flat par_sim buffer."""
+    pm: ParMap
+    names: List[str]
+    routing_names: List[str]
+    n_floats: int
+    B: int
+    T: int
+
+    @property
+    def T_sim(self) -> int:
+        return self.T - self.pm.warmup
+
+    @property
+    def N(self) -> int:
+        return self.B * self.pm.n_members
+
+    def plane(self, flat: torch.Tensor, k: int) -> torch.Tensor:
+        """View of parameter k (routing follows the conceptual ones): [T_sim,N] dynamic, [N] static, [B] routing."""
+        off = self.pm.sim_off[k]
+        if k >= self.pm.n_par:
+            return flat[off:off + self.B]
+        if self.pm.dynamic[k]:
+            return flat[off:off + self.T_sim * self.N].view(self.T_sim, self.N)
+        return flat[off:off + self.N]
+
+
+def make_layout(ranges: Dict[str, Tuple[float, float]], dynamic: Sequence[str], n_members: int, warmup: int,
+                routing_ranges: Optional[Dict[str, Tuple[float, float]]], B: int, T: int) -> ParLayout:
+    pm = ParMap()
+    names = list(ranges)
+    if len(names) > _lib.MAX_PAR:
+        raise ValueError(f"at most {_lib.MAX_PAR} conceptual parameters are supported")
+    pm.n_par, pm.n_members, pm.warmup = len(names), n_members, warmup
+    rnames = list(routing_ranges) if routing_ranges else []
+    pm.n_routing = len(rnames)
+    for k, n in enumerate(names):
+        pm.dynamic[k] = 1 if n in dynamic else 0
+        pm.lo[k], pm.hi[k] = ranges[n]
+    for r, n in enumerate(rnames):
+        pm.lo[len(names) + r], pm.hi[len(names) + r] = routing_ranges[n]
+    nf = _lib.load().hy2dl_parmap_layout(C.byref(pm), B, T)
+    if nf < 0:
+        raise RuntimeError("hy2dl_parmap_layout failed")
+    return ParLayout(pm, names, rnames, int(nf), B, T)
+
+
+class HeadMapFunction(torch.autograd.Function):
+    """(h_seq, W, b) -> (par_sim flat planes, par_warm [P,N]); par_warm carries no gradient."""
+
+    @staticmethod
+    def forward(ctx, h_seq, w, bias, layout: ParLayout):
+        require_cuda(h_seq, "h_seq"); require_cuda(w, "linear.weight"); require_cuda(bias, "linear.bias")
+        T, B, H = h_seq.shape
+        dev = h_seq.device
+        h_seq = h_seq.contiguous()
+        w_c, b_c = w.detach().contiguous(), bias.detach().contiguous()
+        par_sim = torch.empty(layout.n_floats, dtype=torch.float32, device=dev)
+        par_warm = torch.empty(layout.pm.n_par, layout.N, dtype=torch.float32, device=dev)
+        call("hy2dl_head_map_fwd", ptr(h_seq), B, T, H, ptr(w_c), ptr(b_c), C.byref(layout.pm), ptr(par_sim),
+             ptr(par_warm), stream())
+        ctx.save_for_backward(h_seq, w_c, par_sim)
+        ctx.layout = layout
+        ctx.mark_non_differentiable(par_warm)
+        return par_sim, par_warm
+
+    @staticmethod
+    def backward(ctx, dpar_sim, _dpar_warm):
+        h_seq, w, par_sim = ctx.saved_tensors
+        layout = ctx.layout
+        T, B, H = h_seq.shape
+        dev = h_seq.device
+        dpar_sim = dpar_sim.contiguous()
+        dh_seq = torch.empty(T, B, H, dtype=torch.float32, device=dev)  # rows < warmup stay uninitialised (dh_t0)
+        dw = torch.empty_like(w)
+        db = torch.empty(w.shape[0], dtype=torch.float32, device=dev)
+        call("hy2dl_head_map_bwd", ptr(h_seq), ptr(par_sim), ptr(dpar_sim), B, T, H, ptr(w), C.byref(layout.pm),
+             ptr(dh_seq), ptr(dw), ptr(db), stream())
+        return dh_seq, dw, db, None
+
+
+def head_map(h_seq, w, bias, layout: ParLayout):
+    return HeadMapFunction.apply(h_seq, w, bias, layout)
+
+
+# --------------------------------------------------------------------------------------------------
+# conceptual models
+# --------------------------------------------------------------------------------------------------
+def _ptr_array(ptrs: Sequence[Optional[int]]):
+    arr = (C.c_void_p * _lib.MAX_PAR)()
+    for k, p in enumerate(ptrs):
+        arr[k] = p
+    return arr
+
+
+def _i64_array(vals: Sequence[int]):
+    arr = (C.c_int64 * _lib.MAX_PAR)()
+    for k, v in enumerate(vals):
+        arr[k] = v
+    return arr
+
+
+class ConceptualFunction(torch.autograd.Function):
+    """Bucket model over forcing rows [t0, t0+Tn).
+
+    par_flat: flat buffer, parameter k's plane at offs[k] (None: parameter absent), dynamic[k] says
+    whether the plane is [Tn,N] or [N].  Returns (states [Tn,5,N], q [Tn,B]).
+    """
+
+    @staticmethod
+    def forward(ctx, forc, par_flat, init, model: int, B: int, m: int, t0: int, Tn: int, offs, dynamic):
+        require_cuda(forc, "forcing"); require_cuda(par_flat, "parameters")
+        dev = forc.device
+        N = B * m
+        forc = forc.contiguous()
+        par_flat = par_flat.contiguous()
+        if init is not None:
+            init = require_cuda(init, "initial_states").contiguous()
+        base = par_flat.data_ptr()
+        ptrs = [None if o is None else base + 4 * o for o in offs]
+        ts = [0 if (o is None or not d) else N for o, d in zip(offs, dynamic)]
+        states = torch.empty(Tn, _lib.N_STATES, N, dtype=torch.float32, device=dev)
+        q = torch.empty(Tn, B, dtype=torch.float32, device=dev)
+        call("hy2dl_conceptual_fwd", model, ptr(forc), B, t0, Tn, m, _ptr_array(ptrs), _i64_array(ts), ptr(init),
+             ptr(states), ptr(q), stream())
+        ctx.save_for_backward(forc, par_flat, init, states)
+        ctx.meta = (model, B, m, t0, Tn, tuple(offs), tuple(dynamic))
+        return states, q
+
+    @staticmethod
+    def backward(ctx, dstates, dq):
+        forc, par_flat, init, states = ctx.saved_tensors
+        model, B, m, t0, Tn, offs, dynamic = ctx.meta
+        dev = forc.device
+        N = B * m
+        base = par_flat.data_ptr()
+        ptrs = [None if o is None else base + 4 * o for o in offs]
+        ts = [0 if (o is None or not d) else N for o, d in zip(offs, dynamic)]
+        dpar = torch.zeros_like(par_flat)  # zeros: the padding between planes must not leak garbage into autograd
+        dbase = dpar.data_ptr()
+        dptrs = [None if o is None else dbase + 4 * o for o in offs]
+        dq = torch.zeros(Tn, B, dtype=torch.float32, device=dev) if dq is None else dq.contiguous()
+        dstates = None if dstates is None else dstates.contiguous()
+        dinit = torch.empty_like(init) if (init is not None and ctx.needs_input_grad[2]) else None
+        call("hy2dl_conceptual_bwd", model, ptr(forc), B, t0, Tn, m, _ptr_array(ptrs), _i64_array(ts), ptr(init),
+             ptr(states), ptr(dq), ptr(dstates), _ptr_array(dptrs), ptr(dinit), stream())
+        return None, dpar, dinit, None, None, None, None, None, None, None
+
+
+def conceptual(forc, par_flat, init, model: int, B: int, m: int, t0: int, Tn: int, offs, dynamic):
+    return ConceptualFunction.apply(forc, par_flat, init, model, B, m, t0, Tn, offs, dynamic)
+
+
+# --------------------------------------------------------------------------------------------------
+# routing
+# --------------------------------------------------------------------------------------------------
+class UHFunction(torch.autograd.Function):
+    """q [T,B], alpha [B], beta [B] -> routed y [T,B]."""
+
+    @staticmethod
+    def forward(ctx, q, alpha, beta):
+        require_cuda(q, "discharge"); require_cuda(alpha, "alpha"); require_cuda(beta, "beta")
+        T, B = q.shape
+        q, alpha, beta = q.contiguous(), alpha.contiguous(), beta.contiguous()
+        uh = torch.empty(15, B, dtype=torch.float32, device=q.device)
+        y = torch.empty_like(q)
+        call("hy2dl_uh_fwd", ptr(q), ptr(alpha), ptr(beta), B, T, ptr(uh), ptr(y), stream())
+        ctx.save_for_backward(q, alpha, beta, uh)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        q, alpha, beta, uh = ctx.saved_tensors
+        T, B = q.shape
+        dy = dy.contiguous()
+        dq = torch.empty_like(q)
+        da = torch.empty_like(alpha)
+        db = torch.empty_like(beta)
+        call("hy2dl_uh_bwd", ptr(q), ptr(alpha), ptr(beta), ptr(uh), ptr(dy), B, T, ptr(dq), ptr(da), ptr(db), stream())
+        return dq, da, db
+
+
+def uh_route(q, alpha, beta):
+    return UHFunction.apply(q, alpha, beta)
+
+
+# --------------------------------------------------------------------------------------------------
+# losses
+# --------------------------------------------------------------------------------------------------
+def _allreduce_sum(t: torch.Tensor, group):
+    """Sum the masked partial sums over the data-parallel group so that every rank forms the
+    GLOBAL mean. group=None: single process, nothing to do."""
+    if group is None:
+        return
+    import torch.distributed as dist
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=None if group == "world" else group)
+
+
+class NseLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y_sim, y_obs, std, group):
+        require_cuda(y_sim, "y_sim"); require_cuda(y_obs, "y_obs"); require_cuda(std, "per_basin_target_std")
+        n = y_sim.numel()
+        acc = torch.zeros(4, dtype=torch.float32, device=y_sim.device)
+        call("hy2dl_loss_nse_reduce", ptr(y_sim), ptr(y_obs), ptr(std), n, ptr(acc), stream())
+        _allreduce_sum(acc, group)
+        loss = torch.empty((), dtype=torch.float32, device=y_sim.device)
+        call("hy2dl_loss_nse_finish", ptr(y_sim), ptr(y_obs), ptr(std), n, ptr(acc), None, ptr(loss), None, stream())
+        ctx.save_for_backward(y_sim, y_obs, std, acc)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        y_sim, y_obs, std, acc = ctx.saved_tensors
+        dy = torch.empty_like(y_sim)
+        tmp = torch.empty((), dtype=torch.float32, device=y_sim.device)
+        g = g.contiguous().to(torch.float32)
+        call("hy2dl_loss_nse_finish", ptr(y_sim), ptr(y_obs), ptr(std), y_sim.numel(), ptr(acc), ptr(g), ptr(tmp),
+             ptr(dy), stream())
+        return dy, None, None, None
+
+
+class WrmseLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y_sim, y_obs, group):
+        require_cuda(y_sim, "y_sim"); require_cuda(y_obs, "y_obs")
+        n = y_sim.numel()
+        acc = torch.zeros(4, dtype=torch.float32, device=y_sim.device)
+        call("hy2dl_loss_wrmse_reduce", ptr(y_sim), ptr(y_obs), n, ptr(acc), stream())
+        _allreduce_sum(acc, group)
+        loss = torch.empty((), dtype=torch.float32, device=y_sim.device)
+        call("hy2dl_loss_wrmse_finish", ptr(y_sim), ptr(y_obs), n, ptr(acc), None, ptr(loss), None, stream())
+        ctx.save_for_backward(y_sim, y_obs, acc)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        y_sim, y_obs, acc = ctx.saved_tensors
+        dy = torch.empty_like(y_sim)
+        tmp = torch.empty((), dtype=torch.float32, device=y_sim.device)
+        g = g.contiguous().to(torch.float32)
+        call("hy2dl_loss_wrmse_finish", ptr(y_sim), ptr(y_obs), y_sim.numel(), ptr(acc), ptr(g), ptr(tmp), ptr(dy),
+             stream())
+        return dy, None, None

@@ -1,0 +1,184 @@
+/*
+ * hy2dl_b200.h -- C ABI of the B200-native Hy2DL hot path (libhy2dl_b200.so, sm_100a).
+ *
+ * The reference (KIT-HYD/Hy2DL) is pure Python: it has no FFI / plugin layer, its "operator API"
+ * for this path is the nn.Module surface of modelzoo/ and the loss functions of aux_functions/.
+ * Each entry point below replaces the arithmetic behind one of those call sites (cited per
+ * function, paths relative to /root/reference/Hy2DL); the Python classes in hy2dl_b200/ keep the
+ * reference's class names, constructor arguments, state-dict keys and return dicts and reach
+ * this library through ctypes (see INTEGRATION.md for the binding a maintainer would add).
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, int64 sizes, a CUDA stream handle; no C++/torch types.
+ *   - every function is an asynchronous launch on `stream`; it never allocates, frees or
+ *     synchronises.  Scratch space is passed in (`ws`, size from hy2dl_workspace_bytes()).
+ *   - returns 0 on success, a negative HY2DL_ERR_* otherwise; hy2dl_last_error() gives a
+ *     thread-local message.  There is no CPU fallback anywhere.
+ *   - all floating-point buffers are fp32 and 16-byte aligned.
+ *
+ * Device layouts ("native", time-major so one step of one batch tile is one contiguous run)
+ *   xT      [T][B][IP]      LSTM inputs, IP = I rounded up to a multiple of 8, zero padded
+ *   h_seq   [T][B][H]       hidden state tape          c_seq [T][B][H]  cell state tape
+ *   gates   [T][B][4][H]    activated gates i,f,g,o (tape); overwritten in place by dG in bwd
+ *   forc    [T][3][B]       conceptual forcings P, PET, Tmean
+ *   N = B*m series (sample b, member j -> n = b*m + j)
+ *   par     planes: dynamic parameter -> [T_sim][N], static parameter -> [N]   (see hy2dl_parmap)
+ *   states  [T][5][N]       bucket storages after each step
+ *   q       [T][B]          member-mean outflow
+ */
+#ifndef HY2DL_B200_H
+#define HY2DL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HY2DL_ABI_VERSION 1
+
+#define HY2DL_OK 0
+#define HY2DL_ERR_SHAPE (-1)   /* unsupported or inconsistent sizes            */
+#define HY2DL_ERR_ALIGN (-2)   /* pointer not 16-byte aligned / null           */
+#define HY2DL_ERR_ARCH (-3)    /* device is not sm_100                         */
+#define HY2DL_ERR_LAUNCH (-4)  /* CUDA launch failed (message has the reason)  */
+#define HY2DL_ERR_WORKSPACE (-5) /* workspace too small                        */
+
+typedef void* hy2dl_stream_t; /* cudaStream_t */
+
+/* precision of the recurrent / projection matmuls */
+#define HY2DL_PREC_FP32 0   /* CUDA-core FMA, fp32-exact (parity path, rtol 1e-4)            */
+#define HY2DL_PREC_TF32X3 1 /* tcgen05 kind::tf32, 3-term split (fp32-class accuracy)         */
+#define HY2DL_PREC_BF16 2   /* tcgen05 kind::f16 bf16 operands, fp32 accumulate (throughput)  */
+
+/* conceptual models */
+#define HY2DL_MODEL_SHM 0 /* 8 parameters: dd f_thr sumax beta perc kf ki kb     (modelzoo/shm.py:193-204) */
+#define HY2DL_MODEL_HBV 1 /* 13 parameters: BETA FC K0 K1 K2 LP PERC UZL TT CFMAX CFR CWH BETAET (hbv.py:199-215) */
+#define HY2DL_MAX_PAR 16
+#define HY2DL_N_STATES 5
+
+/* workspace kinds for hy2dl_workspace_bytes */
+#define HY2DL_WS_LSTM_FWD 0
+#define HY2DL_WS_LSTM_BWD 1
+#define HY2DL_WS_LSTM_WGRAD 2
+
+int hy2dl_abi_version(void);
+const char* hy2dl_last_error(void);
+/* 0 if device `dev` is compute capability 10.x, HY2DL_ERR_ARCH otherwise */
+int hy2dl_check_device(int dev);
+int64_t hy2dl_workspace_bytes(int kind, int64_t B, int64_t T, int64_t I, int64_t H, int64_t C);
+
+/* ---- layout packing --------------------------------------------------------------------------
+ * x [B][T][I] (reference batch-first layout, modelzoo/cudalstm.py:34, hybrid.py:72) -> xT [T][B][IP].
+ * xc [B][T][nc], nc = 3 (P, PET, T) or 4 (P, PET, Tmax, Tmin -> mean; shm.py:74-80, hbv.py:70-77)
+ *    -> forc [T][3][B]. */
+int hy2dl_pack_x(const float* x, int64_t B, int64_t T, int64_t I, int64_t IP, float* xT, hy2dl_stream_t stream);
+int hy2dl_pack_forcing(const float* xc, int64_t B, int64_t T, int64_t nc, float* forc, hy2dl_stream_t stream);
+
+/* ---- LSTM (replaces torch.nn.LSTM at modelzoo/cudalstm.py:50 and hybrid.py:92; one layer,
+ * unidirectional, h0 = c0 = 0, gate order i|f|g|o as torch/nn/modules/rnn.py:935-941) -------------
+ * Weights come in PyTorch layout: w_ih [4H][I], w_hh [4H][H], b_ih [4H], b_hh [4H].
+ * Tape outputs may be NULL (inference): c_seq, gates; h_seq may be NULL if only h_last is wanted. */
+int hy2dl_lstm_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H,
+                   const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                   float* h_seq, float* c_seq, float* gates, float* h_last,
+                   void* ws, int64_t ws_bytes, int precision, hy2dl_stream_t stream);
+/* Back-propagation through time. External gradient: dh_seq [T][B][H] used for steps t >= dh_t0
+ * (NULL: none) plus dh_last [B][H] added at t = T-1 (NULL: none).  dG [T][B][4][H] receives the
+ * pre-activation gate gradients and MAY alias `gates`. */
+int hy2dl_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh,
+                   const float* gates, const float* c_seq, const float* dh_seq, int64_t dh_t0,
+                   const float* dh_last, float* dG,
+                   void* ws, int64_t ws_bytes, int precision, hy2dl_stream_t stream);
+/* Weight gradients from dG: dw_ih [4H][I] = dG^T xT, dw_hh [4H][H] = dG^T h_{t-1}, db [4H] = sum dG
+ * (db is the gradient of both b_ih and b_hh).  Outputs are overwritten, not accumulated. */
+int hy2dl_lstm_wgrad(const float* dG, const float* h_seq, const float* xT,
+                     int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H,
+                     float* dw_ih, float* dw_hh, float* db,
+                     void* ws, int64_t ws_bytes, int precision, hy2dl_stream_t stream);
+
+/* ---- head: Linear(H, C) on the needed steps + sigmoid range mapping ---------------------------
+ * replaces modelzoo/hybrid.py:93-97,110-113 and baseconceptualmodel.py:53-76.
+ * Column c = p*m + j for conceptual parameter p, member j; routing parameters (m = 1) follow. */
+typedef struct {
+  int32_t n_par;                    /* conceptual parameters P (8 SHM, 13 HBV)                   */
+  int32_t n_members;                /* m                                                          */
+  int32_t n_routing;                /* 0 or 2 (alpha, beta), static, taken at t = T-1             */
+  int32_t warmup;                   /* warm-up steps, >= 1 (hybrid.py:39)                         */
+  int32_t dynamic[HY2DL_MAX_PAR];   /* 1 = dynamic, 0 = static (baseconceptualmodel.py:80-104)    */
+  float lo[HY2DL_MAX_PAR + 2];      /* range low per parameter, then routing                      */
+  float hi[HY2DL_MAX_PAR + 2];      /* range high                                                 */
+  int64_t sim_off[HY2DL_MAX_PAR + 2]; /* float offset of each parameter's plane in par_sim        */
+} hy2dl_parmap;
+/* fills sim_off for (B, T) and returns the number of floats par_sim needs; par_warm needs
+ * n_par * B * m floats (plane p at p*B*m). */
+int64_t hy2dl_parmap_layout(hy2dl_parmap* pm, int64_t B, int64_t T);
+int hy2dl_head_map_fwd(const float* h_seq, int64_t B, int64_t T, int64_t H,
+                       const float* w, const float* bias, const hy2dl_parmap* pm,
+                       float* par_sim, float* par_warm, hy2dl_stream_t stream);
+/* par_sim: the forward output; dpar_sim has the same layout.  Writes dh_seq rows t >= warmup
+ * (the warm-up runs under no_grad, hybrid.py:99-102, so row warmup-1 and earlier get no gradient
+ * and are left untouched), and overwrites dw [C][H], dbias [C]. */
+int hy2dl_head_map_bwd(const float* h_seq, const float* par_sim, const float* dpar_sim, int64_t B, int64_t T,
+                       int64_t H, const float* w, const hy2dl_parmap* pm, float* dh_seq, float* dw, float* dbias,
+                       hy2dl_stream_t stream);
+
+/* ---- conceptual models (replace SHM.forward shm.py:135-182, HBV.forward hbv.py:127-188) --------
+ * par[p] / tstride[p]: device pointer of parameter p's plane and its stride in floats between
+ * time steps (N for dynamic, 0 for static).  HBV: par[12] (BETAET) may be NULL (hbv.py:157-162).
+ * init [5][N] or NULL (model defaults 0.001).  Steps simulated: forc rows t0 .. t0+Tn-1. */
+int hy2dl_conceptual_fwd(int model, const float* forc, int64_t B, int64_t t0, int64_t Tn, int64_t m,
+                         const float* const* par, const int64_t* tstride, const float* init,
+                         float* states, float* q, hy2dl_stream_t stream);
+/* Adjoint. dq [Tn][B] (gradient of q), dstates [Tn][5][N] or NULL.  dpar[p] has par[p]'s shape
+ * (overwritten); dinit [5][N] or NULL. */
+int hy2dl_conceptual_bwd(int model, const float* forc, int64_t B, int64_t t0, int64_t Tn, int64_t m,
+                         const float* const* par, const int64_t* tstride, const float* init,
+                         const float* states, const float* dq, const float* dstates,
+                         float* const* dpar, float* dinit, hy2dl_stream_t stream);
+
+/* ---- unit-hydrograph routing (replaces UH_routing.forward, modelzoo/uh_routing.py:42-44,64-74,
+ * 92-109): alpha, beta [B]; q, y [T][B]; uh [15][B] scratch/tape ---------------------------------- */
+int hy2dl_uh_fwd(const float* q, const float* alpha, const float* beta, int64_t B, int64_t T,
+                 float* uh, float* y, hy2dl_stream_t stream);
+int hy2dl_uh_bwd(const float* q, const float* alpha, const float* beta, const float* uh, const float* dy,
+                 int64_t B, int64_t T, float* dq, float* dalpha, float* dbeta, hy2dl_stream_t stream);
+
+/* ---- losses (replace aux_functions/functions_training.py:32-41 and :72-81) ----------------------
+ * y_sim, y_obs, basin_std: n elements in the same order; NaN in y_obs = missing.
+ * *_reduce writes partial sums to acc (NSE: {sum w*e^2, count}; wRMSE: {sum e^2, sum le^2, count});
+ * acc must be zeroed by the caller and can be all-reduced across ranks before *_finish.
+ * *_finish writes the scalar loss and, if dy != NULL, dL/dy_sim scaled by *gscale (device scalar
+ * or NULL = 1). */
+int hy2dl_loss_nse_reduce(const float* y_sim, const float* y_obs, const float* basin_std, int64_t n,
+                          float* acc, hy2dl_stream_t stream);
+int hy2dl_loss_nse_finish(const float* y_sim, const float* y_obs, const float* basin_std, int64_t n,
+                          const float* acc, const float* gscale, float* loss, float* dy, hy2dl_stream_t stream);
+int hy2dl_loss_wrmse_reduce(const float* y_sim, const float* y_obs, int64_t n, float* acc, hy2dl_stream_t stream);
+int hy2dl_loss_wrmse_finish(const float* y_sim, const float* y_obs, int64_t n, const float* acc,
+                            const float* gscale, float* loss, float* dy, hy2dl_stream_t stream);
+
+/* ---- GPU-resident sliding-window sampler (replaces BaseDataset.__getitem__ + collate,
+ * datasetzoo/basedataset.py:168-195).  Resident series are the concatenation of all basins:
+ * x_d [R][nd], x_conc [R][nc] (or NULL), y_obs [R], x_s [nb][ns] (or NULL), basin_std [nb],
+ * row0 [nb].  Sample k = (basin[k], end[k]).  Outputs in native layouts:
+ * xT [L][B][IP], forc [L][3][B] (or NULL), y_win [n_last][B], std_win [n_last][B]. */
+int hy2dl_window_gather(const float* x_d, const float* x_s, const float* x_conc, const float* y_obs,
+                        const float* basin_std, const int64_t* row0, const int64_t* basin, const int64_t* end,
+                        int64_t B, int64_t L, int64_t n_last, int64_t nd, int64_t ns, int64_t nc, int64_t IP,
+                        float* xT, float* forc, float* y_win, float* std_win, hy2dl_stream_t stream);
+
+/* ---- optimiser tail on one flat buffer (replaces clip_grad_norm_(.., max_norm) + Adam.step,
+ * experiments/LSTM_CAMELS_GB.ipynb:298-299).  norm_sq: device scalar, zeroed by the caller before
+ * hy2dl_grad_sqnorm (can be all-reduced);  lr: device scalar (so a scheduler can change it under a
+ * captured CUDA graph);  step_count: device int64, incremented by the kernel;  the gradient is
+ * first multiplied by grad_scale (e.g. 1/world_size), then clipped to max_norm (<= 0: no clipping). */
+int hy2dl_grad_sqnorm(const float* grad, int64_t n, float* norm_sq, hy2dl_stream_t stream);
+int hy2dl_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                    const float* norm_sq, float grad_scale, float max_norm, const float* lr, float beta1,
+                    float beta2, float eps, int64_t* step_count, hy2dl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HY2DL_B200_H */

@@ -252,7 +252,7 @@ def case_sampler():
 
 def case_train_steps():
     """Three notebook-style updates (zero_grad, fwd, loss, bwd, clip 1, Adam 1e-3) on the hybrid SHM."""
-    B, T, n_last, H = 8, 60, 30, 16
+    B, T, n_last, H = 8, 60, 30, 64
     data = make_basins("gb", n_basins=6, n_rows=T + 60, seed=42)
     I = 25
     hp = {"input_size_lstm": I, "hidden_size": H, "no_of_layers": 1, "seq_length": T, "predict_last_n": n_last,
@@ -284,11 +284,11 @@ if __name__ == "__main__":
     case_cudalstm("cudalstm_c3", "us_lstm", B=2, T=120, H=256, wseed=2, store_full_grads=False)
     case_hybrid("hybrid_shm_c2", "gb", SHM, "shm", B=4, T=365, n_last=182, H=64, m=1,
                 dynamic=["dd", "f_thr", "sumax", "beta", "perc", "kf", "ki", "kb"], wseed=3, loss_kind="nse")
-    case_hybrid("hybrid_shm_mixed", "us", SHM, "shm", B=3, T=90, n_last=40, H=16, m=3,
+    case_hybrid("hybrid_shm_mixed", "us", SHM, "shm", B=3, T=90, n_last=40, H=64, m=3,
                 dynamic=["dd", "beta", "ki"], wseed=4, loss_kind="wrmse")
-    case_hybrid("hybrid_hbv_c4", "us", HBV, "hbv", B=3, T=140, n_last=70, H=32, m=16,
+    case_hybrid("hybrid_hbv_c4", "us", HBV, "hbv", B=3, T=140, n_last=70, H=64, m=16,
                 dynamic=["BETA", "BETAET"], wseed=5, loss_kind="wrmse")
-    case_hybrid("hybrid_hbv_norouting", "gb", HBV, "hbv", B=3, T=80, n_last=30, H=16, m=2,
+    case_hybrid("hybrid_hbv_norouting", "gb", HBV, "hbv", B=3, T=80, n_last=30, H=128, m=2,
                 dynamic=["TT", "FC", "K1", "CFMAX"], wseed=6, loss_kind="nse", routing=False)
     case_direct("shm_direct", SHM, lambda mdl: mdl.parameter_ranges, B=6, T=120, m=2, ncols=3)
     case_direct("shm_direct_static4", SHM, lambda mdl: mdl.parameter_ranges, B=5, T=60, m=1, ncols=4,
