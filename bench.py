@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: train sequences/s of the hybrid LSTM(64)+SHM(+UH) chain, seq 365,
+on synthetic CAMELS-GB-shaped basins (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = GPU-resident window gather -> LSTM fwd -> head -> SHM warm-up + simulation -> routing
+-> masked NSE loss -> adjoints -> BPTT -> weight gradients -> (all-reduce) -> clip + Adam.
+Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` runs the
+same step through the public nn.Module API from pinned HOST tensors, copies in the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+T_SEQ, N_LAST, HID, N_DYN, N_STAT, N_CONC = 365, 182, 64, 3, 22, 3
+I_LSTM = N_DYN + N_STAT
+DYNAMIC = ["dd", "f_thr", "sumax", "beta", "perc", "kf", "ki", "kb"]
+METRIC = "train sequences/sec (seq 365)"
+WORKLOAD = "hybrid LSTM(64)+SHM(8 dynamic params, 1 member)+UH routing, synthetic CAMELS-GB shape (671 basins), " \
+           "seq 365 = 183 warm-up + 182 simulated, nse_basin_averaged, clip 1 + Adam 1e-3"
+
+
+def hyper():
+    return {"input_size_lstm": I_LSTM, "hidden_size": HID, "no_of_layers": 1, "seq_length": T_SEQ,
+            "predict_last_n": N_LAST, "n_conceptual_models": 1, "conceptual_dynamic_parameterization": DYNAMIC}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+# algorithmic bytes per sequence, fp32, store-gates convention (SURVEY.md 8d / DESIGN.md)
+def algo_bytes():
+    T, I, H = T_SEQ, I_LSTM, HID
+    return {
+        "hy2dl_lstm_fwd": 4 * T * (I + 6 * H),        # read x, write h c i f g o
+        "hy2dl_lstm_bwd": 4 * T * 6 * H,              # re-read the tape
+        "hy2dl_lstm_wgrad": 4 * T * I,                # re-read x (dG / h re-reads are implementation traffic)
+        "hy2dl_conceptual_fwd": 4 * N_LAST * (8 + 5) + 4 * N_LAST * (N_CONC + 1) + 4 * (T - N_LAST) * N_CONC,
+        "hy2dl_conceptual_bwd": 4 * N_LAST * (8 + 5 + 8) + 4 * N_LAST * (N_CONC + 1),
+        "total": 4 * T * (2 * I + 12 * H) + 4 * N_LAST * (3 * 8 + 2 * 5) + 4 * N_LAST * (2 * N_CONC + 2)
+                 + 4 * (T - N_LAST) * N_CONC + 16 * N_LAST,
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            self.th.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port (torch fp32 on the host, nn.LSTM via oneDNN)
+# ------------------------------------------------------------------------------------------------
+def cpu_train_steps(steps, warmup, batch=256, seed=42):
+    """Reference-style train step on the host CPU with the oracle port; returns seq/s and details.
+    The reference itself is pure Python under /root/reference and cannot travel to the GPU box, so
+    the port (same torch ops: _VF.lstm + per-step elementwise bucket loop + autograd + clip + Adam)
+    is what is timed (kind = "port")."""
+    from oracle import hy2dl_oracle as O
+    from hy2dl_b200.synthetic import lstm_weights, make_basins
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    data = make_basins("gb", n_basins=16, n_rows=T_SEQ + 64, seed=seed)
+    rng = np.random.default_rng(seed)
+    w = {k: torch.tensor(v, requires_grad=True) for k, v in lstm_weights(I_LSTM, HID, 10, seed=seed).items()}
+    keys = list(w)
+    opt = torch.optim.Adam([w[k] for k in keys], lr=1e-3)
+
+    def make_batch():
+        bi = rng.integers(0, 16, batch)
+        e = rng.integers(T_SEQ - 1, data.x_d.shape[1], batch)
+        xd = np.stack([data.x_d[b, i - T_SEQ + 1:i + 1] for b, i in zip(bi, e)])
+        xs = np.repeat(data.x_s[bi][:, None, :], T_SEQ, axis=1)
+        xl = np.concatenate([(xd - xd.mean((0, 1))) / (xd.std((0, 1)) + 1e-6), xs], axis=2).astype(np.float32)
+        xc = np.stack([data.x_conc[b, i - T_SEQ + 1:i + 1] for b, i in zip(bi, e)])
+        yo = np.stack([data.y_obs[b, i - N_LAST + 1:i + 1] for b, i in zip(bi, e)])
+        sd = np.full((batch, N_LAST, 1), 1.0, dtype=np.float32)
+        return [torch.tensor(a) for a in (xl, xc, yo, sd)]
+
+    batches = [make_batch() for _ in range(2)]
+    times = []
+    for s in range(warmup + steps):
+        xl, xc, yo, sd = batches[s % 2]
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        pred = O.hybrid_forward(w, xl, xc, model="shm", n_models=1, dynamic=DYNAMIC, warmup=T_SEQ - N_LAST, library=True)
+        loss = O.nse_basin_averaged(pred["y_hat"], yo, sd)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([w[k] for k in keys], 1)
+        opt.step()
+        loss.item()
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    per_step = float(np.mean(times))
+    return {"value": batch / per_step, "unit": "sequences/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} train steps of batch {batch} after {warmup} warm-up (oracle port, torch {torch.__version__} "
+                      f"CPU fp32, {cores} threads)", "ms_per_step": per_step * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    r = cpu_train_steps(steps, max(1, min(args.warmup, 1)))
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "sequences/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": 1, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_step": 256},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from hy2dl_b200 import _lib
+    from hy2dl_b200.aux_functions import nse_basin_averaged
+    from hy2dl_b200.datasetzoo import ResidentDataset
+    from hy2dl_b200.modelzoo import SHM, Hybrid, UH_routing
+    from hy2dl_b200.synthetic import make_basins
+    from hy2dl_b200.training import FusedClipAdam, Trainer, shard_basins
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        group = "world"
+    _lib.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- data: synthetic CAMELS-GB shape, basins sharded over ranks, resident in HBM
+    full = make_basins("gb", seed=42)
+    mine = shard_basins(full.x_d.shape[0], rank, world)
+    ds = ResidentDataset(full.x_d, full.y_obs, T_SEQ, N_LAST, x_s=full.x_s, x_conc=full.x_conc, device=dev, basins=mine)
+    ds.calculate_basin_std()
+    # global scaler from the full set so that every rank standardises identically
+    allds = ResidentDataset.__new__(ResidentDataset)
+    allds._x_d, allds._y, allds._x_s, allds.nd, allds.scaler = full.x_d, full.y_obs, full.x_s, N_DYN, {}
+    ResidentDataset.calculate_global_statistics(allds)
+    ds.scaler = allds.scaler
+    ds.standardize_data(standardize_output=False)
+    del full, allds
+
+    torch.manual_seed(42)
+    model = Hybrid(hyper(), conceptual_model=SHM, routing_model=UH_routing)
+    model.lstm.bias_hh_l0.data[HID:2 * HID] = 3.0   # set_forget_gate (HybridModel_GB.ipynb)
+    model = model.to(dev)
+    B = args.batch
+    trainer = Trainer(model, ds, loss="nse", lr=1e-3, max_norm=1.0, group=group, use_graph=False)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    n_valid = len(ds)
+
+    def draw():
+        return torch.randint(0, n_valid, (B,), device=dev, generator=gen)
+
+    # ---- per-call device timing (CUDA events on the launching stream) for the roofline object
+    ev = {}
+    orig_call = _lib.call
+    timing = {"on": False}
+    launches = {"n": 0}
+    LAUNCHES = {"hy2dl_lstm_fwd": 2, "hy2dl_lstm_wgrad": 2, "hy2dl_uh_fwd": 2, "hy2dl_uh_bwd": 2, "hy2dl_clip_adam": 2,
+                "hy2dl_head_map_fwd": 2, "hy2dl_head_map_bwd": 2}
+
+    def timed_call(name, *a):
+        if not timing["on"]:
+            return orig_call(name, *a)
+        launches["n"] += LAUNCHES.get(name, 1)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        orig_call(name, *a)
+        e.record()
+        ev.setdefault(name, []).append((s, e))
+
+    import hy2dl_b200.ops as ops_mod
+    import hy2dl_b200.training as tr_mod
+    import hy2dl_b200.datasetzoo.resident as res_mod
+    for mod in (ops_mod, tr_mod, res_mod, _lib):
+        mod.call = timed_call
+
+    # ---- value: resident inputs, device-timed
+    for _ in range(args.warmup):
+        trainer.step(draw())
+    barrier()
+    timing["on"] = True
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        t_start.record()
+        for _ in range(args.steps):
+            loss = trainer.step(draw())
+        t_end.record()
+        barrier()
+    timing["on"] = False
+    ms = t_start.elapsed_time(t_end)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = B * world * args.steps / (ms * 1e-3)
+    final_loss = float(loss.item())
+
+    # ---- roofline of the dominant kernel
+    per_call = {k: float(np.mean([s.elapsed_time(e) for s, e in v])) for k, v in ev.items()}
+    share = {k: per_call[k] * len(ev[k]) / ms for k in per_call}
+    top = max((k for k in per_call if k in algo_bytes()), key=lambda k: per_call[k] * len(ev[k]))
+    pk, pk_kind = peaks()
+    achieved = algo_bytes()[top] * B / (per_call[top] * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(top)
+    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind,
+                "ms_per_launch": per_call[top], "share_of_step": share[top],
+                "step_frac_of_hbm_roofline": algo_bytes()["total"] * value / world / 1e9 / pk["hbm_gbs"],
+                "kernel_ms": {k: round(v, 4) for k, v in sorted(per_call.items(), key=lambda kv: -kv[1])}}
+
+    # ---- e2e: public API, pinned host inputs, H2D copies + loss read-back inside the timed region
+    for mod in (ops_mod, tr_mod, res_mod, _lib):
+        mod.call = orig_call
+    opt = trainer.opt
+    Be = args.e2e_batch or B
+    host = []
+    for _ in range(2):
+        ref = ds.gather(torch.randint(0, n_valid, (Be,), device=dev, generator=gen)).as_reference()
+        host.append({k: v.cpu().pin_memory() for k, v in ref.items()})
+        del ref
+    h2d = sum(v.numel() * 4 for v in host[0].values())
+
+    def e2e_step(hb):
+        d = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+        opt.zero_grad()
+        pred = model(x_lstm=d["x_lstm"], x_conceptual=d["x_conceptual"])
+        l = nse_basin_averaged(y_sim=pred["y_hat"], y_obs=d["y_obs"], per_basin_target_std=d["basin_std"], group=group)
+        l.backward()
+        opt.step()
+        return l.item()   # device -> host read of the step's result
+
+    e2e_steps = max(3, args.steps // 2)
+    for i in range(2):
+        e2e_step(host[i % 2])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(host[i % 2])
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e = {"value": Be * world * e2e_steps / float(dt.item()), "unit": "sequences/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": 4, "steps": e2e_steps, "batch_per_gpu": Be}
+
+    # ---- reference batch size (256 per GPU), CUDA-graph replayed: the latency-bound regime
+    small = None
+    if args.small_batch:
+        model2 = Hybrid(hyper(), conceptual_model=SHM, routing_model=UH_routing).to(dev)
+        tr2 = Trainer(model2, ds, loss="nse", group=group, use_graph=(world == 1))
+        ids = [torch.randint(0, n_valid, (args.small_batch,), device=dev, generator=gen) for _ in range(4)]
+        for i in range(4):
+            tr2.step(ids[i % 4])
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        n_small = 20
+        for i in range(n_small):
+            tr2.step(ids[i % 4])
+        e.record()
+        barrier()
+        small = {"batch_per_gpu": args.small_batch, "value": args.small_batch * world * n_small / (s.elapsed_time(e) * 1e-3),
+                 "ms_per_step": s.elapsed_time(e) / n_small, "cuda_graph": world == 1}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_train_steps(3, 1)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "sequences/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "seq_len": T_SEQ,
+                           "hidden": HID, "precision": "fp32 (CUDA-core FMA recurrent path)",
+                           "parallelism": f"dp{world} over basins, flat-gradient NCCL all-reduce" if world > 1 else "single GPU",
+                           "l2_policy": "inputs larger than L2: every step gathers a new random batch; the per-step tape "
+                                        f"({4 * T_SEQ * 12 * HID * B / 1e9:.1f} GB) exceeds the 126 MB L2"},
+                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches["n"], "roofline": roofline,
+                "cpu_baseline": cpu, "reference_batch": small, "final_loss": final_loss}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=9472, help="sequences per GPU per step (saturating: 64 x 148 SMs)")
+    ap.add_argument("--e2e-batch", type=int, default=0)
+    ap.add_argument("--small-batch", type=int, default=256, help="also report the reference batch size (0: skip)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,168 @@
+"""CPU-side checks: the C-ABI library loads here (no GPU) and exports every symbol the header
+declares; host logic (window validity, parameter layout, basin sharding); and the data-parallel
+loss/gradient semantics on a world_size-2 gloo group."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from _util import O, ROOT, assert_close, golden, tt, weights
+
+
+def test_library_loads_and_exports_header_symbols():
+    from hy2dl_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "hy2dl_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(hy2dl_[a-z0-9_]+)\s*\(", header)))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/hy2dl_b200.h but not exported"
+    assert sorted(_lib.exported_symbols()) == declared
+    assert lib.hy2dl_abi_version() == 1
+    # no compute call without a GPU: the device probe must fail loudly, not fall back
+    assert lib.hy2dl_check_device(0) != 0 and _lib.last_error()
+
+
+def test_product_path_refuses_cpu_tensors():
+    from hy2dl_b200.modelzoo import CudaLSTM
+    from hy2dl_b200.aux_functions import nse_basin_averaged
+    model = CudaLSTM({"input_size_lstm": 8, "hidden_size": 64, "no_of_layers": 1, "drop_out_rate": 0.0})
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(torch.zeros(2, 5, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        nse_basin_averaged(torch.zeros(3, 1), torch.zeros(3, 1), torch.ones(3, 1))
+
+
+def test_product_code_never_imports_the_oracle():
+    bad = []
+    for d, _, files in os.walk(os.path.join(ROOT, "hy2dl_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")) and re.search(r"\boracle\b", open(os.path.join(d, f)).read()):
+                bad.append(f)
+    assert not bad, f"product files mention the oracle: {bad}"
+
+
+def test_state_dict_layout_matches_reference_keys():
+    from hy2dl_b200.modelzoo import HBV, SHM, CudaLSTM, Hybrid, UH_routing
+    m = CudaLSTM({"input_size_lstm": 25, "hidden_size": 64, "no_of_layers": 1, "drop_out_rate": 0.4})
+    sd = m.state_dict()
+    assert list(sd) == ["lstm.weight_ih_l0", "lstm.weight_hh_l0", "lstm.bias_ih_l0", "lstm.bias_hh_l0",
+                        "linear.weight", "linear.bias"]
+    assert [tuple(v.shape) for v in sd.values()] == [(256, 25), (256, 64), (256,), (256,), (1, 64), (1,)]
+    # same seed -> same initial weights as torch.nn.LSTM + nn.Linear built in the reference's order
+    torch.manual_seed(42)
+    a = CudaLSTM({"input_size_lstm": 25, "hidden_size": 64, "no_of_layers": 1, "drop_out_rate": 0.4})
+    torch.manual_seed(42)
+    ref_lstm = torch.nn.LSTM(25, 64, batch_first=True, num_layers=1)
+    ref_lin = torch.nn.Linear(64, 1)
+    assert torch.equal(a.lstm.weight_hh_l0, ref_lstm.weight_hh_l0) and torch.equal(a.linear.weight, ref_lin.weight)
+    hp = {"input_size_lstm": 41, "hidden_size": 256, "no_of_layers": 1, "seq_length": 730, "predict_last_n": 365,
+          "n_conceptual_models": 16, "conceptual_dynamic_parameterization": ["BETA", "BETAET"]}
+    h = Hybrid(hp, conceptual_model=HBV, routing_model=UH_routing)
+    assert h.linear.out_features == 13 * 16 + 2 and h.warmup_period == 365
+    assert h.n_conceptual_model_params == 208 and h.n_routing_params == 2
+    assert h.conceptual_model.parameter_type["BETA"] == "dynamic" and h.conceptual_model.parameter_type["FC"] == "static"
+    assert list(SHM().parameter_ranges) == ["dd", "f_thr", "sumax", "beta", "perc", "kf", "ki", "kb"]
+    assert h.conceptual_model.output_size == 1 and h.conceptual_model.n_conceptual_models == 16
+
+
+def test_flat_aliases_resolve_reference_import_names():
+    import hy2dl_b200
+    hy2dl_b200.install_flat_aliases()
+    from hybrid import Hybrid  # noqa: F401
+    from shm import SHM  # noqa: F401
+    from functions_training import nse_basin_averaged  # noqa: F401
+    import sys
+    for k in ("hybrid", "shm", "hbv", "cudalstm", "uh_routing", "baseconceptualmodel", "functions_training",
+              "functions_evaluation"):
+        sys.modules.pop(k, None)
+
+
+def test_valid_window_flags_match_reference():
+    from hy2dl_b200.datasetzoo import valid_window_flags
+    g = golden("sampler")
+    nb, nr, L, n_last = [int(v) for v in g["meta"]]
+    ve = []
+    for b in range(nb):
+        ok = valid_window_flags(g["x_d"][b], g["y_obs"][b], L, n_last, g["x_s"][b])
+        ve += [(b, int(i)) for i in np.nonzero(ok)[0]]
+    assert np.array_equal(np.array(ve, dtype=np.int64), g["valid_entities"])
+    # edge cases: too short, NaN attribute, check disabled
+    assert not valid_window_flags(np.zeros((5, 2)), np.zeros((5, 1)), 6, 1).any()
+    assert not valid_window_flags(np.zeros((9, 2)), np.zeros((9, 1)), 3, 1, np.array([np.nan])).any()
+    x = np.zeros((9, 2)); x[4, 0] = np.nan
+    assert valid_window_flags(x, np.zeros((9, 1)), 3, 1, check_nan=False).sum() == 7
+
+
+def test_parmap_layout():
+    from hy2dl_b200 import ops
+    from hy2dl_b200.modelzoo import HBV, UH_routing
+    B, T, m, warm = 6, 50, 16, 20
+    lay = ops.make_layout(HBV().parameter_ranges, ["BETA", "BETAET"], m, warm, UH_routing().parameter_ranges, B, T)
+    N, Ts = B * m, T - warm
+    sizes = [(Ts * N if n in ("BETA", "BETAET") else N) for n in lay.names] + [B, B]
+    offs = [lay.pm.sim_off[k] for k in range(15)]
+    assert offs[0] == 0 and all(o % 4 == 0 for o in offs)
+    assert all(offs[k + 1] >= offs[k] + sizes[k] for k in range(14))
+    assert lay.n_floats >= offs[-1] + B
+    flat = torch.arange(lay.n_floats, dtype=torch.float32)
+    assert lay.plane(flat, 0).shape == (Ts, N) and lay.plane(flat, 1).shape == (N,) and lay.plane(flat, 14).shape == (B,)
+
+
+def test_shard_basins_partition():
+    from hy2dl_b200.training import shard_basins
+    for world in (1, 2, 4, 8):
+        parts = [shard_basins(671, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(671))
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+# ---- data-parallel semantics on CPU (gloo, world_size 2) ------------------------------------------
+def _dp_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g = golden("train_steps")
+    B, T, n_last, I, H, m, wseed = [int(v) for v in g["meta"]]
+    w = weights(I, H, 8 * m + 2, wseed, torch.float64)
+    sl = slice(rank * B // world, (rank + 1) * B // world)
+    yo = g["step0.y_obs"].copy()
+    yo[0, :25] = np.nan   # unequal NaN counts between the two shards
+    pred = O.hybrid_forward(w, tt(g["step0.x_lstm"][sl], torch.float64), tt(g["step0.x_conceptual"][sl], torch.float64),
+                            model="shm", n_models=m, dynamic=["dd", "kf", "beta"], warmup=T - n_last)
+    y, o, s = pred["y_hat"].flatten(), tt(yo[sl], torch.float64).flatten(), tt(g["step0.basin_std"][sl], torch.float64).flatten()
+    keep = ~torch.isnan(o)
+    # the rule the CUDA loss implements: all-reduce (sum, count), every rank divides by the GLOBAL count
+    acc = torch.stack([(((y[keep] - o[keep]) ** 2) / (s[keep] + 0.1) ** 2).sum().detach(), keep.sum().double()])
+    dist.all_reduce(acc)
+    local = (((y[keep] - o[keep]) ** 2) / (s[keep] + 0.1) ** 2).sum() / acc[1]
+    local.backward()
+    flat = torch.cat([w[k].grad.flatten() for k in sorted(w)])
+    dist.all_reduce(flat)
+    if rank == 0:
+        ret["loss"] = float(acc[0] / acc[1])
+        ret["grad"] = flat.numpy()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_equals_single_process_with_unequal_nan_counts():
+    import torch.multiprocessing as mp
+    g = golden("train_steps")
+    B, T, n_last, I, H, m, wseed = [int(v) for v in g["meta"]]
+    yo = g["step0.y_obs"].copy()
+    yo[0, :25] = np.nan
+    w = weights(I, H, 8 * m + 2, wseed, torch.float64)
+    pred = O.hybrid_forward(w, tt(g["step0.x_lstm"], torch.float64), tt(g["step0.x_conceptual"], torch.float64),
+                            model="shm", n_models=m, dynamic=["dd", "kf", "beta"], warmup=T - n_last)
+    loss = O.nse_basin_averaged(pred["y_hat"], tt(yo, torch.float64), tt(g["step0.basin_std"], torch.float64))
+    loss.backward()
+    single = torch.cat([w[k].grad.flatten() for k in sorted(w)]).numpy()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + os.getpid() % 1000
+    mp.spawn(_dp_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert_close(ret["loss"], loss.item(), rtol=1e-12, what="DP loss")
+    assert_close(ret["grad"], single, rtol=1e-10, what="DP gradient")

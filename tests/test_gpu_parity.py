@@ -1,0 +1,372 @@
+"""Parity of the CUDA path (through the drop-in classes -> ctypes -> C ABI) against
+(a) the golden vectors of the unmodified reference and (b) the CPU oracle on fresh seeded inputs.
+
+Tolerances (north star): per-step discharge / states / loss rtol 1e-4 in fp32; parameter gradients
+rtol 1e-4 against the fp64 oracle where the reference's own fp32 noise allows, stated per test.
+`assert_close` is tensor-level: max|a-b| <= atol + rtol*max|b|.
+"""
+import numpy as np
+import pytest
+import torch
+
+from _util import O, PARAM_KEYS, assert_close, golden, oracle_hybrid, tt, weights
+
+pytestmark = pytest.mark.gpu
+
+TOL = dict(rtol=1e-4, atol=1e-6)
+GTOL = dict(rtol=3e-4, atol=1e-6)   # gradients vs the reference's fp32 autograd (its noise ~1e-4, see test_oracle_golden)
+
+
+@pytest.fixture(scope="module")
+def dev(cuda_lib):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def cu(a, dev, grad=False):
+    return torch.tensor(np.asarray(a), dtype=torch.float32, device=dev).requires_grad_(grad)
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def load(model, I, H, n_out, seed, dev):
+    from hy2dl_b200.synthetic import lstm_weights
+    model.load_state_dict({k: torch.tensor(v) for k, v in lstm_weights(I, H, n_out, seed=seed).items()})
+    return model.to(dev)
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel-level cases
+# ------------------------------------------------------------------------------------------------
+def test_pack_layouts(dev):
+    from hy2dl_b200 import ops
+    rng = np.random.default_rng(0)
+    for B, T, I in [(5, 17, 25), (33, 9, 31), (8, 8, 8), (1, 1, 3)]:
+        x = rng.normal(size=(B, T, I)).astype(np.float32)
+        xT = npy(ops.pack_x(cu(x, dev)))
+        assert xT.shape == (T, B, (I + 7) // 8 * 8)
+        assert np.array_equal(xT[:, :, :I], x.transpose(1, 0, 2)) and not xT[:, :, I:].any()
+    for nc in (3, 4):
+        xc = rng.normal(size=(7, 11, nc)).astype(np.float32)
+        f = npy(ops.pack_forcing(cu(xc, dev)))
+        tm = (xc[:, :, 2] + xc[:, :, 3]) / 2 if nc == 4 else xc[:, :, 2]
+        assert np.array_equal(f[:, 0], xc[:, :, 0].T) and np.array_equal(f[:, 1], xc[:, :, 1].T)
+        assert np.array_equal(f[:, 2], tm.T)
+
+
+@pytest.mark.parametrize("name", ["shm_direct", "shm_direct_static4", "hbv_direct", "hbv_direct_nobetaet"])
+def test_bucket_models_direct(dev, name):
+    from hy2dl_b200.modelzoo import HBV, SHM
+    g = golden(name)
+    B, T, m, ncols, dyn = [int(v) for v in g["meta"]]
+    model = (SHM if name.startswith("shm") else HBV)(n_models=m)
+    leaves = {k: cu(g["param." + k], dev, True) for k in model.parameter_ranges if "param." + k in g}
+    pars = {k: (v if dyn else v.expand(-1, T, -1)) for k, v in leaves.items()}
+    init = {k: cu(g["init." + k], dev, True) for k in model._initial_states}
+    pred = model(x_conceptual=cu(g["x_conceptual"], dev), parameters=pars, initial_states=init)
+    fun = (pred["y_hat"] * cu(g["wq"], dev)).sum()
+    for k in init:
+        fun = fun + (pred["internal_states"][k] * cu(g["ws." + k], dev)).sum()
+    fun.backward()
+    assert_close(npy(pred["y_hat"]), g["y_hat"], what="y_hat", **TOL)
+    for k in init:
+        assert_close(npy(pred["internal_states"][k]), g["state." + k], what="state " + k, **TOL)
+        assert_close(npy(pred["final_states"][k]), g["state." + k][:, -1], what="final " + k, **TOL)
+        assert_close(npy(init[k].grad), g["grad.init." + k], what="grad init " + k, **TOL)
+    for k, v in leaves.items():
+        assert_close(npy(v.grad), g["grad.param." + k], what="grad param " + k, **TOL)
+
+
+def test_uh_routing(dev):
+    from hy2dl_b200.modelzoo import UH_routing
+    g = golden("uh_direct")
+    B, T = g["q"].shape[:2]
+    a, b, q = cu(g["alpha"], dev, True), cu(g["beta"], dev, True), cu(g["q"], dev, True)
+    y = UH_routing()(discharge=q, parameters={"alpha": a.reshape(B, 1, 1).expand(B, T, 1),
+                                              "beta": b.reshape(B, 1, 1).expand(B, T, 1)})
+    (y * cu(g["w"], dev)).sum().backward()
+    assert_close(npy(y), g["y"], what="y", **TOL)
+    assert_close(npy(q.grad), g["grad_q"], what="grad q", **TOL)
+    assert_close(npy(a.grad), g["grad_alpha"], what="grad alpha", **GTOL)
+    assert_close(npy(b.grad), g["grad_beta"], what="grad beta", **GTOL)
+
+
+def test_losses(dev):
+    from hy2dl_b200.aux_functions import nse_basin_averaged, weighted_rmse
+    g = golden("losses")
+    ys = cu(g["y_sim"], dev, True)
+    l1 = nse_basin_averaged(y_sim=ys, y_obs=cu(g["y_obs"], dev), per_basin_target_std=cu(g["basin_std"], dev))
+    (g1,) = torch.autograd.grad(l1, ys)
+    l2 = weighted_rmse(y_sim=ys, y_obs=cu(g["y_obs"], dev))
+    (g2,) = torch.autograd.grad(3.0 * l2, ys)   # exercises the upstream gradient scale
+    assert_close(l1.item(), g["nse"], what="nse", **TOL)
+    assert_close(npy(g1), g["grad_nse"], what="grad nse", **TOL)
+    assert_close(l2.item(), g["wrmse"], what="wrmse", **TOL)
+    assert_close(npy(g2) / 3.0, g["grad_wrmse"], what="grad wrmse", **TOL)
+
+
+def test_loss_all_nan_sample_and_transposed_input(dev):
+    """y_sim handed over as a transposed view (what Hybrid returns) gives the same value."""
+    from hy2dl_b200.aux_functions import nse_basin_averaged
+    g = golden("losses")
+    ys_t = cu(np.ascontiguousarray(g["y_sim"][:, :, 0].T), dev)       # [T,B] buffer
+    view = ys_t.t().unsqueeze(2)                                       # [B,T,1] strided view
+    l1 = nse_basin_averaged(y_sim=view, y_obs=cu(g["y_obs"], dev), per_basin_target_std=cu(g["basin_std"], dev))
+    assert_close(l1.item(), g["nse"], what="nse (strided)", **TOL)
+
+
+def test_sampler_gather(dev):
+    from hy2dl_b200.datasetzoo import ResidentDataset
+    g = golden("sampler")
+    nb, nr, L, n_last = [int(v) for v in g["meta"]]
+    ds = ResidentDataset(g["x_d"], g["y_obs"], L, n_last, x_s=g["x_s"], x_conc=g["x_d"], device=dev)
+    assert np.array_equal(ds.valid_entities, g["valid_entities"])
+    ds.calculate_basin_std()
+    ds.calculate_global_statistics()
+    assert_close(ds.basin_std, g["std_per_basin"], rtol=1e-6, what="basin std")
+    for k in ("x_d_mean", "x_d_std", "x_s_mean", "x_s_std", "y_mean", "y_std"):
+        assert_close(ds.scaler[k], g["scaler_" + k], rtol=1e-5, what=k)
+    ds.standardize_data(standardize_output=False)
+    batch = ds.gather(torch.tensor(g["pick"], device=dev))
+    ref = batch.as_reference()
+    assert_close(npy(ref["x_lstm"]), g["x_lstm"], rtol=1e-5, atol=1e-6, what="x_lstm")
+    assert_close(npy(ref["x_conceptual"]), g["x_conceptual"], rtol=0, what="x_conceptual")
+    assert_close(npy(ref["y_obs"]), g["y_win"], rtol=0, what="y window")
+    assert_close(npy(ref["basin_std"]), g["basin_std"], rtol=1e-6, what="basin_std")
+    assert not npy(batch.xT)[:, :, ds.input_size:].any()
+
+
+# ------------------------------------------------------------------------------------------------
+# model-level cases against the reference's golden vectors
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["cudalstm_c1", "cudalstm_c3"])
+def test_cudalstm_golden(dev, name):
+    from hy2dl_b200.aux_functions import nse_basin_averaged
+    from hy2dl_b200.modelzoo import CudaLSTM
+    g = golden(name)
+    B, T, I, H, wseed = [int(v) for v in g["meta"]]
+    model = load(CudaLSTM({"input_size_lstm": I, "hidden_size": H, "no_of_layers": 1, "drop_out_rate": 0.0}),
+                 I, H, 1, wseed, dev)
+    y = model(cu(g["x_lstm"], dev))["y_hat"]
+    loss = nse_basin_averaged(y_sim=y, y_obs=cu(g["y_obs"], dev), per_basin_target_std=cu(g["basin_std"], dev))
+    loss.backward()
+    assert_close(npy(y), g["y_hat"], what="y_hat", **TOL)
+    assert_close(loss.item(), g["loss"], what="loss", **TOL)
+    for k, p in model.named_parameters():
+        ref, got = g["grad." + k], npy(p.grad)
+        if ref.shape != got.shape:
+            assert_close(np.linalg.norm(got.astype(np.float64)), g["grad." + k + ".norm"], what=k + ".norm", **GTOL)
+            got = got[::16, ::8]
+        assert_close(got, ref, what="grad " + k, **GTOL)
+
+
+def build_hybrid(g, dev):
+    from hy2dl_b200.modelzoo import HBV, SHM, Hybrid, UH_routing
+    B, T, n_last, I, H, m, wseed, routing = [int(v) for v in g["meta"]]
+    cls = {"shm": SHM, "hbv": HBV}[str(g["model"])]
+    hp = {"input_size_lstm": I, "hidden_size": H, "no_of_layers": 1, "seq_length": T, "predict_last_n": n_last,
+          "n_conceptual_models": m, "conceptual_dynamic_parameterization": [str(s) for s in g["dynamic"]]}
+    model = Hybrid(hp, conceptual_model=cls, routing_model=UH_routing if routing else None)
+    return load(model, I, H, model.linear.out_features, wseed, dev)
+
+
+@pytest.mark.parametrize("name", ["hybrid_shm_c2", "hybrid_shm_mixed", "hybrid_hbv_c4", "hybrid_hbv_norouting"])
+def test_hybrid_golden(dev, name):
+    from hy2dl_b200.aux_functions import nse_basin_averaged, weighted_rmse
+    g = golden(name)
+    model = build_hybrid(g, dev)
+    pred = model(x_lstm=cu(g["x_lstm"], dev), x_conceptual=cu(g["x_conceptual"], dev))
+    if str(g["loss_kind"]) == "nse":
+        loss = nse_basin_averaged(y_sim=pred["y_hat"], y_obs=cu(g["y_obs"], dev),
+                                  per_basin_target_std=cu(g["basin_std"], dev))
+    else:
+        loss = weighted_rmse(y_sim=pred["y_hat"], y_obs=cu(g["y_obs"], dev))
+    loss.backward()
+    assert set(pred) == {"y_hat", "parameters", "internal_states", "final_states"}
+    assert_close(npy(pred["y_hat"]), g["y_hat"], what="y_hat", **TOL)
+    assert_close(loss.item(), g["loss"], what="loss", **TOL)
+    for k, v in pred["internal_states"].items():
+        assert_close(npy(v), g["state." + k], what="state " + k, **TOL)
+    for k, v in pred["final_states"].items():
+        assert_close(npy(v), g["final." + k], what="final " + k, **TOL)
+    for k, v in pred["parameters"].items():
+        assert_close(npy(v), g["param." + k], what="param " + k, **TOL)
+    for k, p in model.named_parameters():
+        assert_close(npy(p.grad), g["grad." + k], what="grad " + k, **GTOL)
+
+
+def test_train_steps_golden(dev):
+    """zero_grad -> fwd -> loss -> bwd -> fused clip+Adam, three times; final weights rtol 1e-5."""
+    from hy2dl_b200.aux_functions import nse_basin_averaged
+    from hy2dl_b200.modelzoo import SHM, Hybrid, UH_routing
+    from hy2dl_b200.training import FusedClipAdam
+    g = golden("train_steps")
+    B, T, n_last, I, H, m, wseed = [int(v) for v in g["meta"]]
+    hp = {"input_size_lstm": I, "hidden_size": H, "no_of_layers": 1, "seq_length": T, "predict_last_n": n_last,
+          "n_conceptual_models": m, "conceptual_dynamic_parameterization": ["dd", "kf", "beta"]}
+    model = load(Hybrid(hp, conceptual_model=SHM, routing_model=UH_routing), I, H, 8 * m + 2, wseed, dev)
+    opt = FusedClipAdam(model.parameters(), lr=1e-3, max_norm=1.0)
+    for step in range(3):
+        opt.zero_grad()
+        pred = model(x_lstm=cu(g[f"step{step}.x_lstm"], dev), x_conceptual=cu(g[f"step{step}.x_conceptual"], dev))
+        loss = nse_basin_averaged(y_sim=pred["y_hat"], y_obs=cu(g[f"step{step}.y_obs"], dev),
+                                  per_basin_target_std=cu(g[f"step{step}.basin_std"], dev))
+        loss.backward()
+        opt.step()
+        assert_close(loss.item(), g["losses"][step], rtol=2e-4, what=f"loss {step}")
+        assert_close(opt.grad_norm().item(), g["norms"][step], rtol=3e-4, what=f"grad norm {step}")
+    sd = model.state_dict()
+    assert list(sd) == list(PARAM_KEYS)
+    for k in PARAM_KEYS:
+        assert_close(npy(sd[k]), g["final." + k], rtol=2e-5, atol=1e-6, what="final " + k)
+
+
+# ------------------------------------------------------------------------------------------------
+# fresh seeded inputs against the oracle: reference batch size, ragged tiles, larger H
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,T,I,H", [(256, 365, 25, 64), (37, 50, 31, 256), (5, 33, 7, 128), (70, 40, 41, 64)])
+def test_lstm_vs_oracle(dev, B, T, I, H):
+    from hy2dl_b200.modelzoo import LSTM
+    from hy2dl_b200.synthetic import lstm_weights
+    rng = np.random.default_rng(B + T)
+    x = rng.normal(0, 1, (B, T, I)).astype(np.float32)
+    gh = rng.normal(0, 1, (B, T, H)).astype(np.float32)
+    w = lstm_weights(I, H, 1, seed=9)
+    lstm = LSTM(I, H).to(dev)
+    lstm.load_state_dict({k[5:] if k.startswith("lstm.") else k: torch.tensor(v) for k, v in w.items()
+                          if k.startswith("lstm.")})
+    out, (hn, _) = lstm(cu(x, dev))
+    assert out.shape == (B, T, H) and hn.shape == (1, B, H)
+    (out * cu(gh, dev)).sum().backward()
+    wd = {k: tt(v, torch.float64, True) for k, v in w.items() if k.startswith("lstm.")}
+    ref = O.lstm_cell_sequence(tt(x, torch.float64), wd["lstm.weight_ih_l0"], wd["lstm.weight_hh_l0"],
+                               wd["lstm.bias_ih_l0"], wd["lstm.bias_hh_l0"])
+    (ref * tt(gh, torch.float64)).sum().backward()
+    assert_close(npy(out), ref.detach().numpy(), what="h_seq", **TOL)
+    assert_close(npy(hn[0]), ref[:, -1].detach().numpy(), what="h_n", **TOL)
+    for k, p in lstm.named_parameters():
+        assert_close(npy(p.grad), wd["lstm." + k].grad.numpy(), what="grad " + k, **TOL)
+
+
+@pytest.mark.parametrize("model_key,B,T,n_last,H,m,dyn", [
+    ("shm", 64, 365, 182, 64, 1, ["dd", "f_thr", "sumax", "beta", "perc", "kf", "ki", "kb"]),
+    ("hbv", 9, 120, 50, 64, 16, ["BETA", "BETAET"]),
+    ("shm", 33, 48, 24, 128, 4, ["kf"]),
+])
+def test_hybrid_vs_oracle(dev, model_key, B, T, n_last, H, m, dyn):
+    from hy2dl_b200.aux_functions import nse_basin_averaged
+    from hy2dl_b200.modelzoo import HBV, SHM, Hybrid, UH_routing
+    from hy2dl_b200.synthetic import lstm_weights, make_basins
+    shape = "gb" if model_key == "shm" else "us"
+    data = make_basins(shape, n_basins=8, n_rows=T + 10, seed=5)
+    rng = np.random.default_rng(B)
+    I = data.x_d.shape[2] + data.x_s.shape[1]
+    xl = rng.normal(0, 1, (B, T, I)).astype(np.float32)
+    bi = rng.integers(0, 8, B)
+    xc = np.stack([data.x_conc[b, :T] for b in bi]).astype(np.float32)
+    yo = np.stack([data.y_obs[b, T - n_last:T] for b in bi]).astype(np.float32)
+    sd = np.repeat(rng.uniform(0.5, 2.0, (B, 1, 1)).astype(np.float32), n_last, axis=1)
+    cls = {"shm": SHM, "hbv": HBV}[model_key]
+    hp = {"input_size_lstm": I, "hidden_size": H, "no_of_layers": 1, "seq_length": T, "predict_last_n": n_last,
+          "n_conceptual_models": m, "conceptual_dynamic_parameterization": dyn}
+    model = Hybrid(hp, conceptual_model=cls, routing_model=UH_routing)
+    n_out = model.linear.out_features
+    w = lstm_weights(I, H, n_out, seed=17)
+    model.load_state_dict({k: torch.tensor(v) for k, v in w.items()})
+    model = model.to(dev)
+    pred = model(x_lstm=cu(xl, dev), x_conceptual=cu(xc, dev))
+    loss = nse_basin_averaged(y_sim=pred["y_hat"], y_obs=cu(yo, dev), per_basin_target_std=cu(sd, dev))
+    loss.backward()
+    wd = {k: tt(v, torch.float64, True) for k, v in w.items()}
+    ref = O.hybrid_forward(wd, tt(xl, torch.float64), tt(xc, torch.float64), model=model_key, n_models=m,
+                           dynamic=dyn, warmup=T - n_last)
+    rloss = O.nse_basin_averaged(ref["y_hat"], tt(yo, torch.float64), tt(sd, torch.float64))
+    rloss.backward()
+    assert_close(npy(pred["y_hat"]), ref["y_hat"].detach().numpy(), what="y_hat", **TOL)
+    assert_close(loss.item(), rloss.item(), what="loss", **TOL)
+    for k, v in pred["internal_states"].items():
+        assert_close(npy(v), ref["internal_states"][k].detach().numpy(), what="state " + k, **TOL)
+    for k, p in model.named_parameters():
+        assert_close(npy(p.grad), wd[k].grad.numpy(), what="grad " + k, rtol=2e-4, atol=1e-7)
+    # basin-level NSE agreement (acceptance metric, 1e-3)
+    from hy2dl_b200.aux_functions import nse
+    ours = {i: {"y_sim": npy(pred["y_hat"])[i, :, 0], "y_obs": yo[i, :, 0]} for i in range(B)}
+    refd = {i: {"y_sim": ref["y_hat"].detach().numpy()[i, :, 0], "y_obs": yo[i, :, 0]} for i in range(B)}
+    a, b = nse(ours, average=False), nse(refd, average=False)
+    assert np.nanmax(np.abs(a - b) / (1 + np.abs(b))) < 1e-3
+
+
+def test_inference_no_grad_and_eval(dev):
+    """Forward under no_grad (the notebooks' test loop) takes the tape-free path and matches."""
+    g = golden("hybrid_shm_c2")
+    model = build_hybrid(g, dev).eval()
+    with torch.no_grad():
+        pred = model(x_lstm=cu(g["x_lstm"], dev), x_conceptual=cu(g["x_conceptual"], dev))
+    assert_close(npy(pred["y_hat"]), g["y_hat"], what="y_hat", **TOL)
+
+
+def test_trainer_native_path_matches_api_path(dev):
+    """Sampler -> native layouts -> Trainer.step equals the API path (pack_x from [B,T,I]) step."""
+    from hy2dl_b200.datasetzoo import ResidentDataset
+    from hy2dl_b200.modelzoo import SHM, Hybrid, UH_routing
+    from hy2dl_b200.synthetic import lstm_weights, make_basins
+    from hy2dl_b200.training import Trainer, forward_loss
+    data = make_basins("gb", n_basins=5, n_rows=150, seed=8)
+    L, n_last, H = 40, 20, 64
+    ds = ResidentDataset(data.x_d, data.y_obs, L, n_last, x_s=data.x_s, x_conc=data.x_conc, device=dev)
+    ds.calculate_basin_std(); ds.calculate_global_statistics(); ds.standardize_data(standardize_output=False)
+    hp = {"input_size_lstm": ds.input_size, "hidden_size": H, "no_of_layers": 1, "seq_length": L,
+          "predict_last_n": n_last, "n_conceptual_models": 1,
+          "conceptual_dynamic_parameterization": ["dd", "f_thr", "sumax", "beta", "perc", "kf", "ki", "kb"]}
+    w = {k: torch.tensor(v) for k, v in lstm_weights(ds.input_size, H, 10, seed=2).items()}
+    ids = torch.randperm(len(ds), device=dev)[:48]
+    losses = []
+    for graph in (False, True):
+        model = Hybrid(hp, conceptual_model=SHM, routing_model=UH_routing)
+        model.load_state_dict(w)
+        tr = Trainer(model.to(dev), ds, loss="nse", use_graph=graph)
+        ls = [tr.step(ids).item() for _ in range(3)]
+        losses.append(ls)
+        final = {k: npy(v).copy() for k, v in model.state_dict().items()}
+        if not graph:
+            first = final
+    assert losses[0][0] > 0 and losses[0][2] != losses[0][0]
+    assert_close(losses[1], losses[0], rtol=1e-5, what="graph replay losses")
+    for k in first:
+        assert_close(final[k], first[k], rtol=1e-5, atol=1e-7, what="graph replay " + k)
+    # API path on the same samples
+    batch = ds.gather(ids)
+    ref = batch.as_reference()
+    model = Hybrid(hp, conceptual_model=SHM, routing_model=UH_routing)
+    model.load_state_dict(w)
+    model = model.to(dev)
+    from hy2dl_b200.aux_functions import nse_basin_averaged
+    pred = model(x_lstm=ref["x_lstm"], x_conceptual=ref["x_conceptual"])
+    l_api = nse_basin_averaged(y_sim=pred["y_hat"], y_obs=ref["y_obs"], per_basin_target_std=ref["basin_std"])
+    assert_close(l_api.item(), losses[0][0], rtol=1e-6, what="API vs native loss")
+
+
+# ------------------------------------------------------------------------------------------------
+# error behaviour: no silent fallback
+# ------------------------------------------------------------------------------------------------
+def test_cpu_tensor_raises(dev):
+    from hy2dl_b200.modelzoo import CudaLSTM
+    model = CudaLSTM({"input_size_lstm": 8, "hidden_size": 64, "no_of_layers": 1, "drop_out_rate": 0.0})
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(torch.zeros(2, 5, 8))
+
+
+def test_unsupported_shapes_raise(dev):
+    from hy2dl_b200.modelzoo import SHM, CudaLSTM, Hybrid
+    model = CudaLSTM({"input_size_lstm": 8, "hidden_size": 48, "no_of_layers": 1, "drop_out_rate": 0.0}).to(dev)
+    with pytest.raises(RuntimeError, match="hidden_size"):
+        model(torch.zeros(2, 5, 8, device=dev))
+    with pytest.raises(NotImplementedError):
+        CudaLSTM({"input_size_lstm": 8, "hidden_size": 64, "no_of_layers": 2, "drop_out_rate": 0.0})
+    hp = {"input_size_lstm": 8, "hidden_size": 64, "no_of_layers": 1, "seq_length": 10, "predict_last_n": 10,
+          "n_conceptual_models": 1, "conceptual_dynamic_parameterization": []}
+    hyb = Hybrid(hp, conceptual_model=SHM).to(dev)
+    with pytest.raises(ValueError, match="warmup"):
+        hyb(torch.zeros(2, 10, 8, device=dev), torch.zeros(2, 10, 3, device=dev))
