@@ -119,12 +119,18 @@ class Trainer:
             return self._step_eager(ids)
         if self._graph is None:
             self._static_ids = ids.clone()
+            # warm-up outside capture (lazy allocations, kernel attributes); the updates it makes
+            # are rolled back so that the captured step is the first real one
+            o = self.opt
+            saved = [t.clone() for t in (o.flat, o.exp_avg, o.exp_avg_sq, o.step_count)]
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                for _ in range(2):  # warm-up outside capture (lazy allocations, func attributes)
+                for _ in range(2):
                     self._step_eager(self._static_ids)
             torch.cuda.current_stream().wait_stream(side)
+            for t, v in zip((o.flat, o.exp_avg, o.exp_avg_sq, o.step_count), saved):
+                t.copy_(v)
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):
                 self._static_loss = self._step_eager(self._static_ids)
