@@ -284,11 +284,11 @@ def run_ours(args):
     opt = trainer.opt
     Be = args.e2e_batch or B
     host = []
-    for _ in range(2):
+    for _ in range(0 if args.quick else 2):
         ref = ds.gather(torch.randint(0, n_valid, (Be,), device=dev, generator=gen)).as_reference()
         host.append({k: v.cpu().pin_memory() for k, v in ref.items()})
         del ref
-    h2d = sum(v.numel() * 4 for v in host[0].values())
+    h2d = sum(v.numel() * 4 for v in host[0].values()) if host else 0
 
     def e2e_step(hb):
         d = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
@@ -299,8 +299,8 @@ def run_ours(args):
         opt.step()
         return l.item()   # device -> host read of the step's result
 
-    e2e_steps = max(3, args.steps // 2)
-    for i in range(2):
+    e2e_steps = 0 if args.quick else max(3, args.steps // 2)
+    for i in range(2 if e2e_steps else 0):
         e2e_step(host[i % 2])
     barrier()
     t0 = time.perf_counter()
@@ -310,12 +310,12 @@ def run_ours(args):
     dt = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e = {"value": Be * world * e2e_steps / float(dt.item()), "unit": "sequences/s", "h2d_bytes_per_step": h2d,
+    e2e = {"value": Be * world * e2e_steps / float(dt.item()) if e2e_steps else None, "unit": "sequences/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": 4, "steps": e2e_steps, "batch_per_gpu": Be}
 
     # ---- reference batch size (256 per GPU), CUDA-graph replayed: the latency-bound regime
     small = None
-    if args.small_batch:
+    if args.small_batch and not args.quick:
         model2 = Hybrid(hyper(), conceptual_model=SHM, routing_model=UH_routing).to(dev)
         tr2 = Trainer(model2, ds, loss="nse", group=group, use_graph=(world == 1))
         ids = [torch.randint(0, n_valid, (args.small_batch,), device=dev, generator=gen) for _ in range(4)]
@@ -333,7 +333,7 @@ def run_ours(args):
                  "ms_per_step": s.elapsed_time(e) / n_small, "cuda_graph": world == 1}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:
         r = cpu_train_steps(3, 1)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
@@ -363,6 +363,7 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=0)
     ap.add_argument("--small-batch", type=int, default=256, help="also report the reference batch size (0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="device-timed value only (profiling runs): no e2e / small batch / cpu legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
