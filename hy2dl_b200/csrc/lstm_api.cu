@@ -10,6 +10,13 @@ int lstm_fp32_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const floa
 int lstm_fp32_wgrad(const float* dG, const float* h_seq, const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
                     int64_t H, float* dw_ih, float* dw_hh, float* db, void* ws, int64_t ws_bytes, cudaStream_t s);
 int64_t lstm_fp32_workspace(int kind, int64_t B, int64_t T, int64_t I, int64_t H);
+namespace tc {
+int lstm_tc_fwd(const float* x_ri, int64_t B, int64_t T, int64_t I, int64_t IP, const float* w_ih, const float* w_hh,
+                const float* b_ih, const float* b_hh, float* h_seq, float* c_seq, float* gates, float* h_last, void* ws,
+                int64_t ws_bytes, cudaStream_t s);
+int64_t lstm_tc_workspace(int kind, int64_t B, int64_t T, int64_t I, int64_t H);
+bool lstm_tc_supported(int64_t I, int64_t H);
+}  // namespace tc
 
 static int check_lstm_shape(const char* who, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H) {
   HY_REQUIRE(B > 0 && T > 0, HY2DL_ERR_SHAPE, "%s: empty batch or sequence (B=%lld T=%lld)", who, (long long)B, (long long)T);
@@ -21,10 +28,11 @@ static int check_lstm_shape(const char* who, int64_t B, int64_t T, int64_t I, in
 }  // namespace hy2dl
 using namespace hy2dl;
 
-extern "C" int64_t hy2dl_workspace_bytes(int kind, int64_t B, int64_t T, int64_t I, int64_t H, int64_t C) {
-  (void)C;
-  if (kind == HY2DL_WS_LSTM_FWD || kind == HY2DL_WS_LSTM_BWD || kind == HY2DL_WS_LSTM_WGRAD)
+extern "C" int64_t hy2dl_workspace_bytes(int kind, int64_t B, int64_t T, int64_t I, int64_t H, int64_t precision) {
+  if (kind == HY2DL_WS_LSTM_FWD || kind == HY2DL_WS_LSTM_BWD || kind == HY2DL_WS_LSTM_WGRAD) {
+    if (precision == HY2DL_PREC_TF32X3) return tc::lstm_tc_workspace(kind, B, T, I, H);
     return lstm_fp32_workspace(kind, B, T, I, H);
+  }
   hy2dl::set_error("hy2dl_workspace_bytes: unknown kind %d", kind);
   return -1;
 }
@@ -38,6 +46,13 @@ extern "C" int hy2dl_lstm_fwd(const float* xT, int64_t B, int64_t T, int64_t I, 
   HY_PTR(xT); HY_PTR(w_ih); HY_PTR(w_hh); HY_PTR(b_ih); HY_PTR(b_hh);
   HY_PTR_OPT(h_seq); HY_PTR_OPT(c_seq); HY_PTR_OPT(gates); HY_PTR_OPT(h_last);
   HY_REQUIRE(h_seq || h_last, HY2DL_ERR_ALIGN, "hy2dl_lstm_fwd: both h_seq and h_last are null");
+  if (precision == HY2DL_PREC_TF32X3) {
+    HY_REQUIRE(tc::lstm_tc_supported(I, H), HY2DL_ERR_SHAPE,
+               "hy2dl_lstm_fwd: the tf32x3 tensor-core path supports hidden_size 64 and input_size <= 32 (got H=%lld I=%lld)",
+               (long long)H, (long long)I);
+    return tc::lstm_tc_fwd(xT, B, T, I, IP, w_ih, w_hh, b_ih, b_hh, h_seq, c_seq, gates, h_last, ws, ws_bytes,
+                           (cudaStream_t)stream);
+  }
   HY_REQUIRE(precision == HY2DL_PREC_FP32, HY2DL_ERR_SHAPE, "hy2dl_lstm_fwd: precision %d not built", precision);
   return lstm_fp32_fwd(xT, B, T, I, IP, H, w_ih, w_hh, b_ih, b_hh, h_seq, c_seq, gates, h_last, ws, ws_bytes,
                        (cudaStream_t)stream);

@@ -23,8 +23,24 @@ def round_up(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
 
-def _ws(kind: int, B: int, T: int, I: int, H: int, device) -> torch.Tensor:
-    n = _lib.load().hy2dl_workspace_bytes(kind, B, T, I, H, 0)
+def to_ri32(x: torch.Tensor) -> torch.Tensor:
+    """Row-major [T,B,F] -> RI32 [T,G,F/4,32,4] (G = ceil(B/32), zero padded rows). Torch ops; used at
+    API boundaries and in tests, not on the training fast path (the sampler writes RI32 directly)."""
+    T, B, F = x.shape
+    G = (B + 31) // 32
+    if G * 32 != B:
+        x = torch.cat([x, x.new_zeros(T, G * 32 - B, F)], dim=1)
+    return x.view(T, G, 32, F // 4, 4).permute(0, 1, 3, 2, 4).contiguous()
+
+
+def from_ri32(x: torch.Tensor, B: int) -> torch.Tensor:
+    """RI32 [T,G,F/4,32,4] -> row-major [T,B,F]."""
+    T, G, F4 = x.shape[:3]
+    return x.permute(0, 1, 3, 2, 4).reshape(T, G * 32, F4 * 4)[:, :B]
+
+
+def _ws(kind: int, B: int, T: int, I: int, H: int, device, precision: int = 0) -> torch.Tensor:
+    n = _lib.load().hy2dl_workspace_bytes(kind, B, T, I, H, precision)
     if n < 0:
         raise RuntimeError(_lib.last_error())
     return torch.empty(max(int(n), 16), dtype=torch.uint8, device=device)

@@ -21,6 +21,11 @@
  *   h_seq   [T][B][H]       hidden state tape          c_seq [T][B][H]  cell state tape
  *   gates   [T][B][4][H]    activated gates i,f,g,o (tape); overwritten in place by dG in bwd
  *   forc    [T][3][B]       conceptual forcings P, PET, Tmean
+ *   With HY2DL_PREC_TF32X3 the LSTM streams (xT, h_seq, c_seq, gates, dG, dh_seq) use the
+ *   row-interleaved layout RI32 instead: [T][ceil(B/32)][F/4][32 rows][4 floats] -- the 32 rows
+ *   of a group are interleaved at 16-byte granularity, so the row-owning threads of the tcgen05
+ *   kernels access it fully coalesced and a group is directly a no-swizzle MN-major UMMA operand.
+ *   gates/dG then order their 4H columns as n = 4*unit + gate.
  *   N = B*m series (sample b, member j -> n = b*m + j)
  *   par     planes: dynamic parameter -> [T_sim][N], static parameter -> [N]   (see hy2dl_parmap)
  *   states  [T][5][N]       bucket storages after each step
@@ -66,7 +71,7 @@ int hy2dl_abi_version(void);
 const char* hy2dl_last_error(void);
 /* 0 if device `dev` is compute capability 10.x, HY2DL_ERR_ARCH otherwise */
 int hy2dl_check_device(int dev);
-int64_t hy2dl_workspace_bytes(int kind, int64_t B, int64_t T, int64_t I, int64_t H, int64_t C);
+int64_t hy2dl_workspace_bytes(int kind, int64_t B, int64_t T, int64_t I, int64_t H, int64_t precision);
 
 /* ---- layout packing --------------------------------------------------------------------------
  * x [B][T][I] (reference batch-first layout, modelzoo/cudalstm.py:34, hybrid.py:72) -> xT [T][B][IP].
