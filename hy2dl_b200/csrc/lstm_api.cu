@@ -14,6 +14,8 @@ namespace tc {
 int lstm_tc_fwd(const float* x_ri, int64_t B, int64_t T, int64_t I, int64_t IP, const float* w_ih, const float* w_hh,
                 const float* b_ih, const float* b_hh, float* h_seq, float* c_seq, float* gates, float* h_last, void* ws,
                 int64_t ws_bytes, cudaStream_t s);
+int lstm_tc_bwd(int64_t B, int64_t T, const float* w_hh, const float* gates, const float* c_seq, const float* dh_seq,
+                int64_t dh_t0, const float* dh_last, float* dG, void* ws, int64_t ws_bytes, cudaStream_t s);
 int64_t lstm_tc_workspace(int kind, int64_t B, int64_t T, int64_t I, int64_t H);
 bool lstm_tc_supported(int64_t I, int64_t H);
 }  // namespace tc
@@ -61,12 +63,15 @@ extern "C" int hy2dl_lstm_fwd(const float* xT, int64_t B, int64_t T, int64_t I, 
 extern "C" int hy2dl_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const float* gates,
                               const float* c_seq, const float* dh_seq, int64_t dh_t0, const float* dh_last, float* dG,
                               void* ws, int64_t ws_bytes, int precision, hy2dl_stream_t stream) {
-  (void)ws; (void)ws_bytes;
   int rc = check_lstm_shape("hy2dl_lstm_bwd", B, T, 8, 8, H);
   if (rc) return rc;
   HY_PTR(w_hh); HY_PTR(gates); HY_PTR(c_seq); HY_PTR(dG); HY_PTR_OPT(dh_seq); HY_PTR_OPT(dh_last);
   HY_REQUIRE(dh_seq || dh_last, HY2DL_ERR_ALIGN, "hy2dl_lstm_bwd: no external gradient given");
   HY_REQUIRE(dh_t0 >= 0 && dh_t0 <= T, HY2DL_ERR_SHAPE, "hy2dl_lstm_bwd: dh_t0=%lld out of range", (long long)dh_t0);
+  if (precision == HY2DL_PREC_TF32X3) {
+    HY_REQUIRE(H == 64, HY2DL_ERR_SHAPE, "hy2dl_lstm_bwd: the tf32x3 tensor-core path supports hidden_size 64 (got %lld)", (long long)H);
+    return tc::lstm_tc_bwd(B, T, w_hh, gates, c_seq, dh_seq, dh_t0, dh_last, dG, ws, ws_bytes, (cudaStream_t)stream);
+  }
   HY_REQUIRE(precision == HY2DL_PREC_FP32, HY2DL_ERR_SHAPE, "hy2dl_lstm_bwd: precision %d not built", precision);
   return lstm_fp32_bwd(B, T, H, w_hh, gates, c_seq, dh_seq, dh_t0, dh_last, dG, (cudaStream_t)stream);
 }

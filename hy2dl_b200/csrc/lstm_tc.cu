@@ -260,6 +260,7 @@ int64_t lstm_tc_workspace(int kind, int64_t B, int64_t T, int64_t I, int64_t H) 
   (void)B; (void)T;
   const int64_t IP = round_up(I, 8), K = IP + H;
   if (kind == HY2DL_WS_LSTM_FWD) return sizeof(float) * (2 * K * 4 * H + 4 * H);
+  if (kind == HY2DL_WS_LSTM_BWD) return sizeof(float) * 2 * 4 * H * H;
   return 16;
 }
 
@@ -285,6 +286,228 @@ int lstm_tc_fwd(const float* x_ri, int64_t B, int64_t T, int64_t I, int64_t IP, 
   const size_t smem = tc_fwd_smem(K);
   cudaFuncSetAttribute(lstm_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   lstm_tc_fwd_kernel<<<(unsigned)cdiv(B, kRows), kFwdThreads, smem, s>>>(a);
+  HY_LAUNCH_CHECK();
+  return HY2DL_OK;
+}
+
+}  // namespace tc
+}  // namespace hy2dl
+
+// ================================================================================================
+// K2' on tcgen05: back-propagation through time, H = 64.
+//
+// Per step (reverse time) and per 128-sequence tile:
+//   row threads : gate gradients dG[row][4u+g] from the tape (gates, c_t, c_{t-1}) and
+//                 dh = dh_ext + dh_rec; dG goes to HBM (for the weight-gradient GEMM) and, split
+//                 hi/lo, into TMEM as the A operand
+//   MMA thread  : dh_rec[128 x 64] = dG[128 x 256] * W_hh[256 x 64]  (3xTF32, M128 N64 K8 MMAs)
+// The K = 256 reduction is pipelined in four quarters of 64 columns (16 hidden units): while the
+// tensor core multiplies quarter k, the row threads are already computing quarter k+1.  A-operand
+// quarters live in a 2-slot TMEM ring, the dh accumulator is double buffered across steps.
+// TMEM columns: D0 [0,64) D1 [64,128) slot0 [128,256) slot1 [256,384)  (hi = first 64, lo = last 64).
+// ================================================================================================
+namespace hy2dl {
+namespace tc {
+
+constexpr int kBwdThreads = 160;
+constexpr uint32_t kColDh0 = 0, kColSlot0 = 128;
+
+// W_hh as the B operand of dh = dG * W_hh: B[n = k_out][kdim = gate column 4u+g], K-major no-swizzle
+// layout [256/4][64][4]; element = W_hh[g*64 + u][k_out].
+__global__ void lstm_tc_pack_whh_kernel(const float* __restrict__ w_hh, float* __restrict__ hi_out, float* __restrict__ lo_out) {
+  const int total = kN * kH;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int kk = e & 3, n = (e >> 2) & 63, kc = e >> 8;
+    const int col = kc * 4 + kk, u = col >> 2, g = col & 3;
+    uint32_t hi, lo;
+    split_tf32(w_hh[(g * kH + u) * kH + n], hi, lo);
+    hi_out[e] = __uint_as_float(hi);
+    lo_out[e] = __uint_as_float(lo);
+  }
+}
+
+struct TcBwdArgs {
+  const float* w_hi;      // [64][64][4] packed W_hh (hi)
+  const float* w_lo;
+  const float4* gates;    // RI32 F = 256 (n = 4u + g)
+  const float4* c_seq;    // RI32 F = 64
+  const float4* dh_seq;   // RI32 F = 64 or null
+  const float* dh_last;   // row-major [B][64] or null
+  float4* dG;             // RI32 F = 256; may alias gates
+  int64_t B, T, G, dh_t0;
+};
+
+struct BwdChunk {   // tape of 4 hidden units of one row at one step
+  float4 g[4], ct, cp, dh;
+};
+
+__device__ __forceinline__ void bwd_load_chunk(const TcBwdArgs& a, int64_t t, int q, int64_t gidx, int lane, bool live, BwdChunk& c) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool on = live && t >= 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) c.g[j] = on ? __ldg(a.gates + ri32_chunk(t, a.G, gidx, 64, 4 * q + j, lane)) : z;
+  c.ct = on ? __ldg(a.c_seq + ri32_chunk(t, a.G, gidx, 16, q, lane)) : z;
+  c.cp = (on && t > 0) ? __ldg(a.c_seq + ri32_chunk(t - 1, a.G, gidx, 16, q, lane)) : z;
+  c.dh = (on && a.dh_seq && t >= a.dh_t0) ? __ldg(a.dh_seq + ri32_chunk(t, a.G, gidx, 16, q, lane)) : z;
+  if (on && a.dh_last && t == a.T - 1) {
+    const int64_t b = gidx * 32 + lane;
+    if (b < a.B) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(a.dh_last + b * kH + 4 * q));
+      c.dh.x += v.x; c.dh.y += v.y; c.dh.z += v.z; c.dh.w += v.w;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1) lstm_tc_bwd_kernel(TcBwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  float* s_whi = reinterpret_cast<float*>(smem_raw);
+  float* s_wlo = s_whi + kN * kH;
+  float* s_dc = s_wlo + kN * kH;                                        // [64][128] cell-state adjoint, per row thread
+  uint64_t* bar_ready = reinterpret_cast<uint64_t*>(s_dc + kH * kRows);  // [2] rows -> MMA, per slot
+  uint64_t* bar_free = bar_ready + 2;                                   // [2] MMA commit -> rows, per slot
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_free + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  {
+    const float4* g_hi = reinterpret_cast<const float4*>(a.w_hi);
+    const float4* g_lo = reinterpret_cast<const float4*>(a.w_lo);
+    float4* d_hi = reinterpret_cast<float4*>(s_whi);
+    float4* d_lo = reinterpret_cast<float4*>(s_wlo);
+    for (int e = tid; e < kN * kH / 4; e += kBwdThreads) { d_hi[e] = __ldg(g_hi + e); d_lo[e] = __ldg(g_lo + e); }
+  }
+  if (tid == 0) {
+    mbar_init(bar_ready + 0, kRows); mbar_init(bar_ready + 1, kRows);
+    mbar_init(bar_free + 0, 1); mbar_init(bar_free + 1, 1);
+    mbar_fence_init();
+  }
+  if (warp == 4) tmem_alloc(s_tmem, kTmemCols);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp < 4) {
+    const int64_t gidx = (int64_t)blockIdx.x * 4 + warp;
+    const bool live = gidx < a.G;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    float* dcp = s_dc + tid;     // dc[u] at dcp[u * 128]: conflict-free, keeps the chunk loop rolled and small
+    for (int u = 0; u < kH; ++u) dcp[u * kRows] = 0.f;
+
+    BwdChunk cur, nxt;
+    bwd_load_chunk(a, a.T - 1, 0, gidx, lane, live, cur);
+    for (int64_t s = 0; s < a.T; ++s) {
+      const int64_t t = a.T - 1 - s;
+      const uint32_t d_prev = lane_base + kColDh0 + 64 * (uint32_t)((s & 1) ^ 1);   // dh_rec from step s-1
+      if (s > 0) {
+        mbar_wait(bar_free + 1, 1);     // last quarter of step s-1 committed => dh_rec complete, both slots free
+        tc_fence_after();
+      }
+#pragma unroll 1
+      for (int q = 0; q < 16; ++q) {     // 4 hidden units (16 gate columns) per iteration
+        // prefetch the next chunk (next step's chunk 0 after the last one)
+        if (q < 15) bwd_load_chunk(a, t, q + 1, gidx, lane, live, nxt);
+        else bwd_load_chunk(a, t - 1, 0, gidx, lane, live, nxt);
+        uint32_t r[4] = {0, 0, 0, 0};
+        if (s > 0) {
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                       : "r"(d_prev + 4 * q));
+          tmem_ld_wait();
+        }
+        const float dhe[4] = {cur.dh.x, cur.dh.y, cur.dh.z, cur.dh.w};
+        const float ctv[4] = {cur.ct.x, cur.ct.y, cur.ct.z, cur.ct.w};
+        const float cpv[4] = {cur.cp.x, cur.cp.y, cur.cp.z, cur.cp.w};
+        float dg[16];
+#pragma unroll
+        for (int uu = 0; uu < 4; ++uu) {
+          const int u = 4 * q + uu;
+          const float gi = cur.g[uu].x, gf = cur.g[uu].y, gg = cur.g[uu].z, go = cur.g[uu].w;
+          const float dh = dhe[uu] + __uint_as_float(r[uu]);
+          const float tcv = fast_tanh(ctv[uu]);
+          const float dct = dcp[u * kRows] + dh * go * (1.f - tcv * tcv);
+          dg[4 * uu + 0] = dct * gg * gi * (1.f - gi);
+          dg[4 * uu + 1] = dct * cpv[uu] * gf * (1.f - gf);
+          dg[4 * uu + 2] = dct * gi * (1.f - gg * gg);
+          dg[4 * uu + 3] = dh * tcv * go * (1.f - go);
+          dcp[u * kRows] = dct * gf;
+        }
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            a.dG[ri32_chunk(t, a.G, gidx, 64, 4 * q + j, lane)] = make_float4(dg[4 * j], dg[4 * j + 1], dg[4 * j + 2], dg[4 * j + 3]);
+        }
+        // quarter k = q / 4 lives in slot k & 1; the second use of a slot in a step waits for its first MMAs
+        const int k = q >> 2, slot = k & 1;
+        if ((q & 3) == 0 && k >= 2) {
+          mbar_wait(bar_free + slot, 0);
+          tc_fence_after();
+        }
+        const uint32_t sbase = lane_base + kColSlot0 + 128 * slot + 16 * (q & 3);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) split_tf32(dg[8 * j + e], hi[e], lo[e]);
+          tmem_st8(sbase + 8 * j, hi);
+          tmem_st8(sbase + 64 + 8 * j, lo);
+        }
+        if ((q & 3) == 3) {
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(bar_ready + slot);
+        }
+        cur = nxt;
+      }
+    }
+  } else {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(kRows, kH, 0, 0);
+      const uint32_t whi = smem_u32(s_whi), wlo = smem_u32(s_wlo);
+      const uint32_t lbo = kH * 16, sbo = 128;
+      for (int64_t s = 0; s < a.T; ++s) {
+        const uint32_t d = tmem + kColDh0 + 64 * (uint32_t)(s & 1);
+        for (int k = 0; k < 4; ++k) {
+          const int slot = k & 1;
+          mbar_wait(bar_ready + slot, (uint32_t)(k >> 1));
+          tc_fence_after();
+          const uint32_t abase = tmem + kColSlot0 + 128 * slot;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t J = 8 * k + j;
+            const uint64_t d_hi = smem_desc(whi + J * 2 * lbo, lbo, sbo);
+            const uint64_t d_lo = smem_desc(wlo + J * 2 * lbo, lbo, sbo);
+            mma_tf32_ts(d, abase + 64 + 8 * j, d_hi, idesc, (k | j) != 0);
+            mma_tf32_ts(d, abase + 8 * j, d_lo, idesc, 1);
+            mma_tf32_ts(d, abase + 8 * j, d_hi, idesc, 1);
+          }
+          mma_commit(bar_free + slot);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, kTmemCols);
+}
+
+int lstm_tc_bwd(int64_t B, int64_t T, const float* w_hh, const float* gates, const float* c_seq, const float* dh_seq,
+                int64_t dh_t0, const float* dh_last, float* dG, void* ws, int64_t ws_bytes, cudaStream_t s) {
+  const int64_t need = sizeof(float) * 2 * kN * kH;
+  HY_REQUIRE(ws != nullptr && ws_bytes >= need, HY2DL_ERR_WORKSPACE, "hy2dl_lstm_bwd(tf32x3): workspace %lld < %lld bytes",
+             (long long)ws_bytes, (long long)need);
+  float* w_hi = reinterpret_cast<float*>(ws);
+  float* w_lo = w_hi + kN * kH;
+  lstm_tc_pack_whh_kernel<<<64, 256, 0, s>>>(w_hh, w_hi, w_lo);
+  TcBwdArgs a{};
+  a.w_hi = w_hi; a.w_lo = w_lo;
+  a.gates = reinterpret_cast<const float4*>(gates); a.c_seq = reinterpret_cast<const float4*>(c_seq);
+  a.dh_seq = reinterpret_cast<const float4*>(dh_seq); a.dh_last = dh_last; a.dG = reinterpret_cast<float4*>(dG);
+  a.B = B; a.T = T; a.G = cdiv(B, 32); a.dh_t0 = dh_t0;
+  const size_t smem = (size_t)kN * kH * 4 * 2 + (size_t)kH * kRows * 4 + 64;
+  cudaFuncSetAttribute(lstm_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  lstm_tc_bwd_kernel<<<(unsigned)cdiv(B, kRows), kBwdThreads, smem, s>>>(a);
   HY_LAUNCH_CHECK();
   return HY2DL_OK;
 }

@@ -57,3 +57,73 @@ def test_tc_fwd_vs_oracle(B, T, I):
     assert_close(h.transpose(1, 0, 2), ref, rtol=1e-4, atol=1e-6, what="h_seq")
     assert_close(hl, ref[:, -1], rtol=1e-4, atol=1e-6, what="h_last")
     assert_close(c, cf, rtol=1e-4, atol=1e-6, what="c_seq vs fp32 kernel")
+
+
+def _bwd_both(dev, B, T, I, dh_t0, use_last, seed=3):
+    """Run fwd+bwd with both precisions on the same inputs; return row-major dG (g*H+u order) of each."""
+    from hy2dl_b200 import _lib, ops
+    from hy2dl_b200.synthetic import lstm_weights
+    H, IP = 64, (I + 7) // 8 * 8
+    rng = np.random.default_rng(seed)
+    x = rng.normal(0, 1, (B, T, I)).astype(np.float32)
+    gh = rng.normal(0, 1, (T, B, H)).astype(np.float32)
+    gh[:dh_t0] = 0
+    gl = rng.normal(0, 1, (B, H)).astype(np.float32)
+    w = lstm_weights(I, H, 1, seed=seed + 1)
+    cu = lambda a: torch.tensor(a, device=dev)
+    wd = [cu(w[k]) for k in ("lstm.weight_ih_l0", "lstm.weight_hh_l0", "lstm.bias_ih_l0", "lstm.bias_hh_l0")]
+    xT = ops.pack_x(cu(x))
+    G = (B + 31) // 32
+    out = {}
+    for prec in (_lib.PREC_FP32, _lib.PREC_TF32X3):
+        ri = prec == _lib.PREC_TF32X3
+        Bp = G * 32 if ri else B
+        x_in = ops.to_ri32(xT) if ri else xT
+        h = torch.zeros(T, Bp, H, device=dev); c = torch.zeros(T, Bp, H, device=dev)
+        g = torch.zeros(T, Bp, 4 * H, device=dev); hl = torch.zeros(B, H, device=dev)
+        ws = ops._ws(_lib.WS_LSTM_FWD, B, T, I, H, dev, prec)
+        _lib.call("hy2dl_lstm_fwd", x_in.data_ptr(), B, T, I, IP, H, *[t.data_ptr() for t in wd], h.data_ptr(),
+                  c.data_ptr(), g.data_ptr(), hl.data_ptr(), ws.data_ptr(), ws.numel(), prec, _lib.stream())
+        dh = cu(gh)
+        dh_in = ops.to_ri32(dh) if ri else dh
+        dl = cu(gl) if use_last else None
+        wsb = ops._ws(_lib.WS_LSTM_BWD, B, T, I, H, dev, prec)
+        _lib.call("hy2dl_lstm_bwd", B, T, H, wd[1].data_ptr(), g.data_ptr(), c.data_ptr(), dh_in.data_ptr(), dh_t0,
+                  None if dl is None else dl.data_ptr(), g.data_ptr(), wsb.data_ptr(), wsb.numel(), prec, _lib.stream())
+        torch.cuda.synchronize()
+        if ri:
+            dG = ops.from_ri32(g.view(T, G, H, 32, 4), B).reshape(T, B, H, 4).permute(0, 1, 3, 2).reshape(T, B, 4 * H)
+            hh = ops.from_ri32(h.view(T, G, H // 4, 32, 4), B)
+        else:
+            dG, hh = g, h
+        out[prec] = (dG.cpu().double().numpy(), hh.cpu().double().numpy())
+    # oracle gradients (fp64 autograd)
+    wd64 = {k: tt(v, torch.float64, True) for k, v in w.items() if k.startswith("lstm.")}
+    ref = O.lstm_cell_sequence(tt(x, torch.float64), wd64["lstm.weight_ih_l0"], wd64["lstm.weight_hh_l0"],
+                               wd64["lstm.bias_ih_l0"], wd64["lstm.bias_hh_l0"])
+    f = (ref * tt(gh.transpose(1, 0, 2), torch.float64)).sum()
+    if use_last:
+        f = f + (ref[:, -1] * tt(gl, torch.float64)).sum()
+    f.backward()
+    return out, {k: v.grad.numpy() for k, v in wd64.items()}, x
+
+
+@pytest.mark.parametrize("B,T,I,dh_t0,use_last", [(128, 3, 25, 0, False), (200, 40, 25, 17, True), (96, 365, 25, 183, False)])
+def test_tc_bwd_vs_fp32_kernel_and_oracle(B, T, I, dh_t0, use_last):
+    from hy2dl_b200 import _lib
+    dev = torch.device("cuda:0")
+    out, ref, x = _bwd_both(dev, B, T, I, dh_t0, use_last)
+    dG32, h32 = out[_lib.PREC_FP32]
+    dGtc, htc = out[_lib.PREC_TF32X3]
+    for t in sorted({T - 1, max(T - 2, 0), 0}, reverse=True):
+        print(f"t={t}: |dG_tc - dG_fp32| max {np.abs(dGtc[t] - dG32[t]).max():.3e} (scale {np.abs(dG32[t]).max():.3e})")
+    assert_close(dGtc[T - 1], dG32[T - 1], rtol=1e-5, atol=1e-7, what="dG at the last step")
+    assert_close(dGtc, dG32, rtol=1e-4, atol=1e-7, what="dG all steps (tc vs fp32 kernel)")
+    # weight gradients from the tc tape, contracted in fp64 on the host, against oracle autograd
+    hprev = np.concatenate([np.zeros_like(htc[:1]), htc[:-1]], axis=0)
+    dw_hh = np.einsum("tbm,tbk->mk", dGtc, hprev)
+    db = dGtc.sum((0, 1))
+    dw_ih = np.einsum("tbm,bti->mi", dGtc, x.astype(np.float64))
+    assert_close(dw_hh, ref["lstm.weight_hh_l0"], rtol=1e-4, atol=1e-7, what="dW_hh")
+    assert_close(dw_ih, ref["lstm.weight_ih_l0"], rtol=1e-4, atol=1e-7, what="dW_ih")
+    assert_close(db, ref["lstm.bias_ih_l0"], rtol=1e-4, atol=1e-7, what="db")
