@@ -32,9 +32,13 @@ WORKLOAD = "hybrid LSTM(64)+SHM(8 dynamic params, 1 member)+UH routing, syntheti
            "seq 365 = 183 warm-up + 182 simulated, nse_basin_averaged, clip 1 + Adam 1e-3"
 
 
+PRECISION = "tf32x3"
+
+
 def hyper():
     return {"input_size_lstm": I_LSTM, "hidden_size": HID, "no_of_layers": 1, "seq_length": T_SEQ,
-            "predict_last_n": N_LAST, "n_conceptual_models": 1, "conceptual_dynamic_parameterization": DYNAMIC}
+            "predict_last_n": N_LAST, "n_conceptual_models": 1, "conceptual_dynamic_parameterization": DYNAMIC,
+            "precision": PRECISION}
 
 
 def peaks():
@@ -342,7 +346,9 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "seq_len": T_SEQ,
-                           "hidden": HID, "precision": "fp32 (CUDA-core FMA recurrent path)",
+                           "hidden": HID,
+                           "precision": {"fp32": "fp32 (CUDA-core FMA recurrent path)",
+                                         "tf32x3": "fp32-class: tcgen05 kind::tf32 with 3-term operand split, fp32 accumulate"}[PRECISION],
                            "parallelism": f"dp{world} over basins, flat-gradient NCCL all-reduce" if world > 1 else "single GPU",
                            "l2_policy": "inputs larger than L2: every step gathers a new random batch; the per-step tape "
                                         f"({4 * T_SEQ * 12 * HID * B / 1e9:.1f} GB) exceeds the 126 MB L2"},
@@ -359,13 +365,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=9472, help="sequences per GPU per step (saturating: 64 x 148 SMs)")
+    ap.add_argument("--batch", type=int, default=18944, help="sequences per GPU per step (saturating: 128-row tiles x 148 SMs)")
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3"], help="recurrent-kernel arithmetic")
     ap.add_argument("--e2e-batch", type=int, default=0)
     ap.add_argument("--small-batch", type=int, default=256, help="also report the reference batch size (0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="device-timed value only (profiling runs): no e2e / small batch / cpu legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    global PRECISION
+    PRECISION = args.precision
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -18,6 +18,7 @@ N_STATES = 5
 PREC_FP32, PREC_TF32X3, PREC_BF16 = 0, 1, 2
 MODEL_SHM, MODEL_HBV = 0, 1
 WS_LSTM_FWD, WS_LSTM_BWD, WS_LSTM_WGRAD = 0, 1, 2
+LAYOUT_ROWMAJOR, LAYOUT_RI32 = 0, 1
 
 p_f = C.c_void_p  # device pointers travel as integers
 i64 = C.c_int64
@@ -39,14 +40,14 @@ _SIGNATURES = {
     "hy2dl_last_error": (C.c_char_p, []),
     "hy2dl_check_device": (i32, [i32]),
     "hy2dl_workspace_bytes": (i64, [i32, i64, i64, i64, i64, i64]),
-    "hy2dl_pack_x": (i32, [p_f, i64, i64, i64, i64, p_f, p_f]),
+    "hy2dl_pack_x": (i32, [p_f, i64, i64, i64, i64, p_f, i32, p_f]),
     "hy2dl_pack_forcing": (i32, [p_f, i64, i64, i64, p_f, p_f]),
     "hy2dl_lstm_fwd": (i32, [p_f, i64, i64, i64, i64, i64, p_f, p_f, p_f, p_f, p_f, p_f, p_f, p_f, p_f, i64, i32, p_f]),
     "hy2dl_lstm_bwd": (i32, [i64, i64, i64, p_f, p_f, p_f, p_f, i64, p_f, p_f, p_f, i64, i32, p_f]),
     "hy2dl_lstm_wgrad": (i32, [p_f, p_f, p_f, i64, i64, i64, i64, i64, p_f, p_f, p_f, p_f, i64, i32, p_f]),
     "hy2dl_parmap_layout": (i64, [C.POINTER(ParMap), i64, i64]),
-    "hy2dl_head_map_fwd": (i32, [p_f, i64, i64, i64, p_f, p_f, C.POINTER(ParMap), p_f, p_f, p_f]),
-    "hy2dl_head_map_bwd": (i32, [p_f, p_f, p_f, i64, i64, i64, p_f, C.POINTER(ParMap), p_f, p_f, p_f, p_f]),
+    "hy2dl_head_map_fwd": (i32, [p_f, i64, i64, i64, p_f, p_f, C.POINTER(ParMap), p_f, p_f, i32, p_f]),
+    "hy2dl_head_map_bwd": (i32, [p_f, p_f, p_f, i64, i64, i64, p_f, C.POINTER(ParMap), p_f, p_f, p_f, i32, p_f]),
     "hy2dl_conceptual_fwd": (i32, [i32, p_f, i64, i64, i64, i64, C.POINTER(p_f), C.POINTER(i64), p_f, p_f, p_f, p_f]),
     "hy2dl_conceptual_bwd": (i32, [i32, p_f, i64, i64, i64, i64, C.POINTER(p_f), C.POINTER(i64), p_f, p_f, p_f, p_f,
                                    C.POINTER(p_f), p_f, p_f]),
@@ -56,7 +57,7 @@ _SIGNATURES = {
     "hy2dl_loss_nse_finish": (i32, [p_f, p_f, p_f, i64, p_f, p_f, p_f, p_f, p_f]),
     "hy2dl_loss_wrmse_reduce": (i32, [p_f, p_f, i64, p_f, p_f]),
     "hy2dl_loss_wrmse_finish": (i32, [p_f, p_f, i64, p_f, p_f, p_f, p_f, p_f]),
-    "hy2dl_window_gather": (i32, [p_f] * 8 + [i64] * 7 + [p_f] * 5),
+    "hy2dl_window_gather": (i32, [p_f] * 8 + [i64] * 7 + [p_f] * 4 + [i32, p_f]),
     "hy2dl_grad_sqnorm": (i32, [p_f, i64, p_f, p_f]),
     "hy2dl_clip_adam": (i32, [p_f, p_f, p_f, p_f, i64, p_f, C.c_float, C.c_float, p_f, C.c_float, C.c_float, C.c_float,
                               p_f, p_f]),

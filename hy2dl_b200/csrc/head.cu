@@ -15,6 +15,10 @@ constexpr int kRows = 32;     // rows (samples of one step) per tile
 constexpr int kChunk = 32;    // head columns per launch
 constexpr int kThreads = 128;
 
+// RI32 slab of one (step, 32-row group): float e of [F/32][32 rows][32 floats] holds (row, feature)
+__device__ __forceinline__ int ri32_row(int e) { return (e >> 5) & 31; }
+__device__ __forceinline__ int ri32_feat(int e) { return (e >> 10) * 32 + ((((e >> 3) ^ (e >> 5)) & 3) << 3) + (e & 7); }
+
 struct HeadChunk {
   // one launch handles <= kChunk head columns of the same kind (all dynamic or all static)
   int32_t ncol;
@@ -39,6 +43,7 @@ struct HeadArgs {
   int64_t B, T, H;
   int32_t m, n_par, warmup;
   int32_t accumulate_dh;
+  int32_t ri32;   // h_seq / dh_seq in RI32 [T][G][H/4][32][4] instead of [T][B][H]
 };
 
 // smem: hs[kRows][H+1] | ws[kChunk][H] | (bwd) dzs[kChunk][kRows+1] | (bwd) dws[kChunk][H] | dbs[kChunk]
@@ -71,8 +76,13 @@ __global__ void __launch_bounds__(kThreads) head_kernel(HeadArgs a, HeadChunk ch
     const int nb = (int)min((int64_t)kRows, a.B - b0);
     __syncthreads();
     // the [nb][H] slab of step t is contiguous in h_seq
-    const float* src = a.h_seq + (t * a.B + b0) * H;
-    for (int e = tid; e < nb * H; e += kThreads) hs[(e / H) * (H + 1) + (e % H)] = __ldg(src + e);
+    if (a.ri32) {   // tile = one 32-row group, contiguous as [H/32][32 rows][32 floats], units swizzled
+      const float* src = a.h_seq + (t * tiles_b + b0 / kRows) * kRows * H;
+      for (int e = tid; e < kRows * H; e += kThreads) hs[ri32_row(e) * (H + 1) + ri32_feat(e)] = __ldg(src + e);
+    } else {
+      const float* src = a.h_seq + (t * a.B + b0) * H;
+      for (int e = tid; e < nb * H; e += kThreads) hs[(e / H) * (H + 1) + (e % H)] = __ldg(src + e);
+    }
     __syncthreads();
 
     if (!BWD) {
@@ -115,12 +125,22 @@ __global__ void __launch_bounds__(kThreads) head_kernel(HeadArgs a, HeadChunk ch
       }
       __syncthreads();
       // phase B: dh[r][k] (+)= sum_c dz[c][r] w[c][k]; consecutive threads -> consecutive k
-      float* dst = a.dh_seq + (t * a.B + b0) * H;
-      for (int e = tid; e < nb * H; e += kThreads) {
-        const int r = e / H, k = e % H;
-        float acc = 0.f;
-        for (int c = 0; c < ch.ncol; ++c) acc = fmaf(dzs[c * (kRows + 1) + r], ws[c * H + k], acc);
-        dst[e] = a.accumulate_dh ? dst[e] + acc : acc;
+      if (a.ri32) {   // all 32 rows of the group are written (dz = 0 for rows >= nb)
+        float* dst = a.dh_seq + (t * tiles_b + b0 / kRows) * kRows * H;
+        for (int e = tid; e < kRows * H; e += kThreads) {
+          const int r = ri32_row(e), k = ri32_feat(e);
+          float acc = 0.f;
+          for (int c = 0; c < ch.ncol; ++c) acc = fmaf(dzs[c * (kRows + 1) + r], ws[c * H + k], acc);
+          dst[e] = a.accumulate_dh ? dst[e] + acc : acc;
+        }
+      } else {
+        float* dst = a.dh_seq + (t * a.B + b0) * H;
+        for (int e = tid; e < nb * H; e += kThreads) {
+          const int r = e / H, k = e % H;
+          float acc = 0.f;
+          for (int c = 0; c < ch.ncol; ++c) acc = fmaf(dzs[c * (kRows + 1) + r], ws[c * H + k], acc);
+          dst[e] = a.accumulate_dh ? dst[e] + acc : acc;
+        }
       }
       // phase C: dw[c][k] += sum_r dz[c][r] h[r][k]; each thread owns fixed (c,k) entries
       for (int e = tid; e < ch.ncol * H; e += kThreads) {
@@ -212,7 +232,7 @@ extern "C" int64_t hy2dl_parmap_layout(hy2dl_parmap* pm, int64_t B, int64_t T) {
 
 extern "C" int hy2dl_head_map_fwd(const float* h_seq, int64_t B, int64_t T, int64_t H, const float* w,
                                   const float* bias, const hy2dl_parmap* pm, float* par_sim, float* par_warm,
-                                  hy2dl_stream_t stream) {
+                                  int layout, hy2dl_stream_t stream) {
   int rc = check_parmap(pm, T, "hy2dl_head_map_fwd");
   if (rc) return rc;
   HY_REQUIRE(B > 0 && H > 0 && H <= 512, HY2DL_ERR_SHAPE, "hy2dl_head_map_fwd: bad sizes B=%lld H=%lld", (long long)B, (long long)H);
@@ -223,6 +243,9 @@ extern "C" int hy2dl_head_map_fwd(const float* h_seq, int64_t B, int64_t T, int6
   HeadArgs a{};
   a.h_seq = h_seq; a.w = w; a.bias = bias; a.par_sim = par_sim; a.par_warm = par_warm;
   a.B = B; a.T = T; a.H = H; a.m = pm->n_members; a.n_par = pm->n_par; a.warmup = pm->warmup;
+  HY_REQUIRE(layout == HY2DL_LAYOUT_ROWMAJOR || (layout == HY2DL_LAYOUT_RI32 && H % 32 == 0), HY2DL_ERR_SHAPE,
+             "hy2dl_head_map_fwd: unknown layout %d (RI32 needs H %% 32 == 0)", layout);
+  a.ri32 = layout == HY2DL_LAYOUT_RI32;
   const size_t smem = head_smem(H, false);
   cudaFuncSetAttribute(head_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   for (int i = 0; i < n; ++i) {
@@ -236,7 +259,7 @@ extern "C" int hy2dl_head_map_fwd(const float* h_seq, int64_t B, int64_t T, int6
 
 extern "C" int hy2dl_head_map_bwd(const float* h_seq, const float* par_sim, const float* dpar_sim, int64_t B, int64_t T,
                                   int64_t H, const float* w, const hy2dl_parmap* pm, float* dh_seq, float* dw,
-                                  float* dbias, hy2dl_stream_t stream) {
+                                  float* dbias, int layout, hy2dl_stream_t stream) {
   int rc = check_parmap(pm, T, "hy2dl_head_map_bwd");
   if (rc) return rc;
   HY_REQUIRE(B > 0 && H > 0 && H <= 512, HY2DL_ERR_SHAPE, "hy2dl_head_map_bwd: bad sizes B=%lld H=%lld", (long long)B, (long long)H);
@@ -252,13 +275,17 @@ extern "C" int hy2dl_head_map_bwd(const float* h_seq, const float* par_sim, cons
   a.h_seq = h_seq; a.w = w; a.par_sim = const_cast<float*>(par_sim);
   a.B = B; a.T = T; a.H = H; a.m = pm->n_members; a.n_par = pm->n_par; a.warmup = pm->warmup;
   a.dpar_sim = dpar_sim; a.dh_seq = dh_seq; a.dw = dw; a.dbias = dbias;
+  HY_REQUIRE(layout == HY2DL_LAYOUT_ROWMAJOR || (layout == HY2DL_LAYOUT_RI32 && H % 32 == 0), HY2DL_ERR_SHAPE,
+             "hy2dl_head_map_bwd: unknown layout %d (RI32 needs H %% 32 == 0)", layout);
+  a.ri32 = layout == HY2DL_LAYOUT_RI32;
+  const int64_t Bp = a.ri32 ? cdiv(B, 32) * 32 : B;   // rows per step in dh_seq
   const size_t smem = head_smem(H, true);
   cudaFuncSetAttribute(head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   bool dyn_written = false;
   for (int i = 0; i < n; ++i) {
     if (!chunks[i].is_dynamic && !dyn_written) {
       // no dynamic launch has initialised rows warmup .. T-1: zero them once
-      cudaMemsetAsync(dh_seq + (int64_t)pm->warmup * B * H, 0, sizeof(float) * (T - pm->warmup) * B * H, s);
+      cudaMemsetAsync(dh_seq + (int64_t)pm->warmup * Bp * H, 0, sizeof(float) * (T - pm->warmup) * Bp * H, s);
       dyn_written = true;
     }
     a.accumulate_dh = chunks[i].is_dynamic ? (dyn_written ? 1 : 0) : 1;

@@ -16,13 +16,20 @@ int lstm_tc_fwd(const float* x_ri, int64_t B, int64_t T, int64_t I, int64_t IP, 
                 int64_t ws_bytes, cudaStream_t s);
 int lstm_tc_bwd(int64_t B, int64_t T, const float* w_hh, const float* gates, const float* c_seq, const float* dh_seq,
                 int64_t dh_t0, const float* dh_last, float* dG, void* ws, int64_t ws_bytes, cudaStream_t s);
+int lstm_tc_wgrad(const float* dG, const float* h_seq, const float* x_ri, int64_t B, int64_t T, int64_t I, int64_t IP,
+                  float* dw_ih, float* dw_hh, float* db, void* ws, int64_t ws_bytes, cudaStream_t s);
 int64_t lstm_tc_workspace(int kind, int64_t B, int64_t T, int64_t I, int64_t H);
 bool lstm_tc_supported(int64_t I, int64_t H);
 }  // namespace tc
 
-static int check_lstm_shape(const char* who, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H) {
+static int check_lstm_shape(const char* who, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H, int precision) {
   HY_REQUIRE(B > 0 && T > 0, HY2DL_ERR_SHAPE, "%s: empty batch or sequence (B=%lld T=%lld)", who, (long long)B, (long long)T);
   HY_REQUIRE(H == 64 || H == 128 || H == 256, HY2DL_ERR_SHAPE, "%s: hidden_size=%lld not supported (64, 128, 256)", who, (long long)H);
+  if (precision == HY2DL_PREC_TF32X3) {
+    HY_REQUIRE(I > 0 && I <= 32 && IP == 32, HY2DL_ERR_SHAPE,
+               "%s: the tf32x3 path takes input_size <= 32 in a 32-column RI32 stream (I=%lld IP=%lld)", who, (long long)I, (long long)IP);
+    return HY2DL_OK;
+  }
   HY_REQUIRE(I > 0 && I <= 64 && IP == round_up(I, 8), HY2DL_ERR_SHAPE,
              "%s: input_size=%lld (<= 64) with IP=%lld (must be I rounded up to 8)", who, (long long)I, (long long)IP);
   return HY2DL_OK;
@@ -43,7 +50,7 @@ extern "C" int hy2dl_lstm_fwd(const float* xT, int64_t B, int64_t T, int64_t I, 
                               const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* h_seq,
                               float* c_seq, float* gates, float* h_last, void* ws, int64_t ws_bytes, int precision,
                               hy2dl_stream_t stream) {
-  int rc = check_lstm_shape("hy2dl_lstm_fwd", B, T, I, IP, H);
+  int rc = check_lstm_shape("hy2dl_lstm_fwd", B, T, I, IP, H, precision);
   if (rc) return rc;
   HY_PTR(xT); HY_PTR(w_ih); HY_PTR(w_hh); HY_PTR(b_ih); HY_PTR(b_hh);
   HY_PTR_OPT(h_seq); HY_PTR_OPT(c_seq); HY_PTR_OPT(gates); HY_PTR_OPT(h_last);
@@ -63,7 +70,7 @@ extern "C" int hy2dl_lstm_fwd(const float* xT, int64_t B, int64_t T, int64_t I, 
 extern "C" int hy2dl_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const float* gates,
                               const float* c_seq, const float* dh_seq, int64_t dh_t0, const float* dh_last, float* dG,
                               void* ws, int64_t ws_bytes, int precision, hy2dl_stream_t stream) {
-  int rc = check_lstm_shape("hy2dl_lstm_bwd", B, T, 8, 8, H);
+  int rc = check_lstm_shape("hy2dl_lstm_bwd", B, T, 8, precision == HY2DL_PREC_TF32X3 ? 32 : 8, H, precision);
   if (rc) return rc;
   HY_PTR(w_hh); HY_PTR(gates); HY_PTR(c_seq); HY_PTR(dG); HY_PTR_OPT(dh_seq); HY_PTR_OPT(dh_last);
   HY_REQUIRE(dh_seq || dh_last, HY2DL_ERR_ALIGN, "hy2dl_lstm_bwd: no external gradient given");
@@ -79,9 +86,15 @@ extern "C" int hy2dl_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh
 extern "C" int hy2dl_lstm_wgrad(const float* dG, const float* h_seq, const float* xT, int64_t B, int64_t T, int64_t I,
                                 int64_t IP, int64_t H, float* dw_ih, float* dw_hh, float* db, void* ws,
                                 int64_t ws_bytes, int precision, hy2dl_stream_t stream) {
-  int rc = check_lstm_shape("hy2dl_lstm_wgrad", B, T, I, IP, H);
+  int rc = check_lstm_shape("hy2dl_lstm_wgrad", B, T, I, IP, H, precision);
   if (rc) return rc;
   HY_PTR(dG); HY_PTR(h_seq); HY_PTR(xT); HY_PTR(dw_ih); HY_PTR(dw_hh); HY_PTR(db);
+  if (precision == HY2DL_PREC_TF32X3) {
+    HY_REQUIRE(tc::lstm_tc_supported(I, H), HY2DL_ERR_SHAPE,
+               "hy2dl_lstm_wgrad: the tf32x3 tensor-core path supports hidden_size 64 and input_size <= 32 (got H=%lld I=%lld)",
+               (long long)H, (long long)I);
+    return tc::lstm_tc_wgrad(dG, h_seq, xT, B, T, I, IP, dw_ih, dw_hh, db, ws, ws_bytes, (cudaStream_t)stream);
+  }
   HY_REQUIRE(precision == HY2DL_PREC_FP32, HY2DL_ERR_SHAPE, "hy2dl_lstm_wgrad: precision %d not built", precision);
   return lstm_fp32_wgrad(dG, h_seq, xT, B, T, I, IP, H, dw_ih, dw_hh, db, ws, ws_bytes, (cudaStream_t)stream);
 }

@@ -15,9 +15,9 @@
 //     registers, and writes h_t (hi and lo parts) straight back into the A columns with tcgen05.st.
 //     No shared-memory round trip, no swizzle, no cross-thread exchange on the recurrent path.
 //   * all time-major streams (x, h, c, gates) use the row-interleaved RI32 layout
-//     [t][B/32][F/4][32 rows][4 floats], so a warp-wide 16-byte-per-lane access by the row-owning
-//     threads is one fully coalesced 512-byte transaction, and a 32-row group is also exactly the
-//     MN-major no-swizzle UMMA operand layout that the weight-gradient GEMM consumes via bulk copies.
+//     [t][B/32][F/32][32 rows][32 floats] (tc_common.cuh): a row thread moves whole 32-byte sectors /
+//     128-byte lines of its own row, and a (group, 32-feature block) slab is exactly the MN-major
+//     SWIZZLE_128B_BASE32B UMMA operand tile that the weight-gradient GEMM consumes via bulk copies.
 //
 // Gate column order inside D is n = 4*u + g (unit-major), so one 32-column TMEM load gives the four
 // gates of 8 hidden units.
@@ -33,12 +33,6 @@ constexpr int kRows = 128;         // sequences per CTA
 constexpr int kFwdThreads = 160;   // 4 row warps + 1 MMA warp
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColD = 0, kColAhi = 256, kColAlo = 384;   // K <= 128 columns each
-
-// ---- RI32 addressing: element (row, f) of a [rows][F] slab at step t --------------------------
-// float4 index of chunk j (4 floats) of row r in group gidx: ((t*G + gidx) * (F/4) + j) * 32 + (r & 31)
-__device__ __forceinline__ int64_t ri32_chunk(int64_t t, int64_t G, int64_t gidx, int F4, int j, int lane) {
-  return ((t * G + gidx) * F4 + j) * 32 + lane;
-}
 
 // ---- weight packing for the tc path ------------------------------------------------------------
 // Wt_hi / Wt_lo: [K/4][256][4] with n = 4u + g; k < IP: W_ih (zero padded), else W_hh.  bias_n[256].
@@ -62,7 +56,7 @@ __global__ void lstm_tc_pack_w_kernel(const float* __restrict__ w_ih, const floa
 }
 
 struct TcFwdArgs {
-  const float4* x;      // RI32 [T][G][IP/4][32][4]
+  const float4* x;      // RI32, F = IP = 32
   const float* w_hi;    // [K/4][256][4]
   const float* w_lo;
   const float* bias_n;  // [256]
@@ -130,7 +124,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_tc_fwd_kernel(TcFwdArgs a
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (live) v = __ldg(a.x + ri32_chunk(0, a.G, gidx, XC, j2 + jj, lane));
+          if (live) v = ri32_ld(a.x, 0, a.G, gidx, 1, j2 + jj, lane);
           split_tf32(v.x, hi[4 * jj + 0], lo[4 * jj + 0]);
           split_tf32(v.y, hi[4 * jj + 1], lo[4 * jj + 1]);
           split_tf32(v.z, hi[4 * jj + 2], lo[4 * jj + 2]);
@@ -151,7 +145,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_tc_fwd_kernel(TcFwdArgs a
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         xn[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < XC && more && live) xn[j] = __ldg(a.x + ri32_chunk(t + 1, a.G, gidx, XC, j, lane));
+        if (j < XC && more && live) xn[j] = ri32_ld(a.x, t + 1, a.G, gidx, 1, j, lane);
       }
       mbar_wait(bar_mma_done, (uint32_t)(t & 1));
       tc_fence_after();
@@ -186,17 +180,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_tc_fwd_kernel(TcFwdArgs a
         }
         if (live) {
           if (a.h_seq) {
-            a.h_seq[ri32_chunk(t, a.G, gidx, 16, 2 * q, lane)] = make_float4(hv[0], hv[1], hv[2], hv[3]);
-            a.h_seq[ri32_chunk(t, a.G, gidx, 16, 2 * q + 1, lane)] = make_float4(hv[4], hv[5], hv[6], hv[7]);
+            ri32_st(a.h_seq, t, a.G, gidx, 2, 2 * q, lane, make_float4(hv[0], hv[1], hv[2], hv[3]));
+            ri32_st(a.h_seq, t, a.G, gidx, 2, 2 * q + 1, lane, make_float4(hv[4], hv[5], hv[6], hv[7]));
           }
           if (a.c_seq) {
-            a.c_seq[ri32_chunk(t, a.G, gidx, 16, 2 * q, lane)] = make_float4(cv[0], cv[1], cv[2], cv[3]);
-            a.c_seq[ri32_chunk(t, a.G, gidx, 16, 2 * q + 1, lane)] = make_float4(cv[4], cv[5], cv[6], cv[7]);
+            ri32_st(a.c_seq, t, a.G, gidx, 2, 2 * q, lane, make_float4(cv[0], cv[1], cv[2], cv[3]));
+            ri32_st(a.c_seq, t, a.G, gidx, 2, 2 * q + 1, lane, make_float4(cv[4], cv[5], cv[6], cv[7]));
           }
           if (a.gates) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              a.gates[ri32_chunk(t, a.G, gidx, 64, 8 * q + j, lane)] = make_float4(gv[4 * j], gv[4 * j + 1], gv[4 * j + 2], gv[4 * j + 3]);
+              ri32_st(a.gates, t, a.G, gidx, 8, 8 * q + j, lane, make_float4(gv[4 * j], gv[4 * j + 1], gv[4 * j + 2], gv[4 * j + 3]));
           }
           if (a.h_last && t == a.T - 1) {
             const int64_t b = gidx * 32 + lane;
@@ -256,15 +250,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_tc_fwd_kernel(TcFwdArgs a
 
 static size_t tc_fwd_smem(int K) { return (size_t)K * kN * 4 * 2 + kN * 4 + 64; }
 
+int64_t lstm_tc_wgrad_workspace(int64_t B, int64_t T, int64_t I);
+
 int64_t lstm_tc_workspace(int kind, int64_t B, int64_t T, int64_t I, int64_t H) {
-  (void)B; (void)T;
-  const int64_t IP = round_up(I, 8), K = IP + H;
+  (void)I;
+  const int64_t IP = 32, K = IP + H;      // the RI32 input stream is always 32 columns wide
   if (kind == HY2DL_WS_LSTM_FWD) return sizeof(float) * (2 * K * 4 * H + 4 * H);
   if (kind == HY2DL_WS_LSTM_BWD) return sizeof(float) * 2 * 4 * H * H;
+  if (kind == HY2DL_WS_LSTM_WGRAD) return lstm_tc_wgrad_workspace(B, T, I);
   return 16;
 }
 
-bool lstm_tc_supported(int64_t I, int64_t H) { return H == 64 && round_up(I, 8) <= 32; }
+bool lstm_tc_supported(int64_t I, int64_t H) { return H == 64 && I <= 32; }
 
 int lstm_tc_fwd(const float* x_ri, int64_t B, int64_t T, int64_t I, int64_t IP, const float* w_ih, const float* w_hh,
                 const float* b_ih, const float* b_hh, float* h_seq, float* c_seq, float* gates, float* h_last, void* ws,
@@ -345,10 +342,10 @@ __device__ __forceinline__ void bwd_load_chunk(const TcBwdArgs& a, int64_t t, in
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   const bool on = live && t >= 0;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) c.g[j] = on ? __ldg(a.gates + ri32_chunk(t, a.G, gidx, 64, 4 * q + j, lane)) : z;
-  c.ct = on ? __ldg(a.c_seq + ri32_chunk(t, a.G, gidx, 16, q, lane)) : z;
-  c.cp = (on && t > 0) ? __ldg(a.c_seq + ri32_chunk(t - 1, a.G, gidx, 16, q, lane)) : z;
-  c.dh = (on && a.dh_seq && t >= a.dh_t0) ? __ldg(a.dh_seq + ri32_chunk(t, a.G, gidx, 16, q, lane)) : z;
+  for (int j = 0; j < 4; ++j) c.g[j] = on ? ri32_ld(a.gates, t, a.G, gidx, 8, 4 * q + j, lane) : z;
+  c.ct = on ? ri32_ld(a.c_seq, t, a.G, gidx, 2, q, lane) : z;
+  c.cp = (on && t > 0) ? ri32_ld(a.c_seq, t - 1, a.G, gidx, 2, q, lane) : z;
+  c.dh = (on && a.dh_seq && t >= a.dh_t0) ? ri32_ld(a.dh_seq, t, a.G, gidx, 2, q, lane) : z;
   if (on && a.dh_last && t == a.T - 1) {
     const int64_t b = gidx * 32 + lane;
     if (b < a.B) {
@@ -435,7 +432,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_tc_bwd_kernel(TcBwdArgs a
         if (live) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            a.dG[ri32_chunk(t, a.G, gidx, 64, 4 * q + j, lane)] = make_float4(dg[4 * j], dg[4 * j + 1], dg[4 * j + 2], dg[4 * j + 3]);
+            ri32_st(a.dG, t, a.G, gidx, 8, 4 * q + j, lane, make_float4(dg[4 * j], dg[4 * j + 1], dg[4 * j + 2], dg[4 * j + 3]));
         }
         // quarter k = q / 4 lives in slot k & 1; the second use of a slot in a step waits for its first MMAs
         const int k = q >> 2, slot = k & 1;

@@ -11,6 +11,7 @@ struct GatherArgs {
   const int64_t *row0, *basin, *end;
   int64_t B, L, n_last, nd, ns, nc, IP;
   float *xT, *forc, *y_win, *std_win;
+  int32_t ri32;   // xT in RI32 [L][G][IP/4][32][4] (rows >= B of the last group are zero filled)
 };
 
 // grid: (ceil(B/32), L). Each block handles one time step of 32 samples; threads sweep the IP
@@ -30,12 +31,26 @@ __global__ void __launch_bounds__(256) window_gather_kernel(GatherArgs a) {
   __syncthreads();
   const int64_t nb = min((int64_t)32, a.B - b0);
   const int64_t I = a.nd + a.ns;
-  for (int64_t e = threadIdx.x; e < nb * a.IP; e += blockDim.x) {
-    const int64_t lb = e / a.IP, c = e - lb * a.IP;
-    float v = 0.f;
-    if (c < a.nd) v = __ldg(a.x_d + s_row[lb] * a.nd + c);
-    else if (c < I) v = __ldg(a.x_s + s_basin[lb] * a.ns + (c - a.nd));
-    a.xT[(t * a.B + b0) * a.IP + e] = v;
+  if (a.ri32) {
+    // one block = one RI32 group of step t: [32 rows][32 floats], 8-float unit u of row r at u ^ (r & 3)
+    float* dst = a.xT + (t * gridDim.x + blockIdx.x) * 1024;
+    for (int64_t e = threadIdx.x; e < 1024; e += blockDim.x) {
+      const int64_t lb = e >> 5, c = ((((e >> 3) & 3) ^ (lb & 3)) << 3) | (e & 7);   // feature stored at word e
+      float v = 0.f;
+      if (lb < nb) {
+        if (c < a.nd) v = __ldg(a.x_d + s_row[lb] * a.nd + c);
+        else if (c < I) v = __ldg(a.x_s + s_basin[lb] * a.ns + (c - a.nd));
+      }
+      dst[e] = v;
+    }
+  } else {
+    for (int64_t e = threadIdx.x; e < nb * a.IP; e += blockDim.x) {
+      const int64_t lb = e / a.IP, c = e - lb * a.IP;
+      float v = 0.f;
+      if (c < a.nd) v = __ldg(a.x_d + s_row[lb] * a.nd + c);
+      else if (c < I) v = __ldg(a.x_s + s_basin[lb] * a.ns + (c - a.nd));
+      a.xT[(t * a.B + b0) * a.IP + e] = v;
+    }
   }
   if (a.forc) {
     for (int64_t e = threadIdx.x; e < nb * 3; e += blockDim.x) {
@@ -57,6 +72,7 @@ __global__ void __launch_bounds__(256) window_gather_kernel(GatherArgs a) {
 
 // [B][T][I] -> [T][B][IP] (zero padded).  Tile transpose through shared memory: reads are
 // contiguous along (t, i) of one sample, writes contiguous along (b, i) of one step.
+template <bool RI32>
 __global__ void __launch_bounds__(256) pack_x_kernel(const float* __restrict__ x, int64_t B, int64_t T, int64_t I,
                                                       int64_t IP, float* __restrict__ xT) {
   extern __shared__ float tile[];  // [8 samples][8 steps * I]
@@ -71,7 +87,13 @@ __global__ void __launch_bounds__(256) pack_x_kernel(const float* __restrict__ x
   for (int64_t e = threadIdx.x; e < nt * nb * IP; e += blockDim.x) {
     const int64_t lt = e / (nb * IP), r = e - lt * nb * IP;
     const int64_t lb = r / IP, c = r - lb * IP;
-    xT[((t0 + lt) * B + b0) * IP + r] = c < I ? tile[lb * 8 * I + lt * I + c] : 0.f;
+    const float v = c < I ? tile[lb * 8 * I + lt * I + c] : 0.f;
+    if (RI32) {   // IP = 32: one block per group
+      const int64_t b = b0 + lb, G = (B + 31) / 32;
+      xT[((t0 + lt) * G + (b >> 5)) * 1024 + (b & 31) * 32 + ((((c >> 3) ^ b) & 3) << 3) + (c & 7)] = v;
+    } else {
+      xT[((t0 + lt) * B + b0) * IP + r] = v;
+    }
   }
 }
 
@@ -82,7 +104,7 @@ extern "C" int hy2dl_window_gather(const float* x_d, const float* x_s, const flo
                                    const float* basin_std, const int64_t* row0, const int64_t* basin,
                                    const int64_t* end, int64_t B, int64_t L, int64_t n_last, int64_t nd, int64_t ns,
                                    int64_t nc, int64_t IP, float* xT, float* forc, float* y_win, float* std_win,
-                                   hy2dl_stream_t stream) {
+                                   int layout, hy2dl_stream_t stream) {
   HY_REQUIRE(B > 0 && L > 0 && n_last > 0 && n_last <= L && nd > 0 && ns >= 0, HY2DL_ERR_SHAPE,
              "hy2dl_window_gather: bad sizes B=%lld L=%lld n_last=%lld nd=%lld ns=%lld", (long long)B, (long long)L,
              (long long)n_last, (long long)nd, (long long)ns);
@@ -93,14 +115,18 @@ extern "C" int hy2dl_window_gather(const float* x_d, const float* x_s, const flo
   HY_PTR(xT); HY_NONNULL(y_win); HY_NONNULL(std_win);
   HY_REQUIRE(ns == 0 || x_s != nullptr, HY2DL_ERR_ALIGN, "hy2dl_window_gather: x_s is null but ns > 0");
   HY_REQUIRE(forc == nullptr || x_conc != nullptr, HY2DL_ERR_ALIGN, "hy2dl_window_gather: x_conc is null");
-  GatherArgs a{x_d, x_s, x_conc, y_obs, basin_std, row0, basin, end, B, L, n_last, nd, ns, nc, IP, xT, forc, y_win, std_win};
+  HY_REQUIRE(layout == HY2DL_LAYOUT_ROWMAJOR || layout == HY2DL_LAYOUT_RI32, HY2DL_ERR_SHAPE, "hy2dl_window_gather: unknown layout %d", layout);
+  HY_REQUIRE(layout != HY2DL_LAYOUT_RI32 || IP == 32, HY2DL_ERR_SHAPE, "hy2dl_window_gather: RI32 streams are 32 columns wide (IP=%lld)", (long long)IP);
+  GatherArgs a{x_d, x_s, x_conc, y_obs, basin_std, row0, basin, end, B, L, n_last, nd, ns, nc, IP, xT, forc, y_win, std_win,
+               layout == HY2DL_LAYOUT_RI32};
   dim3 grid((unsigned)cdiv(B, 32), (unsigned)L);
   window_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   HY_LAUNCH_CHECK();
   return HY2DL_OK;
 }
 
-extern "C" int hy2dl_pack_x(const float* x, int64_t B, int64_t T, int64_t I, int64_t IP, float* xT, hy2dl_stream_t stream) {
+extern "C" int hy2dl_pack_x(const float* x, int64_t B, int64_t T, int64_t I, int64_t IP, float* xT, int layout,
+                            hy2dl_stream_t stream) {
   HY_REQUIRE(B > 0 && T > 0 && I > 0 && IP >= I && IP % 4 == 0, HY2DL_ERR_SHAPE,
              "hy2dl_pack_x: bad sizes B=%lld T=%lld I=%lld IP=%lld", (long long)B, (long long)T, (long long)I, (long long)IP);
   HY_REQUIRE(I <= 1024, HY2DL_ERR_SHAPE, "hy2dl_pack_x: I=%lld exceeds 1024", (long long)I);
@@ -108,7 +134,14 @@ extern "C" int hy2dl_pack_x(const float* x, int64_t B, int64_t T, int64_t I, int
   dim3 grid((unsigned)cdiv(B, 8), (unsigned)cdiv(T, 8));
   HY_REQUIRE(grid.y <= 65535, HY2DL_ERR_SHAPE, "hy2dl_pack_x: T=%lld too long", (long long)T);
   const size_t smem = (size_t)(8 * 8 * I) * sizeof(float);
-  pack_x_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, B, T, I, IP, xT);
+  if (layout == HY2DL_LAYOUT_RI32) {
+    HY_REQUIRE(IP == 32, HY2DL_ERR_SHAPE, "hy2dl_pack_x: RI32 streams are 32 columns wide (IP=%lld)", (long long)IP);
+    if (B % 32) cudaMemsetAsync(xT, 0, sizeof(float) * T * cdiv(B, 32) * 32 * IP, (cudaStream_t)stream);   // padded rows = 0
+    pack_x_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(x, B, T, I, IP, xT);
+  } else {
+    HY_REQUIRE(layout == HY2DL_LAYOUT_ROWMAJOR, HY2DL_ERR_SHAPE, "hy2dl_pack_x: unknown layout %d", layout);
+    pack_x_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(x, B, T, I, IP, xT);
+  }
   HY_LAUNCH_CHECK();
   return HY2DL_OK;
 }

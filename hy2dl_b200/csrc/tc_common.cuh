@@ -68,6 +68,30 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
          (1ull << 46);
 }
 
+// Same, SWIZZLE_128B_BASE32B (layout type 1): the only MN-major layout kind::tf32 accepts.  Atom = 32 MN
+// elements (128 B) x 4 K-rows 128 B apart; LBO = step between 32-element MN blocks, SBO = step between
+// 4-row K groups; in K-row k the 32-byte unit u of the 128-byte row sits at unit position u ^ (k & 3)
+// (byte-address bits [7,9) XORed into bits [5,7); verified on hardware, tools/dbg_wgrad.py).
+__device__ __forceinline__ uint64_t smem_desc_mn32(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return smem_desc(saddr, lbo_bytes, sbo_bytes) | (1ull << 61);
+}
+
+// ---- RI32 stream layout -------------------------------------------------------------------------
+// [t][G = ceil(B/32)][F/32][32 rows][32 floats]; in row r the 8-float unit u is stored at unit u ^ (r & 3):
+// a (t, group, 32-feature block) slab is 4 KB contiguous and is exactly the SWIZZLE_128B_BASE32B MN-major
+// operand tile for K = 32 rows.  A row thread reads/writes 16-byte chunks c = feature / 4; the 8 chunks
+// of a block are one 128-byte line of its row, two consecutive chunks one 32-byte sector.
+__device__ __forceinline__ int64_t ri32_idx4(int64_t t, int64_t G, int64_t gidx, int FB, int c, int row) {
+  const int pos = ((((c & 7) >> 1) ^ (row & 3)) << 1) | (c & 1);
+  return ((t * G + gidx) * FB + (c >> 3)) * 256 + row * 8 + pos;         // float4 index; FB = F / 32
+}
+__device__ __forceinline__ float4 ri32_ld(const float4* base, int64_t t, int64_t G, int64_t gidx, int FB, int c, int row) {
+  return __ldg(base + ri32_idx4(t, G, gidx, FB, c, row));
+}
+__device__ __forceinline__ void ri32_st(float4* base, int64_t t, int64_t G, int64_t gidx, int FB, int c, int row, float4 v) {
+  base[ri32_idx4(t, G, gidx, FB, c, row)] = v;
+}
+
 // ---- MMA issue (single thread) ---------------------------------------------------------------
 // D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {

@@ -46,7 +46,7 @@ def valid_window_flags(x: np.ndarray, y: np.ndarray, seq_length: int, predict_la
 @dataclass
 class Batch:
     """One gathered batch in native layouts (include/hy2dl_b200.h)."""
-    xT: torch.Tensor                 # [L, B, IP]
+    xT: torch.Tensor                 # [L, B, IP], or RI32 [L, G, 1, 32, 32]
     forc: Optional[torch.Tensor]     # [L, 3, B]
     y_obs: torch.Tensor              # [n_last, B]
     basin_std: torch.Tensor          # [n_last, B]
@@ -54,9 +54,15 @@ class Batch:
     end: torch.Tensor                # [B] int64 end row within the basin
     input_size: int
 
+    @property
+    def B(self) -> int:
+        return self.basin.numel()
+
     def as_reference(self) -> Dict[str, torch.Tensor]:
         """The reference's sample dict ([B, T, ...] tensors), for API-level comparisons."""
-        d = {"x_lstm": self.xT[:, :, :self.input_size].permute(1, 0, 2).contiguous(),
+        from ..ops import from_ri32, is_ri32
+        xT = from_ri32(self.xT, self.B) if is_ri32(self.xT) else self.xT
+        d = {"x_lstm": xT[:, :, :self.input_size].permute(1, 0, 2).contiguous(),
              "y_obs": self.y_obs.t().unsqueeze(2).contiguous(),
              "basin_std": self.basin_std.t().unsqueeze(2).contiguous()}
         if self.forc is not None:
@@ -94,6 +100,7 @@ class ResidentDataset:
         self.scaler: Dict[str, np.ndarray] = {}
         self.basin_std = np.zeros(self.nb, dtype=np.float32)
         self._resident = False
+        self.layout = "rowmajor"   # layout gather() writes xT in; "ri32" for precision tf32x3 models
 
     def __len__(self) -> int:
         return len(self.valid_entities)
@@ -149,13 +156,18 @@ class ResidentDataset:
     def gather_pairs(self, basin: torch.Tensor, end: torch.Tensor) -> Batch:
         _lib.require_cuda(self.d_x_d, "resident series")
         B, L, n_last, dev = basin.numel(), self.sequence_length, self.predict_last_n, self.device
-        xT = torch.empty(L, B, self.IP, dtype=torch.float32, device=dev)
+        ri = self.layout == "ri32"
+        if ri and self.input_size > 32:
+            raise RuntimeError(f"hy2dl_b200: the RI32 / tf32x3 path takes input_size <= 32 (got {self.input_size})")
+        IP = 32 if ri else self.IP
+        xT = (torch.empty(L, (B + 31) // 32, 1, 32, 32, dtype=torch.float32, device=dev) if ri
+              else torch.empty(L, B, IP, dtype=torch.float32, device=dev))
         forc = torch.empty(L, 3, B, dtype=torch.float32, device=dev) if self.nc else None
         y_win = torch.empty(n_last, B, dtype=torch.float32, device=dev)
         std_win = torch.empty(n_last, B, dtype=torch.float32, device=dev)
         call("hy2dl_window_gather", ptr(self.d_x_d), ptr(self.d_x_s), ptr(self.d_x_conc), ptr(self.d_y),
-             ptr(self.d_std), ptr(self.d_row0), ptr(basin), ptr(end), B, L, n_last, self.nd, self.ns, self.nc, self.IP,
-             ptr(xT), ptr(forc), ptr(y_win), ptr(std_win), stream())
+             ptr(self.d_std), ptr(self.d_row0), ptr(basin), ptr(end), B, L, n_last, self.nd, self.ns, self.nc, IP,
+             ptr(xT), ptr(forc), ptr(y_win), ptr(std_win), _lib.LAYOUT_RI32 if ri else _lib.LAYOUT_ROWMAJOR, stream())
         return Batch(xT, forc, y_win, std_win, basin, end, self.input_size)
 
     def epoch(self, batch_size: int, generator: Optional[torch.Generator] = None, drop_last: bool = True,

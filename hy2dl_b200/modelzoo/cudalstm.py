@@ -31,10 +31,10 @@ class CudaLSTM(nn.Module):
 
     def forward(self, x: torch.Tensor):
         """x: [batch_size, time_steps, input_size_lstm] on the GPU."""
-        return self.forward_native(ops.pack_x(x))
+        return self.forward_native(ops.pack_x(x, self.lstm.layout), B=x.shape[0])
 
-    def forward_native(self, xT: torch.Tensor):
-        """xT: [T, B, IP] as written by the GPU-resident sampler."""
-        _, h_last = self.lstm.run_native(xT, want_seq=False)
+    def forward_native(self, xT: torch.Tensor, B: int = None):
+        """xT: [T, B, IP] (or RI32 with B given) as written by the GPU-resident sampler."""
+        _, h_last = self.lstm.run_native(xT, want_seq=False, B=B)
         out = self.dropout(h_last)  # PyTorch's op on [B, H]: RNG semantics stay PyTorch's
         return {"y_hat": self.linear(out)}

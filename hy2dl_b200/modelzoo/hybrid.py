@@ -73,19 +73,21 @@ class Hybrid(nn.Module):
         y_hat [B,T_sim,1], parameters / internal_states {name: [B,T_sim,m]}, final_states {name: [B,m]}."""
         if x_lstm.shape[:2] != x_conceptual.shape[:2]:
             raise ValueError("x_lstm and x_conceptual must share batch and time dimensions")
-        return self.forward_native(ops.pack_x(x_lstm), ops.pack_forcing(x_conceptual))
+        return self.forward_native(ops.pack_x(x_lstm, self.lstm.layout), ops.pack_forcing(x_conceptual))
 
     def forward_native(self, xT: torch.Tensor, forc: torch.Tensor):
-        """Same as forward() for inputs already in native layout (xT [T,B,IP], forc [T,3,B]), as the
-        GPU-resident sampler writes them."""
-        T, B, _ = xT.shape
+        """Same as forward() for inputs already in native layout (xT [T,B,IP] or RI32, forc [T,3,B]), as
+        the GPU-resident sampler writes them."""
+        T, B = forc.shape[0], forc.shape[2]
+        if xT.shape[0] != T:
+            raise ValueError("xT and forc must share the time dimension")
         layout = self._layout(B, T)
         pm, cm = layout.pm, self.conceptual_model
         warmup, m, n_par = pm.warmup, self.n_conceptual_models, pm.n_par
         N, T_sim = B * m, T - warmup
 
         # LSTM over all T steps; only steps >= warmup receive gradient from the head
-        h_seq, _ = self.lstm.run_native(xT, dh_t0=warmup, want_seq=True)
+        h_seq, _ = self.lstm.run_native(xT, dh_t0=warmup, want_seq=True, B=B)
         par_sim, par_warm = ops.head_map(h_seq, self.linear.weight, self.linear.bias, layout)
 
         # warm-up: frozen parameters, no gradient (hybrid.py:99-102)

@@ -46,9 +46,15 @@ class LSTM(nn.Module):
     def weights(self):
         return self.weight_ih_l0, self.weight_hh_l0, self.bias_ih_l0, self.bias_hh_l0
 
-    def run_native(self, xT: torch.Tensor, dh_t0: int = 0, want_seq: bool = True):
-        """xT: native [T,B,IP] input -> (h_seq [T,B,H] or empty, h_last [B,H])."""
-        return ops.lstm(xT, *self.weights(), self.input_size, dh_t0, want_seq, self.precision)
+    @property
+    def layout(self) -> str:
+        """Layout of the native streams this module reads and writes ("rowmajor" | "ri32")."""
+        return ops.layout_of(self.precision)
+
+    def run_native(self, xT: torch.Tensor, dh_t0: int = 0, want_seq: bool = True, B: Optional[int] = None):
+        """xT: native input ([T,B,IP], or RI32 for precision tf32x3 with B given) ->
+        (h_seq in the same layout or empty, h_last [B,H])."""
+        return ops.lstm(xT, *self.weights(), self.input_size, dh_t0, want_seq, self.precision, B)
 
     def forward(self, x: torch.Tensor, hx: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
         """nn.LSTM-compatible call: x [B,T,I] -> (out [B,T,H], (h_n [1,B,H], c_n=None)).
@@ -58,7 +64,10 @@ class LSTM(nn.Module):
         """
         if x.dim() != 3 or x.shape[2] != self.input_size:
             raise ValueError(f"expected x of shape [B, T, {self.input_size}], got {tuple(x.shape)}")
-        h_seq, h_last = self.run_native(ops.pack_x(x))
+        B = x.shape[0]
+        h_seq, h_last = self.run_native(ops.pack_x(x, self.layout), B=B)
+        if ops.is_ri32(h_seq):
+            h_seq = ops.from_ri32(h_seq, B)
         return h_seq.permute(1, 0, 2), (h_last.unsqueeze(0), None)
 
     def extra_repr(self) -> str:

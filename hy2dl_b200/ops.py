@@ -23,20 +23,33 @@ def round_up(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
 
+def _ri32_unit_perm(device) -> torch.Tensor:
+    """[32 rows, 4 units] index: unit u of row r is stored at position u ^ (r & 3) (an involution)."""
+    r = torch.arange(32, device=device).view(32, 1)
+    u = torch.arange(4, device=device).view(1, 4)
+    return u ^ (r & 3)
+
+
 def to_ri32(x: torch.Tensor) -> torch.Tensor:
-    """Row-major [T,B,F] -> RI32 [T,G,F/4,32,4] (G = ceil(B/32), zero padded rows). Torch ops; used at
-    API boundaries and in tests, not on the training fast path (the sampler writes RI32 directly)."""
+    """Row-major [T,B,F] (F % 32 == 0) -> RI32 [T,G,F/32,32,32] (G = ceil(B/32), zero padded rows, 8-float
+    units of each row swizzled; include/hy2dl_b200.h). Torch ops; used at API boundaries and in tests,
+    not on the training fast path (the sampler writes RI32 directly)."""
     T, B, F = x.shape
+    assert F % 32 == 0, "RI32 streams are multiples of 32 features wide"
     G = (B + 31) // 32
     if G * 32 != B:
         x = torch.cat([x, x.new_zeros(T, G * 32 - B, F)], dim=1)
-    return x.view(T, G, 32, F // 4, 4).permute(0, 1, 3, 2, 4).contiguous()
+    y = x.view(T, G, 32, F // 32, 4, 8).permute(0, 1, 3, 2, 4, 5)                   # [T,G,FB,row,unit,8]
+    idx = _ri32_unit_perm(x.device).view(1, 1, 1, 32, 4, 1).expand(T, G, F // 32, 32, 4, 8)
+    return torch.gather(y, 4, idx).reshape(T, G, F // 32, 32, 32).contiguous()
 
 
 def from_ri32(x: torch.Tensor, B: int) -> torch.Tensor:
-    """RI32 [T,G,F/4,32,4] -> row-major [T,B,F]."""
-    T, G, F4 = x.shape[:3]
-    return x.permute(0, 1, 3, 2, 4).reshape(T, G * 32, F4 * 4)[:, :B]
+    """RI32 [T,G,F/32,32,32] -> row-major [T,B,F]."""
+    T, G, FB = x.shape[:3]
+    y = x.reshape(T, G, FB, 32, 4, 8)
+    y = torch.gather(y, 4, _ri32_unit_perm(x.device).view(1, 1, 1, 32, 4, 1).expand(T, G, FB, 32, 4, 8))
+    return y.permute(0, 1, 3, 2, 4, 5).reshape(T, G * 32, FB * 32)[:, :B]
 
 
 def _ws(kind: int, B: int, T: int, I: int, H: int, device, precision: int = 0) -> torch.Tensor:
@@ -49,14 +62,30 @@ def _ws(kind: int, B: int, T: int, I: int, H: int, device, precision: int = 0) -
 # --------------------------------------------------------------------------------------------------
 # layout packing (no gradient w.r.t. inputs: the reference never asks for dL/dx either)
 # --------------------------------------------------------------------------------------------------
-def pack_x(x: torch.Tensor) -> torch.Tensor:
-    """[B,T,I] -> native [T,B,IP]."""
+def is_ri32(t: torch.Tensor) -> bool:
+    """Native LSTM-side streams are 3-D [T,B,F] (row-major) or 5-D [T,G,F/32,32,32] (RI32)."""
+    return t.dim() == 5
+
+
+def layout_of(precision: str) -> str:
+    """The stream layout a recurrent-kernel precision works in."""
+    return "ri32" if precision == "tf32x3" else "rowmajor"
+
+
+def pack_x(x: torch.Tensor, layout: str = "rowmajor") -> torch.Tensor:
+    """[B,T,I] -> native [T,B,IP] (layout "rowmajor") or RI32 [T,G,1,32,32] (layout "ri32", I <= 32)."""
     require_cuda(x, "x_lstm")
     x = x.detach().contiguous()
     B, T, I = x.shape
     IP = round_up(I, 8)
-    xT = torch.empty(T, B, IP, dtype=torch.float32, device=x.device)
-    call("hy2dl_pack_x", ptr(x), B, T, I, IP, ptr(xT), stream())
+    if layout == "ri32":
+        if I > 32:
+            raise RuntimeError(f"hy2dl_b200: the tf32x3 path takes input_size <= 32 (got {I})")
+        xT = torch.empty(T, (B + 31) // 32, 1, 32, 32, dtype=torch.float32, device=x.device)
+        call("hy2dl_pack_x", ptr(x), B, T, I, 32, ptr(xT), _lib.LAYOUT_RI32, stream())
+    else:
+        xT = torch.empty(T, B, IP, dtype=torch.float32, device=x.device)
+        call("hy2dl_pack_x", ptr(x), B, T, I, IP, ptr(xT), _lib.LAYOUT_ROWMAJOR, stream())
     return xT
 
 
@@ -74,26 +103,37 @@ def pack_forcing(xc: torch.Tensor) -> torch.Tensor:
 # LSTM
 # --------------------------------------------------------------------------------------------------
 class LstmFunction(torch.autograd.Function):
-    """h_seq [T,B,H] and h_last [B,H] from xT [T,B,IP]; one layer, h0 = c0 = 0.
+    """h_seq and h_last [B,H] from xT; one layer, h0 = c0 = 0.
 
+    Row-major precisions: xT [T,B,IP] -> h_seq [T,B,H].  tf32x3: xT RI32 [T,G,1,32,32] ->
+    h_seq RI32 [T,G,H/32,32,32] (B = number of real rows, given explicitly).
     `dh_t0`: the caller promises that the gradient flowing into h_seq is zero (and may be
     uninitialised memory) for steps t < dh_t0 -- the hybrid head only feeds steps >= warm-up.
     """
 
     @staticmethod
-    def forward(ctx, xT, w_ih, w_hh, b_ih, b_hh, I: int, dh_t0: int, want_seq: bool, precision: int):
+    def forward(ctx, xT, w_ih, w_hh, b_ih, b_hh, I: int, dh_t0: int, want_seq: bool, precision: int, B: int):
         for n, t in (("xT", xT), ("weight_ih", w_ih), ("weight_hh", w_hh), ("bias_ih", b_ih), ("bias_hh", b_hh)):
             require_cuda(t, n)
-        T, B, IP = xT.shape
+        ri = precision == _lib.PREC_TF32X3
+        if ri != is_ri32(xT):
+            raise RuntimeError("hy2dl_b200: precision 'tf32x3' works on RI32 inputs and the other precisions on "
+                               f"row-major ones (got a {xT.dim()}-D xT); pack / gather with layout=ops.layout_of(precision)")
         H = w_hh.shape[1]
         dev = xT.device
+        if ri:
+            T, G, IP = xT.shape[0], xT.shape[1], xT.shape[2] * 32
+            seq = lambda F: torch.empty(T, G, F // 32, 32, 32, dtype=torch.float32, device=dev)
+        else:
+            T, B, IP = xT.shape
+            seq = lambda F: torch.empty(T, B, F, dtype=torch.float32, device=dev)
         need_grad = any(ctx.needs_input_grad[1:5])
         w_ih, w_hh, b_ih, b_hh = (t.detach().contiguous() for t in (w_ih, w_hh, b_ih, b_hh))
-        h_seq = torch.empty(T, B, H, dtype=torch.float32, device=dev) if (want_seq or need_grad) else None
+        h_seq = seq(H) if (want_seq or need_grad) else None
         h_last = torch.empty(B, H, dtype=torch.float32, device=dev)
-        c_seq = torch.empty(T, B, H, dtype=torch.float32, device=dev) if need_grad else None
-        gates = torch.empty(T, B, 4, H, dtype=torch.float32, device=dev) if need_grad else None
-        ws = _ws(_lib.WS_LSTM_FWD, B, T, I, H, dev)
+        c_seq = seq(H) if need_grad else None
+        gates = seq(4 * H) if need_grad else None
+        ws = _ws(_lib.WS_LSTM_FWD, B, T, I, H, dev, precision)
         call("hy2dl_lstm_fwd", ptr(xT), B, T, I, IP, H, ptr(w_ih), ptr(w_hh), ptr(b_ih), ptr(b_hh), ptr(h_seq),
              ptr(c_seq), ptr(gates), ptr(h_last), ptr(ws), ws.numel(), precision, stream())
         ctx.save_for_backward(xT, w_hh, h_seq, c_seq, gates)
@@ -116,8 +156,8 @@ class LstmFunction(torch.autograd.Function):
         if dh_last is not None:
             dh_last = dh_last.contiguous()
         if dh_seq is None and dh_last is None:
-            return (None,) * 9
-        ws_b = _ws(_lib.WS_LSTM_BWD, B, T, I, H, dev)
+            return (None,) * 10
+        ws_b = _ws(_lib.WS_LSTM_BWD, B, T, I, H, dev, precision)
         # dG overwrites the gate tape in place (the kernel reads each element before writing it)
         dG = gates
         call("hy2dl_lstm_bwd", B, T, H, ptr(w_hh), ptr(gates), ptr(c_seq), ptr(dh_seq), dh_t0, ptr(dh_last), ptr(dG),
@@ -125,15 +165,20 @@ class LstmFunction(torch.autograd.Function):
         dw_ih = torch.empty(4 * H, I, dtype=torch.float32, device=dev)
         dw_hh = torch.empty(4 * H, H, dtype=torch.float32, device=dev)
         db = torch.empty(4 * H, dtype=torch.float32, device=dev)
-        ws_w = _ws(_lib.WS_LSTM_WGRAD, B, T, I, H, dev)
+        ws_w = _ws(_lib.WS_LSTM_WGRAD, B, T, I, H, dev, precision)
         call("hy2dl_lstm_wgrad", ptr(dG), ptr(h_seq), ptr(xT), B, T, I, IP, H, ptr(dw_ih), ptr(dw_hh), ptr(db),
              ptr(ws_w), ws_w.numel(), precision, stream())
-        return None, dw_ih, dw_hh, db, db.clone(), None, None, None, None
+        return None, dw_ih, dw_hh, db, db.clone(), None, None, None, None, None
 
 
 def lstm(xT, w_ih, w_hh, b_ih, b_hh, input_size: int, dh_t0: int = 0, want_seq: bool = True,
-         precision: str = "fp32") -> Tuple[torch.Tensor, torch.Tensor]:
-    return LstmFunction.apply(xT, w_ih, w_hh, b_ih, b_hh, input_size, dh_t0, want_seq, PRECISIONS[precision])
+         precision: str = "fp32", B: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """B: number of sequences; required for RI32 inputs (whose row count is padded to 32)."""
+    if B is None:
+        if is_ri32(xT):
+            raise ValueError("hy2dl_b200.ops.lstm: pass B (the number of sequences) with an RI32 input")
+        B = xT.shape[1]
+    return LstmFunction.apply(xT, w_ih, w_hh, b_ih, b_hh, input_size, dh_t0, want_seq, PRECISIONS[precision], B)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -193,14 +238,16 @@ class HeadMapFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h_seq, w, bias, layout: ParLayout):
         require_cuda(h_seq, "h_seq"); require_cuda(w, "linear.weight"); require_cuda(bias, "linear.bias")
-        T, B, H = h_seq.shape
+        ri = is_ri32(h_seq)
+        T, B, H = h_seq.shape[0], layout.B, w.shape[1]
+        lay = _lib.LAYOUT_RI32 if ri else _lib.LAYOUT_ROWMAJOR
         dev = h_seq.device
         h_seq = h_seq.contiguous()
         w_c, b_c = w.detach().contiguous(), bias.detach().contiguous()
         par_sim = torch.empty(layout.n_floats, dtype=torch.float32, device=dev)
         par_warm = torch.empty(layout.pm.n_par, layout.N, dtype=torch.float32, device=dev)
         call("hy2dl_head_map_fwd", ptr(h_seq), B, T, H, ptr(w_c), ptr(b_c), C.byref(layout.pm), ptr(par_sim),
-             ptr(par_warm), stream())
+             ptr(par_warm), lay, stream())
         ctx.save_for_backward(h_seq, w_c, par_sim)
         ctx.layout = layout
         ctx.mark_non_differentiable(par_warm)
@@ -210,14 +257,15 @@ class HeadMapFunction(torch.autograd.Function):
     def backward(ctx, dpar_sim, _dpar_warm):
         h_seq, w, par_sim = ctx.saved_tensors
         layout = ctx.layout
-        T, B, H = h_seq.shape
+        T, B, H = h_seq.shape[0], layout.B, w.shape[1]
+        lay = _lib.LAYOUT_RI32 if is_ri32(h_seq) else _lib.LAYOUT_ROWMAJOR
         dev = h_seq.device
         dpar_sim = dpar_sim.contiguous()
-        dh_seq = torch.empty(T, B, H, dtype=torch.float32, device=dev)  # rows < warmup stay uninitialised (dh_t0)
+        dh_seq = torch.empty_like(h_seq)  # rows < warmup stay uninitialised (dh_t0)
         dw = torch.empty_like(w)
         db = torch.empty(w.shape[0], dtype=torch.float32, device=dev)
         call("hy2dl_head_map_bwd", ptr(h_seq), ptr(par_sim), ptr(dpar_sim), B, T, H, ptr(w), C.byref(layout.pm),
-             ptr(dh_seq), ptr(dw), ptr(db), stream())
+             ptr(dh_seq), ptr(dw), ptr(db), lay, stream())
         return dh_seq, dw, db, None
 
 

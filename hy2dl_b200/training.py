@@ -84,7 +84,7 @@ def forward_loss(model: nn.Module, batch: Batch, loss: str, group=None) -> torch
         pred = model.forward_native(batch.xT, batch.forc)
         y = pred["y_hat"][:, :, 0].t()       # the contiguous [T_sim, B] buffer underneath the API view
     else:
-        pred = model.forward_native(batch.xT)
+        pred = model.forward_native(batch.xT, B=batch.B)
         y = pred["y_hat"].t()                # [1, B]
     if loss == "nse":
         return nse_basin_averaged(y_sim=y, y_obs=batch.y_obs, per_basin_target_std=batch.basin_std, group=group)
@@ -99,6 +99,7 @@ class Trainer:
     def __init__(self, model: nn.Module, dataset: ResidentDataset, loss: str = "nse", lr: float = 1e-3,
                  max_norm: float = 1.0, group=None, use_graph: bool = False):
         self.model, self.dataset, self.loss_kind, self.group = model, dataset, loss, group
+        dataset.layout = model.lstm.layout   # the sampler writes the layout the recurrent kernels read
         self.opt = FusedClipAdam(model.parameters(), lr=lr, max_norm=max_norm, group=group)
         self.use_graph = use_graph
         self._graph = None

@@ -22,10 +22,12 @@
  *   gates   [T][B][4][H]    activated gates i,f,g,o (tape); overwritten in place by dG in bwd
  *   forc    [T][3][B]       conceptual forcings P, PET, Tmean
  *   With HY2DL_PREC_TF32X3 the LSTM streams (xT, h_seq, c_seq, gates, dG, dh_seq) use the
- *   row-interleaved layout RI32 instead: [T][ceil(B/32)][F/4][32 rows][4 floats] -- the 32 rows
- *   of a group are interleaved at 16-byte granularity, so the row-owning threads of the tcgen05
- *   kernels access it fully coalesced and a group is directly a no-swizzle MN-major UMMA operand.
- *   gates/dG then order their 4H columns as n = 4*unit + gate.
+ *   row-interleaved layout RI32 instead: [T][ceil(B/32)][F/32][32 rows][32 floats], and in row r the
+ *   8-float unit u (= (feature % 32) / 8) is stored at unit position u ^ (r & 3).  A (step, group,
+ *   32-feature block) slab is 4 KB contiguous and is exactly the MN-major SWIZZLE_128B_BASE32B UMMA
+ *   operand tile of the weight-gradient GEMM, while the row-owning threads of the recurrent kernels
+ *   move whole 32-byte sectors / 128-byte lines.  F is a multiple of 32: xT is 32 columns wide
+ *   (IP = 32, I <= 32).  gates/dG order their 4H columns as n = 4*unit + gate.
  *   N = B*m series (sample b, member j -> n = b*m + j)
  *   par     planes: dynamic parameter -> [T_sim][N], static parameter -> [N]   (see hy2dl_parmap)
  *   states  [T][5][N]       bucket storages after each step
@@ -56,6 +58,10 @@ typedef void* hy2dl_stream_t; /* cudaStream_t */
 #define HY2DL_PREC_TF32X3 1 /* tcgen05 kind::tf32, 3-term split (fp32-class accuracy)         */
 #define HY2DL_PREC_BF16 2   /* tcgen05 kind::f16 bf16 operands, fp32 accumulate (throughput)  */
 
+/* layout of the LSTM-side streams handled by the packing / sampler / head functions */
+#define HY2DL_LAYOUT_ROWMAJOR 0 /* [T][B][F]                                                      */
+#define HY2DL_LAYOUT_RI32 1     /* [T][ceil(B/32)][F/32][32][32] swizzled, the layout of HY2DL_PREC_TF32X3 */
+
 /* conceptual models */
 #define HY2DL_MODEL_SHM 0 /* 8 parameters: dd f_thr sumax beta perc kf ki kb     (modelzoo/shm.py:193-204) */
 #define HY2DL_MODEL_HBV 1 /* 13 parameters: BETA FC K0 K1 K2 LP PERC UZL TT CFMAX CFR CWH BETAET (hbv.py:199-215) */
@@ -76,8 +82,9 @@ int64_t hy2dl_workspace_bytes(int kind, int64_t B, int64_t T, int64_t I, int64_t
 /* ---- layout packing --------------------------------------------------------------------------
  * x [B][T][I] (reference batch-first layout, modelzoo/cudalstm.py:34, hybrid.py:72) -> xT [T][B][IP].
  * xc [B][T][nc], nc = 3 (P, PET, T) or 4 (P, PET, Tmax, Tmin -> mean; shm.py:74-80, hbv.py:70-77)
- *    -> forc [T][3][B]. */
-int hy2dl_pack_x(const float* x, int64_t B, int64_t T, int64_t I, int64_t IP, float* xT, hy2dl_stream_t stream);
+ *    -> forc [T][3][B].
+ * layout = HY2DL_LAYOUT_RI32: xT is written as RI32 (rows >= B of the last group zero filled). */
+int hy2dl_pack_x(const float* x, int64_t B, int64_t T, int64_t I, int64_t IP, float* xT, int layout, hy2dl_stream_t stream);
 int hy2dl_pack_forcing(const float* xc, int64_t B, int64_t T, int64_t nc, float* forc, hy2dl_stream_t stream);
 
 /* ---- LSTM (replaces torch.nn.LSTM at modelzoo/cudalstm.py:50 and hybrid.py:92; one layer,
@@ -104,6 +111,7 @@ int hy2dl_lstm_wgrad(const float* dG, const float* h_seq, const float* xT,
 
 /* ---- head: Linear(H, C) on the needed steps + sigmoid range mapping ---------------------------
  * replaces modelzoo/hybrid.py:93-97,110-113 and baseconceptualmodel.py:53-76.
+ * `layout` is the layout of h_seq (fwd) and of h_seq + dh_seq (bwd); RI32 dh_seq rows >= B are zero.
  * Column c = p*m + j for conceptual parameter p, member j; routing parameters (m = 1) follow. */
 typedef struct {
   int32_t n_par;                    /* conceptual parameters P (8 SHM, 13 HBV)                   */
@@ -120,13 +128,13 @@ typedef struct {
 int64_t hy2dl_parmap_layout(hy2dl_parmap* pm, int64_t B, int64_t T);
 int hy2dl_head_map_fwd(const float* h_seq, int64_t B, int64_t T, int64_t H,
                        const float* w, const float* bias, const hy2dl_parmap* pm,
-                       float* par_sim, float* par_warm, hy2dl_stream_t stream);
+                       float* par_sim, float* par_warm, int layout, hy2dl_stream_t stream);
 /* par_sim: the forward output; dpar_sim has the same layout.  Writes dh_seq rows t >= warmup
  * (the warm-up runs under no_grad, hybrid.py:99-102, so row warmup-1 and earlier get no gradient
  * and are left untouched), and overwrites dw [C][H], dbias [C]. */
 int hy2dl_head_map_bwd(const float* h_seq, const float* par_sim, const float* dpar_sim, int64_t B, int64_t T,
                        int64_t H, const float* w, const hy2dl_parmap* pm, float* dh_seq, float* dw, float* dbias,
-                       hy2dl_stream_t stream);
+                       int layout, hy2dl_stream_t stream);
 
 /* ---- conceptual models (replace SHM.forward shm.py:135-182, HBV.forward hbv.py:127-188) --------
  * par[p] / tstride[p]: device pointer of parameter p's plane and its stride in floats between
@@ -167,11 +175,11 @@ int hy2dl_loss_wrmse_finish(const float* y_sim, const float* y_obs, int64_t n, c
  * datasetzoo/basedataset.py:168-195).  Resident series are the concatenation of all basins:
  * x_d [R][nd], x_conc [R][nc] (or NULL), y_obs [R], x_s [nb][ns] (or NULL), basin_std [nb],
  * row0 [nb].  Sample k = (basin[k], end[k]).  Outputs in native layouts:
- * xT [L][B][IP], forc [L][3][B] (or NULL), y_win [n_last][B], std_win [n_last][B]. */
+ * xT [L][B][IP] (or RI32 per `layout`), forc [L][3][B] (or NULL), y_win [n_last][B], std_win [n_last][B]. */
 int hy2dl_window_gather(const float* x_d, const float* x_s, const float* x_conc, const float* y_obs,
                         const float* basin_std, const int64_t* row0, const int64_t* basin, const int64_t* end,
                         int64_t B, int64_t L, int64_t n_last, int64_t nd, int64_t ns, int64_t nc, int64_t IP,
-                        float* xT, float* forc, float* y_win, float* std_win, hy2dl_stream_t stream);
+                        float* xT, float* forc, float* y_win, float* std_win, int layout, hy2dl_stream_t stream);
 
 /* ---- optimiser tail on one flat buffer (replaces clip_grad_norm_(.., max_norm) + Adam.step,
  * experiments/LSTM_CAMELS_GB.ipynb:298-299).  norm_sq: device scalar, zeroed by the caller before

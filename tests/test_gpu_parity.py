@@ -48,6 +48,9 @@ def test_pack_layouts(dev):
         xT = npy(ops.pack_x(cu(x, dev)))
         assert xT.shape == (T, B, (I + 7) // 8 * 8)
         assert np.array_equal(xT[:, :, :I], x.transpose(1, 0, 2)) and not xT[:, :, I:].any()
+        xr = ops.pack_x(cu(x, dev), "ri32")                                      # always 32 columns wide
+        x32 = torch.zeros(T, B, 32, device=dev); x32[:, :, :I] = cu(x, dev).permute(1, 0, 2)
+        assert torch.equal(xr, ops.to_ri32(x32))
     for nc in (3, 4):
         xc = rng.normal(size=(7, 11, nc)).astype(np.float32)
         f = npy(ops.pack_forcing(cu(xc, dev)))
@@ -136,19 +139,28 @@ def test_sampler_gather(dev):
     assert_close(npy(ref["y_obs"]), g["y_win"], rtol=0, what="y window")
     assert_close(npy(ref["basin_std"]), g["basin_std"], rtol=1e-6, what="basin_std")
     assert not npy(batch.xT)[:, :, ds.input_size:].any()
+    # the same batch gathered straight into the RI32 layout of the tensor-core path
+    from hy2dl_b200 import ops
+    ds.layout = "ri32"
+    b2 = ds.gather(torch.tensor(g["pick"], device=dev))
+    assert ops.is_ri32(b2.xT) and b2.xT.shape[1] == (b2.B + 31) // 32
+    x32 = torch.zeros(batch.xT.shape[0], b2.B, 32, device=dev); x32[:, :, :batch.xT.shape[2]] = batch.xT
+    assert torch.equal(ops.from_ri32(b2.xT, b2.B), x32)
+    assert torch.equal(b2.xT, ops.to_ri32(x32))               # padded rows and columns are zero
+    assert torch.equal(b2.as_reference()["x_lstm"], ref["x_lstm"])
 
 
 # ------------------------------------------------------------------------------------------------
 # model-level cases against the reference's golden vectors
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["cudalstm_c1", "cudalstm_c3"])
-def test_cudalstm_golden(dev, name):
+@pytest.mark.parametrize("name,precision", [("cudalstm_c1", "fp32"), ("cudalstm_c3", "fp32"), ("cudalstm_c1", "tf32x3")])
+def test_cudalstm_golden(dev, name, precision):
     from hy2dl_b200.aux_functions import nse_basin_averaged
     from hy2dl_b200.modelzoo import CudaLSTM
     g = golden(name)
     B, T, I, H, wseed = [int(v) for v in g["meta"]]
-    model = load(CudaLSTM({"input_size_lstm": I, "hidden_size": H, "no_of_layers": 1, "drop_out_rate": 0.0}),
-                 I, H, 1, wseed, dev)
+    model = load(CudaLSTM({"input_size_lstm": I, "hidden_size": H, "no_of_layers": 1, "drop_out_rate": 0.0,
+                           "precision": precision}), I, H, 1, wseed, dev)
     y = model(cu(g["x_lstm"], dev))["y_hat"]
     loss = nse_basin_averaged(y_sim=y, y_obs=cu(g["y_obs"], dev), per_basin_target_std=cu(g["basin_std"], dev))
     loss.backward()
@@ -162,21 +174,27 @@ def test_cudalstm_golden(dev, name):
         assert_close(got, ref, what="grad " + k, **GTOL)
 
 
-def build_hybrid(g, dev):
+def build_hybrid(g, dev, precision="fp32"):
     from hy2dl_b200.modelzoo import HBV, SHM, Hybrid, UH_routing
     B, T, n_last, I, H, m, wseed, routing = [int(v) for v in g["meta"]]
     cls = {"shm": SHM, "hbv": HBV}[str(g["model"])]
     hp = {"input_size_lstm": I, "hidden_size": H, "no_of_layers": 1, "seq_length": T, "predict_last_n": n_last,
-          "n_conceptual_models": m, "conceptual_dynamic_parameterization": [str(s) for s in g["dynamic"]]}
+          "n_conceptual_models": m, "conceptual_dynamic_parameterization": [str(s) for s in g["dynamic"]],
+          "precision": precision}
     model = Hybrid(hp, conceptual_model=cls, routing_model=UH_routing if routing else None)
     return load(model, I, H, model.linear.out_features, wseed, dev)
 
 
-@pytest.mark.parametrize("name", ["hybrid_shm_c2", "hybrid_shm_mixed", "hybrid_hbv_c4", "hybrid_hbv_norouting"])
-def test_hybrid_golden(dev, name):
+@pytest.mark.parametrize("name,precision", [("hybrid_shm_c2", "fp32"), ("hybrid_shm_mixed", "fp32"), ("hybrid_hbv_c4", "fp32"),
+                                            ("hybrid_hbv_norouting", "fp32"), ("hybrid_shm_c2", "tf32x3"),
+                                            ("hybrid_shm_mixed", "tf32x3")])
+def test_hybrid_golden(dev, name, precision):
     from hy2dl_b200.aux_functions import nse_basin_averaged, weighted_rmse
     g = golden(name)
-    model = build_hybrid(g, dev)
+    B, T, n_last, I, H = [int(v) for v in g["meta"]][:5]
+    if precision == "tf32x3" and (H != 64 or I > 32):
+        pytest.skip("tensor-core path: H = 64, I <= 32")
+    model = build_hybrid(g, dev, precision)
     pred = model(x_lstm=cu(g["x_lstm"], dev), x_conceptual=cu(g["x_conceptual"], dev))
     if str(g["loss_kind"]) == "nse":
         loss = nse_basin_averaged(y_sim=pred["y_hat"], y_obs=cu(g["y_obs"], dev),
@@ -226,15 +244,17 @@ def test_train_steps_golden(dev):
 # ------------------------------------------------------------------------------------------------
 # fresh seeded inputs against the oracle: reference batch size, ragged tiles, larger H
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("B,T,I,H", [(256, 365, 25, 64), (37, 50, 31, 256), (5, 33, 7, 128), (70, 40, 41, 64)])
-def test_lstm_vs_oracle(dev, B, T, I, H):
+@pytest.mark.parametrize("B,T,I,H,precision", [(256, 365, 25, 64, "fp32"), (37, 50, 31, 256, "fp32"), (5, 33, 7, 128, "fp32"),
+                                                (70, 40, 41, 64, "fp32"), (256, 365, 25, 64, "tf32x3"), (70, 40, 31, 64, "tf32x3"),
+                                                (5, 33, 7, 64, "tf32x3")])
+def test_lstm_vs_oracle(dev, B, T, I, H, precision):
     from hy2dl_b200.modelzoo import LSTM
     from hy2dl_b200.synthetic import lstm_weights
     rng = np.random.default_rng(B + T)
     x = rng.normal(0, 1, (B, T, I)).astype(np.float32)
     gh = rng.normal(0, 1, (B, T, H)).astype(np.float32)
     w = lstm_weights(I, H, 1, seed=9)
-    lstm = LSTM(I, H).to(dev)
+    lstm = LSTM(I, H, precision=precision).to(dev)
     lstm.load_state_dict({k[5:] if k.startswith("lstm.") else k: torch.tensor(v) for k, v in w.items()
                           if k.startswith("lstm.")})
     out, (hn, _) = lstm(cu(x, dev))
@@ -250,12 +270,14 @@ def test_lstm_vs_oracle(dev, B, T, I, H):
         assert_close(npy(p.grad), wd["lstm." + k].grad.numpy(), what="grad " + k, **TOL)
 
 
-@pytest.mark.parametrize("model_key,B,T,n_last,H,m,dyn", [
-    ("shm", 64, 365, 182, 64, 1, ["dd", "f_thr", "sumax", "beta", "perc", "kf", "ki", "kb"]),
-    ("hbv", 9, 120, 50, 64, 16, ["BETA", "BETAET"]),
-    ("shm", 33, 48, 24, 128, 4, ["kf"]),
+@pytest.mark.parametrize("model_key,B,T,n_last,H,m,dyn,precision", [
+    ("shm", 64, 365, 182, 64, 1, ["dd", "f_thr", "sumax", "beta", "perc", "kf", "ki", "kb"], "fp32"),
+    ("hbv", 9, 120, 50, 64, 16, ["BETA", "BETAET"], "fp32"),
+    ("shm", 33, 48, 24, 128, 4, ["kf"], "fp32"),
+    ("shm", 64, 365, 182, 64, 1, ["dd", "f_thr", "sumax", "beta", "perc", "kf", "ki", "kb"], "tf32x3"),
+    ("shm", 45, 48, 24, 64, 4, ["kf", "beta"], "tf32x3"),
 ])
-def test_hybrid_vs_oracle(dev, model_key, B, T, n_last, H, m, dyn):
+def test_hybrid_vs_oracle(dev, model_key, B, T, n_last, H, m, dyn, precision):
     from hy2dl_b200.aux_functions import nse_basin_averaged
     from hy2dl_b200.modelzoo import HBV, SHM, Hybrid, UH_routing
     from hy2dl_b200.synthetic import lstm_weights, make_basins
@@ -270,7 +292,7 @@ def test_hybrid_vs_oracle(dev, model_key, B, T, n_last, H, m, dyn):
     sd = np.repeat(rng.uniform(0.5, 2.0, (B, 1, 1)).astype(np.float32), n_last, axis=1)
     cls = {"shm": SHM, "hbv": HBV}[model_key]
     hp = {"input_size_lstm": I, "hidden_size": H, "no_of_layers": 1, "seq_length": T, "predict_last_n": n_last,
-          "n_conceptual_models": m, "conceptual_dynamic_parameterization": dyn}
+          "n_conceptual_models": m, "conceptual_dynamic_parameterization": dyn, "precision": precision}
     model = Hybrid(hp, conceptual_model=cls, routing_model=UH_routing)
     n_out = model.linear.out_features
     w = lstm_weights(I, H, n_out, seed=17)
@@ -307,7 +329,8 @@ def test_inference_no_grad_and_eval(dev):
     assert_close(npy(pred["y_hat"]), g["y_hat"], what="y_hat", **TOL)
 
 
-def test_trainer_native_path_matches_api_path(dev):
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_trainer_native_path_matches_api_path(dev, precision):
     """Sampler -> native layouts -> Trainer.step equals the API path (pack_x from [B,T,I]) step."""
     from hy2dl_b200.datasetzoo import ResidentDataset
     from hy2dl_b200.modelzoo import SHM, Hybrid, UH_routing
@@ -318,7 +341,7 @@ def test_trainer_native_path_matches_api_path(dev):
     ds = ResidentDataset(data.x_d, data.y_obs, L, n_last, x_s=data.x_s, x_conc=data.x_conc, device=dev)
     ds.calculate_basin_std(); ds.calculate_global_statistics(); ds.standardize_data(standardize_output=False)
     hp = {"input_size_lstm": ds.input_size, "hidden_size": H, "no_of_layers": 1, "seq_length": L,
-          "predict_last_n": n_last, "n_conceptual_models": 1,
+          "predict_last_n": n_last, "n_conceptual_models": 1, "precision": precision,
           "conceptual_dynamic_parameterization": ["dd", "f_thr", "sumax", "beta", "perc", "kf", "ki", "kb"]}
     w = {k: torch.tensor(v) for k, v in lstm_weights(ds.input_size, H, 10, seed=2).items()}
     ids = torch.randperm(len(ds), device=dev)[:48]

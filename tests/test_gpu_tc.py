@@ -12,13 +12,13 @@ pytestmark = pytest.mark.gpu
 def _run_fwd(dev, B, T, I, precision, seed=0, tape=True):
     from hy2dl_b200 import _lib, ops
     from hy2dl_b200.synthetic import lstm_weights
-    H, IP = 64, (I + 7) // 8 * 8
+    ri = precision == _lib.PREC_TF32X3
+    H, IP = 64, 32 if ri else (I + 7) // 8 * 8
     rng = np.random.default_rng(seed)
     x = rng.normal(0, 1, (B, T, I)).astype(np.float32)
     w = lstm_weights(I, H, 1, seed=seed + 1)
     cu = lambda a: torch.tensor(a, device=dev)
-    xT = ops.pack_x(cu(x))                               # [T,B,IP] row-major
-    x_in = ops.to_ri32(xT) if precision == _lib.PREC_TF32X3 else xT
+    x_in = ops.pack_x(cu(x), "ri32" if ri else "rowmajor")
     G = (B + 31) // 32
     Bp = G * 32 if precision == _lib.PREC_TF32X3 else B
     h = torch.zeros(T, Bp, H, device=dev)
@@ -32,7 +32,7 @@ def _run_fwd(dev, B, T, I, precision, seed=0, tape=True):
               ws.numel(), precision, _lib.stream())
     torch.cuda.synchronize()
     if precision == _lib.PREC_TF32X3:
-        unri = lambda a, F: ops.from_ri32(a.view(T, G, F // 4, 32, 4), B)
+        unri = lambda a, F: ops.from_ri32(a.view(T, G, F // 32, 32, 32), B)
         h = unri(h, H)
         if tape:
             c = unri(c, H)
@@ -63,7 +63,7 @@ def _bwd_both(dev, B, T, I, dh_t0, use_last, seed=3):
     """Run fwd+bwd with both precisions on the same inputs; return row-major dG (g*H+u order) of each."""
     from hy2dl_b200 import _lib, ops
     from hy2dl_b200.synthetic import lstm_weights
-    H, IP = 64, (I + 7) // 8 * 8
+    H = 64
     rng = np.random.default_rng(seed)
     x = rng.normal(0, 1, (B, T, I)).astype(np.float32)
     gh = rng.normal(0, 1, (T, B, H)).astype(np.float32)
@@ -72,13 +72,13 @@ def _bwd_both(dev, B, T, I, dh_t0, use_last, seed=3):
     w = lstm_weights(I, H, 1, seed=seed + 1)
     cu = lambda a: torch.tensor(a, device=dev)
     wd = [cu(w[k]) for k in ("lstm.weight_ih_l0", "lstm.weight_hh_l0", "lstm.bias_ih_l0", "lstm.bias_hh_l0")]
-    xT = ops.pack_x(cu(x))
     G = (B + 31) // 32
-    out = {}
+    out, wg = {}, {}
     for prec in (_lib.PREC_FP32, _lib.PREC_TF32X3):
         ri = prec == _lib.PREC_TF32X3
         Bp = G * 32 if ri else B
-        x_in = ops.to_ri32(xT) if ri else xT
+        IP = 32 if ri else (I + 7) // 8 * 8
+        x_in = ops.pack_x(cu(x), "ri32" if ri else "rowmajor")
         h = torch.zeros(T, Bp, H, device=dev); c = torch.zeros(T, Bp, H, device=dev)
         g = torch.zeros(T, Bp, 4 * H, device=dev); hl = torch.zeros(B, H, device=dev)
         ws = ops._ws(_lib.WS_LSTM_FWD, B, T, I, H, dev, prec)
@@ -90,10 +90,18 @@ def _bwd_both(dev, B, T, I, dh_t0, use_last, seed=3):
         wsb = ops._ws(_lib.WS_LSTM_BWD, B, T, I, H, dev, prec)
         _lib.call("hy2dl_lstm_bwd", B, T, H, wd[1].data_ptr(), g.data_ptr(), c.data_ptr(), dh_in.data_ptr(), dh_t0,
                   None if dl is None else dl.data_ptr(), g.data_ptr(), wsb.data_ptr(), wsb.numel(), prec, _lib.stream())
+        # weight gradients with the same precision's kernel
+        dwi = torch.full((4 * H, I), np.nan, device=dev); dwh = torch.full((4 * H, H), np.nan, device=dev)
+        dbb = torch.full((4 * H,), np.nan, device=dev)
+        wsw = ops._ws(_lib.WS_LSTM_WGRAD, B, T, I, H, dev, prec)
+        _lib.call("hy2dl_lstm_wgrad", g.data_ptr(), h.data_ptr(), x_in.data_ptr(), B, T, I, IP, H, dwi.data_ptr(),
+                  dwh.data_ptr(), dbb.data_ptr(), wsw.data_ptr(), wsw.numel(), prec, _lib.stream())
         torch.cuda.synchronize()
+        wg[prec] = {"lstm.weight_ih_l0": dwi.cpu().numpy(), "lstm.weight_hh_l0": dwh.cpu().numpy(),
+                    "lstm.bias_ih_l0": dbb.cpu().numpy()}
         if ri:
-            dG = ops.from_ri32(g.view(T, G, H, 32, 4), B).reshape(T, B, H, 4).permute(0, 1, 3, 2).reshape(T, B, 4 * H)
-            hh = ops.from_ri32(h.view(T, G, H // 4, 32, 4), B)
+            dG = ops.from_ri32(g.view(T, G, 4 * H // 32, 32, 32), B).reshape(T, B, H, 4).permute(0, 1, 3, 2).reshape(T, B, 4 * H)
+            hh = ops.from_ri32(h.view(T, G, H // 32, 32, 32), B)
         else:
             dG, hh = g, h
         out[prec] = (dG.cpu().double().numpy(), hh.cpu().double().numpy())
@@ -105,19 +113,20 @@ def _bwd_both(dev, B, T, I, dh_t0, use_last, seed=3):
     if use_last:
         f = f + (ref[:, -1] * tt(gl, torch.float64)).sum()
     f.backward()
-    return out, {k: v.grad.numpy() for k, v in wd64.items()}, x
+    return out, {k: v.grad.numpy() for k, v in wd64.items()}, x, wg
 
 
 @pytest.mark.parametrize("B,T,I,dh_t0,use_last", [(128, 3, 25, 0, False), (200, 40, 25, 17, True), (96, 365, 25, 183, False)])
 def test_tc_bwd_vs_fp32_kernel_and_oracle(B, T, I, dh_t0, use_last):
     from hy2dl_b200 import _lib
     dev = torch.device("cuda:0")
-    out, ref, x = _bwd_both(dev, B, T, I, dh_t0, use_last)
+    out, ref, x, wg = _bwd_both(dev, B, T, I, dh_t0, use_last)
     dG32, h32 = out[_lib.PREC_FP32]
     dGtc, htc = out[_lib.PREC_TF32X3]
     for t in sorted({T - 1, max(T - 2, 0), 0}, reverse=True):
         print(f"t={t}: |dG_tc - dG_fp32| max {np.abs(dGtc[t] - dG32[t]).max():.3e} (scale {np.abs(dG32[t]).max():.3e})")
-    assert_close(dGtc[T - 1], dG32[T - 1], rtol=1e-5, atol=1e-7, what="dG at the last step")
+    # at T = 365 the two forward tapes have drifted apart by ~1e-5 already, hence 1e-4 here as well
+    assert_close(dGtc[T - 1], dG32[T - 1], rtol=1e-5 if T < 100 else 1e-4, atol=1e-7, what="dG at the last step")
     assert_close(dGtc, dG32, rtol=1e-4, atol=1e-7, what="dG all steps (tc vs fp32 kernel)")
     # weight gradients from the tc tape, contracted in fp64 on the host, against oracle autograd
     hprev = np.concatenate([np.zeros_like(htc[:1]), htc[:-1]], axis=0)
@@ -127,3 +136,32 @@ def test_tc_bwd_vs_fp32_kernel_and_oracle(B, T, I, dh_t0, use_last):
     assert_close(dw_hh, ref["lstm.weight_hh_l0"], rtol=1e-4, atol=1e-7, what="dW_hh")
     assert_close(dw_ih, ref["lstm.weight_ih_l0"], rtol=1e-4, atol=1e-7, what="dW_ih")
     assert_close(db, ref["lstm.bias_ih_l0"], rtol=1e-4, atol=1e-7, what="db")
+    # the tcgen05 weight-gradient GEMM (RI32 slabs as MN-major UMMA operands) and the fp32 one
+    for prec, name in ((_lib.PREC_FP32, "fp32"), (_lib.PREC_TF32X3, "tf32x3")):
+        for k in ("lstm.weight_hh_l0", "lstm.weight_ih_l0", "lstm.bias_ih_l0"):
+            assert_close(wg[prec][k], ref[k], rtol=1e-4, atol=1e-7, what=f"wgrad kernel ({name}) {k}")
+
+
+@pytest.mark.parametrize("B,T,I", [(32, 1, 8), (70, 5, 31), (4800, 3, 16)])
+def test_tc_wgrad_shapes(B, T, I):
+    """Ragged groups, several input sizes, more groups than CTAs; checked against an fp64 contraction."""
+    from hy2dl_b200 import _lib, ops
+    dev = torch.device("cuda:0")
+    H, IP, G = 64, 32, (B + 31) // 32
+    rng = np.random.default_rng(B + I)
+    dG = rng.normal(0, 1, (T, B, 4 * H)).astype(np.float32)       # columns n = 4u + g
+    h = rng.normal(0, 1, (T, B, H)).astype(np.float32)
+    x = np.zeros((T, B, IP), np.float32); x[:, :, :I] = rng.normal(0, 1, (T, B, I))
+    cu = lambda a: torch.tensor(a, device=dev)
+    dwi = torch.full((4 * H, I), np.nan, device=dev); dwh = torch.full((4 * H, H), np.nan, device=dev)
+    dbb = torch.full((4 * H,), np.nan, device=dev)
+    ws = ops._ws(_lib.WS_LSTM_WGRAD, B, T, I, H, dev, _lib.PREC_TF32X3)
+    args = [ops.to_ri32(cu(a)) for a in (dG, h, x)]
+    _lib.call("hy2dl_lstm_wgrad", *[a.data_ptr() for a in args], B, T, I, IP, H, dwi.data_ptr(), dwh.data_ptr(),
+              dbb.data_ptr(), ws.data_ptr(), ws.numel(), _lib.PREC_TF32X3, _lib.stream())
+    torch.cuda.synchronize()
+    d = dG.astype(np.float64).reshape(T, B, H, 4).transpose(0, 1, 3, 2).reshape(T, B, 4 * H)   # -> g*H + u
+    hprev = np.concatenate([np.zeros_like(h[:1]), h[:-1]]).astype(np.float64)
+    assert_close(dwi.cpu().numpy(), np.einsum("tbm,tbi->mi", d, x[:, :, :I].astype(np.float64)), rtol=2e-6, what="dW_ih")
+    assert_close(dwh.cpu().numpy(), np.einsum("tbm,tbk->mk", d, hprev), rtol=2e-6, atol=1e-30, what="dW_hh")
+    assert_close(dbb.cpu().numpy(), d.sum((0, 1)), rtol=2e-6, what="db")
