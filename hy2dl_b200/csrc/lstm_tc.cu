@@ -4,7 +4,7 @@
 //     D[128 x 256] = [x_t | h_{t-1}] [128 x K]  *  [W_ih | W_hh]^T [K x 256],   K = IP + 64
 // are one tcgen05 accumulation in TMEM (input projection fused by K-concatenation, so no
 // Gx[B,T,4H] ever reaches HBM).  fp32-class accuracy comes from the 3-term TF32 split
-//     a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo      (hi = top 19 bits, lo = exact remainder)
+//     a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo      (hi = a rounded to tf32, lo = exact remainder)
 // i.e. 3 x K/8 MMAs of shape M128 N256 K8 per step.
 //
 // Data placement (why this maps well onto Blackwell):
@@ -48,7 +48,7 @@ __global__ void lstm_tc_pack_w_kernel(const float* __restrict__ w_ih, const floa
     if (k < IP) v = k < I ? w_ih[row * I + k] : 0.f;
     else v = w_hh[row * kH + (k - IP)];
     uint32_t hi, lo;
-    split_tf32(v, hi, lo);
+    split_tf32_rr(v, hi, lo);
     w_hi[e] = __uint_as_float(hi);
     w_lo[e] = __uint_as_float(lo);
     if (k == 0) bias_n[n] = b_ih[row] + b_hh[row];
@@ -230,11 +230,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_tc_fwd_kernel(TcFwdArgs a
       for (int64_t t = 0; t < a.T; ++t) {
         mbar_wait(bar_a_ready, (uint32_t)(t & 1));
         tc_fence_after();
+        // all correction terms first, while the accumulator is still ~2^-11 of its final size: the
+        // tensor core's fp32 accumulation loses up to an ulp of the ACCUMULATOR per MMA, so only the
+        // K/8 hi*hi instructions round at full magnitude
         for (int j = 0; j < KS; ++j) {
           const uint64_t d_hi = smem_desc(whi + (uint32_t)j * 2 * lbo, lbo, sbo);
           const uint64_t d_lo = smem_desc(wlo + (uint32_t)j * 2 * lbo, lbo, sbo);
-          mma_tf32_ts(tmem + kColD, tmem + kColAlo + 8 * j, d_hi, idesc, j > 0);   // small terms first
+          mma_tf32_ts(tmem + kColD, tmem + kColAlo + 8 * j, d_hi, idesc, j > 0);
           mma_tf32_ts(tmem + kColD, tmem + kColAhi + 8 * j, d_lo, idesc, 1);
+        }
+        for (int j = 0; j < KS; ++j) {
+          const uint64_t d_hi = smem_desc(whi + (uint32_t)j * 2 * lbo, lbo, sbo);
           mma_tf32_ts(tmem + kColD, tmem + kColAhi + 8 * j, d_hi, idesc, 1);
         }
         mma_commit(bar_mma_done);
@@ -317,7 +323,7 @@ __global__ void lstm_tc_pack_whh_kernel(const float* __restrict__ w_hh, float* _
     const int kk = e & 3, n = (e >> 2) & 63, kc = e >> 8;
     const int col = kc * 4 + kk, u = col >> 2, g = col & 3;
     uint32_t hi, lo;
-    split_tf32(w_hh[(g * kH + u) * kH + n], hi, lo);
+    split_tf32_rr(w_hh[(g * kH + u) * kH + n], hi, lo);
     hi_out[e] = __uint_as_float(hi);
     lo_out[e] = __uint_as_float(lo);
   }
@@ -391,8 +397,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_tc_bwd_kernel(TcBwdArgs a
     float* dcp = s_dc + tid;     // dc[u] at dcp[u * 128]: conflict-free, keeps the chunk loop rolled and small
     for (int u = 0; u < kH; ++u) dcp[u * kRows] = 0.f;
 
-    BwdChunk cur, nxt;
-    bwd_load_chunk(a, a.T - 1, 0, gidx, lane, live, cur);
+    // tape chunks travel through a 4-deep register ring: chunk q + 4 is requested as soon as chunk q has
+    // been consumed, so ~4 x 112 B per thread (57 KB per SM) are in flight -- one warp per scheduler has
+    // no other way to cover the HBM latency
+    BwdChunk ring[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) bwd_load_chunk(a, a.T - 1, kk, gidx, lane, live, ring[kk]);
     for (int64_t s = 0; s < a.T; ++s) {
       const int64_t t = a.T - 1 - s;
       const uint32_t d_prev = lane_base + kColDh0 + 64 * (uint32_t)((s & 1) ^ 1);   // dh_rec from step s-1
@@ -401,60 +411,61 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_tc_bwd_kernel(TcBwdArgs a
         tc_fence_after();
       }
 #pragma unroll 1
-      for (int q = 0; q < 16; ++q) {     // 4 hidden units (16 gate columns) per iteration
-        // prefetch the next chunk (next step's chunk 0 after the last one)
-        if (q < 15) bwd_load_chunk(a, t, q + 1, gidx, lane, live, nxt);
-        else bwd_load_chunk(a, t - 1, 0, gidx, lane, live, nxt);
-        uint32_t r[4] = {0, 0, 0, 0};
-        if (s > 0) {
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                       : "r"(d_prev + 4 * q));
-          tmem_ld_wait();
-        }
-        const float dhe[4] = {cur.dh.x, cur.dh.y, cur.dh.z, cur.dh.w};
-        const float ctv[4] = {cur.ct.x, cur.ct.y, cur.ct.z, cur.ct.w};
-        const float cpv[4] = {cur.cp.x, cur.cp.y, cur.cp.z, cur.cp.w};
-        float dg[16];
-#pragma unroll
-        for (int uu = 0; uu < 4; ++uu) {
-          const int u = 4 * q + uu;
-          const float gi = cur.g[uu].x, gf = cur.g[uu].y, gg = cur.g[uu].z, go = cur.g[uu].w;
-          const float dh = dhe[uu] + __uint_as_float(r[uu]);
-          const float tcv = fast_tanh(ctv[uu]);
-          const float dct = dcp[u * kRows] + dh * go * (1.f - tcv * tcv);
-          dg[4 * uu + 0] = dct * gg * gi * (1.f - gi);
-          dg[4 * uu + 1] = dct * cpv[uu] * gf * (1.f - gf);
-          dg[4 * uu + 2] = dct * gi * (1.f - gg * gg);
-          dg[4 * uu + 3] = dh * tcv * go * (1.f - go);
-          dcp[u * kRows] = dct * gf;
-        }
-        if (live) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            ri32_st(a.dG, t, a.G, gidx, 8, 4 * q + j, lane, make_float4(dg[4 * j], dg[4 * j + 1], dg[4 * j + 2], dg[4 * j + 3]));
-        }
-        // quarter k = q / 4 lives in slot k & 1; the second use of a slot in a step waits for its first MMAs
-        const int k = q >> 2, slot = k & 1;
-        if ((q & 3) == 0 && k >= 2) {
+      for (int k = 0; k < 4; ++k) {      // quarter k = 16 hidden units = 64 gate columns, lives in slot k & 1
+        const int slot = k & 1;
+        if (k >= 2) {                    // the second use of a slot in a step waits for its first MMAs
           mbar_wait(bar_free + slot, 0);
           tc_fence_after();
         }
-        const uint32_t sbase = lane_base + kColSlot0 + 128 * slot + 16 * (q & 3);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          uint32_t hi[8], lo[8];
+        for (int kk = 0; kk < 4; ++kk) { // 4 hidden units (16 gate columns) per chunk
+          const int q = 4 * k + kk;
+          BwdChunk& cur = ring[kk];
+          uint32_t r[4] = {0, 0, 0, 0};
+          if (s > 0) {
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                         : "r"(d_prev + 4 * q));
+            tmem_ld_wait();
+          }
+          const float dhe[4] = {cur.dh.x, cur.dh.y, cur.dh.z, cur.dh.w};
+          const float ctv[4] = {cur.ct.x, cur.ct.y, cur.ct.z, cur.ct.w};
+          const float cpv[4] = {cur.cp.x, cur.cp.y, cur.cp.z, cur.cp.w};
+          float dg[16];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) split_tf32(dg[8 * j + e], hi[e], lo[e]);
-          tmem_st8(sbase + 8 * j, hi);
-          tmem_st8(sbase + 64 + 8 * j, lo);
+          for (int uu = 0; uu < 4; ++uu) {
+            const int u = 4 * q + uu;
+            const float gi = cur.g[uu].x, gf = cur.g[uu].y, gg = cur.g[uu].z, go = cur.g[uu].w;
+            const float dh = dhe[uu] + __uint_as_float(r[uu]);
+            const float tcv = fast_tanh(ctv[uu]);
+            const float dct = dcp[u * kRows] + dh * go * (1.f - tcv * tcv);
+            dg[4 * uu + 0] = dct * gg * gi * (1.f - gi);
+            dg[4 * uu + 1] = dct * cpv[uu] * gf * (1.f - gf);
+            dg[4 * uu + 2] = dct * gi * (1.f - gg * gg);
+            dg[4 * uu + 3] = dh * tcv * go * (1.f - go);
+            dcp[u * kRows] = dct * gf;
+          }
+          // refill this ring slot: chunk q + 4 of this step, or chunk kk of the next (earlier) step
+          if (k < 3) bwd_load_chunk(a, t, q + 4, gidx, lane, live, cur);
+          else bwd_load_chunk(a, t - 1, kk, gidx, lane, live, cur);
+          if (live) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              ri32_st(a.dG, t, a.G, gidx, 8, 4 * q + j, lane, make_float4(dg[4 * j], dg[4 * j + 1], dg[4 * j + 2], dg[4 * j + 3]));
+          }
+          const uint32_t sbase = lane_base + kColSlot0 + 128 * slot + 16 * kk;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split_tf32(dg[8 * j + e], hi[e], lo[e]);
+            tmem_st8(sbase + 8 * j, hi);
+            tmem_st8(sbase + 64 + 8 * j, lo);
+          }
         }
-        if ((q & 3) == 3) {
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(bar_ready + slot);
-        }
-        cur = nxt;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar_ready + slot);
       }
     }
   } else {

@@ -9,23 +9,30 @@
 // operands go HBM -> shared memory with plain bulk async copies (TMA engine, no tensor map) and are
 // consumed by tcgen05.mma (A and B from shared memory) without any reshuffle.
 //
-// fp32-class accuracy: 3-term TF32 split, hi = top 19 bits, lo = exact remainder.  The converter
+// fp32-class accuracy: 3-term TF32 split, hi = x rounded to tf32, lo = exact remainder.  The converter
 // warps turn each landed slab into (hi in place, lo in a second buffer); the MMA thread then issues
-// lo*hi + hi*lo + hi*hi.  Accumulators (2 x [128 lanes x 112 columns] fp32) live in TMEM for the whole
-// kernel; every CTA writes its partial sum once and a small kernel adds the partials in a fixed
-// order (deterministic) and scatters them into PyTorch's [4H, I] / [4H, H] / [4H] layouts.
+// lo*hi + hi*lo + hi*hi.
+// The tensor core's fp32 accumulation TRUNCATES (measured, tools/dbg_rz.py: relative bias -2.8e-8 per
+// accumulating MMA, -8.5e-5 after 3072), so a TMEM accumulator is only trusted for kChain = 8 slabs
+// (96 MMAs): after every chain the converter warps add the chain accumulator D (2 halves x [128 lanes x
+// 112 columns]) into a running sum S kept in a second TMEM region, in registers with round-to-nearest
+// (tcgen05.ld D, S -> FADD -> tcgen05.st S), and the next chain starts by overwriting D.  The MMA pipe
+// idles for the ~0.5 us of a drain, once per 8 slabs.  Every CTA writes its sum S once and a
+// small kernel adds the partials in a fixed order (deterministic) and scatters them into PyTorch's
+// [4H, I] / [4H, H] / [4H] layouts.
 //
-// Warp roles (192 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer, warps 2-5 = split
-// converters, then epilogue.  3 raw stages (48 KB each) + 1 lo buffer.
+// Warp roles (320 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer, warps 2-9 = split
+// converters + accumulator drain + epilogue.  3 raw stages (48 KB each) + 1 lo buffer.
 #include "common.cuh"
 #include "tc_common.cuh"
 
 namespace hy2dl {
 namespace tc {
 
-constexpr int kWgThreads = 192;
+constexpr int kWgThreads = 320;
 constexpr int kWgStages = 3;
-constexpr int kWgConv = 128;                // converter threads
+constexpr int kWgConv = 256;                // converter / drain threads (warps 2..9)
+constexpr int kChain = 8;                   // slabs accumulated in TMEM before a drain
 constexpr int kBlk = 4096;                  // bytes of one [32 rows][32 floats] block
 constexpr int kABlocks = 8;                 // 256 gate columns
 constexpr int kABytes = kABlocks * kBlk;    // 32 KB: one (t, group) slab of dG
@@ -65,7 +72,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
     mbar_init(bar_conv, kWgConv); mbar_init(bar_lo_free, 1); mbar_init(bar_done, 1);
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(s_tmem, 256);
+  if (warp == 1) tmem_alloc(s_tmem, 512);
   for (int e = tid; e < kBlk / 16; e += kWgThreads) {           // float4 e = row * 8 + chunk
     const float4 one = make_float4((e & 7) == 2 * ((e >> 3) & 3) ? 1.f : 0.f, 0.f, 0.f, 0.f);   // unit 0 of row r sits at unit r & 3
     for (int s = 0; s < kWgStages; ++s)
@@ -104,6 +111,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
         const uint32_t hi_a = smem_u32(smem_raw + s * kStageBytes), hi_b = hi_a + kABytes;
         mbar_wait(bar_conv, (uint32_t)(i & 1));
         tc_fence_after();
+        const uint32_t dbuf = tmem;                                         // chain accumulator D
+        const bool first = (i % kChain) == 0;                               // first slab of a chain overwrites
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {           // 8 sequences (K = 8 = two 4-row groups) per MMA
           const uint64_t b_hi = smem_desc_mn32(hi_b + kb * 1024, kBlk, 512), b_lo = smem_desc_mn32(lo_b + kb * 1024, kBlk, 512);
@@ -111,8 +120,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
           for (int hf = 0; hf < 2; ++hf) {         // gate columns [128 hf, 128 hf + 128)
             const uint64_t a_hi = smem_desc_mn32(hi_a + hf * 4 * kBlk + kb * 1024, kBlk, 512);
             const uint64_t a_lo = smem_desc_mn32(lo_a + hf * 4 * kBlk + kb * 1024, kBlk, 512);
-            const uint32_t d = tmem + 128 * hf;
-            mma_tf32_ss(d, a_lo, b_hi, idesc, 1);
+            const uint32_t d = dbuf + 128 * hf;
+            mma_tf32_ss(d, a_lo, b_hi, idesc, !(first && kb == 0));
             mma_tf32_ss(d, a_hi, b_lo, idesc, 1);
             mma_tf32_ss(d, a_hi, b_hi, idesc, 1);
           }
@@ -125,34 +134,51 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
     __syncwarp();
   } else {
     // =========================== converters, then epilogue ======================================
-    const int ct = tid - 64;                                  // 0 .. 127
-    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    // D = 0 (every MMA accumulates)
+    const int ct = tid - 64;                                  // 0 .. 255
+    const int hf = ct >> 7;                                   // drain: warps 2-5 own half 0, warps 6-9 half 1
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 128 * hf;
+    // S = 0
     {
       uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int c = 0; c < kND; c += 8) { tmem_st8(lane_base + c, z); tmem_st8(lane_base + 128 + c, z); }
+      for (int c = 0; c < kND; c += 8) tmem_st8(lane_base + 256 + c, z);
+      tmem_st_wait();
+    }
+    auto drain = [&]() {                                      // S += D (every MMA into D has retired)
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < kND; c += 16) {
+        uint32_t d[16], sacc[16];
+        tmem_ld16(lane_base + c, d);
+        tmem_ld16(lane_base + 256 + c, sacc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sacc[j] = __float_as_uint(__uint_as_float(sacc[j]) + __uint_as_float(d[j]));
+        tmem_st8(lane_base + 256 + c, *reinterpret_cast<uint32_t(*)[8]>(&sacc[0]));
+        tmem_st8(lane_base + 256 + c + 8, *reinterpret_cast<uint32_t(*)[8]>(&sacc[8]));
+      }
       tmem_st_wait();
       tc_fence_before();
-    }
+    };
     float4* lo = reinterpret_cast<float4*>(s_lo);
     for (int64_t i = 0; i < n_my; ++i) {
       const int s = (int)(i % kWgStages);
       const int64_t id = blockIdx.x + i * gridDim.x, t = id / a.G;
       float4* raw = reinterpret_cast<float4*>(smem_raw + s * kStageBytes);
       mbar_wait(bar_full + s, (uint32_t)((i / kWgStages) & 1));
-      if (i > 0) mbar_wait(bar_lo_free, (uint32_t)((i - 1) & 1));
+      if (i > 0) mbar_wait(bar_lo_free, (uint32_t)((i - 1) & 1));       // => every MMA up to slab i-1 has retired
+      if (i > 0 && (i % kChain) == 0) drain();                          // chain complete; slab i will overwrite D
       auto split4 = [&](int e) {
         const float4 v = raw[e];
         float4 hv, lv;
-        hv.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lv.x = v.x - hv.x;
-        hv.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lv.y = v.y - hv.y;
-        hv.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lv.z = v.z - hv.z;
-        hv.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lv.w = v.w - hv.w;
+        hv.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u); lv.x = v.x - hv.x;
+        hv.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u); lv.y = v.y - hv.y;
+        hv.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u); lv.z = v.z - hv.z;
+        hv.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u); lv.w = v.w - hv.w;
         raw[e] = hv;
         lo[e] = lv;
       };
       constexpr int kA4 = kABytes / 16, kBlk4 = kBlk / 16;
-#pragma unroll 4
+#pragma unroll 2
       for (int e = ct; e < kA4; e += kWgConv) split4(e);                        // dG
       for (int e = ct; e < kBlk4; e += kWgConv) split4(kA4 + 2 * kBlk4 + e);    // x
       if (t > 0) {
@@ -164,26 +190,26 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
       fence_async_smem();
       mbar_arrive(bar_conv);
     }
-    // epilogue: this CTA's partial sums, row n of half hf = TMEM lane
+    // last chain, then this CTA's sums
     mbar_wait(bar_done, 0);
+    if (n_my > 0) drain();
     tc_fence_after();
-    const int row = (warp & 3) * 32 + lane;
-    for (int hf = 0; hf < 2; ++hf) {
-      float* dst = a.partial + ((int64_t)blockIdx.x * 256 + hf * 128 + row) * kND;
-      for (int c = 0; c < kND; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(lane_base + 128 * hf + c, v);
-        tmem_ld_wait();
+    const int row = hf * 128 + (warp & 3) * 32 + lane;
+    float* dst = a.partial + ((int64_t)blockIdx.x * 256 + row) * kND;
+#pragma unroll 1
+    for (int c = 0; c < kND; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(lane_base + 256 + c, v);
+      tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<float4*>(dst + c + j) =
-              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-      }
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(dst + c + j) =
+            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 256);
+  if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
 // partial [n_part][256][kND] -> dw_hh [256][64], dw_ih [256][I], db [256] (row = g*64 + u from n = 4u + g)

@@ -153,10 +153,17 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                : "memory");
 }
 
-// ---- 3xTF32 operand split: hi keeps the top 19 bits (exact tf32), lo = x - hi (exact in fp32) --
+// ---- 3xTF32 operand split: x = hi + lo with hi = x rounded to tf32 (nearest, ties away: the integer
+// add carries into the exponent exactly like cvt.rna.tf32.f32), lo = x - hi exact in fp32, |lo| <= 2^-11 |x|.
+// The tensor core reads the top 19 bits of lo, i.e. drops <= 2^-21 |x|.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(x) & 0xFFFFE000u;
+  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
+}
+// same with lo rounded to tf32 as well (used where the split is computed once: packed weights)
+__device__ __forceinline__ void split_tf32_rr(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+  lo = (__float_as_uint(x - __uint_as_float(hi)) + 0x1000u) & 0xFFFFE000u;
 }
 
 // fast, accurate-enough activations on the MUFU ex2/rcp path (abs error ~1e-7)
