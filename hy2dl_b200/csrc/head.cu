@@ -13,7 +13,8 @@ namespace hy2dl {
 
 constexpr int kRows = 32;     // rows (samples of one step) per tile
 constexpr int kChunk = 32;    // head columns per launch
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;
+constexpr int kDz = kChunk + 4;   // row stride of the dz tile in shared memory
 
 // RI32 slab of one (step, 32-row group): float e of [F/32][32 rows][32 floats] holds (row, feature)
 __device__ __forceinline__ int ri32_row(int e) { return (e >> 5) & 31; }
@@ -46,26 +47,102 @@ struct HeadArgs {
   int32_t ri32;   // h_seq / dh_seq in RI32 [T][G][H/4][32][4] instead of [T][B][H]
 };
 
-// smem: hs[kRows][H+1] | ws[kChunk][H] | (bwd) dzs[kChunk][kRows+1] | (bwd) dws[kChunk][H] | dbs[kChunk]
-template <bool BWD>
-__global__ void __launch_bounds__(kThreads) head_kernel(HeadArgs a, HeadChunk ch) {
-  extern __shared__ float sm[];
+// ---- forward ------------------------------------------------------------------------------------
+// Tile = one time slot x 32 rows.  256 threads: lane = row, warp = group of 4 head columns, so a thread
+// accumulates 4 dot products over H with one conflict-free LDS (h, row stride H+1) and one broadcast
+// LDS.128 (W^T[k][4 columns]) per k.  smem: hs[32][H+1] | wT[H][kChunk]
+__global__ void __launch_bounds__(kThreads) head_fwd_kernel(HeadArgs a, HeadChunk ch) {
+  extern __shared__ __align__(16) float sm[];
   const int H = (int)a.H;
-  float* hs = sm;
-  float* ws = hs + kRows * (H + 1);
-  float* dzs = ws + kChunk * H;
-  float* dws = dzs + kChunk * (kRows + 1);
-  float* dbs = dws + kChunk * H;
+  float* wT = sm;                       // [H][kChunk]
+  float* hs = wT + H * kChunk;          // [kRows][H+1]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t N = a.B * a.m;
-
-  for (int e = tid; e < ch.ncol * H; e += kThreads) ws[e] = __ldg(a.w + (int64_t)ch.col[e / H] * H + (e % H));
-  if (BWD) {
-    for (int e = tid; e < kChunk * H; e += kThreads) dws[e] = 0.f;
-    if (tid < kChunk) dbs[tid] = 0.f;
+  for (int e = tid; e < H * kChunk; e += kThreads) {
+    const int k = e / kChunk, c = e % kChunk;
+    wT[e] = c < ch.ncol ? __ldg(a.w + (int64_t)ch.col[c] * H + k) : 0.f;
   }
-  // time slots: dynamic fwd: warmup-1 .. T-1 (T_sim+1 slots); dynamic bwd: warmup .. T-1; static: T-1
-  const int64_t t_first = ch.is_dynamic ? (BWD ? a.warmup : a.warmup - 1) : a.T - 1;
+  // time slots: dynamic: warmup-1 .. T-1 (T_sim+1 slots); static: T-1
+  const int64_t t_first = ch.is_dynamic ? a.warmup - 1 : a.T - 1;
+  const int64_t n_slots = a.T - t_first;
+  const int64_t tiles_b = cdiv(a.B, kRows);
+  const int64_t n_tiles = n_slots * tiles_b;
+  const int c0 = 4 * warp;
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t t = t_first + tile / tiles_b;
+    const int64_t b0 = (tile % tiles_b) * kRows;
+    const int nb = (int)min((int64_t)kRows, a.B - b0);
+    __syncthreads();
+    if (a.ri32) {   // tile = one 32-row group, contiguous as [H/32][32 rows][32 floats], units swizzled
+      const float* src = a.h_seq + (t * tiles_b + b0 / kRows) * kRows * H;
+      for (int e = tid; e < kRows * H; e += kThreads) hs[ri32_row(e) * (H + 1) + ri32_feat(e)] = __ldg(src + e);
+    } else {        // the [nb][H] slab of step t is contiguous in h_seq
+      const float* src = a.h_seq + (t * a.B + b0) * H;
+      for (int e = tid; e < nb * H; e += kThreads) hs[(e / H) * (H + 1) + (e % H)] = __ldg(src + e);
+    }
+    __syncthreads();
+    if (c0 < ch.ncol && lane < nb) {
+      const float* hr = hs + lane * (H + 1);
+      float z[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+      for (int k = 0; k < H; ++k) {
+        const float hk = hr[k];
+        const float4 w4 = *reinterpret_cast<const float4*>(wT + k * kChunk + c0);
+        z[0] = fmaf(hk, w4.x, z[0]); z[1] = fmaf(hk, w4.y, z[1]); z[2] = fmaf(hk, w4.z, z[2]); z[3] = fmaf(hk, w4.w, z[3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = c0 + j;
+        if (c >= ch.ncol) break;
+        const float val = ch.lo[c] + sigmoidf_acc(z[j] + __ldg(a.bias + ch.col[c])) * (ch.hi[c] - ch.lo[c]);
+        const int64_t b = b0 + lane;
+        const bool routing = ch.par[c] >= a.n_par;
+        if (ch.is_dynamic) {
+          if (t == a.warmup - 1) a.par_warm[(int64_t)ch.par[c] * N + b * a.m + ch.mem[c]] = val;
+          else a.par_sim[ch.off[c] + (t - a.warmup) * N + b * a.m + ch.mem[c]] = val;
+        } else if (routing) {
+          a.par_sim[ch.off[c] + b] = val;
+        } else {
+          a.par_sim[ch.off[c] + b * a.m + ch.mem[c]] = val;
+          a.par_warm[(int64_t)ch.par[c] * N + b * a.m + ch.mem[c]] = val;
+        }
+      }
+    }
+  }
+}
+
+// ---- backward -----------------------------------------------------------------------------------
+// Tile = one time slot x 32 rows.  256 threads = 64 hidden columns x 4 row quarters: a thread keeps its
+// column of W (ncol registers per 64-column block) and, for each of its 8 rows, reads the row of dz
+// with broadcast LDS.128 and h[r][k] with one conflict-free LDS; it produces dh[r][k] (written as whole
+// 128-byte lines) and accumulates dW[c][k] in registers across all tiles of the CTA (H = 64) or in
+// shared memory (larger H).  smem: ws[kChunk][H] | hs[32][H] | dzs[32][kChunk] | dws[kChunk][H] | dbs[kChunk]
+template <int NC, bool REG_ACC>   // NC: head columns rounded up (8, 16, 32); REG_ACC: H == 64, dW accumulators in registers
+__global__ void __launch_bounds__(kThreads) head_bwd_kernel(HeadArgs a, HeadChunk ch) {
+  extern __shared__ __align__(16) float sm[];
+  const int H = (int)a.H;
+  float* ws = sm;                          // [kChunk][H]
+  float* hs = ws + kChunk * H;             // [kRows][H]
+  float* dzs = hs + kRows * H;             // [kRows][kDz] (padded: conflict-free column writes, 16-byte rows)
+  float* dws = dzs + kRows * kDz;          // [kChunk][H]
+  float* dbs = dws + kChunk * H;           // [kChunk]
+  const int tid = threadIdx.x, kk = tid & 63, rq = tid >> 6;
+  const int64_t N = a.B * a.m;
+  const int KB = H / 64;
+  constexpr bool reg_acc = REG_ACC;
+
+  for (int e = tid; e < kChunk * H; e += kThreads) {
+    ws[e] = (e / H) < ch.ncol ? __ldg(a.w + (int64_t)ch.col[e / H] * H + (e % H)) : 0.f;
+    dws[e] = 0.f;
+  }
+  if (tid < kChunk) dbs[tid] = 0.f;
+  float acc_dw[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) acc_dw[c] = 0.f;
+  float acc_db = 0.f;
+
+  const int64_t t_first = ch.is_dynamic ? a.warmup : a.T - 1;
   const int64_t n_slots = a.T - t_first;
   const int64_t tiles_b = cdiv(a.B, kRows);
   const int64_t n_tiles = n_slots * tiles_b;
@@ -75,97 +152,90 @@ __global__ void __launch_bounds__(kThreads) head_kernel(HeadArgs a, HeadChunk ch
     const int64_t b0 = (tile % tiles_b) * kRows;
     const int nb = (int)min((int64_t)kRows, a.B - b0);
     __syncthreads();
-    // the [nb][H] slab of step t is contiguous in h_seq
-    if (a.ri32) {   // tile = one 32-row group, contiguous as [H/32][32 rows][32 floats], units swizzled
+    // h tile -> hs[r][k]
+    if (a.ri32) {
       const float* src = a.h_seq + (t * tiles_b + b0 / kRows) * kRows * H;
-      for (int e = tid; e < kRows * H; e += kThreads) hs[ri32_row(e) * (H + 1) + ri32_feat(e)] = __ldg(src + e);
+      for (int e = tid; e < kRows * H; e += kThreads) hs[ri32_row(e) * H + ri32_feat(e)] = __ldg(src + e);
     } else {
       const float* src = a.h_seq + (t * a.B + b0) * H;
-      for (int e = tid; e < nb * H; e += kThreads) hs[(e / H) * (H + 1) + (e % H)] = __ldg(src + e);
+      for (int e = tid; e < kRows * H; e += kThreads) hs[e] = e < nb * H ? __ldg(src + e) : 0.f;
+    }
+    // dz[r][c] = dpar * dval/dz, with sigma recovered from the stored value (0 for rows >= nb, columns >= ncol)
+    for (int e = tid; e < kChunk * kRows; e += kThreads) {
+      const int c = e / kRows, r = e % kRows;
+      float dz = 0.f;
+      if (r < nb && c < ch.ncol) {
+        const int64_t b = b0 + r;
+        const bool routing = ch.par[c] >= a.n_par;
+        const int64_t idx = ch.off[c] + (ch.is_dynamic ? (t - a.warmup) * N : 0) + (routing ? b : b * a.m + ch.mem[c]);
+        const float val = __ldg(a.par_sim + idx);
+        dz = __ldg(a.dpar_sim + idx) * (val - ch.lo[c]) * (ch.hi[c] - val) / (ch.hi[c] - ch.lo[c]);
+      }
+      dzs[r * kDz + c] = dz;
     }
     __syncthreads();
-
-    if (!BWD) {
-      // lanes = rows, warps = column subsets
-      if (lane < nb) {
-        const float* hr = hs + lane * (H + 1);
-        for (int c = warp; c < ch.ncol; c += kThreads / 32) {
-          const float* wr = ws + c * H;
-          float z = 0.f;
-#pragma unroll 8
-          for (int k = 0; k < H; ++k) z = fmaf(hr[k], wr[k], z);
-          z += __ldg(a.bias + ch.col[c]);
-          const float val = ch.lo[c] + sigmoidf_acc(z) * (ch.hi[c] - ch.lo[c]);
-          const int64_t b = b0 + lane;
-          const bool routing = ch.par[c] >= a.n_par;
-          if (ch.is_dynamic) {
-            if (t == a.warmup - 1) a.par_warm[(int64_t)ch.par[c] * N + b * a.m + ch.mem[c]] = val;
-            else a.par_sim[ch.off[c] + (t - a.warmup) * N + b * a.m + ch.mem[c]] = val;
-          } else if (routing) {
-            a.par_sim[ch.off[c] + b] = val;
-          } else {
-            a.par_sim[ch.off[c] + b * a.m + ch.mem[c]] = val;
-            a.par_warm[(int64_t)ch.par[c] * N + b * a.m + ch.mem[c]] = val;
+    if (tid < ch.ncol) {
+      float s = 0.f;
+      for (int r = 0; r < kRows; ++r) s += dzs[r * kDz + tid];
+      acc_db += s;
+    }
+    for (int kb = 0; kb < KB; ++kb) {
+      const int k = kb * 64 + kk;
+      float wreg[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) wreg[c] = ws[c * H + k];
+      float dwt[REG_ACC ? 1 : NC];
+#pragma unroll
+      for (int c = 0; c < (REG_ACC ? 1 : NC); ++c) dwt[c] = 0.f;
+#pragma unroll 2
+      for (int rr = 0; rr < 8; ++rr) {
+        const int r = rq * 8 + rr;
+        const float hk = hs[r * H + k];
+        float dh = 0.f;
+#pragma unroll
+        for (int c4 = 0; c4 < NC; c4 += 4) {
+          {
+            const float4 d4 = *reinterpret_cast<const float4*>(dzs + r * kDz + c4);
+            dh = fmaf(d4.x, wreg[c4], dh); dh = fmaf(d4.y, wreg[c4 + 1], dh);
+            dh = fmaf(d4.z, wreg[c4 + 2], dh); dh = fmaf(d4.w, wreg[c4 + 3], dh);
+            if constexpr (reg_acc) {
+              acc_dw[c4] = fmaf(d4.x, hk, acc_dw[c4]); acc_dw[c4 + 1] = fmaf(d4.y, hk, acc_dw[c4 + 1]);
+              acc_dw[c4 + 2] = fmaf(d4.z, hk, acc_dw[c4 + 2]); acc_dw[c4 + 3] = fmaf(d4.w, hk, acc_dw[c4 + 3]);
+            } else {
+              constexpr int M = REG_ACC ? 0 : ~0;   // keeps the indices in range in the unused instantiation
+              dwt[c4 & M] = fmaf(d4.x, hk, dwt[c4 & M]); dwt[(c4 + 1) & M] = fmaf(d4.y, hk, dwt[(c4 + 1) & M]);
+              dwt[(c4 + 2) & M] = fmaf(d4.z, hk, dwt[(c4 + 2) & M]); dwt[(c4 + 3) & M] = fmaf(d4.w, hk, dwt[(c4 + 3) & M]);
+            }
           }
         }
+        // dh[r][k]: a warp covers 32 consecutive k of one row = one 128-byte line in either layout
+        int64_t o;
+        if (a.ri32) o = (t * tiles_b + b0 / kRows) * kRows * H + (int64_t)(k >> 5) * 1024 + r * 32 + ((((k >> 3) ^ r) & 3) << 3) + (k & 7);
+        else o = (t * a.B + b0 + r) * H + k;
+        if (a.ri32 || r < nb) a.dh_seq[o] = a.accumulate_dh ? a.dh_seq[o] + dh : dh;
       }
-    } else {
-      // phase A: dz[c][r] = dpar * dval/dz, with sigma recovered from the stored value
-      for (int e = tid; e < ch.ncol * kRows; e += kThreads) {
-        const int c = e / kRows, r = e % kRows;
-        float dz = 0.f;
-        if (r < nb) {
-          const int64_t b = b0 + r;
-          const bool routing = ch.par[c] >= a.n_par;
-          const int64_t idx = ch.off[c] + (ch.is_dynamic ? (t - a.warmup) * N : 0) + (routing ? b : b * a.m + ch.mem[c]);
-          const float val = __ldg(a.par_sim + idx);
-          dz = __ldg(a.dpar_sim + idx) * (val - ch.lo[c]) * (ch.hi[c] - val) / (ch.hi[c] - ch.lo[c]);
-        }
-        dzs[c * (kRows + 1) + r] = dz;
-      }
-      __syncthreads();
-      // phase B: dh[r][k] (+)= sum_c dz[c][r] w[c][k]; consecutive threads -> consecutive k
-      if (a.ri32) {   // all 32 rows of the group are written (dz = 0 for rows >= nb)
-        float* dst = a.dh_seq + (t * tiles_b + b0 / kRows) * kRows * H;
-        for (int e = tid; e < kRows * H; e += kThreads) {
-          const int r = ri32_row(e), k = ri32_feat(e);
-          float acc = 0.f;
-          for (int c = 0; c < ch.ncol; ++c) acc = fmaf(dzs[c * (kRows + 1) + r], ws[c * H + k], acc);
-          dst[e] = a.accumulate_dh ? dst[e] + acc : acc;
-        }
-      } else {
-        float* dst = a.dh_seq + (t * a.B + b0) * H;
-        for (int e = tid; e < nb * H; e += kThreads) {
-          const int r = e / H, k = e % H;
-          float acc = 0.f;
-          for (int c = 0; c < ch.ncol; ++c) acc = fmaf(dzs[c * (kRows + 1) + r], ws[c * H + k], acc);
-          dst[e] = a.accumulate_dh ? dst[e] + acc : acc;
-        }
-      }
-      // phase C: dw[c][k] += sum_r dz[c][r] h[r][k]; each thread owns fixed (c,k) entries
-      for (int e = tid; e < ch.ncol * H; e += kThreads) {
-        const int c = e / H, k = e % H;
-        float acc = 0.f;
-        for (int r = 0; r < nb; ++r) acc = fmaf(dzs[c * (kRows + 1) + r], hs[r * (H + 1) + k], acc);
-        dws[e] += acc;
-      }
-      if (tid < ch.ncol) {
-        float acc = 0.f;
-        for (int r = 0; r < nb; ++r) acc += dzs[tid * (kRows + 1) + r];
-        dbs[tid] += acc;
+      if constexpr (!reg_acc) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+          if (c < ch.ncol) atomicAdd(dws + c * H + k, dwt[c]);
       }
     }
   }
-  if (BWD) {
-    __syncthreads();
-    for (int e = tid; e < ch.ncol * H; e += kThreads) atomicAdd(a.dw + (int64_t)ch.col[e / H] * H + (e % H), dws[e]);
-    if (tid < ch.ncol) atomicAdd(a.dbias + ch.col[tid], dbs[tid]);
+  __syncthreads();
+  if constexpr (reg_acc) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      if (c < ch.ncol) atomicAdd(dws + c * H + kk, acc_dw[c]);
   }
+  if (tid < ch.ncol) dbs[tid] = acc_db;
+  __syncthreads();
+  for (int e = tid; e < ch.ncol * H; e += kThreads) atomicAdd(a.dw + (int64_t)ch.col[e / H] * H + (e % H), dws[e]);
+  if (tid < ch.ncol) atomicAdd(a.dbias + ch.col[tid], dbs[tid]);
 }
 
 static size_t head_smem(int64_t H, bool bwd) {
-  size_t f = (size_t)kRows * (H + 1) + (size_t)kChunk * H;
-  if (bwd) f += (size_t)kChunk * (kRows + 1) + (size_t)kChunk * H + kChunk;
+  size_t f = bwd ? (size_t)kChunk * H * 2 + (size_t)kRows * H + (size_t)kRows * kDz + kChunk
+                 : (size_t)H * kChunk + (size_t)kRows * (H + 1);
   return f * sizeof(float);
 }
 
@@ -247,11 +317,11 @@ extern "C" int hy2dl_head_map_fwd(const float* h_seq, int64_t B, int64_t T, int6
              "hy2dl_head_map_fwd: unknown layout %d (RI32 needs H %% 32 == 0)", layout);
   a.ri32 = layout == HY2DL_LAYOUT_RI32;
   const size_t smem = head_smem(H, false);
-  cudaFuncSetAttribute(head_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   for (int i = 0; i < n; ++i) {
     const int64_t slots = chunks[i].is_dynamic ? (T - pm->warmup + 1) : 1;
     const unsigned grid = (unsigned)std::min<int64_t>(slots * cdiv(B, kRows), 8 * (int64_t)sm_count());
-    head_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(a, chunks[i]);
+    head_fwd_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(a, chunks[i]);
   }
   HY_LAUNCH_CHECK();
   return HY2DL_OK;
@@ -262,7 +332,7 @@ extern "C" int hy2dl_head_map_bwd(const float* h_seq, const float* par_sim, cons
                                   float* dbias, int layout, hy2dl_stream_t stream) {
   int rc = check_parmap(pm, T, "hy2dl_head_map_bwd");
   if (rc) return rc;
-  HY_REQUIRE(B > 0 && H > 0 && H <= 512, HY2DL_ERR_SHAPE, "hy2dl_head_map_bwd: bad sizes B=%lld H=%lld", (long long)B, (long long)H);
+  HY_REQUIRE(B > 0 && H > 0 && H <= 512 && H % 64 == 0, HY2DL_ERR_SHAPE, "hy2dl_head_map_bwd: bad sizes B=%lld H=%lld (H must be a multiple of 64)", (long long)B, (long long)H);
   HY_NONNULL(h_seq); HY_NONNULL(par_sim); HY_NONNULL(dpar_sim); HY_NONNULL(w); HY_NONNULL(dh_seq); HY_NONNULL(dw); HY_NONNULL(dbias);
   HeadChunk chunks[32];
   const int n = build_chunks(pm, chunks, 32);
@@ -280,7 +350,10 @@ extern "C" int hy2dl_head_map_bwd(const float* h_seq, const float* par_sim, cons
   a.ri32 = layout == HY2DL_LAYOUT_RI32;
   const int64_t Bp = a.ri32 ? cdiv(B, 32) * 32 : B;   // rows per step in dh_seq
   const size_t smem = head_smem(H, true);
-  cudaFuncSetAttribute(head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto launch = [&](auto kern, unsigned grid, const HeadChunk& chk) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, kThreads, smem, s>>>(a, chk);
+  };
   bool dyn_written = false;
   for (int i = 0; i < n; ++i) {
     if (!chunks[i].is_dynamic && !dyn_written) {
@@ -291,8 +364,17 @@ extern "C" int hy2dl_head_map_bwd(const float* h_seq, const float* par_sim, cons
     a.accumulate_dh = chunks[i].is_dynamic ? (dyn_written ? 1 : 0) : 1;
     if (chunks[i].is_dynamic) dyn_written = true;
     const int64_t slots = chunks[i].is_dynamic ? (T - pm->warmup) : 1;
-    const unsigned grid = (unsigned)std::min<int64_t>(slots * cdiv(B, kRows), 2 * (int64_t)sm_count());
-    head_kernel<true><<<grid, kThreads, smem, s>>>(a, chunks[i]);
+    const unsigned grid = (unsigned)std::min<int64_t>(slots * cdiv(B, kRows), 4 * (int64_t)sm_count());
+    const int nc = chunks[i].ncol;
+    if (H == 64) {
+      if (nc <= 8) launch(head_bwd_kernel<8, true>, grid, chunks[i]);
+      else if (nc <= 16) launch(head_bwd_kernel<16, true>, grid, chunks[i]);
+      else launch(head_bwd_kernel<32, true>, grid, chunks[i]);
+    } else {
+      if (nc <= 8) launch(head_bwd_kernel<8, false>, grid, chunks[i]);
+      else if (nc <= 16) launch(head_bwd_kernel<16, false>, grid, chunks[i]);
+      else launch(head_bwd_kernel<32, false>, grid, chunks[i]);
+    }
   }
   HY_LAUNCH_CHECK();
   return HY2DL_OK;

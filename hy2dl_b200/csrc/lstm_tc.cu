@@ -23,6 +23,7 @@
 // gates of 8 hidden units.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace hy2dl {
 namespace tc {
@@ -30,7 +31,6 @@ namespace tc {
 constexpr int kH = 64;
 constexpr int kN = 256;            // 4H
 constexpr int kRows = 128;         // sequences per CTA
-constexpr int kFwdThreads = 160;   // 4 row warps + 1 MMA warp
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColD = 0, kColAhi = 256, kColAlo = 384;   // K <= 128 columns each
 
@@ -56,29 +56,60 @@ __global__ void lstm_tc_pack_w_kernel(const float* __restrict__ w_ih, const floa
 }
 
 struct TcFwdArgs {
-  const float4* x;      // RI32, F = IP = 32
+  const float* x;       // RI32, F = IP = 32
   const float* w_hi;    // [K/4][256][4]
   const float* w_lo;
   const float* bias_n;  // [256]
-  float4* h_seq;        // RI32 F = 64   (nullable)
-  float4* c_seq;        // RI32 F = 64   (nullable)
-  float4* gates;        // RI32 F = 256, n = 4u + g (nullable)
+  float* h_seq;         // RI32 F = 64   (nullable)
+  float* c_seq;         // RI32 F = 64   (nullable)
+  float* gates;         // RI32 F = 256, n = 4u + g (nullable)
   float* h_last;        // row-major [B][64] (nullable)
   int64_t B, T, G;      // G = ceil(B / 32) groups
   int IP;
 };
 
-__global__ void __launch_bounds__(kFwdThreads, 1) lstm_tc_fwd_kernel(TcFwdArgs a) {
+// One reciprocal for the four gates of a hidden unit: with A = 1 + e^-zi, F = 1 + e^-zf, G = 1 + e^-2zg,
+// O = 1 + e^-zo and r = 1 / (A F G O):  i = r F G O, f = r A G O, o = r A F G, g = tanh(zg) = (2 - G) r A F O.
+// Arguments are clamped (sigmoid below -20 / tanh below -10 differ from their limits by < 4e-9) so that the
+// product stays finite.  5 MUFU (4 ex2 + rcp) instead of 8: the XU pipe is the epilogue's narrowest resource.
+__device__ __forceinline__ void lstm_gates(float zi, float zf, float zg, float zo, float& gi, float& gf, float& gg, float& go) {
+  constexpr float kL2E = 1.4426950408889634f;
+  const float A = 1.f + fast_ex2(-kL2E * fmaxf(zi, -20.f));
+  const float F = 1.f + fast_ex2(-kL2E * fmaxf(zf, -20.f));
+  const float G = 1.f + fast_ex2(-2.f * kL2E * fmaxf(zg, -10.f));
+  const float O = 1.f + fast_ex2(-kL2E * fmaxf(zo, -20.f));
+  const float AF = A * F, GO = G * O;
+  const float r = fast_rcp(AF * GO);
+  const float rAF = r * AF, rGO = r * GO;
+  gi = rGO * F;
+  gf = rGO * A;
+  go = rAF * G;
+  gg = (2.f - G) * (rAF * O);
+}
+
+// NSETS = 2 or 4 sets of four row warps: set s owns hidden units [s*64/NSETS, (s+1)*64/NSETS) of all 128
+// rows (warp w of a set owns TMEM lanes / rows 32 (w & 3) ..), and the step's MMAs are issued per set
+// (N = 256/NSETS gate columns each, committed separately), so the epilogue of set s runs while the tensor
+// core is still busy with sets s+1.. -- and there are NSETS warps per scheduler to hide each other's latencies.
+// The A operand [x_t | h_{t-1}] is shared by all MMAs of a step, so every set holds its new h values in
+// registers until the LAST commit of the step before writing them into TMEM.
+template <int NSETS>
+__global__ void __launch_bounds__(128 * NSETS + 32, 1) lstm_tc_fwd_kernel(TcFwdArgs a) {
+  constexpr int kUPT = kH / NSETS;          // hidden units per thread
+  constexpr int kQ = kUPT / 8;              // 8-unit blocks per thread
+  constexpr int kNS = kN / NSETS;           // gate columns per set
+  constexpr int kMmaWarp = 4 * NSETS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int IP = a.IP, K = IP + kH, KC = K / 4;
   float* s_whi = reinterpret_cast<float*>(smem_raw);
   float* s_wlo = s_whi + K * kN;
   float* s_bias = s_wlo + K * kN;
-  uint64_t* bar_a_ready = reinterpret_cast<uint64_t*>(s_bias + kN);   // 128 row threads -> MMA warp
-  uint64_t* bar_mma_done = bar_a_ready + 1;                           // MMA commit -> row threads
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_mma_done + 1);
+  uint64_t* bar_a_ready = reinterpret_cast<uint64_t*>(s_bias + kN);   // all row threads -> MMA warp
+  uint64_t* bar_done = bar_a_ready + 1;                               // [NSETS] MMA commit of set s -> row threads
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_done + NSETS);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int kThreads = 128 * NSETS + 32;
 
   // ---- one-time setup: weights -> smem, barriers, TMEM
   {
@@ -86,52 +117,50 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_tc_fwd_kernel(TcFwdArgs a
     const float4* g_lo = reinterpret_cast<const float4*>(a.w_lo);
     float4* d_hi = reinterpret_cast<float4*>(s_whi);
     float4* d_lo = reinterpret_cast<float4*>(s_wlo);
-    for (int e = tid; e < KC * kN; e += kFwdThreads) { d_hi[e] = __ldg(g_hi + e); d_lo[e] = __ldg(g_lo + e); }
-    for (int e = tid; e < kN; e += kFwdThreads) s_bias[e] = __ldg(a.bias_n + e);
+    for (int e = tid; e < KC * kN; e += kThreads) { d_hi[e] = __ldg(g_hi + e); d_lo[e] = __ldg(g_lo + e); }
+    for (int e = tid; e < kN; e += kThreads) s_bias[e] = __ldg(a.bias_n + e);
   }
   if (tid == 0) {
-    mbar_init(bar_a_ready, kRows);
-    mbar_init(bar_mma_done, 1);
+    mbar_init(bar_a_ready, 128 * NSETS);
+    for (int s = 0; s < NSETS; ++s) mbar_init(bar_done + s, 1);
     mbar_fence_init();
   }
-  if (warp == 4) tmem_alloc(s_tmem, kTmemCols);
+  if (warp == kMmaWarp) tmem_alloc(s_tmem, kTmemCols);
   fence_async_smem();          // generic-proxy smem writes (weights) -> visible to the MMA's async proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
-  if (warp < 4) {
+  if (warp < kMmaWarp) {
     // =========================== row-owning threads ===========================================
-    const int64_t gidx = (int64_t)blockIdx.x * 4 + warp;      // this warp's 32-row group
-    const bool live = gidx < a.G;                              // warp-uniform
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-    const int XC = IP / 4;                                     // x chunks (float4) per row, <= 8
-    float c[kH];
+    const int set = warp >> 2;
+    const int64_t gidx = (int64_t)blockIdx.x * 4 + (warp & 3);   // this warp's 32-row group
+    const bool live = gidx < a.G;                                 // warp-uniform
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    constexpr int kXU = 4 / NSETS;                                // x units (8 columns) this thread moves
+    float c[kUPT];
 #pragma unroll
-    for (int u = 0; u < kH; ++u) c[u] = 0.f;
+    for (int u = 0; u < kUPT; ++u) c[u] = 0.f;
 
     // A(t = 0) = [x_0 | 0]
     {
       uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-      for (int q = 0; q < kH / 8; ++q) {
-        tmem_st8(lane_base + kColAhi + IP + 8 * q, z);
-        tmem_st8(lane_base + kColAlo + IP + 8 * q, z);
+      for (int q = 0; q < kQ; ++q) {
+        tmem_st8(lane_base + kColAhi + IP + 8 * (kQ * set + q), z);
+        tmem_st8(lane_base + kColAlo + IP + 8 * (kQ * set + q), z);
       }
-      for (int j2 = 0; j2 < XC; j2 += 2) {
-        uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (live) v = ri32_ld(a.x, 0, a.G, gidx, 1, j2 + jj, lane);
-          split_tf32(v.x, hi[4 * jj + 0], lo[4 * jj + 0]);
-          split_tf32(v.y, hi[4 * jj + 1], lo[4 * jj + 1]);
-          split_tf32(v.z, hi[4 * jj + 2], lo[4 * jj + 2]);
-          split_tf32(v.w, hi[4 * jj + 3], lo[4 * jj + 3]);
-        }
-        tmem_st8(lane_base + kColAhi + 4 * j2, hi);
-        tmem_st8(lane_base + kColAlo + 4 * j2, lo);
+      for (int j = 0; j < kXU; ++j) {               // the 32 input columns = 4 units of 8
+        const int U = kXU * set + j;
+        uint32_t hi[8], lo[8];
+        f8 v = f8_zero();
+        if (live) v = ldg256(a.x + ri32_unit(0, a.G, gidx, 1, U, lane));
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_tf32(v.v[e], hi[e], lo[e]);
+        tmem_st8(lane_base + kColAhi + 8 * U, hi);
+        tmem_st8(lane_base + kColAlo + 8 * U, lo);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -140,80 +169,76 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_tc_fwd_kernel(TcFwdArgs a
 
     for (int64_t t = 0; t < a.T; ++t) {
       // prefetch x_{t+1} while the MMAs of step t run
-      float4 xn[8];
+      f8 xn[kXU];
       const bool more = t + 1 < a.T;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        xn[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < XC && more && live) xn[j] = ri32_ld(a.x, t + 1, a.G, gidx, 1, j, lane);
+      for (int j = 0; j < kXU; ++j) {
+        xn[j] = f8_zero();
+        if (more && live) xn[j] = ldg256(a.x + ri32_unit(t + 1, a.G, gidx, 1, kXU * set + j, lane));
       }
-      mbar_wait(bar_mma_done, (uint32_t)(t & 1));
+      mbar_wait(bar_done + set, (uint32_t)(t & 1));
       tc_fence_after();
 
+      f8 hkeep[kQ];                                 // h_t of this thread's units, written to TMEM after the last commit
 #pragma unroll
-      for (int q = 0; q < kH / 8; ++q) {          // 8 hidden units (32 D columns) per iteration
+      for (int q = 0; q < kQ; ++q) {                // 8 hidden units (32 D columns) per iteration
+        const int qg = kQ * set + q;                // unit block 0..7
         uint32_t v[32];
-        tmem_ld32(lane_base + kColD + 32 * q, v);
+        tmem_ld32(lane_base + kColD + 32 * qg, v);
         tmem_ld_wait();
-        float hv[8], cv[8], gv[32];
+        f8 hv, cv, gv[4];
 #pragma unroll
         for (int uu = 0; uu < 8; ++uu) {
-          const int u = 8 * q + uu;
-          const float4 bb = *reinterpret_cast<const float4*>(s_bias + 4 * u);
-          const float gi = fast_sigmoid(__uint_as_float(v[4 * uu + 0]) + bb.x);
-          const float gf = fast_sigmoid(__uint_as_float(v[4 * uu + 1]) + bb.y);
-          const float gg = fast_tanh(__uint_as_float(v[4 * uu + 2]) + bb.z);
-          const float go = fast_sigmoid(__uint_as_float(v[4 * uu + 3]) + bb.w);
-          const float cn = gf * c[u] + gi * gg;
-          c[u] = cn;
-          hv[uu] = go * fast_tanh(cn);
-          cv[uu] = cn;
-          gv[4 * uu + 0] = gi; gv[4 * uu + 1] = gf; gv[4 * uu + 2] = gg; gv[4 * uu + 3] = go;
+          const float4 bb = *reinterpret_cast<const float4*>(s_bias + 4 * (8 * qg + uu));
+          float gi, gf, gg, go;
+          lstm_gates(__uint_as_float(v[4 * uu + 0]) + bb.x, __uint_as_float(v[4 * uu + 1]) + bb.y,
+                     __uint_as_float(v[4 * uu + 2]) + bb.z, __uint_as_float(v[4 * uu + 3]) + bb.w, gi, gf, gg, go);
+          const float cn = gf * c[8 * q + uu] + gi * gg;
+          c[8 * q + uu] = cn;
+          hv.v[uu] = go * fast_tanh(cn);
+          cv.v[uu] = cn;
+          gv[uu >> 1].v[4 * (uu & 1) + 0] = gi; gv[uu >> 1].v[4 * (uu & 1) + 1] = gf;
+          gv[uu >> 1].v[4 * (uu & 1) + 2] = gg; gv[uu >> 1].v[4 * (uu & 1) + 3] = go;
         }
-        // h_t back into the A operand (hi / lo), columns IP + 8q .. IP + 8q + 7
-        {
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int uu = 0; uu < 8; ++uu) split_tf32(hv[uu], hi[uu], lo[uu]);
-          tmem_st8(lane_base + kColAhi + IP + 8 * q, hi);
-          tmem_st8(lane_base + kColAlo + IP + 8 * q, lo);
-        }
+        hkeep[q] = hv;
         if (live) {
-          if (a.h_seq) {
-            ri32_st(a.h_seq, t, a.G, gidx, 2, 2 * q, lane, make_float4(hv[0], hv[1], hv[2], hv[3]));
-            ri32_st(a.h_seq, t, a.G, gidx, 2, 2 * q + 1, lane, make_float4(hv[4], hv[5], hv[6], hv[7]));
-          }
-          if (a.c_seq) {
-            ri32_st(a.c_seq, t, a.G, gidx, 2, 2 * q, lane, make_float4(cv[0], cv[1], cv[2], cv[3]));
-            ri32_st(a.c_seq, t, a.G, gidx, 2, 2 * q + 1, lane, make_float4(cv[4], cv[5], cv[6], cv[7]));
-          }
+          // one 256-bit store = one 32-byte sector of this row; the four gate units are its 128-byte line
+          if (a.h_seq) stg256(a.h_seq + ri32_unit(t, a.G, gidx, 2, qg, lane), hv);
+          if (a.c_seq) stg256(a.c_seq + ri32_unit(t, a.G, gidx, 2, qg, lane), cv);
           if (a.gates) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              ri32_st(a.gates, t, a.G, gidx, 8, 8 * q + j, lane, make_float4(gv[4 * j], gv[4 * j + 1], gv[4 * j + 2], gv[4 * j + 3]));
+            for (int j = 0; j < 4; ++j) stg256(a.gates + ri32_unit(t, a.G, gidx, 8, 4 * qg + j, lane), gv[j]);
           }
           if (a.h_last && t == a.T - 1) {
             const int64_t b = gidx * 32 + lane;
             if (b < a.B) {
-#pragma unroll
-              for (int uu = 0; uu < 8; ++uu) a.h_last[b * kH + 8 * q + uu] = hv[uu];
+              *reinterpret_cast<float4*>(a.h_last + b * kH + 8 * qg) = make_float4(hv.v[0], hv.v[1], hv.v[2], hv.v[3]);
+              *reinterpret_cast<float4*>(a.h_last + b * kH + 8 * qg + 4) = make_float4(hv.v[4], hv.v[5], hv.v[6], hv.v[7]);
             }
           }
         }
       }
-      // x_{t+1} into the A operand
       if (more) {
+        // the A operand may be overwritten once EVERY MMA of this step has retired
+        if (set != NSETS - 1) {
+          mbar_wait(bar_done + (NSETS - 1), (uint32_t)(t & 1));
+          tc_fence_after();
+        }
 #pragma unroll
-        for (int j2 = 0; j2 < 8; j2 += 2) {
-          if (j2 < XC) {
-            uint32_t hi[8], lo[8];
-            split_tf32(xn[j2].x, hi[0], lo[0]); split_tf32(xn[j2].y, hi[1], lo[1]);
-            split_tf32(xn[j2].z, hi[2], lo[2]); split_tf32(xn[j2].w, hi[3], lo[3]);
-            split_tf32(xn[j2 + 1].x, hi[4], lo[4]); split_tf32(xn[j2 + 1].y, hi[5], lo[5]);
-            split_tf32(xn[j2 + 1].z, hi[6], lo[6]); split_tf32(xn[j2 + 1].w, hi[7], lo[7]);
-            tmem_st8(lane_base + kColAhi + 4 * j2, hi);
-            tmem_st8(lane_base + kColAlo + 4 * j2, lo);
-          }
+        for (int q = 0; q < kQ; ++q) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int uu = 0; uu < 8; ++uu) split_tf32(hkeep[q].v[uu], hi[uu], lo[uu]);
+          tmem_st8(lane_base + kColAhi + IP + 8 * (kQ * set + q), hi);
+          tmem_st8(lane_base + kColAlo + IP + 8 * (kQ * set + q), lo);
+        }
+#pragma unroll
+        for (int j = 0; j < kXU; ++j) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) split_tf32(xn[j].v[e], hi[e], lo[e]);
+          tmem_st8(lane_base + kColAhi + 8 * (kXU * set + j), hi);
+          tmem_st8(lane_base + kColAlo + 8 * (kXU * set + j), lo);
         }
         tmem_st_wait();
         tc_fence_before();
@@ -223,27 +248,30 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_tc_fwd_kernel(TcFwdArgs a
   } else {
     // =========================== MMA issuer (one thread) ======================================
     if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(kRows, kN, 0, 0);
+      const uint32_t idesc = idesc_tf32(kRows, kNS, 0, 0);
       const uint32_t whi = smem_u32(s_whi), wlo = smem_u32(s_wlo);
       const uint32_t lbo = kN * 16, sbo = 128;     // K-major no-swizzle: chunk-to-chunk 4096 B, 8-row groups 128 B
       const int KS = K / 8;
       for (int64_t t = 0; t < a.T; ++t) {
         mbar_wait(bar_a_ready, (uint32_t)(t & 1));
         tc_fence_after();
-        // all correction terms first, while the accumulator is still ~2^-11 of its final size: the
-        // tensor core's fp32 accumulation loses up to an ulp of the ACCUMULATOR per MMA, so only the
-        // K/8 hi*hi instructions round at full magnitude
-        for (int j = 0; j < KS; ++j) {
-          const uint64_t d_hi = smem_desc(whi + (uint32_t)j * 2 * lbo, lbo, sbo);
-          const uint64_t d_lo = smem_desc(wlo + (uint32_t)j * 2 * lbo, lbo, sbo);
-          mma_tf32_ts(tmem + kColD, tmem + kColAlo + 8 * j, d_hi, idesc, j > 0);
-          mma_tf32_ts(tmem + kColD, tmem + kColAhi + 8 * j, d_lo, idesc, 1);
+        for (int s = 0; s < NSETS; ++s) {
+          const uint32_t d = tmem + kColD + kNS * s, boff = (uint32_t)(kNS * s) * 16;   // B rows n = kNS*s ..
+          // all correction terms first, while the accumulator is still ~2^-11 of its final size: the
+          // tensor core's fp32 accumulation loses up to an ulp of the ACCUMULATOR per MMA, so only the
+          // K/8 hi*hi instructions round at full magnitude
+          for (int j = 0; j < KS; ++j) {
+            const uint64_t d_hi = smem_desc(whi + boff + (uint32_t)j * 2 * lbo, lbo, sbo);
+            const uint64_t d_lo = smem_desc(wlo + boff + (uint32_t)j * 2 * lbo, lbo, sbo);
+            mma_tf32_ts(d, tmem + kColAlo + 8 * j, d_hi, idesc, j > 0);
+            mma_tf32_ts(d, tmem + kColAhi + 8 * j, d_lo, idesc, 1);
+          }
+          for (int j = 0; j < KS; ++j) {
+            const uint64_t d_hi = smem_desc(whi + boff + (uint32_t)j * 2 * lbo, lbo, sbo);
+            mma_tf32_ts(d, tmem + kColAhi + 8 * j, d_hi, idesc, 1);
+          }
+          mma_commit(bar_done + s);
         }
-        for (int j = 0; j < KS; ++j) {
-          const uint64_t d_hi = smem_desc(whi + (uint32_t)j * 2 * lbo, lbo, sbo);
-          mma_tf32_ts(tmem + kColD, tmem + kColAhi + 8 * j, d_hi, idesc, 1);
-        }
-        mma_commit(bar_mma_done);
       }
     }
     __syncwarp();
@@ -251,10 +279,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_tc_fwd_kernel(TcFwdArgs a
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, kTmemCols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
 }
 
-static size_t tc_fwd_smem(int K) { return (size_t)K * kN * 4 * 2 + kN * 4 + 64; }
+static size_t tc_fwd_smem(int K) { return (size_t)K * kN * 4 * 2 + kN * 4 + 128; }
+constexpr int kFwdSets = 2;   // measured on B200 (B = 18944, T = 365): 2 sets 3.01 ms, 4 sets 3.40 ms, 1 set 4.06 ms
 
 int64_t lstm_tc_wgrad_workspace(int64_t B, int64_t T, int64_t I);
 
@@ -281,14 +310,19 @@ int lstm_tc_fwd(const float* x_ri, int64_t B, int64_t T, int64_t I, int64_t IP, 
   float* bias_n = w_lo + K * kN;
   lstm_tc_pack_w_kernel<<<96, 256, 0, s>>>(w_ih, w_hh, b_ih, b_hh, (int)I, (int)IP, w_hi, w_lo, bias_n);
   TcFwdArgs a{};
-  a.x = reinterpret_cast<const float4*>(x_ri);
+  a.x = x_ri;
   a.w_hi = w_hi; a.w_lo = w_lo; a.bias_n = bias_n;
-  a.h_seq = reinterpret_cast<float4*>(h_seq); a.c_seq = reinterpret_cast<float4*>(c_seq);
-  a.gates = reinterpret_cast<float4*>(gates); a.h_last = h_last;
+  a.h_seq = h_seq; a.c_seq = c_seq; a.gates = gates; a.h_last = h_last;
   a.B = B; a.T = T; a.G = cdiv(B, 32); a.IP = (int)IP;
   const size_t smem = tc_fwd_smem(K);
-  cudaFuncSetAttribute(lstm_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  lstm_tc_fwd_kernel<<<(unsigned)cdiv(B, kRows), kFwdThreads, smem, s>>>(a);
+  static const int sets = [] { const char* e = getenv("HY2DL_FWD_SETS"); return e ? (atoi(e) == 4 ? 4 : 2) : kFwdSets; }();   // tuning knob
+  if (sets == 2) {
+    cudaFuncSetAttribute(lstm_tc_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lstm_tc_fwd_kernel<2><<<(unsigned)cdiv(B, kRows), 128 * 2 + 32, smem, s>>>(a);
+  } else {
+    cudaFuncSetAttribute(lstm_tc_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lstm_tc_fwd_kernel<4><<<(unsigned)cdiv(B, kRows), 128 * 4 + 32, smem, s>>>(a);
+  }
   HY_LAUNCH_CHECK();
   return HY2DL_OK;
 }
@@ -332,31 +366,33 @@ __global__ void lstm_tc_pack_whh_kernel(const float* __restrict__ w_hh, float* _
 struct TcBwdArgs {
   const float* w_hi;      // [64][64][4] packed W_hh (hi)
   const float* w_lo;
-  const float4* gates;    // RI32 F = 256 (n = 4u + g)
-  const float4* c_seq;    // RI32 F = 64
-  const float4* dh_seq;   // RI32 F = 64 or null
+  const float* gates;     // RI32 F = 256 (n = 4u + g)
+  const float* c_seq;     // RI32 F = 64
+  const float* dh_seq;    // RI32 F = 64 or null
   const float* dh_last;   // row-major [B][64] or null
-  float4* dG;             // RI32 F = 256; may alias gates
+  float* dG;              // RI32 F = 256; may alias gates
   int64_t B, T, G, dh_t0;
 };
 
-struct BwdChunk {   // tape of 4 hidden units of one row at one step
-  float4 g[4], ct, cp, dh;
+struct BwdChunk {   // tape of 8 hidden units of one row at one step: one 128-byte line of gates + three sectors
+  f8 g[4], ct, cp, dh;
 };
 
-__device__ __forceinline__ void bwd_load_chunk(const TcBwdArgs& a, int64_t t, int q, int64_t gidx, int lane, bool live, BwdChunk& c) {
-  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+// Q = 0..7: hidden units [8Q, 8Q + 8) = gate block Q (unit j holds units 8Q+2j, 8Q+2j+1 x 4 gates)
+__device__ __forceinline__ void bwd_load_chunk(const TcBwdArgs& a, int64_t t, int Q, int64_t gidx, int lane, bool live, BwdChunk& c) {
   const bool on = live && t >= 0;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) c.g[j] = on ? ri32_ld(a.gates, t, a.G, gidx, 8, 4 * q + j, lane) : z;
-  c.ct = on ? ri32_ld(a.c_seq, t, a.G, gidx, 2, q, lane) : z;
-  c.cp = (on && t > 0) ? ri32_ld(a.c_seq, t - 1, a.G, gidx, 2, q, lane) : z;
-  c.dh = (on && a.dh_seq && t >= a.dh_t0) ? ri32_ld(a.dh_seq, t, a.G, gidx, 2, q, lane) : z;
+  for (int j = 0; j < 4; ++j) c.g[j] = on ? ldg256(a.gates + ri32_unit(t, a.G, gidx, 8, 4 * Q + j, lane)) : f8_zero();
+  c.ct = on ? ldg256(a.c_seq + ri32_unit(t, a.G, gidx, 2, Q, lane)) : f8_zero();
+  c.cp = (on && t > 0) ? ldg256(a.c_seq + ri32_unit(t - 1, a.G, gidx, 2, Q, lane)) : f8_zero();
+  c.dh = (on && a.dh_seq && t >= a.dh_t0) ? ldg256(a.dh_seq + ri32_unit(t, a.G, gidx, 2, Q, lane)) : f8_zero();
   if (on && a.dh_last && t == a.T - 1) {
     const int64_t b = gidx * 32 + lane;
     if (b < a.B) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(a.dh_last + b * kH + 4 * q));
-      c.dh.x += v.x; c.dh.y += v.y; c.dh.z += v.z; c.dh.w += v.w;
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(a.dh_last + b * kH + 8 * Q));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(a.dh_last + b * kH + 8 * Q + 4));
+      c.dh.v[0] += v0.x; c.dh.v[1] += v0.y; c.dh.v[2] += v0.z; c.dh.v[3] += v0.w;
+      c.dh.v[4] += v1.x; c.dh.v[5] += v1.y; c.dh.v[6] += v1.z; c.dh.v[7] += v1.w;
     }
   }
 }
@@ -397,12 +433,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_tc_bwd_kernel(TcBwdArgs a
     float* dcp = s_dc + tid;     // dc[u] at dcp[u * 128]: conflict-free, keeps the chunk loop rolled and small
     for (int u = 0; u < kH; ++u) dcp[u * kRows] = 0.f;
 
-    // tape chunks travel through a 4-deep register ring: chunk q + 4 is requested as soon as chunk q has
-    // been consumed, so ~4 x 112 B per thread (57 KB per SM) are in flight -- one warp per scheduler has
-    // no other way to cover the HBM latency
-    BwdChunk ring[4];
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) bwd_load_chunk(a, a.T - 1, kk, gidx, lane, live, ring[kk]);
+    // tape chunks (8 hidden units = 224 B per row) travel through a 2-deep register ring: chunk Q + 2 is
+    // requested as soon as chunk Q has been consumed, so ~450 B per thread (57 KB per SM) are in flight --
+    // one warp per scheduler has no other way to cover the HBM latency.  Every access is a whole sector.
+    BwdChunk ring[2];
+    bwd_load_chunk(a, a.T - 1, 0, gidx, lane, live, ring[0]);
+    bwd_load_chunk(a, a.T - 1, 1, gidx, lane, live, ring[1]);
     for (int64_t s = 0; s < a.T; ++s) {
       const int64_t t = a.T - 1 - s;
       const uint32_t d_prev = lane_base + kColDh0 + 64 * (uint32_t)((s & 1) ^ 1);   // dh_rec from step s-1
@@ -418,47 +454,43 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_tc_bwd_kernel(TcBwdArgs a
           tc_fence_after();
         }
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) { // 4 hidden units (16 gate columns) per chunk
-          const int q = 4 * k + kk;
+        for (int kk = 0; kk < 2; ++kk) { // two chunks of 8 hidden units per quarter
+          const int Q = 2 * k + kk;
           BwdChunk& cur = ring[kk];
-          uint32_t r[4] = {0, 0, 0, 0};
+          uint32_t r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
           if (s > 0) {
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                         : "r"(d_prev + 4 * q));
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                         : "r"(d_prev + 8 * Q));
             tmem_ld_wait();
           }
-          const float dhe[4] = {cur.dh.x, cur.dh.y, cur.dh.z, cur.dh.w};
-          const float ctv[4] = {cur.ct.x, cur.ct.y, cur.ct.z, cur.ct.w};
-          const float cpv[4] = {cur.cp.x, cur.cp.y, cur.cp.z, cur.cp.w};
-          float dg[16];
+          f8 dg[4];
 #pragma unroll
-          for (int uu = 0; uu < 4; ++uu) {
-            const int u = 4 * q + uu;
-            const float gi = cur.g[uu].x, gf = cur.g[uu].y, gg = cur.g[uu].z, go = cur.g[uu].w;
-            const float dh = dhe[uu] + __uint_as_float(r[uu]);
-            const float tcv = fast_tanh(ctv[uu]);
+          for (int uu = 0; uu < 8; ++uu) {
+            const int u = 8 * Q + uu, j = uu >> 1, o = 4 * (uu & 1);
+            const float gi = cur.g[j].v[o], gf = cur.g[j].v[o + 1], gg = cur.g[j].v[o + 2], go = cur.g[j].v[o + 3];
+            const float dh = cur.dh.v[uu] + __uint_as_float(r[uu]);
+            const float tcv = fast_tanh(cur.ct.v[uu]);
             const float dct = dcp[u * kRows] + dh * go * (1.f - tcv * tcv);
-            dg[4 * uu + 0] = dct * gg * gi * (1.f - gi);
-            dg[4 * uu + 1] = dct * cpv[uu] * gf * (1.f - gf);
-            dg[4 * uu + 2] = dct * gi * (1.f - gg * gg);
-            dg[4 * uu + 3] = dh * tcv * go * (1.f - go);
+            dg[j].v[o + 0] = dct * gg * gi * (1.f - gi);
+            dg[j].v[o + 1] = dct * cur.cp.v[uu] * gf * (1.f - gf);
+            dg[j].v[o + 2] = dct * gi * (1.f - gg * gg);
+            dg[j].v[o + 3] = dh * tcv * go * (1.f - go);
             dcp[u * kRows] = dct * gf;
           }
-          // refill this ring slot: chunk q + 4 of this step, or chunk kk of the next (earlier) step
-          if (k < 3) bwd_load_chunk(a, t, q + 4, gidx, lane, live, cur);
+          // refill this ring slot: chunk Q + 2 of this step, or chunk kk of the next (earlier) step
+          if (k < 3) bwd_load_chunk(a, t, Q + 2, gidx, lane, live, cur);
           else bwd_load_chunk(a, t - 1, kk, gidx, lane, live, cur);
           if (live) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              ri32_st(a.dG, t, a.G, gidx, 8, 4 * q + j, lane, make_float4(dg[4 * j], dg[4 * j + 1], dg[4 * j + 2], dg[4 * j + 3]));
+            for (int j = 0; j < 4; ++j) stg256(a.dG + ri32_unit(t, a.G, gidx, 8, 4 * Q + j, lane), dg[j]);
           }
-          const uint32_t sbase = lane_base + kColSlot0 + 128 * slot + 16 * kk;
+          const uint32_t sbase = lane_base + kColSlot0 + 128 * slot + 32 * kk;
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
+          for (int j = 0; j < 4; ++j) {
             uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) split_tf32(dg[8 * j + e], hi[e], lo[e]);
+            for (int e = 0; e < 8; ++e) split_tf32(dg[j].v[e], hi[e], lo[e]);
             tmem_st8(sbase + 8 * j, hi);
             tmem_st8(sbase + 64 + 8 * j, lo);
           }
@@ -510,8 +542,7 @@ int lstm_tc_bwd(int64_t B, int64_t T, const float* w_hh, const float* gates, con
   lstm_tc_pack_whh_kernel<<<64, 256, 0, s>>>(w_hh, w_hi, w_lo);
   TcBwdArgs a{};
   a.w_hi = w_hi; a.w_lo = w_lo;
-  a.gates = reinterpret_cast<const float4*>(gates); a.c_seq = reinterpret_cast<const float4*>(c_seq);
-  a.dh_seq = reinterpret_cast<const float4*>(dh_seq); a.dh_last = dh_last; a.dG = reinterpret_cast<float4*>(dG);
+  a.gates = gates; a.c_seq = c_seq; a.dh_seq = dh_seq; a.dh_last = dh_last; a.dG = dG;
   a.B = B; a.T = T; a.G = cdiv(B, 32); a.dh_t0 = dh_t0;
   const size_t smem = (size_t)kN * kH * 4 * 2 + (size_t)kH * kRows * 4 + 64;
   cudaFuncSetAttribute(lstm_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

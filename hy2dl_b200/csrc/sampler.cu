@@ -14,10 +14,18 @@ struct GatherArgs {
   int32_t ri32;   // xT in RI32 [L][G][IP/4][32][4] (rows >= B of the last group are zero filled)
 };
 
-// grid: (ceil(B/32), L). Each block handles one time step of 32 samples; threads sweep the IP
-// columns of xT so that the [B][IP] slab of a step is written as one contiguous run.
-__global__ void __launch_bounds__(256) window_gather_kernel(GatherArgs a) {
-  const int64_t t = blockIdx.y;
+// grid: (ceil(B/32), ceil(L / kStepsPerBlock)).  A block owns 32 samples for a run of time steps: the
+// (sample, column) a thread writes does not depend on the step, so it resolves its sources once -- a
+// pointer into the resident dynamic series (advancing nd floats per step), a static attribute value
+// (constant over the window, basedataset.py:175-177) or zero padding -- and then streams one
+// contiguous [32][IP] slab per step.
+constexpr int kStepsPerBlock = 73;
+constexpr int kGatherThreads = 256;
+constexpr int kMaxPerThread = 8;   // 32 rows x IP <= 64 columns / 256 threads
+
+__global__ void __launch_bounds__(kGatherThreads) window_gather_kernel(GatherArgs a) {
+  const int64_t t0 = (int64_t)blockIdx.y * kStepsPerBlock;
+  const int64_t t1 = min(a.L, t0 + kStepsPerBlock);
   const int64_t b0 = (int64_t)blockIdx.x * 32;
   __shared__ int64_t s_row[32], s_basin[32];
   if (threadIdx.x < 32) {
@@ -25,48 +33,59 @@ __global__ void __launch_bounds__(256) window_gather_kernel(GatherArgs a) {
     if (b < a.B) {
       const int64_t bs = a.basin[b];
       s_basin[threadIdx.x] = bs;
-      s_row[threadIdx.x] = a.row0[bs] + a.end[b] - (a.L - 1) + t;   // resident row of step t
+      s_row[threadIdx.x] = a.row0[bs] + a.end[b] - (a.L - 1);   // resident row of step 0
     }
   }
   __syncthreads();
   const int64_t nb = min((int64_t)32, a.B - b0);
   const int64_t I = a.nd + a.ns;
-  if (a.ri32) {
-    // one block = one RI32 group of step t: [32 rows][32 floats], 8-float unit u of row r at u ^ (r & 3)
-    float* dst = a.xT + (t * gridDim.x + blockIdx.x) * 1024;
-    for (int64_t e = threadIdx.x; e < 1024; e += blockDim.x) {
-      const int64_t lb = e >> 5, c = ((((e >> 3) & 3) ^ (lb & 3)) << 3) | (e & 7);   // feature stored at word e
-      float v = 0.f;
+  const int per_slab = 32 * (int)a.IP;                          // floats of one step's slab (RI32: IP = 32)
+  const int n_mine = (per_slab + kGatherThreads - 1) / kGatherThreads;
+
+  const float* src[kMaxPerThread];   // dynamic source at step 0 (nullptr: constant)
+  float cst[kMaxPerThread];
+#pragma unroll
+  for (int i = 0; i < kMaxPerThread; ++i) {
+    src[i] = nullptr; cst[i] = 0.f;
+    const int e = threadIdx.x + i * kGatherThreads;
+    if (i < n_mine && e < per_slab) {
+      int64_t lb, c;
+      if (a.ri32) { lb = e >> 5; c = ((((e >> 3) & 3) ^ (lb & 3)) << 3) | (e & 7); }   // feature stored at word e
+      else { lb = e / a.IP; c = e - lb * a.IP; }
       if (lb < nb) {
-        if (c < a.nd) v = __ldg(a.x_d + s_row[lb] * a.nd + c);
-        else if (c < I) v = __ldg(a.x_s + s_basin[lb] * a.ns + (c - a.nd));
+        if (c < a.nd) src[i] = a.x_d + s_row[lb] * a.nd + c;
+        else if (c < I) cst[i] = __ldg(a.x_s + s_basin[lb] * a.ns + (c - a.nd));
       }
-      dst[e] = v;
     }
-  } else {
-    for (int64_t e = threadIdx.x; e < nb * a.IP; e += blockDim.x) {
-      const int64_t lb = e / a.IP, c = e - lb * a.IP;
-      float v = 0.f;
-      if (c < a.nd) v = __ldg(a.x_d + s_row[lb] * a.nd + c);
-      else if (c < I) v = __ldg(a.x_s + s_basin[lb] * a.ns + (c - a.nd));
-      a.xT[(t * a.B + b0) * a.IP + e] = v;
+  }
+  const int64_t rows_per_step = a.ri32 ? (int64_t)gridDim.x * 32 : a.B;
+  const int64_t slab_in_step = a.ri32 ? (int64_t)blockIdx.x * per_slab : b0 * a.IP;
+  const int live = a.ri32 ? per_slab : (int)(nb * a.IP);        // row-major: rows >= nb do not exist
+  for (int64_t t = t0; t < t1; ++t) {
+    float* dst = a.xT + t * rows_per_step * a.IP + slab_in_step;
+#pragma unroll
+    for (int i = 0; i < kMaxPerThread; ++i) {
+      const int e = threadIdx.x + i * kGatherThreads;
+      if (i < n_mine && e < live) dst[e] = src[i] ? __ldg(src[i] + t * a.nd) : cst[i];
     }
   }
   if (a.forc) {
-    for (int64_t e = threadIdx.x; e < nb * 3; e += blockDim.x) {
-      const int64_t c = e / nb, lb = e - c * nb;
-      const float* r = a.x_conc + s_row[lb] * a.nc;
+    for (int64_t e = threadIdx.x; e < (t1 - t0) * 3 * nb; e += kGatherThreads) {
+      const int64_t lb = e % nb, c = (e / nb) % 3, t = t0 + e / (3 * nb);
+      const float* r = a.x_conc + (s_row[lb] + t) * a.nc;
       float v;
       if (c < 2) v = __ldg(r + c);
       else v = (a.nc == 4) ? (__ldg(r + 2) + __ldg(r + 3)) / 2.f : __ldg(r + 2);
       a.forc[(t * 3 + c) * a.B + b0 + lb] = v;
     }
   }
-  const int64_t tl = t - (a.L - a.n_last);
-  if (tl >= 0 && threadIdx.x < nb) {
-    const int lb = threadIdx.x;
-    a.y_win[tl * a.B + b0 + lb] = __ldg(a.y_obs + s_row[lb]);
-    a.std_win[tl * a.B + b0 + lb] = __ldg(a.basin_std + s_basin[lb]);
+  const int64_t tw = a.L - a.n_last;                            // first step of the target window
+  for (int64_t e = threadIdx.x; e < (t1 - t0) * nb; e += kGatherThreads) {
+    const int64_t lb = e % nb, t = t0 + e / nb;
+    if (t >= tw) {
+      a.y_win[(t - tw) * a.B + b0 + lb] = __ldg(a.y_obs + s_row[lb] + t);
+      a.std_win[(t - tw) * a.B + b0 + lb] = __ldg(a.basin_std + s_basin[lb]);
+    }
   }
 }
 
@@ -119,8 +138,9 @@ extern "C" int hy2dl_window_gather(const float* x_d, const float* x_s, const flo
   HY_REQUIRE(layout != HY2DL_LAYOUT_RI32 || IP == 32, HY2DL_ERR_SHAPE, "hy2dl_window_gather: RI32 streams are 32 columns wide (IP=%lld)", (long long)IP);
   GatherArgs a{x_d, x_s, x_conc, y_obs, basin_std, row0, basin, end, B, L, n_last, nd, ns, nc, IP, xT, forc, y_win, std_win,
                layout == HY2DL_LAYOUT_RI32};
-  dim3 grid((unsigned)cdiv(B, 32), (unsigned)L);
-  window_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  HY_REQUIRE(IP <= 64, HY2DL_ERR_SHAPE, "hy2dl_window_gather: IP=%lld exceeds 64", (long long)IP);
+  dim3 grid((unsigned)cdiv(B, 32), (unsigned)cdiv(L, kStepsPerBlock));
+  window_gather_kernel<<<grid, kGatherThreads, 0, (cudaStream_t)stream>>>(a);
   HY_LAUNCH_CHECK();
   return HY2DL_OK;
 }

@@ -91,6 +91,24 @@ __device__ __forceinline__ float4 ri32_ld(const float4* base, int64_t t, int64_t
 __device__ __forceinline__ void ri32_st(float4* base, int64_t t, int64_t G, int64_t gidx, int FB, int c, int row, float4 v) {
   base[ri32_idx4(t, G, gidx, FB, c, row)] = v;
 }
+// 32-byte unit U = feature / 8 of row `row`: float index.  One unit = one sector = one 256-bit access.
+__device__ __forceinline__ int64_t ri32_unit(int64_t t, int64_t G, int64_t gidx, int FB, int U, int row) {
+  return ((t * G + gidx) * FB + (U >> 2)) * 1024 + row * 32 + (((U & 3) ^ (row & 3)) << 3);
+}
+struct f8 { float v[8]; };
+__device__ __forceinline__ f8 ldg256(const float* p) {                    // read-only path, 32-byte aligned
+  f8 r;
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg256(float* p, const f8& r) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]),
+               "f"(r.v[3]), "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7])
+               : "memory");
+}
+__device__ __forceinline__ f8 f8_zero() { f8 r; for (int i = 0; i < 8; ++i) r.v[i] = 0.f; return r; }
 
 // ---- MMA issue (single thread) ---------------------------------------------------------------
 // D[tmem] (+)= A[tmem] * B[smem]
@@ -167,6 +185,8 @@ __device__ __forceinline__ void split_tf32_rr(float x, uint32_t& hi, uint32_t& l
 }
 
 // fast, accurate-enough activations on the MUFU ex2/rcp path (abs error ~1e-7)
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
