@@ -22,9 +22,13 @@
 // [4H, I] / [4H, H] / [4H] layouts.
 //
 // Warp roles (320 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer, warps 2-9 = split
-// converters + accumulator drain + epilogue.  3 raw stages (48 KB each) + 1 lo buffer.
+// converters + accumulator drain + epilogue.  3 raw stages (48 KB each) + A_lo + 2 x B_lo.  The pipeline unit is
+// half a slab (128 gate columns): while the tensor core works on one half the converters split the next, so
+// the MMA stream is not interrupted by the split.  The kernel is shared-memory-bandwidth bound (SS-mode MMAs
+// read 7.5 KB per 56-cycle instruction), which is why the landed fp32 words double as the hi operand.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace hy2dl {
 namespace tc {
@@ -48,19 +52,21 @@ struct TcWgradArgs {
   const float* x;    // RI32 F = 32
   float* partial;    // [grid][256][kND]
   int64_t T, G;
+  int raw_hi;        // leave the landed fp32 words in place as the "hi" operand: kind::tf32 ignores the low 13 bits
+                     // (verified, tools/dbg_rz.py with HY2DL_WG_RAWHI=0/1), which saves a third of the split's smem traffic
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* smem_raw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_lo = smem_raw + kWgStages * kStageBytes;          // [A_lo | B_lo]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lo + kStageBytes);
+  uint8_t* s_lo = smem_raw + kWgStages * kStageBytes;          // [A_lo (two halves) | B_lo[0] | B_lo[1]]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lo + kABytes + 2 * kBBytes);
   uint64_t* bar_full = bars;                       // [stages] producer (tx bytes) -> converters
   uint64_t* bar_raw_free = bars + kWgStages;       // [stages] MMA commit -> producer
-  uint64_t* bar_conv = bars + 2 * kWgStages;       // converters -> MMA
-  uint64_t* bar_lo_free = bar_conv + 1;            // MMA commit -> converters
-  uint64_t* bar_done = bar_conv + 2;               // all MMAs retired -> epilogue
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_conv + 3);
+  uint64_t* bar_conv = bars + 2 * kWgStages;       // [2] converters -> MMA, per half of the gate columns
+  uint64_t* bar_lo_free = bar_conv + 2;            // [2] MMA commit -> converters, per half
+  uint64_t* bar_done = bar_conv + 4;               // all MMAs retired -> epilogue
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_conv + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_groups = a.T * a.G;
@@ -69,7 +75,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
   // ---- setup: barriers, TMEM, constant block (hi: column 0 of every row = 1; lo: 0)
   if (tid == 0) {
     for (int s = 0; s < kWgStages; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_raw_free + s, 1); }
-    mbar_init(bar_conv, kWgConv); mbar_init(bar_lo_free, 1); mbar_init(bar_done, 1);
+    for (int hf = 0; hf < 2; ++hf) { mbar_init(bar_conv + hf, kWgConv); mbar_init(bar_lo_free + hf, 1); }
+    mbar_init(bar_done, 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(s_tmem, 512);
@@ -78,6 +85,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
     for (int s = 0; s < kWgStages; ++s)
       reinterpret_cast<float4*>(smem_raw + s * kStageBytes + kABytes + 3 * kBlk)[e] = one;
     reinterpret_cast<float4*>(s_lo + kABytes + 3 * kBlk)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    reinterpret_cast<float4*>(s_lo + kABytes + kBBytes + 3 * kBlk)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   fence_async_smem();
   tc_fence_before();
@@ -104,29 +112,29 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
   } else if (warp == 1) {
     // =========================== MMA issuer =====================================================
     if (lane == 0) {
-      const uint32_t lo_a = smem_u32(s_lo), lo_b = lo_a + kABytes;
+      const uint32_t lo_a = smem_u32(s_lo);
       const uint32_t idesc = idesc_tf32(128, kND, 1, 1);
       for (int64_t i = 0; i < n_my; ++i) {
         const int s = (int)(i % kWgStages);
         const uint32_t hi_a = smem_u32(smem_raw + s * kStageBytes), hi_b = hi_a + kABytes;
-        mbar_wait(bar_conv, (uint32_t)(i & 1));
-        tc_fence_after();
-        const uint32_t dbuf = tmem;                                         // chain accumulator D
-        const bool first = (i % kChain) == 0;                               // first slab of a chain overwrites
+        const uint32_t lo_b = lo_a + kABytes + (uint32_t)(i & 1) * kBBytes;
+        const bool first = (i % kChain) == 0;                               // first slab of a chain overwrites D
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {           // 8 sequences (K = 8 = two 4-row groups) per MMA
-          const uint64_t b_hi = smem_desc_mn32(hi_b + kb * 1024, kBlk, 512), b_lo = smem_desc_mn32(lo_b + kb * 1024, kBlk, 512);
+        for (int hf = 0; hf < 2; ++hf) {           // gate columns [128 hf, 128 hf + 128): the pipeline unit
+          mbar_wait(bar_conv + hf, (uint32_t)(i & 1));
+          tc_fence_after();
+          const uint32_t d = tmem + 128 * hf;
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {         // gate columns [128 hf, 128 hf + 128)
+          for (int kb = 0; kb < 4; ++kb) {         // 8 sequences (K = 8 = two 4-row groups) per MMA
+            const uint64_t b_hi = smem_desc_mn32(hi_b + kb * 1024, kBlk, 512), b_lo = smem_desc_mn32(lo_b + kb * 1024, kBlk, 512);
             const uint64_t a_hi = smem_desc_mn32(hi_a + hf * 4 * kBlk + kb * 1024, kBlk, 512);
             const uint64_t a_lo = smem_desc_mn32(lo_a + hf * 4 * kBlk + kb * 1024, kBlk, 512);
-            const uint32_t d = dbuf + 128 * hf;
             mma_tf32_ss(d, a_lo, b_hi, idesc, !(first && kb == 0));
             mma_tf32_ss(d, a_hi, b_lo, idesc, 1);
             mma_tf32_ss(d, a_hi, b_hi, idesc, 1);
           }
+          mma_commit(bar_lo_free + hf);
         }
-        mma_commit(bar_lo_free);
         mma_commit(bar_raw_free + s);
       }
       mma_commit(bar_done);
@@ -159,36 +167,55 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
       tmem_st_wait();
       tc_fence_before();
     };
-    float4* lo = reinterpret_cast<float4*>(s_lo);
+    float4* lo_a4 = reinterpret_cast<float4*>(s_lo);
     for (int64_t i = 0; i < n_my; ++i) {
       const int s = (int)(i % kWgStages);
       const int64_t id = blockIdx.x + i * gridDim.x, t = id / a.G;
       float4* raw = reinterpret_cast<float4*>(smem_raw + s * kStageBytes);
-      mbar_wait(bar_full + s, (uint32_t)((i / kWgStages) & 1));
-      if (i > 0) mbar_wait(bar_lo_free, (uint32_t)((i - 1) & 1));       // => every MMA up to slab i-1 has retired
-      if (i > 0 && (i % kChain) == 0) drain();                          // chain complete; slab i will overwrite D
+      float4* lo_b4 = reinterpret_cast<float4*>(s_lo + kABytes + (i & 1) * kBBytes);
+      constexpr int kA4 = kABytes / 16, kBlk4 = kBlk / 16;
+      // hi/lo split of float4 `e` of the stage: A part -> lo_a4, B part -> lo_b4 (B_lo is double buffered by slab)
       auto split4 = [&](int e) {
         const float4 v = raw[e];
+        float4* lo = e < kA4 ? lo_a4 + e : lo_b4 + (e - kA4);
         float4 hv, lv;
+        if (a.raw_hi) {   // hi = truncation (what the tensor core reads from the raw word), lo = exact remainder
+          hv.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); hv.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+          hv.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); hv.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+          *lo = make_float4(v.x - hv.x, v.y - hv.y, v.z - hv.z, v.w - hv.w);
+          return;
+        }
         hv.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u); lv.x = v.x - hv.x;
         hv.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u); lv.y = v.y - hv.y;
         hv.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u); lv.z = v.z - hv.z;
         hv.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u); lv.w = v.w - hv.w;
         raw[e] = hv;
-        lo[e] = lv;
+        *lo = lv;
       };
-      constexpr int kA4 = kABytes / 16, kBlk4 = kBlk / 16;
-#pragma unroll 2
-      for (int e = ct; e < kA4; e += kWgConv) split4(e);                        // dG
+      mbar_wait(bar_full + s, (uint32_t)((i / kWgStages) & 1));
+      // ---- half 0: the B operand (shared by both halves) + gate columns [0, 128)
+      if (i > 0) mbar_wait(bar_lo_free + 0, (uint32_t)((i - 1) & 1));    // MMAs of (slab i-1, half 0) and everything before retired
+      if (i > 0 && (i % kChain) == 0) {                                   // chain complete: S += D before slab i overwrites D
+        mbar_wait(bar_lo_free + 1, (uint32_t)((i - 1) & 1));
+        drain();
+      }
       for (int e = ct; e < kBlk4; e += kWgConv) split4(kA4 + 2 * kBlk4 + e);    // x
       if (t > 0) {
         for (int e = ct; e < 2 * kBlk4; e += kWgConv) split4(kA4 + e);          // h_{t-1}
       } else {                                                                  // h_{-1} = 0
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int e = ct; e < 2 * kBlk4; e += kWgConv) { raw[kA4 + e] = z; lo[kA4 + e] = z; }
+        for (int e = ct; e < 2 * kBlk4; e += kWgConv) { raw[kA4 + e] = z; lo_b4[e] = z; }
       }
+#pragma unroll 4
+      for (int e = ct; e < kA4 / 2; e += kWgConv) split4(e);
       fence_async_smem();
-      mbar_arrive(bar_conv);
+      mbar_arrive(bar_conv + 0);
+      // ---- half 1: gate columns [128, 256)
+      if (i > 0) mbar_wait(bar_lo_free + 1, (uint32_t)((i - 1) & 1));
+#pragma unroll 4
+      for (int e = ct; e < kA4 / 2; e += kWgConv) split4(kA4 / 2 + e);
+      fence_async_smem();
+      mbar_arrive(bar_conv + 1);
     }
     // last chain, then this CTA's sums
     mbar_wait(bar_done, 0);
@@ -243,7 +270,9 @@ int lstm_tc_wgrad(const float* dG, const float* h_seq, const float* x_ri, int64_
   TcWgradArgs a{};
   a.dG = dG; a.h = h_seq; a.x = x_ri; a.partial = reinterpret_cast<float*>(ws);
   a.T = T; a.G = cdiv(B, 32);
-  const size_t smem = (size_t)(kWgStages + 1) * kStageBytes + 128 + 1024;
+  static const int raw_hi = [] { const char* e = getenv("HY2DL_WG_RAWHI"); return e ? atoi(e) : 1; }();   // 0: write the rounded hi back in place
+  a.raw_hi = raw_hi;
+  const size_t smem = (size_t)kWgStages * kStageBytes + kABytes + 2 * kBBytes + 128 + 1024;
   const int grid = wg_grid(T, a.G);
   cudaFuncSetAttribute(lstm_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   lstm_tc_wgrad_kernel<<<grid, kWgThreads, smem, s>>>(a);

@@ -7,7 +7,7 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-n
 rows = list(csv.reader(io.StringIO(out)))
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
-body = [r for r in rows[2:] if len(r) == len(hdr)]
+body = [r for r in rows[2:] if len(r) == len(hdr) and r[ix["# Samples"]].isdigit()]
 tot = sum(int(r[ix["# Samples"]] or 0) for r in body)
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 agg = {s: sum(int(r[ix[s]] or 0) for r in body) for s in stalls}
