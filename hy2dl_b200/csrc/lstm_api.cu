@@ -26,8 +26,8 @@ static int check_lstm_shape(const char* who, int64_t B, int64_t T, int64_t I, in
   HY_REQUIRE(B > 0 && T > 0, HY2DL_ERR_SHAPE, "%s: empty batch or sequence (B=%lld T=%lld)", who, (long long)B, (long long)T);
   HY_REQUIRE(H == 64 || H == 128 || H == 256, HY2DL_ERR_SHAPE, "%s: hidden_size=%lld not supported (64, 128, 256)", who, (long long)H);
   if (precision == HY2DL_PREC_TF32X3) {
-    HY_REQUIRE(I > 0 && I <= 32 && IP == 32, HY2DL_ERR_SHAPE,
-               "%s: the tf32x3 path takes input_size <= 32 in a 32-column RI32 stream (I=%lld IP=%lld)", who, (long long)I, (long long)IP);
+    HY_REQUIRE(I > 0 && I <= 31 && IP == 32, HY2DL_ERR_SHAPE,
+               "%s: the tf32x3 path takes input_size <= 31 in a 32-column RI32 stream (I=%lld IP=%lld)", who, (long long)I, (long long)IP);
     return HY2DL_OK;
   }
   HY_REQUIRE(I > 0 && I <= 64 && IP == round_up(I, 8), HY2DL_ERR_SHAPE,
@@ -57,7 +57,7 @@ extern "C" int hy2dl_lstm_fwd(const float* xT, int64_t B, int64_t T, int64_t I, 
   HY_REQUIRE(h_seq || h_last, HY2DL_ERR_ALIGN, "hy2dl_lstm_fwd: both h_seq and h_last are null");
   if (precision == HY2DL_PREC_TF32X3) {
     HY_REQUIRE(tc::lstm_tc_supported(I, H), HY2DL_ERR_SHAPE,
-               "hy2dl_lstm_fwd: the tf32x3 tensor-core path supports hidden_size 64 and input_size <= 32 (got H=%lld I=%lld)",
+               "hy2dl_lstm_fwd: the tf32x3 tensor-core path supports hidden_size 64 and input_size <= 31 (got H=%lld I=%lld)",
                (long long)H, (long long)I);
     return tc::lstm_tc_fwd(xT, B, T, I, IP, w_ih, w_hh, b_ih, b_hh, h_seq, c_seq, gates, h_last, ws, ws_bytes,
                            (cudaStream_t)stream);
@@ -91,7 +91,7 @@ extern "C" int hy2dl_lstm_wgrad(const float* dG, const float* h_seq, const float
   HY_PTR(dG); HY_PTR(h_seq); HY_PTR(xT); HY_PTR(dw_ih); HY_PTR(dw_hh); HY_PTR(db);
   if (precision == HY2DL_PREC_TF32X3) {
     HY_REQUIRE(tc::lstm_tc_supported(I, H), HY2DL_ERR_SHAPE,
-               "hy2dl_lstm_wgrad: the tf32x3 tensor-core path supports hidden_size 64 and input_size <= 32 (got H=%lld I=%lld)",
+               "hy2dl_lstm_wgrad: the tf32x3 tensor-core path supports hidden_size 64 and input_size <= 31 (got H=%lld I=%lld)",
                (long long)H, (long long)I);
     return tc::lstm_tc_wgrad(dG, h_seq, xT, B, T, I, IP, dw_ih, dw_hh, db, ws, ws_bytes, (cudaStream_t)stream);
   }

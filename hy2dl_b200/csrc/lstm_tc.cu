@@ -35,23 +35,29 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColD = 0, kColAhi = 256, kColAlo = 384;   // K <= 128 columns each
 
 // ---- weight packing for the tc path ------------------------------------------------------------
-// Wt_hi / Wt_lo: [K/4][256][4] with n = 4u + g; k < IP: W_ih (zero padded), else W_hh.  bias_n[256].
+// Wt_hi / Wt_lo: [K/4][256][4] with n = 4u + g; k < IP: W_ih (zero padded), else W_hh.
+// Two things are folded into the packed weights so that the epilogue gets exp2 arguments directly:
+//   * every row is multiplied by -log2(e) (gates i, f, o) or -2 log2(e) (gate g): the accumulator is
+//     z' with e^-z = 2^z' (sigmoid) and e^-2z = 2^z' (tanh);
+//   * the bias (b_ih + b_hh, scaled the same way) sits in input column IP-1, which the forward kernel
+//     feeds with the constant 1 (input_size <= 31 leaves that column free).
 __global__ void lstm_tc_pack_w_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                                       const float* __restrict__ b_ih, const float* __restrict__ b_hh, int I, int IP,
-                                      float* __restrict__ w_hi, float* __restrict__ w_lo, float* __restrict__ bias_n) {
+                                      float* __restrict__ w_hi, float* __restrict__ w_lo) {
+  constexpr float kL2E = 1.4426950408889634f;
   const int K = IP + kH;
   const int total = K * kN;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int kk = e & 3, n = (e >> 2) & 255, kc = e >> 10;
     const int k = kc * 4 + kk, u = n >> 2, g = n & 3, row = g * kH + u;
     float v;
-    if (k < IP) v = k < I ? w_ih[row * I + k] : 0.f;
+    if (k < IP) v = k < I ? w_ih[row * I + k] : (k == IP - 1 ? b_ih[row] + b_hh[row] : 0.f);
     else v = w_hh[row * kH + (k - IP)];
+    v *= (g == 2) ? -2.f * kL2E : -kL2E;
     uint32_t hi, lo;
     split_tf32_rr(v, hi, lo);
     w_hi[e] = __uint_as_float(hi);
     w_lo[e] = __uint_as_float(lo);
-    if (k == 0) bias_n[n] = b_ih[row] + b_hh[row];
   }
 }
 
@@ -59,7 +65,6 @@ struct TcFwdArgs {
   const float* x;       // RI32, F = IP = 32
   const float* w_hi;    // [K/4][256][4]
   const float* w_lo;
-  const float* bias_n;  // [256]
   float* h_seq;         // RI32 F = 64   (nullable)
   float* c_seq;         // RI32 F = 64   (nullable)
   float* gates;         // RI32 F = 256, n = 4u + g (nullable)
@@ -68,16 +73,17 @@ struct TcFwdArgs {
   int IP;
 };
 
-// One reciprocal for the four gates of a hidden unit: with A = 1 + e^-zi, F = 1 + e^-zf, G = 1 + e^-2zg,
-// O = 1 + e^-zo and r = 1 / (A F G O):  i = r F G O, f = r A G O, o = r A F G, g = tanh(zg) = (2 - G) r A F O.
+// One reciprocal for the four gates of a hidden unit.  The accumulator holds z' = -log2(e) z (i, f, o) and
+// -2 log2(e) z (g), bias included (see lstm_tc_pack_w_kernel).  With A = 1 + 2^zi', F = 1 + 2^zf', G = 1 + 2^zg',
+// O = 1 + 2^zo' and r = 1 / (A F G O):  i = r F G O, f = r A G O, o = r A F G, g = tanh(zg) = (2 - G) r A F O.
 // Arguments are clamped (sigmoid below -20 / tanh below -10 differ from their limits by < 4e-9) so that the
 // product stays finite.  5 MUFU (4 ex2 + rcp) instead of 8: the XU pipe is the epilogue's narrowest resource.
 __device__ __forceinline__ void lstm_gates(float zi, float zf, float zg, float zo, float& gi, float& gf, float& gg, float& go) {
-  constexpr float kL2E = 1.4426950408889634f;
-  const float A = 1.f + fast_ex2(-kL2E * fmaxf(zi, -20.f));
-  const float F = 1.f + fast_ex2(-kL2E * fmaxf(zf, -20.f));
-  const float G = 1.f + fast_ex2(-2.f * kL2E * fmaxf(zg, -10.f));
-  const float O = 1.f + fast_ex2(-kL2E * fmaxf(zo, -20.f));
+  constexpr float kClamp = 28.853900817779268f;   // 20 log2(e)
+  const float A = 1.f + fast_ex2(fminf(zi, kClamp));
+  const float F = 1.f + fast_ex2(fminf(zf, kClamp));
+  const float G = 1.f + fast_ex2(fminf(zg, kClamp));
+  const float O = 1.f + fast_ex2(fminf(zo, kClamp));
   const float AF = A * F, GO = G * O;
   const float r = fast_rcp(AF * GO);
   const float rAF = r * AF, rGO = r * GO;
@@ -85,6 +91,10 @@ __device__ __forceinline__ void lstm_gates(float zi, float zf, float zg, float z
   gf = rGO * A;
   go = rAF * G;
   gg = (2.f - G) * (rAF * O);
+}
+// tanh(x) = 1 - 2 / (1 + e^2x): 2 MUFU + 3 FMA-pipe instructions; saturates correctly at +-inf
+__device__ __forceinline__ float tanh_mufu(float x) {
+  return fmaf(-2.f, fast_rcp(1.f + fast_ex2(2.885390081777927f * x)), 1.f);
 }
 
 // NSETS = 2 or 4 sets of four row warps: set s owns hidden units [s*64/NSETS, (s+1)*64/NSETS) of all 128
@@ -103,8 +113,7 @@ __global__ void __launch_bounds__(128 * NSETS + 32, 1) lstm_tc_fwd_kernel(TcFwdA
   const int IP = a.IP, K = IP + kH, KC = K / 4;
   float* s_whi = reinterpret_cast<float*>(smem_raw);
   float* s_wlo = s_whi + K * kN;
-  float* s_bias = s_wlo + K * kN;
-  uint64_t* bar_a_ready = reinterpret_cast<uint64_t*>(s_bias + kN);   // all row threads -> MMA warp
+  uint64_t* bar_a_ready = reinterpret_cast<uint64_t*>(s_wlo + K * kN);   // all row threads -> MMA warp
   uint64_t* bar_done = bar_a_ready + 1;                               // [NSETS] MMA commit of set s -> row threads
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_done + NSETS);
 
@@ -118,7 +127,6 @@ __global__ void __launch_bounds__(128 * NSETS + 32, 1) lstm_tc_fwd_kernel(TcFwdA
     float4* d_hi = reinterpret_cast<float4*>(s_whi);
     float4* d_lo = reinterpret_cast<float4*>(s_wlo);
     for (int e = tid; e < KC * kN; e += kThreads) { d_hi[e] = __ldg(g_hi + e); d_lo[e] = __ldg(g_lo + e); }
-    for (int e = tid; e < kN; e += kThreads) s_bias[e] = __ldg(a.bias_n + e);
   }
   if (tid == 0) {
     mbar_init(bar_a_ready, 128 * NSETS);
@@ -139,6 +147,25 @@ __global__ void __launch_bounds__(128 * NSETS + 32, 1) lstm_tc_fwd_kernel(TcFwdA
     const bool live = gidx < a.G;                                 // warp-uniform
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     constexpr int kXU = 4 / NSETS;                                // x units (8 columns) this thread moves
+    // this thread's row in the RI32 streams: base pointers at step 0 (advanced once per step) + the four
+    // swizzled unit offsets of its row
+    const int64_t row_off = (int64_t)gidx * 1024 + lane * 32;
+    const float* xp = a.x + row_off;
+    float* hp = a.h_seq ? a.h_seq + 2 * (int64_t)gidx * 1024 + lane * 32 : nullptr;
+    float* cp = a.c_seq ? a.c_seq + 2 * (int64_t)gidx * 1024 + lane * 32 : nullptr;
+    float* gp = a.gates ? a.gates + 8 * (int64_t)gidx * 1024 + lane * 32 : nullptr;
+    const int64_t xs = a.G * 1024;                                // floats per step of a 32-column stream
+    int swz[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) swz[j] = (j ^ (lane & 3)) << 3;
+    auto put_x = [&](const f8& v, int U) {                        // x unit U -> A operand; column IP-1 carries the bias 1
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) split_tf32(v.v[e], hi[e], lo[e]);
+      if (U == 3) { hi[7] = 0x3F800000u; lo[7] = 0u; }
+      tmem_st8(lane_base + kColAhi + 8 * U, hi);
+      tmem_st8(lane_base + kColAlo + 8 * U, lo);
+    };
     float c[kUPT];
 #pragma unroll
     for (int u = 0; u < kUPT; ++u) c[u] = 0.f;
@@ -154,13 +181,9 @@ __global__ void __launch_bounds__(128 * NSETS + 32, 1) lstm_tc_fwd_kernel(TcFwdA
 #pragma unroll
       for (int j = 0; j < kXU; ++j) {               // the 32 input columns = 4 units of 8
         const int U = kXU * set + j;
-        uint32_t hi[8], lo[8];
         f8 v = f8_zero();
-        if (live) v = ldg256(a.x + ri32_unit(0, a.G, gidx, 1, U, lane));
-#pragma unroll
-        for (int e = 0; e < 8; ++e) split_tf32(v.v[e], hi[e], lo[e]);
-        tmem_st8(lane_base + kColAhi + 8 * U, hi);
-        tmem_st8(lane_base + kColAlo + 8 * U, lo);
+        if (live) v = ldg256(xp + swz[U]);
+        put_x(v, U);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -174,7 +197,7 @@ __global__ void __launch_bounds__(128 * NSETS + 32, 1) lstm_tc_fwd_kernel(TcFwdA
 #pragma unroll
       for (int j = 0; j < kXU; ++j) {
         xn[j] = f8_zero();
-        if (more && live) xn[j] = ldg256(a.x + ri32_unit(t + 1, a.G, gidx, 1, kXU * set + j, lane));
+        if (more && live) xn[j] = ldg256(xp + (t + 1) * xs + swz[kXU * set + j]);
       }
       mbar_wait(bar_done + set, (uint32_t)(t & 1));
       tc_fence_after();
@@ -189,13 +212,12 @@ __global__ void __launch_bounds__(128 * NSETS + 32, 1) lstm_tc_fwd_kernel(TcFwdA
         f8 hv, cv, gv[4];
 #pragma unroll
         for (int uu = 0; uu < 8; ++uu) {
-          const float4 bb = *reinterpret_cast<const float4*>(s_bias + 4 * (8 * qg + uu));
           float gi, gf, gg, go;
-          lstm_gates(__uint_as_float(v[4 * uu + 0]) + bb.x, __uint_as_float(v[4 * uu + 1]) + bb.y,
-                     __uint_as_float(v[4 * uu + 2]) + bb.z, __uint_as_float(v[4 * uu + 3]) + bb.w, gi, gf, gg, go);
-          const float cn = gf * c[8 * q + uu] + gi * gg;
+          lstm_gates(__uint_as_float(v[4 * uu + 0]), __uint_as_float(v[4 * uu + 1]), __uint_as_float(v[4 * uu + 2]),
+                     __uint_as_float(v[4 * uu + 3]), gi, gf, gg, go);
+          const float cn = fmaf(gf, c[8 * q + uu], gi * gg);
           c[8 * q + uu] = cn;
-          hv.v[uu] = go * fast_tanh(cn);
+          hv.v[uu] = go * tanh_mufu(cn);
           cv.v[uu] = cn;
           gv[uu >> 1].v[4 * (uu & 1) + 0] = gi; gv[uu >> 1].v[4 * (uu & 1) + 1] = gf;
           gv[uu >> 1].v[4 * (uu & 1) + 2] = gg; gv[uu >> 1].v[4 * (uu & 1) + 3] = go;
@@ -203,11 +225,11 @@ __global__ void __launch_bounds__(128 * NSETS + 32, 1) lstm_tc_fwd_kernel(TcFwdA
         hkeep[q] = hv;
         if (live) {
           // one 256-bit store = one 32-byte sector of this row; the four gate units are its 128-byte line
-          if (a.h_seq) stg256(a.h_seq + ri32_unit(t, a.G, gidx, 2, qg, lane), hv);
-          if (a.c_seq) stg256(a.c_seq + ri32_unit(t, a.G, gidx, 2, qg, lane), cv);
-          if (a.gates) {
+          if (hp) stg256(hp + 2 * t * xs + (qg >> 2) * 1024 + swz[qg & 3], hv);
+          if (cp) stg256(cp + 2 * t * xs + (qg >> 2) * 1024 + swz[qg & 3], cv);
+          if (gp) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) stg256(a.gates + ri32_unit(t, a.G, gidx, 8, 4 * qg + j, lane), gv[j]);
+            for (int j = 0; j < 4; ++j) stg256(gp + 8 * t * xs + qg * 1024 + swz[j], gv[j]);
           }
           if (a.h_last && t == a.T - 1) {
             const int64_t b = gidx * 32 + lane;
@@ -233,13 +255,7 @@ __global__ void __launch_bounds__(128 * NSETS + 32, 1) lstm_tc_fwd_kernel(TcFwdA
           tmem_st8(lane_base + kColAlo + IP + 8 * (kQ * set + q), lo);
         }
 #pragma unroll
-        for (int j = 0; j < kXU; ++j) {
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) split_tf32(xn[j].v[e], hi[e], lo[e]);
-          tmem_st8(lane_base + kColAhi + 8 * (kXU * set + j), hi);
-          tmem_st8(lane_base + kColAlo + 8 * (kXU * set + j), lo);
-        }
+        for (int j = 0; j < kXU; ++j) put_x(xn[j], kXU * set + j);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar_a_ready);
@@ -282,7 +298,7 @@ __global__ void __launch_bounds__(128 * NSETS + 32, 1) lstm_tc_fwd_kernel(TcFwdA
   if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
 }
 
-static size_t tc_fwd_smem(int K) { return (size_t)K * kN * 4 * 2 + kN * 4 + 128; }
+static size_t tc_fwd_smem(int K) { return (size_t)K * kN * 4 * 2 + 128; }
 constexpr int kFwdSets = 2;   // measured on B200 (B = 18944, T = 365): 2 sets 3.01 ms, 4 sets 3.40 ms, 1 set 4.06 ms
 
 int64_t lstm_tc_wgrad_workspace(int64_t B, int64_t T, int64_t I);
@@ -290,13 +306,13 @@ int64_t lstm_tc_wgrad_workspace(int64_t B, int64_t T, int64_t I);
 int64_t lstm_tc_workspace(int kind, int64_t B, int64_t T, int64_t I, int64_t H) {
   (void)I;
   const int64_t IP = 32, K = IP + H;      // the RI32 input stream is always 32 columns wide
-  if (kind == HY2DL_WS_LSTM_FWD) return sizeof(float) * (2 * K * 4 * H + 4 * H);
+  if (kind == HY2DL_WS_LSTM_FWD) return sizeof(float) * (2 * K * 4 * H);
   if (kind == HY2DL_WS_LSTM_BWD) return sizeof(float) * 2 * 4 * H * H;
   if (kind == HY2DL_WS_LSTM_WGRAD) return lstm_tc_wgrad_workspace(B, T, I);
   return 16;
 }
 
-bool lstm_tc_supported(int64_t I, int64_t H) { return H == 64 && I <= 32; }
+bool lstm_tc_supported(int64_t I, int64_t H) { return H == 64 && I <= 31; }   // column 31 of the input stream carries the bias
 
 int lstm_tc_fwd(const float* x_ri, int64_t B, int64_t T, int64_t I, int64_t IP, const float* w_ih, const float* w_hh,
                 const float* b_ih, const float* b_hh, float* h_seq, float* c_seq, float* gates, float* h_last, void* ws,
@@ -307,11 +323,10 @@ int lstm_tc_fwd(const float* x_ri, int64_t B, int64_t T, int64_t I, int64_t IP, 
              (long long)ws_bytes, (long long)need);
   float* w_hi = reinterpret_cast<float*>(ws);
   float* w_lo = w_hi + K * kN;
-  float* bias_n = w_lo + K * kN;
-  lstm_tc_pack_w_kernel<<<96, 256, 0, s>>>(w_ih, w_hh, b_ih, b_hh, (int)I, (int)IP, w_hi, w_lo, bias_n);
+  lstm_tc_pack_w_kernel<<<96, 256, 0, s>>>(w_ih, w_hh, b_ih, b_hh, (int)I, (int)IP, w_hi, w_lo);
   TcFwdArgs a{};
   a.x = x_ri;
-  a.w_hi = w_hi; a.w_lo = w_lo; a.bias_n = bias_n;
+  a.w_hi = w_hi; a.w_lo = w_lo;
   a.h_seq = h_seq; a.c_seq = c_seq; a.gates = gates; a.h_last = h_last;
   a.B = B; a.T = T; a.G = cdiv(B, 32); a.IP = (int)IP;
   const size_t smem = tc_fwd_smem(K);

@@ -157,8 +157,8 @@ class ResidentDataset:
         _lib.require_cuda(self.d_x_d, "resident series")
         B, L, n_last, dev = basin.numel(), self.sequence_length, self.predict_last_n, self.device
         ri = self.layout == "ri32"
-        if ri and self.input_size > 32:
-            raise RuntimeError(f"hy2dl_b200: the RI32 / tf32x3 path takes input_size <= 32 (got {self.input_size})")
+        if ri and self.input_size > 31:
+            raise RuntimeError(f"hy2dl_b200: the RI32 / tf32x3 path takes input_size <= 31 (got {self.input_size})")
         IP = 32 if ri else self.IP
         xT = (torch.empty(L, (B + 31) // 32, 1, 32, 32, dtype=torch.float32, device=dev) if ri
               else torch.empty(L, B, IP, dtype=torch.float32, device=dev))

@@ -73,14 +73,14 @@ def layout_of(precision: str) -> str:
 
 
 def pack_x(x: torch.Tensor, layout: str = "rowmajor") -> torch.Tensor:
-    """[B,T,I] -> native [T,B,IP] (layout "rowmajor") or RI32 [T,G,1,32,32] (layout "ri32", I <= 32)."""
+    """[B,T,I] -> native [T,B,IP] (layout "rowmajor") or RI32 [T,G,1,32,32] (layout "ri32", I <= 31)."""
     require_cuda(x, "x_lstm")
     x = x.detach().contiguous()
     B, T, I = x.shape
     IP = round_up(I, 8)
     if layout == "ri32":
-        if I > 32:
-            raise RuntimeError(f"hy2dl_b200: the tf32x3 path takes input_size <= 32 (got {I})")
+        if I > 31:
+            raise RuntimeError(f"hy2dl_b200: the tf32x3 path takes input_size <= 31 (got {I})")
         xT = torch.empty(T, (B + 31) // 32, 1, 32, 32, dtype=torch.float32, device=x.device)
         call("hy2dl_pack_x", ptr(x), B, T, I, 32, ptr(xT), _lib.LAYOUT_RI32, stream())
     else:

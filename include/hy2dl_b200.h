@@ -27,7 +27,7 @@
  *   32-feature block) slab is 4 KB contiguous and is exactly the MN-major SWIZZLE_128B_BASE32B UMMA
  *   operand tile of the weight-gradient GEMM, while the row-owning threads of the recurrent kernels
  *   move whole 32-byte sectors / 128-byte lines.  F is a multiple of 32: xT is 32 columns wide
- *   (IP = 32, I <= 32).  gates/dG order their 4H columns as n = 4*unit + gate.
+ *   (IP = 32, I <= 31: column 31 carries the bias inside the forward kernel).  gates/dG order their 4H columns as n = 4*unit + gate.
  *   N = B*m series (sample b, member j -> n = b*m + j)
  *   par     planes: dynamic parameter -> [T_sim][N], static parameter -> [N]   (see hy2dl_parmap)
  *   states  [T][5][N]       bucket storages after each step

@@ -125,9 +125,11 @@ def test_tc_bwd_vs_fp32_kernel_and_oracle(B, T, I, dh_t0, use_last):
     dGtc, htc = out[_lib.PREC_TF32X3]
     for t in sorted({T - 1, max(T - 2, 0), 0}, reverse=True):
         print(f"t={t}: |dG_tc - dG_fp32| max {np.abs(dGtc[t] - dG32[t]).max():.3e} (scale {np.abs(dG32[t]).max():.3e})")
-    # at T = 365 the two forward tapes have drifted apart by ~1e-5 already, hence 1e-4 here as well
-    assert_close(dGtc[T - 1], dG32[T - 1], rtol=1e-5 if T < 100 else 1e-4, atol=1e-7, what="dG at the last step")
-    assert_close(dGtc, dG32, rtol=1e-4, atol=1e-7, what="dG all steps (tc vs fp32 kernel)")
+    # kernel against kernel: both carry their own rounding through T recurrent steps (and the backward
+    # pass re-amplifies it), so the two tapes drift apart with T; the parity claims are the oracle checks below
+    long_seq = T >= 100
+    assert_close(dGtc[T - 1], dG32[T - 1], rtol=1e-4 if long_seq else 1e-5, atol=1e-7, what="dG at the last step")
+    assert_close(dGtc, dG32, rtol=5e-4 if long_seq else 1e-4, atol=1e-7, what="dG all steps (tc vs fp32 kernel)")
     # weight gradients from the tc tape, contracted in fp64 on the host, against oracle autograd
     hprev = np.concatenate([np.zeros_like(htc[:1]), htc[:-1]], axis=0)
     dw_hh = np.einsum("tbm,tbk->mk", dGtc, hprev)
