@@ -40,11 +40,16 @@ constexpr uint32_t kColD = 0, kColAhi = 256, kColAlo = 384;   // K <= 128 column
 //   * every row is multiplied by -log2(e) (gates i, f, o) or -2 log2(e) (gate g): the accumulator is
 //     z' with e^-z = 2^z' (sigmoid) and e^-2z = 2^z' (tanh);
 //   * the bias (b_ih + b_hh, scaled the same way) sits in input column IP-1, which the forward kernel
-//     feeds with the constant 1 (input_size <= 31 leaves that column free).
+//     feeds with the constant 1 (input_size <= 31 leaves that column free);
+//   * the tensor core's fp32 accumulation truncates toward zero; over the 36 chained MMAs of a step the
+//     pre-activations come out 2.75e-7 (relative, mean; std 2.8e-7 -- tools/dbg_zbias.py) too small, a
+//     systematic shrink that compounds over hundreds of recurrent steps.  The packed weights carry the
+//     factor 1 + 2.75e-7 that removes the mean of that error.
 __global__ void lstm_tc_pack_w_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                                       const float* __restrict__ b_ih, const float* __restrict__ b_hh, int I, int IP,
                                       float* __restrict__ w_hi, float* __restrict__ w_lo) {
-  constexpr float kL2E = 1.4426950408889634f;
+  constexpr float kScaleIFO = (float)(-1.4426950408889634 * (1.0 + 2.75e-7));        // -log2(e) x truncation compensation
+  constexpr float kScaleG = (float)(-2.0 * 1.4426950408889634 * (1.0 + 2.75e-7));
   const int K = IP + kH;
   const int total = K * kN;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -53,7 +58,7 @@ __global__ void lstm_tc_pack_w_kernel(const float* __restrict__ w_ih, const floa
     float v;
     if (k < IP) v = k < I ? w_ih[row * I + k] : (k == IP - 1 ? b_ih[row] + b_hh[row] : 0.f);
     else v = w_hh[row * kH + (k - IP)];
-    v *= (g == 2) ? -2.f * kL2E : -kL2E;
+    v *= (g == 2) ? kScaleG : kScaleIFO;
     uint32_t hi, lo;
     split_tf32_rr(v, hi, lo);
     w_hi[e] = __uint_as_float(hi);
@@ -355,14 +360,19 @@ int lstm_tc_fwd(const float* x_ri, int64_t B, int64_t T, int64_t I, int64_t IP, 
 //   MMA thread  : dh_rec[128 x 64] = dG[128 x 256] * W_hh[256 x 64]  (3xTF32, M128 N64 K8 MMAs)
 // The K = 256 reduction is pipelined in four quarters of 64 columns (16 hidden units): while the
 // tensor core multiplies quarter k, the row threads are already computing quarter k+1.  A-operand
-// quarters live in a 2-slot TMEM ring, the dh accumulator is double buffered across steps.
-// TMEM columns: D0 [0,64) D1 [64,128) slot0 [128,256) slot1 [256,384)  (hi = first 64, lo = last 64).
+// quarters live in a 2-slot TMEM ring, the dh accumulators are double buffered across steps.
+// The tensor core's fp32 accumulation truncates (-2.8e-8 relative per accumulating MMA, tools/dbg_rz.py), and a
+// bias in dh_rec compounds coherently over the recurrence.  So the 96 MMAs of a step do NOT share one
+// accumulator: quarters {0,1} and {2,3} accumulate separately, each quarter issues its 16 correction MMAs
+// before its 8 hi*hi ones, and the row threads add the two partial sums in registers (round to nearest).
+// TMEM columns: step buffer b at [128 b, 128 b + 128): accumulators of quarters {0,1} | {2,3};
+//               slot0 [256,384) slot1 [384,512)  (hi = first 64, lo = last 64).
 // ================================================================================================
 namespace hy2dl {
 namespace tc {
 
 constexpr int kBwdThreads = 160;
-constexpr uint32_t kColDh0 = 0, kColSlot0 = 128;
+constexpr uint32_t kColDh0 = 0, kColSlot0 = 256;
 
 // W_hh as the B operand of dh = dG * W_hh: B[n = k_out][kdim = gate column 4u+g], K-major no-swizzle
 // layout [256/4][64][4]; element = W_hh[g*64 + u][k_out].
@@ -456,7 +466,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_tc_bwd_kernel(TcBwdArgs a
     bwd_load_chunk(a, a.T - 1, 1, gidx, lane, live, ring[1]);
     for (int64_t s = 0; s < a.T; ++s) {
       const int64_t t = a.T - 1 - s;
-      const uint32_t d_prev = lane_base + kColDh0 + 64 * (uint32_t)((s & 1) ^ 1);   // dh_rec from step s-1
+      const uint32_t d_prev = lane_base + kColDh0 + 128 * (uint32_t)((s & 1) ^ 1);  // dh_rec partial sums from step s-1
       if (s > 0) {
         mbar_wait(bar_free + 1, 1);     // last quarter of step s-1 committed => dh_rec complete, both slots free
         tc_fence_after();
@@ -474,10 +484,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_tc_bwd_kernel(TcBwdArgs a
           BwdChunk& cur = ring[kk];
           uint32_t r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
           if (s > 0) {
+            uint32_t r2[8];
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                          : "r"(d_prev + 8 * Q));
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7])
+                         : "r"(d_prev + 64 + 8 * Q));
             tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 8; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
           }
           f8 dg[4];
 #pragma unroll
@@ -521,19 +537,23 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_tc_bwd_kernel(TcBwdArgs a
       const uint32_t whi = smem_u32(s_whi), wlo = smem_u32(s_wlo);
       const uint32_t lbo = kH * 16, sbo = 128;
       for (int64_t s = 0; s < a.T; ++s) {
-        const uint32_t d = tmem + kColDh0 + 64 * (uint32_t)(s & 1);
         for (int k = 0; k < 4; ++k) {
           const int slot = k & 1;
+          const uint32_t d = tmem + kColDh0 + 128 * (uint32_t)(s & 1) + 64 * (uint32_t)(k >> 1);   // accumulator of quarters {0,1} / {2,3}
           mbar_wait(bar_ready + slot, (uint32_t)(k >> 1));
           tc_fence_after();
           const uint32_t abase = tmem + kColSlot0 + 128 * slot;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 8; ++j) {            // correction terms first (see header)
             const uint32_t J = 8 * k + j;
             const uint64_t d_hi = smem_desc(whi + J * 2 * lbo, lbo, sbo);
             const uint64_t d_lo = smem_desc(wlo + J * 2 * lbo, lbo, sbo);
-            mma_tf32_ts(d, abase + 64 + 8 * j, d_hi, idesc, (k | j) != 0);
+            mma_tf32_ts(d, abase + 64 + 8 * j, d_hi, idesc, ((k & 1) | j) != 0);
             mma_tf32_ts(d, abase + 8 * j, d_lo, idesc, 1);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint64_t d_hi = smem_desc(whi + (uint32_t)(8 * k + j) * 2 * lbo, lbo, sbo);
             mma_tf32_ts(d, abase + 8 * j, d_hi, idesc, 1);
           }
           mma_commit(bar_free + slot);
