@@ -34,6 +34,12 @@ class ParMap(C.Structure):
     ]
 
 
+class HeadFwd(C.Structure):
+    """hy2dl_head_fwd (include/hy2dl_b200.h): optional fusion of the head into hy2dl_lstm_fwd."""
+    _fields_ = [("w", C.c_void_p), ("bias", C.c_void_p), ("pm", C.POINTER(ParMap)), ("par_sim", C.c_void_p),
+                ("par_warm", C.c_void_p)]
+
+
 _SIGNATURES = {
     # name: (restype, argtypes)
     "hy2dl_abi_version": (i32, []),
@@ -42,7 +48,8 @@ _SIGNATURES = {
     "hy2dl_workspace_bytes": (i64, [i32, i64, i64, i64, i64, i64]),
     "hy2dl_pack_x": (i32, [p_f, i64, i64, i64, i64, p_f, i32, p_f]),
     "hy2dl_pack_forcing": (i32, [p_f, i64, i64, i64, p_f, p_f]),
-    "hy2dl_lstm_fwd": (i32, [p_f, i64, i64, i64, i64, i64, p_f, p_f, p_f, p_f, p_f, p_f, p_f, p_f, p_f, i64, i32, p_f]),
+    "hy2dl_lstm_fwd": (i32, [p_f, i64, i64, i64, i64, i64, p_f, p_f, p_f, p_f, p_f, p_f, p_f, p_f, p_f, i64, i32,
+                              C.POINTER(HeadFwd), p_f]),
     "hy2dl_lstm_bwd": (i32, [i64, i64, i64, p_f, p_f, p_f, p_f, i64, p_f, p_f, p_f, i64, i32, p_f]),
     "hy2dl_lstm_wgrad": (i32, [p_f, p_f, p_f, i64, i64, i64, i64, i64, p_f, p_f, p_f, p_f, i64, i32, p_f]),
     "hy2dl_parmap_layout": (i64, [C.POINTER(ParMap), i64, i64]),

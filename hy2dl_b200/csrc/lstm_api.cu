@@ -13,7 +13,7 @@ int64_t lstm_fp32_workspace(int kind, int64_t B, int64_t T, int64_t I, int64_t H
 namespace tc {
 int lstm_tc_fwd(const float* x_ri, int64_t B, int64_t T, int64_t I, int64_t IP, const float* w_ih, const float* w_hh,
                 const float* b_ih, const float* b_hh, float* h_seq, float* c_seq, float* gates, float* h_last, void* ws,
-                int64_t ws_bytes, cudaStream_t s);
+                int64_t ws_bytes, const hy2dl_head_fwd* head, cudaStream_t s);
 int lstm_tc_bwd(int64_t B, int64_t T, const float* w_hh, const float* gates, const float* c_seq, const float* dh_seq,
                 int64_t dh_t0, const float* dh_last, float* dG, void* ws, int64_t ws_bytes, cudaStream_t s);
 int lstm_tc_wgrad(const float* dG, const float* h_seq, const float* x_ri, int64_t B, int64_t T, int64_t I, int64_t IP,
@@ -49,17 +49,19 @@ extern "C" int64_t hy2dl_workspace_bytes(int kind, int64_t B, int64_t T, int64_t
 extern "C" int hy2dl_lstm_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H,
                               const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* h_seq,
                               float* c_seq, float* gates, float* h_last, void* ws, int64_t ws_bytes, int precision,
-                              hy2dl_stream_t stream) {
+                              const hy2dl_head_fwd* head, hy2dl_stream_t stream) {
   int rc = check_lstm_shape("hy2dl_lstm_fwd", B, T, I, IP, H, precision);
   if (rc) return rc;
   HY_PTR(xT); HY_PTR(w_ih); HY_PTR(w_hh); HY_PTR(b_ih); HY_PTR(b_hh);
   HY_PTR_OPT(h_seq); HY_PTR_OPT(c_seq); HY_PTR_OPT(gates); HY_PTR_OPT(h_last);
-  HY_REQUIRE(h_seq || h_last, HY2DL_ERR_ALIGN, "hy2dl_lstm_fwd: both h_seq and h_last are null");
+  HY_REQUIRE(h_seq || h_last || head, HY2DL_ERR_ALIGN, "hy2dl_lstm_fwd: h_seq, h_last and head are all null");
+  HY_REQUIRE(head == nullptr || precision == HY2DL_PREC_TF32X3, HY2DL_ERR_SHAPE,
+             "hy2dl_lstm_fwd: the fused head needs precision tf32x3 (use hy2dl_head_map_fwd otherwise)");
   if (precision == HY2DL_PREC_TF32X3) {
     HY_REQUIRE(tc::lstm_tc_supported(I, H), HY2DL_ERR_SHAPE,
                "hy2dl_lstm_fwd: the tf32x3 tensor-core path supports hidden_size 64 and input_size <= 31 (got H=%lld I=%lld)",
                (long long)H, (long long)I);
-    return tc::lstm_tc_fwd(xT, B, T, I, IP, w_ih, w_hh, b_ih, b_hh, h_seq, c_seq, gates, h_last, ws, ws_bytes,
+    return tc::lstm_tc_fwd(xT, B, T, I, IP, w_ih, w_hh, b_ih, b_hh, h_seq, c_seq, gates, h_last, ws, ws_bytes, head,
                            (cudaStream_t)stream);
   }
   HY_REQUIRE(precision == HY2DL_PREC_FP32, HY2DL_ERR_SHAPE, "hy2dl_lstm_fwd: precision %d not built", precision);

@@ -32,7 +32,8 @@ constexpr int kH = 64;
 constexpr int kN = 256;            // 4H
 constexpr int kRows = 128;         // sequences per CTA
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColD = 0, kColAhi = 256, kColAlo = 384;   // K <= 128 columns each
+constexpr uint32_t kColD = 0, kColHead = 256;                 // gates accumulator [0,256), fused-head accumulator [256,288)
+constexpr uint32_t kColAhi = 288, kColAlo = 384;              // A operand hi / lo, K <= 96 columns each
 
 // ---- weight packing for the tc path ------------------------------------------------------------
 // Wt_hi / Wt_lo: [K/4][256][4] with n = 4u + g; k < IP: W_ih (zero padded), else W_hh.
@@ -46,7 +47,7 @@ constexpr uint32_t kColD = 0, kColAhi = 256, kColAlo = 384;   // K <= 128 column
 //     systematic shrink that compounds over hundreds of recurrent steps.  The packed weights carry the
 //     factor 1 + 2.75e-7 that removes the mean of that error.
 __global__ void lstm_tc_pack_w_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
-                                      const float* __restrict__ b_ih, const float* __restrict__ b_hh, int I, int IP,
+                                      const float* __restrict__ b_ih, const float* __restrict__ b_hh, int I, int IP, int NT,
                                       float* __restrict__ w_hi, float* __restrict__ w_lo) {
   constexpr float kScaleIFO = (float)(-1.4426950408889634 * (1.0 + 2.75e-7));        // -log2(e) x truncation compensation
   constexpr float kScaleG = (float)(-2.0 * 1.4426950408889634 * (1.0 + 2.75e-7));
@@ -61,8 +62,43 @@ __global__ void lstm_tc_pack_w_kernel(const float* __restrict__ w_ih, const floa
     v *= (g == 2) ? kScaleG : kScaleIFO;
     uint32_t hi, lo;
     split_tf32_rr(v, hi, lo);
-    w_hi[e] = __uint_as_float(hi);
-    w_lo[e] = __uint_as_float(lo);
+    const int o = (kc * NT + n) * 4 + kk;        // chunk kc holds NT = 256 (+ NH head) rows
+    w_hi[o] = __uint_as_float(hi);
+    w_lo[o] = __uint_as_float(lo);
+  }
+}
+
+// Head Linear(H, C) + sigmoid range mapping fused into the recurrent kernels (C <= 32 columns).
+// Column c of the head: kind 0 = dynamic parameter, 1 = static parameter, 2 = routing parameter.
+constexpr int kHeadMax = 32;
+struct HeadCols {
+  int32_t C, NH;                 // columns, columns rounded up to 16 (MMA N)
+  int32_t m, warmup;
+  int64_t N;                     // B * m series
+  int64_t off[kHeadMax];         // plane offset in par_sim
+  float lo[kHeadMax], span[kHeadMax];
+  int8_t kind[kHeadMax];
+  int16_t par[kHeadMax], mem[kHeadMax];
+};
+
+// Head weights are NH extra rows (n = 256 ..) of the gates' B operand [K/4][256 + NH][4], rows >= C zero: the
+// last epilogue set's MMAs simply run with N = 128 + NH, so the head pre-activations of time t-1 come out of
+// step t's accumulation at no extra instruction.  The Linear bias sits in input column IP-1 (fed with 1),
+// everything scaled by -log2(e) x truncation compensation.
+__global__ void lstm_tc_pack_head_kernel(const float* __restrict__ w, const float* __restrict__ bias, int C, int NH, int IP,
+                                         float* __restrict__ wh_hi, float* __restrict__ wh_lo) {
+  constexpr float kScale = (float)(-1.4426950408889634 * (1.0 + 2.75e-7));
+  const int K = IP + kH;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < K * NH; e += gridDim.x * blockDim.x) {
+    const int kk = e & 3, n = (e >> 2) % NH, kc = e / (4 * NH), k = 4 * kc + kk;
+    float v = 0.f;
+    if (n < C) v = k < IP ? (k == IP - 1 ? bias[n] : 0.f) : w[n * kH + (k - IP)];
+    v *= kScale;
+    uint32_t hi, lo;
+    split_tf32_rr(v, hi, lo);
+    const int o = (kc * (kN + NH) + kN + n) * 4 + kk;
+    wh_hi[o] = __uint_as_float(hi);
+    wh_lo[o] = __uint_as_float(lo);
   }
 }
 
@@ -76,6 +112,11 @@ struct TcFwdArgs {
   float* h_last;        // row-major [B][64] (nullable)
   int64_t B, T, G;      // G = ceil(B / 32) groups
   int IP;
+  // fused head (has_head == 0: none); its weights are rows 256.. of w_hi / w_lo
+  int has_head;
+  float* par_sim;
+  float* par_warm;
+  HeadCols hc;
 };
 
 // One reciprocal for the four gates of a hidden unit.  The accumulator holds z' = -log2(e) z (i, f, o) and
@@ -116,11 +157,14 @@ __global__ void __launch_bounds__(128 * NSETS + 32, 1) lstm_tc_fwd_kernel(TcFwdA
   constexpr int kMmaWarp = 4 * NSETS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int IP = a.IP, K = IP + kH, KC = K / 4;
+  const bool head = a.has_head != 0;
+  const int NH = head ? a.hc.NH : 0, NT = kN + NH;                     // B-operand rows per K chunk
   float* s_whi = reinterpret_cast<float*>(smem_raw);
-  float* s_wlo = s_whi + K * kN;
-  uint64_t* bar_a_ready = reinterpret_cast<uint64_t*>(s_wlo + K * kN);   // all row threads -> MMA warp
+  float* s_wlo = s_whi + K * NT;
+  uint64_t* bar_a_ready = reinterpret_cast<uint64_t*>(s_wlo + K * NT);   // all row threads -> MMA warp
   uint64_t* bar_done = bar_a_ready + 1;                               // [NSETS] MMA commit of set s -> row threads
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_done + NSETS);
+  uint64_t* bar_head = bar_done + NSETS;                              // head MMAs committed -> row threads
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_head + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int kThreads = 128 * NSETS + 32;
@@ -131,11 +175,12 @@ __global__ void __launch_bounds__(128 * NSETS + 32, 1) lstm_tc_fwd_kernel(TcFwdA
     const float4* g_lo = reinterpret_cast<const float4*>(a.w_lo);
     float4* d_hi = reinterpret_cast<float4*>(s_whi);
     float4* d_lo = reinterpret_cast<float4*>(s_wlo);
-    for (int e = tid; e < KC * kN; e += kThreads) { d_hi[e] = __ldg(g_hi + e); d_lo[e] = __ldg(g_lo + e); }
+    for (int e = tid; e < KC * NT; e += kThreads) { d_hi[e] = __ldg(g_hi + e); d_lo[e] = __ldg(g_lo + e); }
   }
   if (tid == 0) {
     mbar_init(bar_a_ready, 128 * NSETS);
     for (int s = 0; s < NSETS; ++s) mbar_init(bar_done + s, 1);
+    mbar_init(bar_head, 1);
     mbar_fence_init();
   }
   if (warp == kMmaWarp) tmem_alloc(s_tmem, kTmemCols);
@@ -170,6 +215,39 @@ __global__ void __launch_bounds__(128 * NSETS + 32, 1) lstm_tc_fwd_kernel(TcFwdA
       if (U == 3) { hi[7] = 0x3F800000u; lo[7] = 0u; }
       tmem_st8(lane_base + kColAhi + 8 * U, hi);
       tmem_st8(lane_base + kColAlo + 8 * U, lo);
+    };
+    // fused head: set 0 turns the head pre-activations of time th (already in registers) into parameter values
+    const int64_t brow = gidx * 32 + lane;
+    auto head_store = [&](const uint32_t (&z)[kHeadMax], int64_t th) {
+      if (!live || brow >= a.B) return;
+      const HeadCols& hc = a.hc;
+#pragma unroll
+      for (int cc = 0; cc < kHeadMax; ++cc) {
+        if (cc < hc.C) {
+          const float val = fmaf(hc.span[cc], fast_rcp(1.f + fast_ex2(__uint_as_float(z[cc]))), hc.lo[cc]);
+          const int64_t n = brow * hc.m + hc.mem[cc];
+          if (hc.kind[cc] == 0) {
+            if (th == hc.warmup - 1) a.par_warm[(int64_t)hc.par[cc] * hc.N + n] = val;
+            else a.par_sim[hc.off[cc] + (th - hc.warmup) * hc.N + n] = val;
+          } else if (th == a.T - 1) {
+            if (hc.kind[cc] == 2) a.par_sim[hc.off[cc] + brow] = val;
+            else { a.par_sim[hc.off[cc] + n] = val; a.par_warm[(int64_t)hc.par[cc] * hc.N + n] = val; }
+          }
+        }
+      }
+    };
+    auto head_load = [&](uint32_t (&z)[kHeadMax]) {          // D_head -> registers (must precede the next a_ready arrive)
+      uint32_t v16[16];
+      tmem_ld16(lane_base + kColHead, v16);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) z[j] = v16[j];
+      if (NH > 16) {
+        tmem_ld16(lane_base + kColHead + 16, v16);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) z[16 + j] = v16[j];
+      }
     };
     float c[kUPT];
 #pragma unroll
@@ -245,12 +323,16 @@ __global__ void __launch_bounds__(128 * NSETS + 32, 1) lstm_tc_fwd_kernel(TcFwdA
           }
         }
       }
-      if (more) {
+      // a head round (pre-activations of time t-1) was issued with this step's MMAs when t-1 >= warmup-1
+      const bool head_round = head && t >= a.hc.warmup;
+      uint32_t zh[kHeadMax];
+      if (more || head) {
         // the A operand may be overwritten once EVERY MMA of this step has retired
         if (set != NSETS - 1) {
           mbar_wait(bar_done + (NSETS - 1), (uint32_t)(t & 1));
           tc_fence_after();
         }
+        if (head_round && set == 0) head_load(zh);   // rides on the last set's accumulation (columns 256..)
 #pragma unroll
         for (int q = 0; q < kQ; ++q) {
           uint32_t hi[8], lo[8];
@@ -259,40 +341,70 @@ __global__ void __launch_bounds__(128 * NSETS + 32, 1) lstm_tc_fwd_kernel(TcFwdA
           tmem_st8(lane_base + kColAhi + IP + 8 * (kQ * set + q), hi);
           tmem_st8(lane_base + kColAlo + IP + 8 * (kQ * set + q), lo);
         }
+        if (more) {
 #pragma unroll
-        for (int j = 0; j < kXU; ++j) put_x(xn[j], kXU * set + j);
+          for (int j = 0; j < kXU; ++j) put_x(xn[j], kXU * set + j);
+        }
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar_a_ready);
+      }
+      if (head_round && set == 0) head_store(zh, t - 1);
+    }
+    if (head) {                                     // last round: pre-activations of time T-1
+      mbar_wait(bar_head, 0);
+      tc_fence_after();
+      if (set == 0) {
+        uint32_t zh[kHeadMax];
+        head_load(zh);
+        head_store(zh, a.T - 1);
       }
     }
   } else {
     // =========================== MMA issuer (one thread) ======================================
     if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(kRows, kNS, 0, 0);
       const uint32_t whi = smem_u32(s_whi), wlo = smem_u32(s_wlo);
-      const uint32_t lbo = kN * 16, sbo = 128;     // K-major no-swizzle: chunk-to-chunk 4096 B, 8-row groups 128 B
+      const uint32_t sbo = 128;                    // K-major no-swizzle: 8-row groups 128 B apart
       const int KS = K / 8;
+      const uint32_t lbo_t = (uint32_t)NT * 16;    // chunk-to-chunk stride of the [K/4][NT][4] operand
       for (int64_t t = 0; t < a.T; ++t) {
         mbar_wait(bar_a_ready, (uint32_t)(t & 1));
         tc_fence_after();
         for (int s = 0; s < NSETS; ++s) {
+          // the last set also accumulates the NH head columns (D columns 256..)
+          const uint32_t id = idesc_tf32(kRows, kNS + (s == NSETS - 1 ? NH : 0), 0, 0);
           const uint32_t d = tmem + kColD + kNS * s, boff = (uint32_t)(kNS * s) * 16;   // B rows n = kNS*s ..
           // all correction terms first, while the accumulator is still ~2^-11 of its final size: the
           // tensor core's fp32 accumulation loses up to an ulp of the ACCUMULATOR per MMA, so only the
           // K/8 hi*hi instructions round at full magnitude
           for (int j = 0; j < KS; ++j) {
-            const uint64_t d_hi = smem_desc(whi + boff + (uint32_t)j * 2 * lbo, lbo, sbo);
-            const uint64_t d_lo = smem_desc(wlo + boff + (uint32_t)j * 2 * lbo, lbo, sbo);
-            mma_tf32_ts(d, tmem + kColAlo + 8 * j, d_hi, idesc, j > 0);
-            mma_tf32_ts(d, tmem + kColAhi + 8 * j, d_lo, idesc, 1);
+            const uint64_t d_hi = smem_desc(whi + boff + (uint32_t)j * 2 * lbo_t, lbo_t, sbo);
+            const uint64_t d_lo = smem_desc(wlo + boff + (uint32_t)j * 2 * lbo_t, lbo_t, sbo);
+            mma_tf32_ts(d, tmem + kColAlo + 8 * j, d_hi, id, j > 0);
+            mma_tf32_ts(d, tmem + kColAhi + 8 * j, d_lo, id, 1);
           }
           for (int j = 0; j < KS; ++j) {
-            const uint64_t d_hi = smem_desc(whi + boff + (uint32_t)j * 2 * lbo, lbo, sbo);
-            mma_tf32_ts(d, tmem + kColAhi + 8 * j, d_hi, idesc, 1);
+            const uint64_t d_hi = smem_desc(whi + boff + (uint32_t)j * 2 * lbo_t, lbo_t, sbo);
+            mma_tf32_ts(d, tmem + kColAhi + 8 * j, d_hi, id, 1);
           }
           mma_commit(bar_done + s);
         }
+      }
+      if (head) {     // pre-activations of the last time step: one head-only round on A = [. | h_{T-1}]
+        mbar_wait(bar_a_ready, (uint32_t)(a.T & 1));
+        tc_fence_after();
+        const uint32_t id = idesc_tf32(kRows, NH, 0, 0), d = tmem + kColHead, boff = (uint32_t)kN * 16;
+        for (int j = 0; j < KS; ++j) {
+          const uint64_t d_hi = smem_desc(whi + boff + (uint32_t)j * 2 * lbo_t, lbo_t, sbo);
+          const uint64_t d_lo = smem_desc(wlo + boff + (uint32_t)j * 2 * lbo_t, lbo_t, sbo);
+          mma_tf32_ts(d, tmem + kColAlo + 8 * j, d_hi, id, j > 0);
+          mma_tf32_ts(d, tmem + kColAhi + 8 * j, d_lo, id, 1);
+        }
+        for (int j = 0; j < KS; ++j) {
+          const uint64_t d_hi = smem_desc(whi + boff + (uint32_t)j * 2 * lbo_t, lbo_t, sbo);
+          mma_tf32_ts(d, tmem + kColAhi + 8 * j, d_hi, id, 1);
+        }
+        mma_commit(bar_head);
       }
     }
     __syncwarp();
@@ -303,7 +415,30 @@ __global__ void __launch_bounds__(128 * NSETS + 32, 1) lstm_tc_fwd_kernel(TcFwdA
   if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
 }
 
-static size_t tc_fwd_smem(int K) { return (size_t)K * kN * 4 * 2 + 128; }
+static size_t tc_fwd_smem(int K, int NH) { return (size_t)K * (kN + NH) * 4 * 2 + 128; }
+
+// column table of the fused head from the parameter map (same column order as the unfused head kernels:
+// conceptual parameter p, member j -> column p*m + j; routing parameters follow)
+int head_cols_from_parmap(const hy2dl_parmap* pm, int64_t B, HeadCols* hc) {
+  const int C = pm->n_par * pm->n_members + pm->n_routing;
+  if (C > kHeadMax) return -1;
+  hc->C = C; hc->NH = C <= 16 ? 16 : 32;
+  hc->m = pm->n_members; hc->warmup = pm->warmup; hc->N = B * pm->n_members;
+  for (int p = 0; p < pm->n_par + pm->n_routing; ++p) {
+    const bool routing = p >= pm->n_par;
+    const int members = routing ? 1 : pm->n_members;
+    for (int j = 0; j < members; ++j) {
+      const int c = routing ? pm->n_par * pm->n_members + (p - pm->n_par) : p * pm->n_members + j;
+      hc->off[c] = pm->sim_off[p];
+      hc->lo[c] = pm->lo[p];
+      hc->span[c] = pm->hi[p] - pm->lo[p];
+      hc->kind[c] = routing ? 2 : (pm->dynamic[p] ? 0 : 1);
+      hc->par[c] = (int16_t)p;
+      hc->mem[c] = (int16_t)j;
+    }
+  }
+  return 0;
+}
 constexpr int kFwdSets = 2;   // measured on B200 (B = 18944, T = 365): 2 sets 3.01 ms, 4 sets 3.40 ms, 1 set 4.06 ms
 
 int64_t lstm_tc_wgrad_workspace(int64_t B, int64_t T, int64_t I);
@@ -311,7 +446,7 @@ int64_t lstm_tc_wgrad_workspace(int64_t B, int64_t T, int64_t I);
 int64_t lstm_tc_workspace(int kind, int64_t B, int64_t T, int64_t I, int64_t H) {
   (void)I;
   const int64_t IP = 32, K = IP + H;      // the RI32 input stream is always 32 columns wide
-  if (kind == HY2DL_WS_LSTM_FWD) return sizeof(float) * (2 * K * 4 * H);
+  if (kind == HY2DL_WS_LSTM_FWD) return sizeof(float) * (2 * K * 4 * H + 2 * K * kHeadMax);   // packed W (+ packed head)
   if (kind == HY2DL_WS_LSTM_BWD) return sizeof(float) * 2 * 4 * H * H;
   if (kind == HY2DL_WS_LSTM_WGRAD) return lstm_tc_wgrad_workspace(B, T, I);
   return 16;
@@ -321,20 +456,34 @@ bool lstm_tc_supported(int64_t I, int64_t H) { return H == 64 && I <= 31; }   //
 
 int lstm_tc_fwd(const float* x_ri, int64_t B, int64_t T, int64_t I, int64_t IP, const float* w_ih, const float* w_hh,
                 const float* b_ih, const float* b_hh, float* h_seq, float* c_seq, float* gates, float* h_last, void* ws,
-                int64_t ws_bytes, cudaStream_t s) {
+                int64_t ws_bytes, const hy2dl_head_fwd* head, cudaStream_t s) {
   const int K = (int)(IP + kH);
   const int64_t need = lstm_tc_workspace(HY2DL_WS_LSTM_FWD, B, T, I, kH);
   HY_REQUIRE(ws != nullptr && ws_bytes >= need, HY2DL_ERR_WORKSPACE, "hy2dl_lstm_fwd(tf32x3): workspace %lld < %lld bytes",
              (long long)ws_bytes, (long long)need);
-  float* w_hi = reinterpret_cast<float*>(ws);
-  float* w_lo = w_hi + K * kN;
-  lstm_tc_pack_w_kernel<<<96, 256, 0, s>>>(w_ih, w_hh, b_ih, b_hh, (int)I, (int)IP, w_hi, w_lo);
   TcFwdArgs a{};
+  int NH = 0;
+  if (head) {
+    HY_REQUIRE(head->w && head->bias && head->pm && head->par_sim && head->par_warm, HY2DL_ERR_ALIGN, "hy2dl_lstm_fwd: incomplete head description");
+    HY_REQUIRE(head->pm->warmup >= 1 && head->pm->warmup < T, HY2DL_ERR_SHAPE, "hy2dl_lstm_fwd: head warmup=%d must satisfy 1 <= warmup < T=%lld",
+               head->pm->warmup, (long long)T);
+    HY_REQUIRE(head_cols_from_parmap(head->pm, B, &a.hc) == 0, HY2DL_ERR_SHAPE,
+               "hy2dl_lstm_fwd: the fused head takes at most %d columns (use hy2dl_head_map_fwd)", kHeadMax);
+    NH = a.hc.NH;
+  }
+  const int NT = kN + NH;
+  float* w_hi = reinterpret_cast<float*>(ws);
+  float* w_lo = w_hi + K * NT;
+  lstm_tc_pack_w_kernel<<<96, 256, 0, s>>>(w_ih, w_hh, b_ih, b_hh, (int)I, (int)IP, NT, w_hi, w_lo);
+  if (head) {
+    lstm_tc_pack_head_kernel<<<16, 256, 0, s>>>(head->w, head->bias, a.hc.C, NH, (int)IP, w_hi, w_lo);
+    a.has_head = 1; a.par_sim = head->par_sim; a.par_warm = head->par_warm;
+  }
   a.x = x_ri;
   a.w_hi = w_hi; a.w_lo = w_lo;
   a.h_seq = h_seq; a.c_seq = c_seq; a.gates = gates; a.h_last = h_last;
   a.B = B; a.T = T; a.G = cdiv(B, 32); a.IP = (int)IP;
-  const size_t smem = tc_fwd_smem(K);
+  const size_t smem = tc_fwd_smem(K, NH);
   static const int sets = [] { const char* e = getenv("HY2DL_FWD_SETS"); return e ? (atoi(e) == 4 ? 4 : 2) : kFwdSets; }();   // tuning knob
   if (sets == 2) {
     cudaFuncSetAttribute(lstm_tc_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

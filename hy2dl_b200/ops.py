@@ -135,7 +135,7 @@ class LstmFunction(torch.autograd.Function):
         gates = seq(4 * H) if need_grad else None
         ws = _ws(_lib.WS_LSTM_FWD, B, T, I, H, dev, precision)
         call("hy2dl_lstm_fwd", ptr(xT), B, T, I, IP, H, ptr(w_ih), ptr(w_hh), ptr(b_ih), ptr(b_hh), ptr(h_seq),
-             ptr(c_seq), ptr(gates), ptr(h_last), ptr(ws), ws.numel(), precision, stream())
+             ptr(c_seq), ptr(gates), ptr(h_last), ptr(ws), ws.numel(), precision, None, stream())
         ctx.save_for_backward(xT, w_hh, h_seq, c_seq, gates)
         ctx.meta = (B, T, I, IP, H, dh_t0, precision, want_seq)
         if not want_seq:
@@ -271,6 +271,70 @@ class HeadMapFunction(torch.autograd.Function):
 
 def head_map(h_seq, w, bias, layout: ParLayout):
     return HeadMapFunction.apply(h_seq, w, bias, layout)
+
+
+FUSED_HEAD_MAX_COLUMNS = 32
+
+
+class LstmHeadFunction(torch.autograd.Function):
+    """LSTM + head in one forward kernel (precision tf32x3, <= 32 head columns): RI32 xT ->
+    (par_sim flat planes, par_warm [P,N]).  The hidden sequence never leaves the kernels' own layout."""
+
+    @staticmethod
+    def forward(ctx, xT, w_ih, w_hh, b_ih, b_hh, w_head, b_head, I: int, layout: ParLayout):
+        for n, t in (("xT", xT), ("weight_ih", w_ih), ("weight_hh", w_hh), ("bias_ih", b_ih), ("bias_hh", b_hh),
+                     ("linear.weight", w_head), ("linear.bias", b_head)):
+            require_cuda(t, n)
+        if not is_ri32(xT):
+            raise RuntimeError("hy2dl_b200: the fused LSTM + head path works on RI32 inputs (precision 'tf32x3')")
+        precision = _lib.PREC_TF32X3
+        B, H, dev = layout.B, w_hh.shape[1], xT.device
+        T, G, IP = xT.shape[0], xT.shape[1], xT.shape[2] * 32
+        seq = lambda F: torch.empty(T, G, F // 32, 32, 32, dtype=torch.float32, device=dev)
+        need_grad = any(ctx.needs_input_grad[1:7])
+        w_ih, w_hh, b_ih, b_hh, w_head, b_head = (t.detach().contiguous() for t in (w_ih, w_hh, b_ih, b_hh, w_head, b_head))
+        h_seq = seq(H) if need_grad else None
+        c_seq = seq(H) if need_grad else None
+        gates = seq(4 * H) if need_grad else None
+        par_sim = torch.empty(layout.n_floats, dtype=torch.float32, device=dev)
+        par_warm = torch.empty(layout.pm.n_par, layout.N, dtype=torch.float32, device=dev)
+        head = _lib.HeadFwd(ptr(w_head), ptr(b_head), C.pointer(layout.pm), ptr(par_sim), ptr(par_warm))
+        ws = _ws(_lib.WS_LSTM_FWD, B, T, I, H, dev, precision)
+        call("hy2dl_lstm_fwd", ptr(xT), B, T, I, IP, H, ptr(w_ih), ptr(w_hh), ptr(b_ih), ptr(b_hh), ptr(h_seq),
+             ptr(c_seq), ptr(gates), None, ptr(ws), ws.numel(), precision, C.byref(head), stream())
+        ctx.save_for_backward(xT, w_hh, w_head, h_seq, c_seq, gates, par_sim)
+        ctx.meta = (B, T, I, IP, H, precision)
+        ctx.layout = layout
+        ctx.mark_non_differentiable(par_warm)
+        return par_sim, par_warm
+
+    @staticmethod
+    def backward(ctx, dpar_sim, _dpar_warm):
+        xT, w_hh, w_head, h_seq, c_seq, gates, par_sim = ctx.saved_tensors
+        B, T, I, IP, H, precision = ctx.meta
+        layout, dev = ctx.layout, xT.device
+        dpar_sim = dpar_sim.contiguous()
+        # head adjoint: dh_seq on the steps >= warm-up, head weight gradients
+        dh_seq = torch.empty_like(h_seq)
+        dw_head = torch.empty_like(w_head)
+        db_head = torch.empty(w_head.shape[0], dtype=torch.float32, device=dev)
+        call("hy2dl_head_map_bwd", ptr(h_seq), ptr(par_sim), ptr(dpar_sim), B, T, H, ptr(w_head), C.byref(layout.pm),
+             ptr(dh_seq), ptr(dw_head), ptr(db_head), _lib.LAYOUT_RI32, stream())
+        ws_b = _ws(_lib.WS_LSTM_BWD, B, T, I, H, dev, precision)
+        dG = gates   # in place
+        call("hy2dl_lstm_bwd", B, T, H, ptr(w_hh), ptr(gates), ptr(c_seq), ptr(dh_seq), layout.pm.warmup, None, ptr(dG),
+             ptr(ws_b), ws_b.numel(), precision, stream())
+        dw_ih = torch.empty(4 * H, I, dtype=torch.float32, device=dev)
+        dw_hh = torch.empty(4 * H, H, dtype=torch.float32, device=dev)
+        db = torch.empty(4 * H, dtype=torch.float32, device=dev)
+        ws_w = _ws(_lib.WS_LSTM_WGRAD, B, T, I, H, dev, precision)
+        call("hy2dl_lstm_wgrad", ptr(dG), ptr(h_seq), ptr(xT), B, T, I, IP, H, ptr(dw_ih), ptr(dw_hh), ptr(db),
+             ptr(ws_w), ws_w.numel(), precision, stream())
+        return None, dw_ih, dw_hh, db, db.clone(), dw_head, db_head, None, None
+
+
+def lstm_head(xT, w_ih, w_hh, b_ih, b_hh, w_head, b_head, input_size: int, layout: ParLayout):
+    return LstmHeadFunction.apply(xT, w_ih, w_hh, b_ih, b_hh, w_head, b_head, input_size, layout)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -87,28 +87,6 @@ int64_t hy2dl_workspace_bytes(int kind, int64_t B, int64_t T, int64_t I, int64_t
 int hy2dl_pack_x(const float* x, int64_t B, int64_t T, int64_t I, int64_t IP, float* xT, int layout, hy2dl_stream_t stream);
 int hy2dl_pack_forcing(const float* xc, int64_t B, int64_t T, int64_t nc, float* forc, hy2dl_stream_t stream);
 
-/* ---- LSTM (replaces torch.nn.LSTM at modelzoo/cudalstm.py:50 and hybrid.py:92; one layer,
- * unidirectional, h0 = c0 = 0, gate order i|f|g|o as torch/nn/modules/rnn.py:935-941) -------------
- * Weights come in PyTorch layout: w_ih [4H][I], w_hh [4H][H], b_ih [4H], b_hh [4H].
- * Tape outputs may be NULL (inference): c_seq, gates; h_seq may be NULL if only h_last is wanted. */
-int hy2dl_lstm_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H,
-                   const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
-                   float* h_seq, float* c_seq, float* gates, float* h_last,
-                   void* ws, int64_t ws_bytes, int precision, hy2dl_stream_t stream);
-/* Back-propagation through time. External gradient: dh_seq [T][B][H] used for steps t >= dh_t0
- * (NULL: none) plus dh_last [B][H] added at t = T-1 (NULL: none).  dG [T][B][4][H] receives the
- * pre-activation gate gradients and MAY alias `gates`. */
-int hy2dl_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh,
-                   const float* gates, const float* c_seq, const float* dh_seq, int64_t dh_t0,
-                   const float* dh_last, float* dG,
-                   void* ws, int64_t ws_bytes, int precision, hy2dl_stream_t stream);
-/* Weight gradients from dG: dw_ih [4H][I] = dG^T xT, dw_hh [4H][H] = dG^T h_{t-1}, db [4H] = sum dG
- * (db is the gradient of both b_ih and b_hh).  Outputs are overwritten, not accumulated. */
-int hy2dl_lstm_wgrad(const float* dG, const float* h_seq, const float* xT,
-                     int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H,
-                     float* dw_ih, float* dw_hh, float* db,
-                     void* ws, int64_t ws_bytes, int precision, hy2dl_stream_t stream);
-
 /* ---- head: Linear(H, C) on the needed steps + sigmoid range mapping ---------------------------
  * replaces modelzoo/hybrid.py:93-97,110-113 and baseconceptualmodel.py:53-76.
  * `layout` is the layout of h_seq (fwd) and of h_seq + dh_seq (bwd); RI32 dh_seq rows >= B are zero.
@@ -123,6 +101,40 @@ typedef struct {
   float hi[HY2DL_MAX_PAR + 2];      /* range high                                                 */
   int64_t sim_off[HY2DL_MAX_PAR + 2]; /* float offset of each parameter's plane in par_sim        */
 } hy2dl_parmap;
+/* Optional fusion of the head into hy2dl_lstm_fwd (precision HY2DL_PREC_TF32X3, at most 32 head columns):
+ * the forward kernel evaluates Linear(H, C) with its own tensor-core accumulation on the steps the
+ * conceptual model needs and writes par_sim / par_warm exactly like hy2dl_head_map_fwd. */
+typedef struct {
+  const float* w;          /* [C][H] */
+  const float* bias;       /* [C]    */
+  const hy2dl_parmap* pm;  /* layout filled by hy2dl_parmap_layout */
+  float* par_sim;
+  float* par_warm;
+} hy2dl_head_fwd;
+
+/* ---- LSTM (replaces torch.nn.LSTM at modelzoo/cudalstm.py:50 and hybrid.py:92; one layer,
+ * unidirectional, h0 = c0 = 0, gate order i|f|g|o as torch/nn/modules/rnn.py:935-941) -------------
+ * Weights come in PyTorch layout: w_ih [4H][I], w_hh [4H][H], b_ih [4H], b_hh [4H].
+ * Tape outputs may be NULL (inference): c_seq, gates; h_seq may be NULL if only h_last is wanted. */
+int hy2dl_lstm_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H,
+                   const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                   float* h_seq, float* c_seq, float* gates, float* h_last,
+                   void* ws, int64_t ws_bytes, int precision, const hy2dl_head_fwd* head, hy2dl_stream_t stream);
+/* Back-propagation through time. External gradient: dh_seq [T][B][H] used for steps t >= dh_t0
+ * (NULL: none) plus dh_last [B][H] added at t = T-1 (NULL: none).  dG [T][B][4][H] receives the
+ * pre-activation gate gradients and MAY alias `gates`. */
+int hy2dl_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh,
+                   const float* gates, const float* c_seq, const float* dh_seq, int64_t dh_t0,
+                   const float* dh_last, float* dG,
+                   void* ws, int64_t ws_bytes, int precision, hy2dl_stream_t stream);
+/* Weight gradients from dG: dw_ih [4H][I] = dG^T xT, dw_hh [4H][H] = dG^T h_{t-1}, db [4H] = sum dG
+ * (db is the gradient of both b_ih and b_hh).  Outputs are overwritten, not accumulated. */
+int hy2dl_lstm_wgrad(const float* dG, const float* h_seq, const float* xT,
+                     int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H,
+                     float* dw_ih, float* dw_hh, float* db,
+                     void* ws, int64_t ws_bytes, int precision, hy2dl_stream_t stream);
+
+/* ---- head kernels (unfused; any H, any number of columns) --------------------------------------- */
 /* fills sim_off for (B, T) and returns the number of floats par_sim needs; par_warm needs
  * n_par * B * m floats (plane p at p*B*m). */
 int64_t hy2dl_parmap_layout(hy2dl_parmap* pm, int64_t B, int64_t T);

@@ -29,7 +29,7 @@ def _run_fwd(dev, B, T, I, precision, seed=0, tape=True):
     wd = [cu(w[k]) for k in ("lstm.weight_ih_l0", "lstm.weight_hh_l0", "lstm.bias_ih_l0", "lstm.bias_hh_l0")]
     _lib.call("hy2dl_lstm_fwd", x_in.data_ptr(), B, T, I, IP, H, *[t.data_ptr() for t in wd], h.data_ptr(),
               None if c is None else c.data_ptr(), None if g is None else g.data_ptr(), hl.data_ptr(), ws.data_ptr(),
-              ws.numel(), precision, _lib.stream())
+              ws.numel(), precision, None, _lib.stream())
     torch.cuda.synchronize()
     if precision == _lib.PREC_TF32X3:
         unri = lambda a, F: ops.from_ri32(a.view(T, G, F // 32, 32, 32), B)
@@ -83,7 +83,7 @@ def _bwd_both(dev, B, T, I, dh_t0, use_last, seed=3):
         g = torch.zeros(T, Bp, 4 * H, device=dev); hl = torch.zeros(B, H, device=dev)
         ws = ops._ws(_lib.WS_LSTM_FWD, B, T, I, H, dev, prec)
         _lib.call("hy2dl_lstm_fwd", x_in.data_ptr(), B, T, I, IP, H, *[t.data_ptr() for t in wd], h.data_ptr(),
-                  c.data_ptr(), g.data_ptr(), hl.data_ptr(), ws.data_ptr(), ws.numel(), prec, _lib.stream())
+                  c.data_ptr(), g.data_ptr(), hl.data_ptr(), ws.data_ptr(), ws.numel(), prec, None, _lib.stream())
         dh = cu(gh)
         dh_in = ops.to_ri32(dh) if ri else dh
         dl = cu(gl) if use_last else None

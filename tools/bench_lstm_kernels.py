@@ -31,7 +31,7 @@ st = _lib.stream()
 
 def fwd():
     _lib.call("hy2dl_lstm_fwd", x.data_ptr(), B, T, I, IP, H, w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(),
-              h.data_ptr(), c.data_ptr(), g.data_ptr(), hl.data_ptr(), wsf.data_ptr(), wsf.numel(), prec, st)
+              h.data_ptr(), c.data_ptr(), g.data_ptr(), hl.data_ptr(), wsf.data_ptr(), wsf.numel(), prec, None, st)
 def bwd():
     _lib.call("hy2dl_lstm_bwd", B, T, H, w_hh.data_ptr(), g.data_ptr(), c.data_ptr(), dh.data_ptr(), T // 2, None, g.data_ptr(),
               wsb.data_ptr(), wsb.numel(), prec, st)

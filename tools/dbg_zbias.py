@@ -25,7 +25,7 @@ for prec, name in ((_lib.PREC_FP32, "fp32"), (_lib.PREC_TF32X3, "tf32x3")):
     hl = torch.zeros(B, H, device=dev)
     ws = ops._ws(_lib.WS_LSTM_FWD, B, T, I, H, dev, prec)
     _lib.call("hy2dl_lstm_fwd", x_in.data_ptr(), B, T, I, IPx, H, *[t.data_ptr() for t in wd], h.data_ptr(), c.data_ptr(),
-              g.data_ptr(), hl.data_ptr(), ws.data_ptr(), ws.numel(), prec, _lib.stream())
+              g.data_ptr(), hl.data_ptr(), ws.data_ptr(), ws.numel(), prec, None, _lib.stream())
     torch.cuda.synchronize()
     if ri:
         h = ops.from_ri32(h.view(T, G, H // 32, 32, 32), B)
