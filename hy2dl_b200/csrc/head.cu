@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(HeadArgs a, HeadChun
   const int64_t N = a.B * a.m;
   const int KB = H / 64;
   constexpr bool reg_acc = REG_ACC;
+  const bool want_dh = a.dh_seq != nullptr;      // null: weight / bias gradients only
 
   for (int e = tid; e < kChunk * H; e += kThreads) {
     ws[e] = (e / H) < ch.ncol ? __ldg(a.w + (int64_t)ch.col[e / H] * H + (e % H)) : 0.f;
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(HeadArgs a, HeadChun
         int64_t o;
         if (a.ri32) o = (t * tiles_b + b0 / kRows) * kRows * H + (int64_t)(k >> 5) * 1024 + r * 32 + ((((k >> 3) ^ r) & 3) << 3) + (k & 7);
         else o = (t * a.B + b0 + r) * H + k;
-        if (a.ri32 || r < nb) a.dh_seq[o] = a.accumulate_dh ? a.dh_seq[o] + dh : dh;
+        if (want_dh && (a.ri32 || r < nb)) a.dh_seq[o] = a.accumulate_dh ? a.dh_seq[o] + dh : dh;
       }
       if constexpr (!reg_acc) {
 #pragma unroll
@@ -333,7 +334,7 @@ extern "C" int hy2dl_head_map_bwd(const float* h_seq, const float* par_sim, cons
   int rc = check_parmap(pm, T, "hy2dl_head_map_bwd");
   if (rc) return rc;
   HY_REQUIRE(B > 0 && H > 0 && H <= 512 && H % 64 == 0, HY2DL_ERR_SHAPE, "hy2dl_head_map_bwd: bad sizes B=%lld H=%lld (H must be a multiple of 64)", (long long)B, (long long)H);
-  HY_NONNULL(h_seq); HY_NONNULL(par_sim); HY_NONNULL(dpar_sim); HY_NONNULL(w); HY_NONNULL(dh_seq); HY_NONNULL(dw); HY_NONNULL(dbias);
+  HY_NONNULL(h_seq); HY_NONNULL(par_sim); HY_NONNULL(dpar_sim); HY_NONNULL(w); HY_NONNULL(dw); HY_NONNULL(dbias);
   HeadChunk chunks[32];
   const int n = build_chunks(pm, chunks, 32);
   HY_REQUIRE(n > 0, HY2DL_ERR_SHAPE, "hy2dl_head_map_bwd: too many head columns");
@@ -356,7 +357,7 @@ extern "C" int hy2dl_head_map_bwd(const float* h_seq, const float* par_sim, cons
   };
   bool dyn_written = false;
   for (int i = 0; i < n; ++i) {
-    if (!chunks[i].is_dynamic && !dyn_written) {
+    if (!chunks[i].is_dynamic && !dyn_written && dh_seq) {
       // no dynamic launch has initialised rows warmup .. T-1: zero them once
       cudaMemsetAsync(dh_seq + (int64_t)pm->warmup * Bp * H, 0, sizeof(float) * (T - pm->warmup) * Bp * H, s);
       dyn_written = true;

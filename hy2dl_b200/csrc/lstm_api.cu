@@ -15,7 +15,8 @@ int lstm_tc_fwd(const float* x_ri, int64_t B, int64_t T, int64_t I, int64_t IP, 
                 const float* b_ih, const float* b_hh, float* h_seq, float* c_seq, float* gates, float* h_last, void* ws,
                 int64_t ws_bytes, const hy2dl_head_fwd* head, cudaStream_t s);
 int lstm_tc_bwd(int64_t B, int64_t T, const float* w_hh, const float* gates, const float* c_seq, const float* dh_seq,
-                int64_t dh_t0, const float* dh_last, float* dG, void* ws, int64_t ws_bytes, cudaStream_t s);
+                int64_t dh_t0, const float* dh_last, float* dG, void* ws, int64_t ws_bytes, const hy2dl_head_bwd* head,
+                cudaStream_t s);
 int lstm_tc_wgrad(const float* dG, const float* h_seq, const float* x_ri, int64_t B, int64_t T, int64_t I, int64_t IP,
                   float* dw_ih, float* dw_hh, float* db, void* ws, int64_t ws_bytes, cudaStream_t s);
 int64_t lstm_tc_workspace(int kind, int64_t B, int64_t T, int64_t I, int64_t H);
@@ -71,15 +72,18 @@ extern "C" int hy2dl_lstm_fwd(const float* xT, int64_t B, int64_t T, int64_t I, 
 
 extern "C" int hy2dl_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const float* gates,
                               const float* c_seq, const float* dh_seq, int64_t dh_t0, const float* dh_last, float* dG,
-                              void* ws, int64_t ws_bytes, int precision, hy2dl_stream_t stream) {
+                              void* ws, int64_t ws_bytes, int precision, const hy2dl_head_bwd* head,
+                              hy2dl_stream_t stream) {
   int rc = check_lstm_shape("hy2dl_lstm_bwd", B, T, 8, precision == HY2DL_PREC_TF32X3 ? 32 : 8, H, precision);
   if (rc) return rc;
   HY_PTR(w_hh); HY_PTR(gates); HY_PTR(c_seq); HY_PTR(dG); HY_PTR_OPT(dh_seq); HY_PTR_OPT(dh_last);
-  HY_REQUIRE(dh_seq || dh_last, HY2DL_ERR_ALIGN, "hy2dl_lstm_bwd: no external gradient given");
+  HY_REQUIRE(dh_seq || dh_last || head, HY2DL_ERR_ALIGN, "hy2dl_lstm_bwd: no external gradient given");
+  HY_REQUIRE(head == nullptr || precision == HY2DL_PREC_TF32X3, HY2DL_ERR_SHAPE,
+             "hy2dl_lstm_bwd: the fused head needs precision tf32x3 (use hy2dl_head_map_bwd otherwise)");
   HY_REQUIRE(dh_t0 >= 0 && dh_t0 <= T, HY2DL_ERR_SHAPE, "hy2dl_lstm_bwd: dh_t0=%lld out of range", (long long)dh_t0);
   if (precision == HY2DL_PREC_TF32X3) {
     HY_REQUIRE(H == 64, HY2DL_ERR_SHAPE, "hy2dl_lstm_bwd: the tf32x3 tensor-core path supports hidden_size 64 (got %lld)", (long long)H);
-    return tc::lstm_tc_bwd(B, T, w_hh, gates, c_seq, dh_seq, dh_t0, dh_last, dG, ws, ws_bytes, (cudaStream_t)stream);
+    return tc::lstm_tc_bwd(B, T, w_hh, gates, c_seq, dh_seq, dh_t0, dh_last, dG, ws, ws_bytes, head, (cudaStream_t)stream);
   }
   HY_REQUIRE(precision == HY2DL_PREC_FP32, HY2DL_ERR_SHAPE, "hy2dl_lstm_bwd: precision %d not built", precision);
   return lstm_fp32_bwd(B, T, H, w_hh, gates, c_seq, dh_seq, dh_t0, dh_last, dG, (cudaStream_t)stream);

@@ -447,7 +447,7 @@ int64_t lstm_tc_workspace(int kind, int64_t B, int64_t T, int64_t I, int64_t H) 
   (void)I;
   const int64_t IP = 32, K = IP + H;      // the RI32 input stream is always 32 columns wide
   if (kind == HY2DL_WS_LSTM_FWD) return sizeof(float) * (2 * K * 4 * H + 2 * K * kHeadMax);   // packed W (+ packed head)
-  if (kind == HY2DL_WS_LSTM_BWD) return sizeof(float) * 2 * 4 * H * H;
+  if (kind == HY2DL_WS_LSTM_BWD) return sizeof(float) * (2 * 4 * H * H + 2 * kHeadMax * H);   // packed W_hh (+ packed head)
   if (kind == HY2DL_WS_LSTM_WGRAD) return lstm_tc_wgrad_workspace(B, T, I);
   return 16;
 }
@@ -520,7 +520,9 @@ int lstm_tc_fwd(const float* x_ri, int64_t B, int64_t T, int64_t I, int64_t IP, 
 namespace hy2dl {
 namespace tc {
 
-constexpr int kBwdThreads = 160;
+constexpr int kBwdThreads = 160;       // 4 row warps + MMA warp
+constexpr int kBwdThreadsHead = 256;   // + 3 warps that turn dpar into the head's dz operand
+constexpr int kDzThreads = 96;
 constexpr uint32_t kColDh0 = 0, kColSlot0 = 256;
 
 // W_hh as the B operand of dh = dG * W_hh: B[n = k_out][kdim = gate column 4u+g], K-major no-swizzle
@@ -537,6 +539,18 @@ __global__ void lstm_tc_pack_whh_kernel(const float* __restrict__ w_hh, float* _
   }
 }
 
+// W_head^T as the B operand of dh_head = dz * W_head: B[n = k_out][k = head column], K-major no-swizzle
+// [NH/4][64][4]; columns >= C zero.
+__global__ void lstm_tc_pack_headT_kernel(const float* __restrict__ w, int C, int NH, float* __restrict__ hi_out, float* __restrict__ lo_out) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < NH * kH; e += gridDim.x * blockDim.x) {
+    const int kk = e & 3, n = (e >> 2) & 63, kc = e >> 8, k = 4 * kc + kk;
+    uint32_t hi, lo;
+    split_tf32_rr(k < C ? w[k * kH + n] : 0.f, hi, lo);
+    hi_out[e] = __uint_as_float(hi);
+    lo_out[e] = __uint_as_float(lo);
+  }
+}
+
 struct TcBwdArgs {
   const float* w_hi;      // [64][64][4] packed W_hh (hi)
   const float* w_lo;
@@ -546,6 +560,14 @@ struct TcBwdArgs {
   const float* dh_last;   // row-major [B][64] or null
   float* dG;              // RI32 F = 256; may alias gates
   int64_t B, T, G, dh_t0;
+  // fused head adjoint (has_head == 0: none): dh_ext(t) = dz_t * W_head with dz from dpar_sim / par_sim
+  int has_head;
+  const float* wh_hi;     // [NH/4][64][4]
+  const float* wh_lo;
+  const float* par_sim;
+  const float* dpar_sim;
+  int dbg;                // timing experiments only (HY2DL_DBG_BWD): 1 = dz warps skip their loads, 2 = skip the dz MMAs
+  HeadCols hc;
 };
 
 struct BwdChunk {   // tape of 8 hidden units of one row at one step: one 128-byte line of gates + three sectors
@@ -571,26 +593,45 @@ __device__ __forceinline__ void bwd_load_chunk(const TcBwdArgs& a, int64_t t, in
   }
 }
 
-__global__ void __launch_bounds__(kBwdThreads, 1) lstm_tc_bwd_kernel(TcBwdArgs a) {
+__global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const bool head = a.has_head != 0;
+  const int NH = head ? a.hc.NH : 0;
+  // one dz operand buffer (hi | lo): its MMAs open the chain, so it is free again for most of the step -- and
+  // shared memory is precious here: the tape loads need L1 (228 KB minus the carve-out) for their in-flight
+  // lines; measured with the same kernel: 164 KB of shared memory 3.8 ms, 196 KB 4.3 ms, 204+ KB 5.8 ms
+  constexpr int n_dzbuf = 1;
   float* s_whi = reinterpret_cast<float*>(smem_raw);
   float* s_wlo = s_whi + kN * kH;
   float* s_dc = s_wlo + kN * kH;                                        // [64][128] cell-state adjoint, per row thread
-  uint64_t* bar_ready = reinterpret_cast<uint64_t*>(s_dc + kH * kRows);  // [2] rows -> MMA, per slot
+  float* s_hw = s_dc + kH * kRows;                                      // head: W_head^T hi | lo, [NH/4][64][4] each
+  float* s_dz = s_hw + 2 * NH * kH;                                     // head: n_dzbuf x (hi | lo) [NH/4][128 rows][4]
+  uint64_t* bar_ready = reinterpret_cast<uint64_t*>(s_dz + (head ? n_dzbuf * 2 * NH * kRows : 0));  // [2] rows -> MMA, per slot
   uint64_t* bar_free = bar_ready + 2;                                   // [2] MMA commit -> rows, per slot
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_free + 2);
+  uint64_t* bar_dz_full = bar_free + 2;                                 // [2] dz warps -> MMA
+  uint64_t* bar_dz_free = bar_dz_full + 2;                              // [2] MMA commit -> dz warps
+  uint64_t* bar_pre = bar_dz_free + 2;                                  // dh(T-1) = dz_{T-1} W_head ready -> rows
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_pre + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nthreads = blockDim.x;
 
   {
     const float4* g_hi = reinterpret_cast<const float4*>(a.w_hi);
     const float4* g_lo = reinterpret_cast<const float4*>(a.w_lo);
     float4* d_hi = reinterpret_cast<float4*>(s_whi);
     float4* d_lo = reinterpret_cast<float4*>(s_wlo);
-    for (int e = tid; e < kN * kH / 4; e += kBwdThreads) { d_hi[e] = __ldg(g_hi + e); d_lo[e] = __ldg(g_lo + e); }
+    for (int e = tid; e < kN * kH / 4; e += nthreads) { d_hi[e] = __ldg(g_hi + e); d_lo[e] = __ldg(g_lo + e); }
+    if (head) {
+      for (int e = tid; e < NH * kH; e += nthreads) { s_hw[e] = __ldg(a.wh_hi + e); s_hw[NH * kH + e] = __ldg(a.wh_lo + e); }
+      for (int e = tid; e < n_dzbuf * 2 * NH * kRows; e += nthreads) s_dz[e] = 0.f;     // padding columns stay zero
+    }
   }
   if (tid == 0) {
     mbar_init(bar_ready + 0, kRows); mbar_init(bar_ready + 1, kRows);
     mbar_init(bar_free + 0, 1); mbar_init(bar_free + 1, 1);
+    mbar_init(bar_dz_full + 0, kDzThreads); mbar_init(bar_dz_full + 1, kDzThreads);
+    mbar_init(bar_dz_free + 0, 1); mbar_init(bar_dz_free + 1, 1);
+    mbar_init(bar_pre, 1);
     mbar_fence_init();
   }
   if (warp == 4) tmem_alloc(s_tmem, kTmemCols);
@@ -606,6 +647,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_tc_bwd_kernel(TcBwdArgs a
     const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
     float* dcp = s_dc + tid;     // dc[u] at dcp[u * 128]: conflict-free, keeps the chunk loop rolled and small
     for (int u = 0; u < kH; ++u) dcp[u * kRows] = 0.f;
+    if (head) {                  // dh(T-1) comes from the head alone: only accumulator {0,1} of buffer 1 is written
+      uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int cc = 0; cc < 64; cc += 8) tmem_st8(lane_base + kColDh0 + 128 + 64 + cc, z);
+      tmem_st_wait();
+    }
 
     // tape chunks (8 hidden units = 224 B per row) travel through a 2-deep register ring: chunk Q + 2 is
     // requested as soon as chunk Q has been consumed, so ~450 B per thread (57 KB per SM) are in flight --
@@ -619,7 +665,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_tc_bwd_kernel(TcBwdArgs a
       if (s > 0) {
         mbar_wait(bar_free + 1, 1);     // last quarter of step s-1 committed => dh_rec complete, both slots free
         tc_fence_after();
+      } else if (head) {
+        mbar_wait(bar_pre, 0);
+        tc_fence_after();
       }
+      const bool have_prev = s > 0 || head;
 #pragma unroll 1
       for (int k = 0; k < 4; ++k) {      // quarter k = 16 hidden units = 64 gate columns, lives in slot k & 1
         const int slot = k & 1;
@@ -632,7 +682,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_tc_bwd_kernel(TcBwdArgs a
           const int Q = 2 * k + kk;
           BwdChunk& cur = ring[kk];
           uint32_t r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          if (s > 0) {
+          if (have_prev) {
             uint32_t r2[8];
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -680,24 +730,54 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_tc_bwd_kernel(TcBwdArgs a
         mbar_arrive(bar_ready + slot);
       }
     }
-  } else {
+  } else if (warp == 4) {
     if (lane == 0) {
       const uint32_t idesc = idesc_tf32(kRows, kH, 0, 0);
       const uint32_t whi = smem_u32(s_whi), wlo = smem_u32(s_wlo);
       const uint32_t lbo = kH * 16, sbo = 128;
+      // head: dh_ext(th) = dz_th [128 x NH] * W_head [NH x 64], A and B from shared memory, opens the chain of time th
+      const uint32_t hw_hi = smem_u32(s_hw), hw_lo = hw_hi + (uint32_t)NH * kH * 4;
+      const uint32_t dz_buf_bytes = 2u * (uint32_t)NH * kRows * 4, dz_lo_off = (uint32_t)NH * kRows * 4;
+      int64_t dz_i = 0;
+      auto issue_dz = [&](uint32_t d) {
+        const int buf = (int)(dz_i % n_dzbuf);
+        mbar_wait(bar_dz_full + buf, (uint32_t)((dz_i / n_dzbuf) & 1));
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(s_dz) + buf * dz_buf_bytes, a_lo = a_hi + dz_lo_off;
+        for (int j = 0; j < NH / 8 && !(a.dbg & 2); ++j) {
+          const uint64_t ah = smem_desc(a_hi + j * 2 * 2048, 2048, 128), al = smem_desc(a_lo + j * 2 * 2048, 2048, 128);
+          const uint64_t bh = smem_desc(hw_hi + j * 2 * lbo, lbo, sbo), bl = smem_desc(hw_lo + j * 2 * lbo, lbo, sbo);
+          mma_tf32_ss(d, al, bh, idesc, j > 0);
+          mma_tf32_ss(d, ah, bl, idesc, 1);
+        }
+        for (int j = 0; j < NH / 8 && !(a.dbg & 2); ++j) {
+          const uint64_t ah = smem_desc(a_hi + j * 2 * 2048, 2048, 128), bh = smem_desc(hw_hi + j * 2 * lbo, lbo, sbo);
+          mma_tf32_ss(d, ah, bh, idesc, 1);
+        }
+        mma_commit(bar_dz_free + buf);
+        ++dz_i;
+      };
+      if (head) {                                  // chain of time T-1: the head term only
+        issue_dz(tmem + kColDh0 + 128);
+        mma_commit(bar_pre);
+      }
       for (int64_t s = 0; s < a.T; ++s) {
+        const int64_t th = a.T - 2 - s;            // this chain accumulates dh of time th
+        const bool has_dz = head && th >= a.hc.warmup;
         for (int k = 0; k < 4; ++k) {
           const int slot = k & 1;
           const uint32_t d = tmem + kColDh0 + 128 * (uint32_t)(s & 1) + 64 * (uint32_t)(k >> 1);   // accumulator of quarters {0,1} / {2,3}
           mbar_wait(bar_ready + slot, (uint32_t)(k >> 1));
           tc_fence_after();
+          if (k == 0 && has_dz) issue_dz(d);       // (the row threads have finished reading this buffer by now)
           const uint32_t abase = tmem + kColSlot0 + 128 * slot;
+          const bool acc0 = k == 0 && has_dz;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {            // correction terms first (see header)
             const uint32_t J = 8 * k + j;
             const uint64_t d_hi = smem_desc(whi + J * 2 * lbo, lbo, sbo);
             const uint64_t d_lo = smem_desc(wlo + J * 2 * lbo, lbo, sbo);
-            mma_tf32_ts(d, abase + 64 + 8 * j, d_hi, idesc, ((k & 1) | j) != 0);
+            mma_tf32_ts(d, abase + 64 + 8 * j, d_hi, idesc, (((k & 1) | j) != 0) || acc0);
             mma_tf32_ts(d, abase + 8 * j, d_lo, idesc, 1);
           }
 #pragma unroll
@@ -710,6 +790,56 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_tc_bwd_kernel(TcBwdArgs a
       }
     }
     __syncwarp();
+  } else if (head) {
+    // =========================== dz warps ========================================================
+    // dz[row][c] = dpar * dval/dz (sigma recovered from the stored parameter value), for the steps that feed the
+    // head: dynamic columns on th >= warmup, static + routing columns on th = T-1 (baseconceptualmodel.py:61-67)
+    const int dt = tid - kBwdThreads;             // 0 .. 95
+    const HeadCols& hc = a.hc;
+    const int64_t row0 = (int64_t)blockIdx.x * kRows;
+    const int n_items = kRows * hc.C;
+    for (int64_t th = a.T - 1, i = 0; th >= hc.warmup; --th, ++i) {
+      const int buf = (int)(i % n_dzbuf);
+      if (i >= n_dzbuf) mbar_wait_relaxed(bar_dz_free + buf, (uint32_t)((i / n_dzbuf - 1) & 1));
+      float* dz_hi = s_dz + buf * 2 * NH * kRows;
+      float* dz_lo = dz_hi + NH * kRows;
+      // batches of 16 items per thread: all loads of a batch are issued before the first use (one HBM latency
+      // per batch instead of one per item)
+      for (int e0 = dt; e0 < n_items; e0 += 16 * kDzThreads) {
+        float val[16], dp[16];
+#pragma unroll
+        for (int i2 = 0; i2 < 16; ++i2) {
+          const int e = e0 + i2 * kDzThreads;
+          val[i2] = 0.f; dp[i2] = 0.f;
+          if (e < n_items) {
+            const int c = e >> 7, r = e & 127;
+            const int64_t b = row0 + r;
+            const int kind = hc.kind[c];
+            if (b < a.B && (kind == 0 || th == a.T - 1) && !(a.dbg & 1)) {
+              const int64_t idx = hc.off[c] + (kind == 0 ? (th - hc.warmup) * hc.N : 0) + (kind == 2 ? b : b * hc.m + hc.mem[c]);
+              val[i2] = __ldg(a.par_sim + idx);
+              dp[i2] = __ldg(a.dpar_sim + idx);
+            }
+          }
+        }
+#pragma unroll
+        for (int i2 = 0; i2 < 16; ++i2) {
+          const int e = e0 + i2 * kDzThreads;
+          if (e < n_items) {
+            const int c = e >> 7, r = e & 127;
+            const float lo = hc.lo[c], sp = hc.span[c];
+            const float dz = dp[i2] * (val[i2] - lo) * ((lo + sp) - val[i2]) / sp;    // dp = 0 where the column has no gradient
+            uint32_t hi, lw;
+            split_tf32(dz, hi, lw);
+            const int o = ((c >> 2) * kRows + r) * 4 + (c & 3);
+            dz_hi[o] = __uint_as_float(hi);
+            dz_lo[o] = __uint_as_float(lw);
+          }
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(bar_dz_full + buf);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -717,8 +847,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_tc_bwd_kernel(TcBwdArgs a
 }
 
 int lstm_tc_bwd(int64_t B, int64_t T, const float* w_hh, const float* gates, const float* c_seq, const float* dh_seq,
-                int64_t dh_t0, const float* dh_last, float* dG, void* ws, int64_t ws_bytes, cudaStream_t s) {
-  const int64_t need = sizeof(float) * 2 * kN * kH;
+                int64_t dh_t0, const float* dh_last, float* dG, void* ws, int64_t ws_bytes, const hy2dl_head_bwd* head,
+                cudaStream_t s) {
+  const int64_t need = lstm_tc_workspace(HY2DL_WS_LSTM_BWD, B, T, 1, kH);
   HY_REQUIRE(ws != nullptr && ws_bytes >= need, HY2DL_ERR_WORKSPACE, "hy2dl_lstm_bwd(tf32x3): workspace %lld < %lld bytes",
              (long long)ws_bytes, (long long)need);
   float* w_hi = reinterpret_cast<float*>(ws);
@@ -728,9 +859,28 @@ int lstm_tc_bwd(int64_t B, int64_t T, const float* w_hh, const float* gates, con
   a.w_hi = w_hi; a.w_lo = w_lo;
   a.gates = gates; a.c_seq = c_seq; a.dh_seq = dh_seq; a.dh_last = dh_last; a.dG = dG;
   a.B = B; a.T = T; a.G = cdiv(B, 32); a.dh_t0 = dh_t0;
-  const size_t smem = (size_t)kN * kH * 4 * 2 + (size_t)kH * kRows * 4 + 64;
+  size_t smem = (size_t)kN * kH * 4 * 2 + (size_t)kH * kRows * 4 + 128;
+  int threads = kBwdThreads;
+  if (head) {
+    HY_REQUIRE(head->w && head->pm && head->par_sim && head->dpar_sim, HY2DL_ERR_ALIGN, "hy2dl_lstm_bwd: incomplete head description");
+    HY_REQUIRE(head->pm->warmup >= 1 && head->pm->warmup < T, HY2DL_ERR_SHAPE, "hy2dl_lstm_bwd: head warmup=%d must satisfy 1 <= warmup < T=%lld",
+               head->pm->warmup, (long long)T);
+    HY_REQUIRE(head_cols_from_parmap(head->pm, B, &a.hc) == 0, HY2DL_ERR_SHAPE,
+               "hy2dl_lstm_bwd: the fused head takes at most %d columns (use hy2dl_head_map_bwd)", kHeadMax);
+    const int NH = a.hc.NH;
+    float* wh_hi = w_lo + kN * kH;
+    float* wh_lo = wh_hi + NH * kH;
+    lstm_tc_pack_headT_kernel<<<8, 256, 0, s>>>(head->w, a.hc.C, NH, wh_hi, wh_lo);
+    static const int dbg = [] { const char* e = getenv("HY2DL_DBG_BWD"); return e ? atoi(e) : 0; }();
+    a.dbg = dbg;
+    a.has_head = 1; a.wh_hi = wh_hi; a.wh_lo = wh_lo; a.par_sim = head->par_sim; a.dpar_sim = head->dpar_sim;
+    smem += (size_t)2 * NH * kH * 4 + (size_t)2 * NH * kRows * 4;
+    threads = kBwdThreadsHead;
+  }
+  static const int dbg_smem = [] { const char* e = getenv("HY2DL_DBG_SMEM"); return e ? atoi(e) : 0; }();   // experiment: extra smem
+  smem += dbg_smem;
   cudaFuncSetAttribute(lstm_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  lstm_tc_bwd_kernel<<<(unsigned)cdiv(B, kRows), kBwdThreads, smem, s>>>(a);
+  lstm_tc_bwd_kernel<<<(unsigned)cdiv(B, kRows), threads, smem, s>>>(a);
   HY_LAUNCH_CHECK();
   return HY2DL_OK;
 }

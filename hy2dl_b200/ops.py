@@ -161,7 +161,7 @@ class LstmFunction(torch.autograd.Function):
         # dG overwrites the gate tape in place (the kernel reads each element before writing it)
         dG = gates
         call("hy2dl_lstm_bwd", B, T, H, ptr(w_hh), ptr(gates), ptr(c_seq), ptr(dh_seq), dh_t0, ptr(dh_last), ptr(dG),
-             ptr(ws_b), ws_b.numel(), precision, stream())
+             ptr(ws_b), ws_b.numel(), precision, None, stream())
         dw_ih = torch.empty(4 * H, I, dtype=torch.float32, device=dev)
         dw_hh = torch.empty(4 * H, H, dtype=torch.float32, device=dev)
         db = torch.empty(4 * H, dtype=torch.float32, device=dev)
@@ -314,16 +314,17 @@ class LstmHeadFunction(torch.autograd.Function):
         B, T, I, IP, H, precision = ctx.meta
         layout, dev = ctx.layout, xT.device
         dpar_sim = dpar_sim.contiguous()
-        # head adjoint: dh_seq on the steps >= warm-up, head weight gradients
-        dh_seq = torch.empty_like(h_seq)
+        # head weight gradient (reads h_seq and dpar_sim; no dh_seq is formed) ...
         dw_head = torch.empty_like(w_head)
         db_head = torch.empty(w_head.shape[0], dtype=torch.float32, device=dev)
         call("hy2dl_head_map_bwd", ptr(h_seq), ptr(par_sim), ptr(dpar_sim), B, T, H, ptr(w_head), C.byref(layout.pm),
-             ptr(dh_seq), ptr(dw_head), ptr(db_head), _lib.LAYOUT_RI32, stream())
+             None, ptr(dw_head), ptr(db_head), _lib.LAYOUT_RI32, stream())
+        # ... and BPTT with the head adjoint dz * W_head accumulated by the kernel's own MMAs
+        hb = _lib.HeadBwd(ptr(w_head), C.pointer(layout.pm), ptr(par_sim), ptr(dpar_sim))
         ws_b = _ws(_lib.WS_LSTM_BWD, B, T, I, H, dev, precision)
         dG = gates   # in place
-        call("hy2dl_lstm_bwd", B, T, H, ptr(w_hh), ptr(gates), ptr(c_seq), ptr(dh_seq), layout.pm.warmup, None, ptr(dG),
-             ptr(ws_b), ws_b.numel(), precision, stream())
+        call("hy2dl_lstm_bwd", B, T, H, ptr(w_hh), ptr(gates), ptr(c_seq), None, layout.pm.warmup, None, ptr(dG),
+             ptr(ws_b), ws_b.numel(), precision, C.byref(hb), stream())
         dw_ih = torch.empty(4 * H, I, dtype=torch.float32, device=dev)
         dw_hh = torch.empty(4 * H, H, dtype=torch.float32, device=dev)
         db = torch.empty(4 * H, dtype=torch.float32, device=dev)

@@ -111,6 +111,16 @@ typedef struct {
   float* par_sim;
   float* par_warm;
 } hy2dl_head_fwd;
+/* Optional fusion of the head adjoint into hy2dl_lstm_bwd (same conditions): the external gradient of the
+ * hidden state is dz * W_head with dz formed in the kernel from dpar_sim (gradient of par_sim) and par_sim,
+ * added to the recurrent term by the same tensor-core accumulation -- no dh_seq buffer exists.  The head's
+ * weight and bias gradients come from hy2dl_head_map_bwd with dh_seq = NULL. */
+typedef struct {
+  const float* w;          /* [C][H] */
+  const hy2dl_parmap* pm;
+  const float* par_sim;
+  const float* dpar_sim;
+} hy2dl_head_bwd;
 
 /* ---- LSTM (replaces torch.nn.LSTM at modelzoo/cudalstm.py:50 and hybrid.py:92; one layer,
  * unidirectional, h0 = c0 = 0, gate order i|f|g|o as torch/nn/modules/rnn.py:935-941) -------------
@@ -126,7 +136,7 @@ int hy2dl_lstm_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
 int hy2dl_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh,
                    const float* gates, const float* c_seq, const float* dh_seq, int64_t dh_t0,
                    const float* dh_last, float* dG,
-                   void* ws, int64_t ws_bytes, int precision, hy2dl_stream_t stream);
+                   void* ws, int64_t ws_bytes, int precision, const hy2dl_head_bwd* head, hy2dl_stream_t stream);
 /* Weight gradients from dG: dw_ih [4H][I] = dG^T xT, dw_hh [4H][H] = dG^T h_{t-1}, db [4H] = sum dG
  * (db is the gradient of both b_ih and b_hh).  Outputs are overwritten, not accumulated. */
 int hy2dl_lstm_wgrad(const float* dG, const float* h_seq, const float* xT,
@@ -143,7 +153,8 @@ int hy2dl_head_map_fwd(const float* h_seq, int64_t B, int64_t T, int64_t H,
                        float* par_sim, float* par_warm, int layout, hy2dl_stream_t stream);
 /* par_sim: the forward output; dpar_sim has the same layout.  Writes dh_seq rows t >= warmup
  * (the warm-up runs under no_grad, hybrid.py:99-102, so row warmup-1 and earlier get no gradient
- * and are left untouched), and overwrites dw [C][H], dbias [C]. */
+ * and are left untouched), and overwrites dw [C][H], dbias [C].  dh_seq may be NULL: weight and bias
+ * gradients only (the hidden-state gradient is then formed inside hy2dl_lstm_bwd, see hy2dl_head_bwd). */
 int hy2dl_head_map_bwd(const float* h_seq, const float* par_sim, const float* dpar_sim, int64_t B, int64_t T,
                        int64_t H, const float* w, const hy2dl_parmap* pm, float* dh_seq, float* dw, float* dbias,
                        int layout, hy2dl_stream_t stream);

@@ -89,7 +89,7 @@ def _bwd_both(dev, B, T, I, dh_t0, use_last, seed=3):
         dl = cu(gl) if use_last else None
         wsb = ops._ws(_lib.WS_LSTM_BWD, B, T, I, H, dev, prec)
         _lib.call("hy2dl_lstm_bwd", B, T, H, wd[1].data_ptr(), g.data_ptr(), c.data_ptr(), dh_in.data_ptr(), dh_t0,
-                  None if dl is None else dl.data_ptr(), g.data_ptr(), wsb.data_ptr(), wsb.numel(), prec, _lib.stream())
+                  None if dl is None else dl.data_ptr(), g.data_ptr(), wsb.data_ptr(), wsb.numel(), prec, None, _lib.stream())
         # weight gradients with the same precision's kernel
         dwi = torch.full((4 * H, I), np.nan, device=dev); dwh = torch.full((4 * H, H), np.nan, device=dev)
         dbb = torch.full((4 * H,), np.nan, device=dev)

@@ -34,7 +34,7 @@ def fwd():
               h.data_ptr(), c.data_ptr(), g.data_ptr(), hl.data_ptr(), wsf.data_ptr(), wsf.numel(), prec, None, st)
 def bwd():
     _lib.call("hy2dl_lstm_bwd", B, T, H, w_hh.data_ptr(), g.data_ptr(), c.data_ptr(), dh.data_ptr(), T // 2, None, g.data_ptr(),
-              wsb.data_ptr(), wsb.numel(), prec, st)
+              wsb.data_ptr(), wsb.numel(), prec, None, st)
 def wgrad():
     _lib.call("hy2dl_lstm_wgrad", g.data_ptr(), h.data_ptr(), x.data_ptr(), B, T, I, IP, H, dwi.data_ptr(), dwh.data_ptr(), db.data_ptr(),
               wsw.data_ptr(), wsw.numel(), prec, st)

@@ -44,7 +44,7 @@ def bwd(prec, h, c, g):
         g_in, c_in, dh_in = g.clone(), c, dh
     wsb = ops._ws(_lib.WS_LSTM_BWD, B, T, I, H, dev, prec)
     _lib.call("hy2dl_lstm_bwd", B, T, H, wd[1].data_ptr(), g_in.data_ptr(), c_in.data_ptr(), dh_in.data_ptr(), dh_t0, None,
-              g_in.data_ptr(), wsb.data_ptr(), wsb.numel(), prec, _lib.stream())
+              g_in.data_ptr(), wsb.data_ptr(), wsb.numel(), prec, None, _lib.stream())
     torch.cuda.synchronize()
     if ri:
         dG = ops.from_ri32(g_in.view(T, G, 4 * H // 32, 32, 32), B).reshape(T, B, H, 4).permute(0, 1, 3, 2).reshape(T, B, 4 * H)
