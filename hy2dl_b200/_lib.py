@@ -42,7 +42,13 @@ class HeadFwd(C.Structure):
 
 class HeadBwd(C.Structure):
     """hy2dl_head_bwd (include/hy2dl_b200.h): optional fusion of the head adjoint into hy2dl_lstm_bwd."""
-    _fields_ = [("w", C.c_void_p), ("pm", C.POINTER(ParMap)), ("par_sim", C.c_void_p), ("dpar_sim", C.c_void_p)]
+    _fields_ = [("w", C.c_void_p), ("pm", C.POINTER(ParMap)), ("par_sim", C.c_void_p), ("dpar_sim", C.c_void_p),
+                ("dz", C.c_void_p), ("db", C.c_void_p)]
+
+
+class HeadWgrad(C.Structure):
+    """hy2dl_head_wgrad (include/hy2dl_b200.h): optional head part of hy2dl_lstm_wgrad."""
+    _fields_ = [("dz", C.c_void_p), ("t0", C.c_int64), ("n_columns", C.c_int32), ("dw", C.c_void_p)]
 
 
 _SIGNATURES = {
@@ -56,7 +62,7 @@ _SIGNATURES = {
     "hy2dl_lstm_fwd": (i32, [p_f, i64, i64, i64, i64, i64, p_f, p_f, p_f, p_f, p_f, p_f, p_f, p_f, p_f, i64, i32,
                               C.POINTER(HeadFwd), p_f]),
     "hy2dl_lstm_bwd": (i32, [i64, i64, i64, p_f, p_f, p_f, p_f, i64, p_f, p_f, p_f, i64, i32, C.POINTER(HeadBwd), p_f]),
-    "hy2dl_lstm_wgrad": (i32, [p_f, p_f, p_f, i64, i64, i64, i64, i64, p_f, p_f, p_f, p_f, i64, i32, p_f]),
+    "hy2dl_lstm_wgrad": (i32, [p_f, p_f, p_f, i64, i64, i64, i64, i64, p_f, p_f, p_f, p_f, i64, i32, C.POINTER(HeadWgrad), p_f]),
     "hy2dl_parmap_layout": (i64, [C.POINTER(ParMap), i64, i64]),
     "hy2dl_head_map_fwd": (i32, [p_f, i64, i64, i64, p_f, p_f, C.POINTER(ParMap), p_f, p_f, i32, p_f]),
     "hy2dl_head_map_bwd": (i32, [p_f, p_f, p_f, i64, i64, i64, p_f, C.POINTER(ParMap), p_f, p_f, p_f, i32, p_f]),

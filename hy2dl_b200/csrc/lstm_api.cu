@@ -18,7 +18,8 @@ int lstm_tc_bwd(int64_t B, int64_t T, const float* w_hh, const float* gates, con
                 int64_t dh_t0, const float* dh_last, float* dG, void* ws, int64_t ws_bytes, const hy2dl_head_bwd* head,
                 cudaStream_t s);
 int lstm_tc_wgrad(const float* dG, const float* h_seq, const float* x_ri, int64_t B, int64_t T, int64_t I, int64_t IP,
-                  float* dw_ih, float* dw_hh, float* db, void* ws, int64_t ws_bytes, cudaStream_t s);
+                  float* dw_ih, float* dw_hh, float* db, void* ws, int64_t ws_bytes, const hy2dl_head_wgrad* head,
+                  cudaStream_t s);
 int64_t lstm_tc_workspace(int kind, int64_t B, int64_t T, int64_t I, int64_t H);
 bool lstm_tc_supported(int64_t I, int64_t H);
 }  // namespace tc
@@ -91,7 +92,7 @@ extern "C" int hy2dl_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh
 
 extern "C" int hy2dl_lstm_wgrad(const float* dG, const float* h_seq, const float* xT, int64_t B, int64_t T, int64_t I,
                                 int64_t IP, int64_t H, float* dw_ih, float* dw_hh, float* db, void* ws,
-                                int64_t ws_bytes, int precision, hy2dl_stream_t stream) {
+                                int64_t ws_bytes, int precision, const hy2dl_head_wgrad* head, hy2dl_stream_t stream) {
   int rc = check_lstm_shape("hy2dl_lstm_wgrad", B, T, I, IP, H, precision);
   if (rc) return rc;
   HY_PTR(dG); HY_PTR(h_seq); HY_PTR(xT); HY_PTR(dw_ih); HY_PTR(dw_hh); HY_PTR(db);
@@ -99,8 +100,9 @@ extern "C" int hy2dl_lstm_wgrad(const float* dG, const float* h_seq, const float
     HY_REQUIRE(tc::lstm_tc_supported(I, H), HY2DL_ERR_SHAPE,
                "hy2dl_lstm_wgrad: the tf32x3 tensor-core path supports hidden_size 64 and input_size <= 31 (got H=%lld I=%lld)",
                (long long)H, (long long)I);
-    return tc::lstm_tc_wgrad(dG, h_seq, xT, B, T, I, IP, dw_ih, dw_hh, db, ws, ws_bytes, (cudaStream_t)stream);
+    return tc::lstm_tc_wgrad(dG, h_seq, xT, B, T, I, IP, dw_ih, dw_hh, db, ws, ws_bytes, head, (cudaStream_t)stream);
   }
+  HY_REQUIRE(head == nullptr, HY2DL_ERR_SHAPE, "hy2dl_lstm_wgrad: the fused head needs precision tf32x3 (use hy2dl_head_map_bwd otherwise)");
   HY_REQUIRE(precision == HY2DL_PREC_FP32, HY2DL_ERR_SHAPE, "hy2dl_lstm_wgrad: precision %d not built", precision);
   return lstm_fp32_wgrad(dG, h_seq, xT, B, T, I, IP, H, dw_ih, dw_hh, db, ws, ws_bytes, (cudaStream_t)stream);
 }

@@ -566,6 +566,8 @@ struct TcBwdArgs {
   const float* wh_lo;
   const float* par_sim;
   const float* dpar_sim;
+  float* dz_out;          // RI32 F = 32 [T][G][32 rows][32]: dz of time th (columns >= C untouched), for the weight gradient
+  float* db_head;         // [C] head bias gradient, accumulated with atomics (zeroed by the launcher)
   int dbg;                // timing experiments only (HY2DL_DBG_BWD): 1 = dz warps skip their loads, 2 = skip the dz MMAs
   HeadCols hc;
 };
@@ -606,7 +608,8 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
   float* s_dc = s_wlo + kN * kH;                                        // [64][128] cell-state adjoint, per row thread
   float* s_hw = s_dc + kH * kRows;                                      // head: W_head^T hi | lo, [NH/4][64][4] each
   float* s_dz = s_hw + 2 * NH * kH;                                     // head: n_dzbuf x (hi | lo) [NH/4][128 rows][4]
-  uint64_t* bar_ready = reinterpret_cast<uint64_t*>(s_dz + (head ? n_dzbuf * 2 * NH * kRows : 0));  // [2] rows -> MMA, per slot
+  float* s_db = s_dz + (head ? n_dzbuf * 2 * NH * kRows : 0);           // head: bias-gradient partial sums [32]
+  uint64_t* bar_ready = reinterpret_cast<uint64_t*>(s_db + (head ? kHeadMax : 0));  // [2] rows -> MMA, per slot
   uint64_t* bar_free = bar_ready + 2;                                   // [2] MMA commit -> rows, per slot
   uint64_t* bar_dz_full = bar_free + 2;                                 // [2] dz warps -> MMA
   uint64_t* bar_dz_free = bar_dz_full + 2;                              // [2] MMA commit -> dz warps
@@ -624,6 +627,7 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
     if (head) {
       for (int e = tid; e < NH * kH; e += nthreads) { s_hw[e] = __ldg(a.wh_hi + e); s_hw[NH * kH + e] = __ldg(a.wh_lo + e); }
       for (int e = tid; e < n_dzbuf * 2 * NH * kRows; e += nthreads) s_dz[e] = 0.f;     // padding columns stay zero
+      if (tid < kHeadMax) s_db[tid] = 0.f;
     }
   }
   if (tid == 0) {
@@ -798,6 +802,13 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
     const HeadCols& hc = a.hc;
     const int64_t row0 = (int64_t)blockIdx.x * kRows;
     const int n_items = kRows * hc.C;
+    // head bias gradient: item slot (batch, i2) of this thread always has the same column, so its running sum
+    // lives in a register until the end of the kernel (2 batches of 16 cover the 4096 items of 32 columns)
+    float sdb[2][16];
+#pragma unroll
+    for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+      for (int i2 = 0; i2 < 16; ++i2) sdb[bb][i2] = 0.f;
     for (int64_t th = a.T - 1, i = 0; th >= hc.warmup; --th, ++i) {
       const int buf = (int)(i % n_dzbuf);
       if (i >= n_dzbuf) mbar_wait_relaxed(bar_dz_free + buf, (uint32_t)((i / n_dzbuf - 1) & 1));
@@ -805,7 +816,10 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
       float* dz_lo = dz_hi + NH * kRows;
       // batches of 16 items per thread: all loads of a batch are issued before the first use (one HBM latency
       // per batch instead of one per item)
-      for (int e0 = dt; e0 < n_items; e0 += 16 * kDzThreads) {
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb) {
+        const int e0 = dt + bb * 16 * kDzThreads;
+        if (e0 >= n_items) break;
         float val[16], dp[16];
 #pragma unroll
         for (int i2 = 0; i2 < 16; ++i2) {
@@ -834,16 +848,30 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
             const int o = ((c >> 2) * kRows + r) * 4 + (c & 3);
             dz_hi[o] = __uint_as_float(hi);
             dz_lo[o] = __uint_as_float(lw);
+            // for the weight-gradient GEMM: row r of this tile is row r & 31 of group 4 blockIdx + r / 32
+            const int64_t g = (int64_t)blockIdx.x * 4 + (r >> 5);
+            if (a.dz_out && g < a.G && !(a.dbg & 4))
+              a.dz_out[(th * a.G + g) * 1024 + (r & 31) * 32 + ((((c >> 3) ^ r) & 3) << 3) + (c & 7)] = dz;
+            // bias gradient: the 32 lanes of a warp share c (e0 and the stride are multiples of 32, 128 | c boundary)
+            sdb[bb][i2] += dz;
           }
         }
       }
       fence_async_smem();
       mbar_arrive(bar_dz_full + buf);
     }
+#pragma unroll
+    for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+      for (int i2 = 0; i2 < 16; ++i2) {
+        const int e = dt + (bb * 16 + i2) * kDzThreads;
+        if (e < n_items && sdb[bb][i2] != 0.f) atomicAdd(s_db + (e >> 7), sdb[bb][i2]);
+      }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 4) tmem_dealloc(tmem, kTmemCols);
+  if (head && a.db_head && tid < a.hc.C) atomicAdd(a.db_head + tid, s_db[tid]);
 }
 
 int lstm_tc_bwd(int64_t B, int64_t T, const float* w_hh, const float* gates, const float* c_seq, const float* dh_seq,
@@ -874,7 +902,9 @@ int lstm_tc_bwd(int64_t B, int64_t T, const float* w_hh, const float* gates, con
     static const int dbg = [] { const char* e = getenv("HY2DL_DBG_BWD"); return e ? atoi(e) : 0; }();
     a.dbg = dbg;
     a.has_head = 1; a.wh_hi = wh_hi; a.wh_lo = wh_lo; a.par_sim = head->par_sim; a.dpar_sim = head->dpar_sim;
-    smem += (size_t)2 * NH * kH * 4 + (size_t)2 * NH * kRows * 4;
+    a.dz_out = head->dz; a.db_head = head->db;
+    if (head->db) cudaMemsetAsync(head->db, 0, sizeof(float) * a.hc.C, s);
+    smem += (size_t)2 * NH * kH * 4 + (size_t)2 * NH * kRows * 4 + kHeadMax * 4;
     threads = kBwdThreadsHead;
   }
   static const int dbg_smem = [] { const char* e = getenv("HY2DL_DBG_SMEM"); return e ? atoi(e) : 0; }();   // experiment: extra smem

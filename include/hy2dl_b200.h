@@ -113,14 +113,26 @@ typedef struct {
 } hy2dl_head_fwd;
 /* Optional fusion of the head adjoint into hy2dl_lstm_bwd (same conditions): the external gradient of the
  * hidden state is dz * W_head with dz formed in the kernel from dpar_sim (gradient of par_sim) and par_sim,
- * added to the recurrent term by the same tensor-core accumulation -- no dh_seq buffer exists.  The head's
- * weight and bias gradients come from hy2dl_head_map_bwd with dh_seq = NULL. */
+ * added to the recurrent term by the same tensor-core accumulation -- no dh_seq buffer exists.
+ * dz (RI32, F = 32: [T][ceil(B/32)][32][32], steps >= warmup written, columns >= C untouched) feeds
+ * hy2dl_lstm_wgrad's head part; db [C] receives the head bias gradient.  Both may be NULL, in which case
+ * the head's weight and bias gradients come from hy2dl_head_map_bwd with dh_seq = NULL. */
 typedef struct {
   const float* w;          /* [C][H] */
   const hy2dl_parmap* pm;
   const float* par_sim;
   const float* dpar_sim;
+  float* dz;               /* out, nullable */
+  float* db;               /* out, nullable */
 } hy2dl_head_bwd;
+/* Optional head part of hy2dl_lstm_wgrad: dw [C][H] = sum_t dz_t^T h_t over the steps t >= t0, on the h slabs the
+ * kernel loads anyway. */
+typedef struct {
+  const float* dz;         /* as written by hy2dl_lstm_bwd */
+  int64_t t0;              /* first step with a head gradient (= warmup) */
+  int32_t n_columns;       /* C <= 32 */
+  float* dw;               /* [C][H] out */
+} hy2dl_head_wgrad;
 
 /* ---- LSTM (replaces torch.nn.LSTM at modelzoo/cudalstm.py:50 and hybrid.py:92; one layer,
  * unidirectional, h0 = c0 = 0, gate order i|f|g|o as torch/nn/modules/rnn.py:935-941) -------------
@@ -142,7 +154,7 @@ int hy2dl_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh,
 int hy2dl_lstm_wgrad(const float* dG, const float* h_seq, const float* xT,
                      int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H,
                      float* dw_ih, float* dw_hh, float* db,
-                     void* ws, int64_t ws_bytes, int precision, hy2dl_stream_t stream);
+                     void* ws, int64_t ws_bytes, int precision, const hy2dl_head_wgrad* head, hy2dl_stream_t stream);
 
 /* ---- head kernels (unfused; any H, any number of columns) --------------------------------------- */
 /* fills sim_off for (B, T) and returns the number of floats par_sim needs; par_warm needs

@@ -95,7 +95,7 @@ def _bwd_both(dev, B, T, I, dh_t0, use_last, seed=3):
         dbb = torch.full((4 * H,), np.nan, device=dev)
         wsw = ops._ws(_lib.WS_LSTM_WGRAD, B, T, I, H, dev, prec)
         _lib.call("hy2dl_lstm_wgrad", g.data_ptr(), h.data_ptr(), x_in.data_ptr(), B, T, I, IP, H, dwi.data_ptr(),
-                  dwh.data_ptr(), dbb.data_ptr(), wsw.data_ptr(), wsw.numel(), prec, _lib.stream())
+                  dwh.data_ptr(), dbb.data_ptr(), wsw.data_ptr(), wsw.numel(), prec, None, _lib.stream())
         torch.cuda.synchronize()
         wg[prec] = {"lstm.weight_ih_l0": dwi.cpu().numpy(), "lstm.weight_hh_l0": dwh.cpu().numpy(),
                     "lstm.bias_ih_l0": dbb.cpu().numpy()}
@@ -160,7 +160,7 @@ def test_tc_wgrad_shapes(B, T, I):
     ws = ops._ws(_lib.WS_LSTM_WGRAD, B, T, I, H, dev, _lib.PREC_TF32X3)
     args = [ops.to_ri32(cu(a)) for a in (dG, h, x)]
     _lib.call("hy2dl_lstm_wgrad", *[a.data_ptr() for a in args], B, T, I, IP, H, dwi.data_ptr(), dwh.data_ptr(),
-              dbb.data_ptr(), ws.data_ptr(), ws.numel(), _lib.PREC_TF32X3, _lib.stream())
+              dbb.data_ptr(), ws.data_ptr(), ws.numel(), _lib.PREC_TF32X3, None, _lib.stream())
     torch.cuda.synchronize()
     d = dG.astype(np.float64).reshape(T, B, H, 4).transpose(0, 1, 3, 2).reshape(T, B, 4 * H)   # -> g*H + u
     hprev = np.concatenate([np.zeros_like(h[:1]), h[:-1]]).astype(np.float64)

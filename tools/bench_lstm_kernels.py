@@ -37,7 +37,7 @@ def bwd():
               wsb.data_ptr(), wsb.numel(), prec, None, st)
 def wgrad():
     _lib.call("hy2dl_lstm_wgrad", g.data_ptr(), h.data_ptr(), x.data_ptr(), B, T, I, IP, H, dwi.data_ptr(), dwh.data_ptr(), db.data_ptr(),
-              wsw.data_ptr(), wsw.numel(), prec, st)
+              wsw.data_ptr(), wsw.numel(), prec, None, st)
 
 def timeit(f):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -19,7 +19,7 @@ for (B, T) in [(4736, 4), (18944, 16), (18944, 64)]:
     ws = ops._ws(_lib.WS_LSTM_WGRAD, B, T, I, H, dev, _lib.PREC_TF32X3)
     args = [ops.to_ri32(a) for a in (dG, h, x)]
     _lib.call("hy2dl_lstm_wgrad", *[a.data_ptr() for a in args], B, T, I, IP, H, dwi.data_ptr(), dwh.data_ptr(),
-              dbb.data_ptr(), ws.data_ptr(), ws.numel(), _lib.PREC_TF32X3, _lib.stream())
+              dbb.data_ptr(), ws.data_ptr(), ws.numel(), _lib.PREC_TF32X3, None, _lib.stream())
     torch.cuda.synchronize()
     d = dG.double().reshape(T, B, H, 4).permute(0, 1, 3, 2).reshape(T * B, 4 * H)
     ref_i = d.t() @ x.double().reshape(T * B, IP)

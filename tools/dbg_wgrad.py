@@ -25,7 +25,7 @@ ws = ops._ws(_lib.WS_LSTM_WGRAD, B, T, I, H, dev, _lib.PREC_TF32X3)
 ws.zero_()
 args = [ops.to_ri32(cu(a)) for a in (dG, h, x)]
 _lib.call("hy2dl_lstm_wgrad", *[a.data_ptr() for a in args], B, T, I, IP, H, dwi.data_ptr(), dwh.data_ptr(),
-          dbb.data_ptr(), ws.data_ptr(), ws.numel(), _lib.PREC_TF32X3, _lib.stream())
+          dbb.data_ptr(), ws.data_ptr(), ws.numel(), _lib.PREC_TF32X3, None, _lib.stream())
 torch.cuda.synchronize()
 ND = 112
 part = ws.view(torch.float32)[: 2 * 256 * ND].view(2, 256, ND).cpu().numpy()
