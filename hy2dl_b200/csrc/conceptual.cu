@@ -103,29 +103,35 @@ __global__ void __launch_bounds__(kBlock) conceptual_bwd_kernel(ConceptualArgs a
 #pragma unroll
   for (int k = 0; k < M::NP; ++k) { gacc[k] = 0.f; p[k] = a.par[k] ? __ldg(a.par[k] + n) : 0.f; }
 
-  for (int64_t t = a.Tn - 1; t >= 0; --t) {
+  // inputs of one step: forcings, dynamic parameters, the state BEFORE the step, incoming gradients.  The
+  // next (earlier) step's inputs are requested before this step's adjoint chain starts, so their HBM latency
+  // hides behind ~100 dependent flops (one thread per series leaves nothing else to hide it with).
+  struct In { float P, E, Tm, gq, p[M::NP], s[kNS], ds[kNS]; };
+  auto load = [&](int64_t t, In& in) {
     const float* f = a.forc + (a.t0 + t) * 3 * a.B + b;
-    const float P = __ldg(f), E = __ldg(f + a.B), Tm = __ldg(f + 2 * a.B);
+    in.P = __ldg(f); in.E = __ldg(f + a.B); in.Tm = __ldg(f + 2 * a.B);
 #pragma unroll
-    for (int k = 0; k < M::NP; ++k)
-      if (a.ts[k]) p[k] = __ldg(a.par[k] + t * a.ts[k] + n);
-    float s[kNS];
+    for (int k = 0; k < M::NP; ++k) in.p[k] = a.ts[k] ? __ldg(a.par[k] + t * a.ts[k] + n) : p[k];
     if (t > 0) {
       const float* st = a.states + (t - 1) * kNS * a.N + n;
 #pragma unroll
-      for (int k = 0; k < kNS; ++k) s[k] = __ldg(st + k * a.N);
+      for (int k = 0; k < kNS; ++k) in.s[k] = __ldg(st + k * a.N);
     } else {
 #pragma unroll
-      for (int k = 0; k < kNS; ++k) s[k] = a.init ? a.init[k * a.N + n] : M::kInit;
+      for (int k = 0; k < kNS; ++k) in.s[k] = a.init ? a.init[k * a.N + n] : M::kInit;
     }
-    if (a.dstates) {
-      const float* ds = a.dstates + t * kNS * a.N + n;
 #pragma unroll
-      for (int k = 0; k < kNS; ++k) g[k] += __ldg(ds + k * a.N);
-    }
-    const float gq = __ldg(a.dq + t * a.B + b) * inv_m;
+    for (int k = 0; k < kNS; ++k) in.ds[k] = a.dstates ? __ldg(a.dstates + (t * kNS + k) * a.N + n) : 0.f;
+    in.gq = __ldg(a.dq + t * a.B + b) * inv_m;
+  };
+  In cur, nxt;
+  load(a.Tn - 1, cur);
+  for (int64_t t = a.Tn - 1; t >= 0; --t) {
+    if (t > 0) load(t - 1, nxt);
+#pragma unroll
+    for (int k = 0; k < kNS; ++k) g[k] += cur.ds[k];
     float gp[M::NP];
-    M::adjoint(s, p, P, E, Tm, a.has_betaet != 0, g, gq, gp);
+    M::adjoint(cur.s, cur.p, cur.P, cur.E, cur.Tm, a.has_betaet != 0, g, cur.gq, gp);
 #pragma unroll
     for (int k = 0; k < M::NP; ++k) {
       if (a.ts[k]) {
@@ -134,6 +140,7 @@ __global__ void __launch_bounds__(kBlock) conceptual_bwd_kernel(ConceptualArgs a
         gacc[k] += gp[k];
       }
     }
+    cur = nxt;
   }
 #pragma unroll
   for (int k = 0; k < M::NP; ++k)

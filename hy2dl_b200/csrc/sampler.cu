@@ -42,31 +42,58 @@ __global__ void __launch_bounds__(kGatherThreads) window_gather_kernel(GatherArg
   const int per_slab = 32 * (int)a.IP;                          // floats of one step's slab (RI32: IP = 32)
   const int n_mine = (per_slab + kGatherThreads - 1) / kGatherThreads;
 
-  const float* src[kMaxPerThread];   // dynamic source at step 0 (nullptr: constant)
-  float cst[kMaxPerThread];
+  if (a.ri32) {
+    // RI32 slab = 1024 floats: thread i owns words 4i .. 4i+3 (4 consecutive features of one row, inside one
+    // swizzled 8-float unit) and writes them with one 16-byte store per step
+    const int e0 = 4 * threadIdx.x;
+    const int64_t lb = e0 >> 5;
+    const int c0 = ((((e0 >> 3) & 3) ^ (int)(lb & 3)) << 3) | (e0 & 7);
+    const float* src[4];
+    float cst[4];
 #pragma unroll
-  for (int i = 0; i < kMaxPerThread; ++i) {
-    src[i] = nullptr; cst[i] = 0.f;
-    const int e = threadIdx.x + i * kGatherThreads;
-    if (i < n_mine && e < per_slab) {
-      int64_t lb, c;
-      if (a.ri32) { lb = e >> 5; c = ((((e >> 3) & 3) ^ (lb & 3)) << 3) | (e & 7); }   // feature stored at word e
-      else { lb = e / a.IP; c = e - lb * a.IP; }
+    for (int i = 0; i < 4; ++i) {
+      src[i] = nullptr; cst[i] = 0.f;
+      const int c = c0 + i;
       if (lb < nb) {
         if (c < a.nd) src[i] = a.x_d + s_row[lb] * a.nd + c;
         else if (c < I) cst[i] = __ldg(a.x_s + s_basin[lb] * a.ns + (c - a.nd));
       }
     }
-  }
-  const int64_t rows_per_step = a.ri32 ? (int64_t)gridDim.x * 32 : a.B;
-  const int64_t slab_in_step = a.ri32 ? (int64_t)blockIdx.x * per_slab : b0 * a.IP;
-  const int live = a.ri32 ? per_slab : (int)(nb * a.IP);        // row-major: rows >= nb do not exist
-  for (int64_t t = t0; t < t1; ++t) {
-    float* dst = a.xT + t * rows_per_step * a.IP + slab_in_step;
+    const bool any_dyn = src[0] || src[1] || src[2] || src[3];
+    float4* dst = reinterpret_cast<float4*>(a.xT + (t0 * gridDim.x + blockIdx.x) * 1024) + threadIdx.x;
+    for (int64_t t = t0; t < t1; ++t, dst += (int64_t)gridDim.x * 256) {
+      float4 v = make_float4(cst[0], cst[1], cst[2], cst[3]);
+      if (any_dyn) {
+        if (src[0]) v.x = __ldg(src[0] + t * a.nd);
+        if (src[1]) v.y = __ldg(src[1] + t * a.nd);
+        if (src[2]) v.z = __ldg(src[2] + t * a.nd);
+        if (src[3]) v.w = __ldg(src[3] + t * a.nd);
+      }
+      *dst = v;
+    }
+  } else {
+    const float* src[kMaxPerThread];   // dynamic source at step 0 (nullptr: constant)
+    float cst[kMaxPerThread];
 #pragma unroll
     for (int i = 0; i < kMaxPerThread; ++i) {
+      src[i] = nullptr; cst[i] = 0.f;
       const int e = threadIdx.x + i * kGatherThreads;
-      if (i < n_mine && e < live) dst[e] = src[i] ? __ldg(src[i] + t * a.nd) : cst[i];
+      if (i < n_mine && e < per_slab) {
+        const int64_t lb = e / a.IP, c = e - lb * a.IP;
+        if (lb < nb) {
+          if (c < a.nd) src[i] = a.x_d + s_row[lb] * a.nd + c;
+          else if (c < I) cst[i] = __ldg(a.x_s + s_basin[lb] * a.ns + (c - a.nd));
+        }
+      }
+    }
+    const int live = (int)(nb * a.IP);                           // rows >= nb do not exist in the row-major layout
+    for (int64_t t = t0; t < t1; ++t) {
+      float* dst = a.xT + (t * a.B + b0) * a.IP;
+#pragma unroll
+      for (int i = 0; i < kMaxPerThread; ++i) {
+        const int e = threadIdx.x + i * kGatherThreads;
+        if (i < n_mine && e < live) dst[e] = src[i] ? __ldg(src[i] + t * a.nd) : cst[i];
+      }
     }
   }
   if (a.forc) {
