@@ -43,12 +43,12 @@ class HeadFwd(C.Structure):
 class HeadBwd(C.Structure):
     """hy2dl_head_bwd (include/hy2dl_b200.h): optional fusion of the head adjoint into hy2dl_lstm_bwd."""
     _fields_ = [("w", C.c_void_p), ("pm", C.POINTER(ParMap)), ("par_sim", C.c_void_p), ("dpar_sim", C.c_void_p),
-                ("dz", C.c_void_p), ("db", C.c_void_p)]
+                ("dz", C.c_void_p)]
 
 
 class HeadWgrad(C.Structure):
     """hy2dl_head_wgrad (include/hy2dl_b200.h): optional head part of hy2dl_lstm_wgrad."""
-    _fields_ = [("dz", C.c_void_p), ("t0", C.c_int64), ("n_columns", C.c_int32), ("dw", C.c_void_p)]
+    _fields_ = [("dz", C.c_void_p), ("t0", C.c_int64), ("n_columns", C.c_int32), ("dw", C.c_void_p), ("db", C.c_void_p)]
 
 
 _SIGNATURES = {

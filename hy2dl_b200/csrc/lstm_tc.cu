@@ -520,8 +520,9 @@ int lstm_tc_fwd(const float* x_ri, int64_t B, int64_t T, int64_t I, int64_t IP, 
 namespace hy2dl {
 namespace tc {
 
-constexpr int kBwdThreads = 160;       // 4 row warps + MMA warp
-constexpr int kBwdThreadsHead = 256;   // + 3 warps that turn dpar into the head's dz operand
+constexpr int kBwdRowWarps = 8;        // two sets of four row warps: set s owns hidden units 8Q + 4s .. 8Q + 4s + 3 of every block Q
+constexpr int kBwdThreads = 32 * kBwdRowWarps + 32;   // + MMA warp
+constexpr int kBwdThreadsHead = kBwdThreads + 96;     // + 3 warps that turn dpar into the head's dz operand
 constexpr int kDzThreads = 96;
 constexpr uint32_t kColDh0 = 0, kColSlot0 = 256;
 
@@ -567,30 +568,30 @@ struct TcBwdArgs {
   const float* par_sim;
   const float* dpar_sim;
   float* dz_out;          // RI32 F = 32 [T][G][32 rows][32]: dz of time th (columns >= C untouched), for the weight gradient
-  float* db_head;         // [C] head bias gradient, accumulated with atomics (zeroed by the launcher)
-  int dbg;                // timing experiments only (HY2DL_DBG_BWD): 1 = dz warps skip their loads, 2 = skip the dz MMAs
   HeadCols hc;
 };
 
-struct BwdChunk {   // tape of 8 hidden units of one row at one step: one 128-byte line of gates + three sectors
-  f8 g[4], ct, cp, dh;
+struct BwdChunk {   // tape of 4 hidden units of one row at one step: half a 128-byte line of gates + three half sectors
+  f8 g[2];
+  float4 ct, cp, dh;
 };
 
-// Q = 0..7: hidden units [8Q, 8Q + 8) = gate block Q (unit j holds units 8Q+2j, 8Q+2j+1 x 4 gates)
-__device__ __forceinline__ void bwd_load_chunk(const TcBwdArgs& a, int64_t t, int Q, int64_t gidx, int lane, bool live, BwdChunk& c) {
+// chunk (Q, set): hidden units [8Q + 4 set, 8Q + 4 set + 4) = 32-byte units 4Q + 2 set, 4Q + 2 set + 1 of the gates stream
+// (unit j holds 2 hidden units x 4 gates) and half `set` of unit Q of the c / dh streams
+__device__ __forceinline__ void bwd_load_chunk(const TcBwdArgs& a, int64_t t, int Q, int set, int64_t gidx, int lane, bool live,
+                                               BwdChunk& c) {
   const bool on = live && t >= 0;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) c.g[j] = on ? ldg256(a.gates + ri32_unit(t, a.G, gidx, 8, 4 * Q + j, lane)) : f8_zero();
-  c.ct = on ? ldg256(a.c_seq + ri32_unit(t, a.G, gidx, 2, Q, lane)) : f8_zero();
-  c.cp = (on && t > 0) ? ldg256(a.c_seq + ri32_unit(t - 1, a.G, gidx, 2, Q, lane)) : f8_zero();
-  c.dh = (on && a.dh_seq && t >= a.dh_t0) ? ldg256(a.dh_seq + ri32_unit(t, a.G, gidx, 2, Q, lane)) : f8_zero();
+  for (int j = 0; j < 2; ++j) c.g[j] = on ? ldg256(a.gates + ri32_unit(t, a.G, gidx, 8, 4 * Q + 2 * set + j, lane)) : f8_zero();
+  c.ct = on ? __ldg(reinterpret_cast<const float4*>(a.c_seq + ri32_unit(t, a.G, gidx, 2, Q, lane) + 4 * set)) : z4;
+  c.cp = (on && t > 0) ? __ldg(reinterpret_cast<const float4*>(a.c_seq + ri32_unit(t - 1, a.G, gidx, 2, Q, lane) + 4 * set)) : z4;
+  c.dh = (on && a.dh_seq && t >= a.dh_t0) ? __ldg(reinterpret_cast<const float4*>(a.dh_seq + ri32_unit(t, a.G, gidx, 2, Q, lane) + 4 * set)) : z4;
   if (on && a.dh_last && t == a.T - 1) {
     const int64_t b = gidx * 32 + lane;
     if (b < a.B) {
-      const float4 v0 = __ldg(reinterpret_cast<const float4*>(a.dh_last + b * kH + 8 * Q));
-      const float4 v1 = __ldg(reinterpret_cast<const float4*>(a.dh_last + b * kH + 8 * Q + 4));
-      c.dh.v[0] += v0.x; c.dh.v[1] += v0.y; c.dh.v[2] += v0.z; c.dh.v[3] += v0.w;
-      c.dh.v[4] += v1.x; c.dh.v[5] += v1.y; c.dh.v[6] += v1.z; c.dh.v[7] += v1.w;
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(a.dh_last + b * kH + 8 * Q + 4 * set));
+      c.dh.x += v0.x; c.dh.y += v0.y; c.dh.z += v0.z; c.dh.w += v0.w;
     }
   }
 }
@@ -608,8 +609,7 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
   float* s_dc = s_wlo + kN * kH;                                        // [64][128] cell-state adjoint, per row thread
   float* s_hw = s_dc + kH * kRows;                                      // head: W_head^T hi | lo, [NH/4][64][4] each
   float* s_dz = s_hw + 2 * NH * kH;                                     // head: n_dzbuf x (hi | lo) [NH/4][128 rows][4]
-  float* s_db = s_dz + (head ? n_dzbuf * 2 * NH * kRows : 0);           // head: bias-gradient partial sums [32]
-  uint64_t* bar_ready = reinterpret_cast<uint64_t*>(s_db + (head ? kHeadMax : 0));  // [2] rows -> MMA, per slot
+  uint64_t* bar_ready = reinterpret_cast<uint64_t*>(s_dz + (head ? n_dzbuf * 2 * NH * kRows : 0));  // [2] rows -> MMA, per slot
   uint64_t* bar_free = bar_ready + 2;                                   // [2] MMA commit -> rows, per slot
   uint64_t* bar_dz_full = bar_free + 2;                                 // [2] dz warps -> MMA
   uint64_t* bar_dz_free = bar_dz_full + 2;                              // [2] MMA commit -> dz warps
@@ -627,42 +627,48 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
     if (head) {
       for (int e = tid; e < NH * kH; e += nthreads) { s_hw[e] = __ldg(a.wh_hi + e); s_hw[NH * kH + e] = __ldg(a.wh_lo + e); }
       for (int e = tid; e < n_dzbuf * 2 * NH * kRows; e += nthreads) s_dz[e] = 0.f;     // padding columns stay zero
-      if (tid < kHeadMax) s_db[tid] = 0.f;
     }
   }
   if (tid == 0) {
-    mbar_init(bar_ready + 0, kRows); mbar_init(bar_ready + 1, kRows);
+    mbar_init(bar_ready + 0, 32 * kBwdRowWarps); mbar_init(bar_ready + 1, 32 * kBwdRowWarps);
     mbar_init(bar_free + 0, 1); mbar_init(bar_free + 1, 1);
     mbar_init(bar_dz_full + 0, kDzThreads); mbar_init(bar_dz_full + 1, kDzThreads);
     mbar_init(bar_dz_free + 0, 1); mbar_init(bar_dz_free + 1, 1);
     mbar_init(bar_pre, 1);
     mbar_fence_init();
   }
-  if (warp == 4) tmem_alloc(s_tmem, kTmemCols);
+  if (warp == kBwdRowWarps) tmem_alloc(s_tmem, kTmemCols);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
-  if (warp < 4) {
-    const int64_t gidx = (int64_t)blockIdx.x * 4 + warp;
+  if (warp < kBwdRowWarps) {
+    // two warps per scheduler (set 0 / set 1 of the same 32 rows) hide each other's latencies: the chunk loop is
+    // a chain of tape loads, TMEM loads, ~40 dependent flops per unit, stores and TMEM stores
+    const int set = warp >> 2, wq = warp & 3;
+    const int64_t gidx = (int64_t)blockIdx.x * 4 + wq;
     const bool live = gidx < a.G;
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-    float* dcp = s_dc + tid;     // dc[u] at dcp[u * 128]: conflict-free, keeps the chunk loop rolled and small
-    for (int u = 0; u < kH; ++u) dcp[u * kRows] = 0.f;
-    if (head) {                  // dh(T-1) comes from the head alone: only accumulator {0,1} of buffer 1 is written
+    const uint32_t lane_base = tmem + ((uint32_t)(wq * 32) << 16);
+    float* dcp = s_dc + wq * 32 + lane;     // dc[u] at dcp[u * 128]: conflict-free
+    for (int u = 4 * set; u < kH; u += 8)
+      for (int uu = 0; uu < 4; ++uu) dcp[(u + uu) * kRows] = 0.f;
+    if (head && set == 0) {      // dh(T-1) comes from the head alone: only accumulator {0,1} of buffer 1 is written
       uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       for (int cc = 0; cc < 64; cc += 8) tmem_st8(lane_base + kColDh0 + 128 + 64 + cc, z);
       tmem_st_wait();
+      tc_fence_before();
     }
+    if (head) asm volatile("bar.sync 1, 256;" ::: "memory");   // row warps only: set 1 also reads those columns at s = 0
+    if (head) tc_fence_after();
 
-    // tape chunks (8 hidden units = 224 B per row) travel through a 2-deep register ring: chunk Q + 2 is
-    // requested as soon as chunk Q has been consumed, so ~450 B per thread (57 KB per SM) are in flight --
-    // one warp per scheduler has no other way to cover the HBM latency.  Every access is a whole sector.
+    // tape chunks (4 hidden units = 112 B per row) travel through a 2-deep register ring: the chunk of block Q + 2
+    // is requested as soon as the one of block Q has been consumed.  Gate loads are whole sectors; the two sets
+    // share the c / dh sectors of a block (16 bytes each, requested at about the same time).
     BwdChunk ring[2];
-    bwd_load_chunk(a, a.T - 1, 0, gidx, lane, live, ring[0]);
-    bwd_load_chunk(a, a.T - 1, 1, gidx, lane, live, ring[1]);
+    bwd_load_chunk(a, a.T - 1, 0, set, gidx, lane, live, ring[0]);
+    bwd_load_chunk(a, a.T - 1, 1, set, gidx, lane, live, ring[1]);
     for (int64_t s = 0; s < a.T; ++s) {
       const int64_t t = a.T - 1 - s;
       const uint32_t d_prev = lane_base + kColDh0 + 128 * (uint32_t)((s & 1) ^ 1);  // dh_rec partial sums from step s-1
@@ -682,46 +688,49 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
           tc_fence_after();
         }
 #pragma unroll
-        for (int kk = 0; kk < 2; ++kk) { // two chunks of 8 hidden units per quarter
+        for (int kk = 0; kk < 2; ++kk) { // blocks Q = 2k, 2k+1; this thread's 4 hidden units of each
           const int Q = 2 * k + kk;
           BwdChunk& cur = ring[kk];
-          uint32_t r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          uint32_t r[4] = {0, 0, 0, 0};
           if (have_prev) {
-            uint32_t r2[8];
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                         : "r"(d_prev + 8 * Q));
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                         : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7])
-                         : "r"(d_prev + 64 + 8 * Q));
+            uint32_t r2[4];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                         : "r"(d_prev + 8 * Q + 4 * set));
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3])
+                         : "r"(d_prev + 64 + 8 * Q + 4 * set));
             tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 8; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+            for (int e = 0; e < 4; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
           }
-          f8 dg[4];
+          const float dhe[4] = {cur.dh.x, cur.dh.y, cur.dh.z, cur.dh.w};
+          const float ctv[4] = {cur.ct.x, cur.ct.y, cur.ct.z, cur.ct.w};
+          const float cpv[4] = {cur.cp.x, cur.cp.y, cur.cp.z, cur.cp.w};
+          f8 dg[2];
 #pragma unroll
-          for (int uu = 0; uu < 8; ++uu) {
-            const int u = 8 * Q + uu, j = uu >> 1, o = 4 * (uu & 1);
+          for (int uu = 0; uu < 4; ++uu) {
+            const int u = 8 * Q + 4 * set + uu, j = uu >> 1, o = 4 * (uu & 1);
             const float gi = cur.g[j].v[o], gf = cur.g[j].v[o + 1], gg = cur.g[j].v[o + 2], go = cur.g[j].v[o + 3];
-            const float dh = cur.dh.v[uu] + __uint_as_float(r[uu]);
-            const float tcv = fast_tanh(cur.ct.v[uu]);
+            const float dh = dhe[uu] + __uint_as_float(r[uu]);
+            const float tcv = fast_tanh(ctv[uu]);
             const float dct = dcp[u * kRows] + dh * go * (1.f - tcv * tcv);
             dg[j].v[o + 0] = dct * gg * gi * (1.f - gi);
-            dg[j].v[o + 1] = dct * cur.cp.v[uu] * gf * (1.f - gf);
+            dg[j].v[o + 1] = dct * cpv[uu] * gf * (1.f - gf);
             dg[j].v[o + 2] = dct * gi * (1.f - gg * gg);
             dg[j].v[o + 3] = dh * tcv * go * (1.f - go);
             dcp[u * kRows] = dct * gf;
           }
-          // refill this ring slot: chunk Q + 2 of this step, or chunk kk of the next (earlier) step
-          if (k < 3) bwd_load_chunk(a, t, Q + 2, gidx, lane, live, cur);
-          else bwd_load_chunk(a, t - 1, kk, gidx, lane, live, cur);
+          // refill this ring slot: block Q + 2 of this step, or block kk of the next (earlier) step
+          if (k < 3) bwd_load_chunk(a, t, Q + 2, set, gidx, lane, live, cur);
+          else bwd_load_chunk(a, t - 1, kk, set, gidx, lane, live, cur);
           if (live) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) stg256(a.dG + ri32_unit(t, a.G, gidx, 8, 4 * Q + j, lane), dg[j]);
+            for (int j = 0; j < 2; ++j) stg256(a.dG + ri32_unit(t, a.G, gidx, 8, 4 * Q + 2 * set + j, lane), dg[j]);
           }
-          const uint32_t sbase = lane_base + kColSlot0 + 128 * slot + 32 * kk;
+          const uint32_t sbase = lane_base + kColSlot0 + 128 * slot + 32 * kk + 16 * set;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 2; ++j) {
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) split_tf32(dg[j].v[e], hi[e], lo[e]);
@@ -734,7 +743,7 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
         mbar_arrive(bar_ready + slot);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == kBwdRowWarps) {
     if (lane == 0) {
       const uint32_t idesc = idesc_tf32(kRows, kH, 0, 0);
       const uint32_t whi = smem_u32(s_whi), wlo = smem_u32(s_wlo);
@@ -748,13 +757,13 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
         mbar_wait(bar_dz_full + buf, (uint32_t)((dz_i / n_dzbuf) & 1));
         tc_fence_after();
         const uint32_t a_hi = smem_u32(s_dz) + buf * dz_buf_bytes, a_lo = a_hi + dz_lo_off;
-        for (int j = 0; j < NH / 8 && !(a.dbg & 2); ++j) {
+        for (int j = 0; j < NH / 8; ++j) {
           const uint64_t ah = smem_desc(a_hi + j * 2 * 2048, 2048, 128), al = smem_desc(a_lo + j * 2 * 2048, 2048, 128);
           const uint64_t bh = smem_desc(hw_hi + j * 2 * lbo, lbo, sbo), bl = smem_desc(hw_lo + j * 2 * lbo, lbo, sbo);
           mma_tf32_ss(d, al, bh, idesc, j > 0);
           mma_tf32_ss(d, ah, bl, idesc, 1);
         }
-        for (int j = 0; j < NH / 8 && !(a.dbg & 2); ++j) {
+        for (int j = 0; j < NH / 8; ++j) {
           const uint64_t ah = smem_desc(a_hi + j * 2 * 2048, 2048, 128), bh = smem_desc(hw_hi + j * 2 * lbo, lbo, sbo);
           mma_tf32_ss(d, ah, bh, idesc, 1);
         }
@@ -802,13 +811,6 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
     const HeadCols& hc = a.hc;
     const int64_t row0 = (int64_t)blockIdx.x * kRows;
     const int n_items = kRows * hc.C;
-    // head bias gradient: item slot (batch, i2) of this thread always has the same column, so its running sum
-    // lives in a register until the end of the kernel (2 batches of 16 cover the 4096 items of 32 columns)
-    float sdb[2][16];
-#pragma unroll
-    for (int bb = 0; bb < 2; ++bb)
-#pragma unroll
-      for (int i2 = 0; i2 < 16; ++i2) sdb[bb][i2] = 0.f;
     for (int64_t th = a.T - 1, i = 0; th >= hc.warmup; --th, ++i) {
       const int buf = (int)(i % n_dzbuf);
       if (i >= n_dzbuf) mbar_wait_relaxed(bar_dz_free + buf, (uint32_t)((i / n_dzbuf - 1) & 1));
@@ -829,7 +831,7 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
             const int c = e >> 7, r = e & 127;
             const int64_t b = row0 + r;
             const int kind = hc.kind[c];
-            if (b < a.B && (kind == 0 || th == a.T - 1) && !(a.dbg & 1)) {
+            if (b < a.B && (kind == 0 || th == a.T - 1)) {
               const int64_t idx = hc.off[c] + (kind == 0 ? (th - hc.warmup) * hc.N : 0) + (kind == 2 ? b : b * hc.m + hc.mem[c]);
               val[i2] = __ldg(a.par_sim + idx);
               dp[i2] = __ldg(a.dpar_sim + idx);
@@ -850,28 +852,18 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
             dz_lo[o] = __uint_as_float(lw);
             // for the weight-gradient GEMM: row r of this tile is row r & 31 of group 4 blockIdx + r / 32
             const int64_t g = (int64_t)blockIdx.x * 4 + (r >> 5);
-            if (a.dz_out && g < a.G && !(a.dbg & 4))
+            if (a.dz_out && g < a.G)
               a.dz_out[(th * a.G + g) * 1024 + (r & 31) * 32 + ((((c >> 3) ^ r) & 3) << 3) + (c & 7)] = dz;
-            // bias gradient: the 32 lanes of a warp share c (e0 and the stride are multiples of 32, 128 | c boundary)
-            sdb[bb][i2] += dz;
           }
         }
       }
       fence_async_smem();
       mbar_arrive(bar_dz_full + buf);
     }
-#pragma unroll
-    for (int bb = 0; bb < 2; ++bb)
-#pragma unroll
-      for (int i2 = 0; i2 < 16; ++i2) {
-        const int e = dt + (bb * 16 + i2) * kDzThreads;
-        if (e < n_items && sdb[bb][i2] != 0.f) atomicAdd(s_db + (e >> 7), sdb[bb][i2]);
-      }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, kTmemCols);
-  if (head && a.db_head && tid < a.hc.C) atomicAdd(a.db_head + tid, s_db[tid]);
+  if (warp == kBwdRowWarps) tmem_dealloc(tmem, kTmemCols);
 }
 
 int lstm_tc_bwd(int64_t B, int64_t T, const float* w_hh, const float* gates, const float* c_seq, const float* dh_seq,
@@ -899,16 +891,11 @@ int lstm_tc_bwd(int64_t B, int64_t T, const float* w_hh, const float* gates, con
     float* wh_hi = w_lo + kN * kH;
     float* wh_lo = wh_hi + NH * kH;
     lstm_tc_pack_headT_kernel<<<8, 256, 0, s>>>(head->w, a.hc.C, NH, wh_hi, wh_lo);
-    static const int dbg = [] { const char* e = getenv("HY2DL_DBG_BWD"); return e ? atoi(e) : 0; }();
-    a.dbg = dbg;
     a.has_head = 1; a.wh_hi = wh_hi; a.wh_lo = wh_lo; a.par_sim = head->par_sim; a.dpar_sim = head->dpar_sim;
-    a.dz_out = head->dz; a.db_head = head->db;
-    if (head->db) cudaMemsetAsync(head->db, 0, sizeof(float) * a.hc.C, s);
-    smem += (size_t)2 * NH * kH * 4 + (size_t)2 * NH * kRows * 4 + kHeadMax * 4;
+    a.dz_out = head->dz;
+    smem += (size_t)2 * NH * kH * 4 + (size_t)2 * NH * kRows * 4;
     threads = kBwdThreadsHead;
   }
-  static const int dbg_smem = [] { const char* e = getenv("HY2DL_DBG_SMEM"); return e ? atoi(e) : 0; }();   // experiment: extra smem
-  smem += dbg_smem;
   cudaFuncSetAttribute(lstm_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   lstm_tc_bwd_kernel<<<(unsigned)cdiv(B, kRows), threads, smem, s>>>(a);
   HY_LAUNCH_CHECK();

@@ -6,9 +6,10 @@
 // i.e. dW_hh, dW_ih and db in one accumulation (x's unused 32nd column is set to 1 and produces the bias
 // gradient), plus, when the head is fused,
 //
-//     dW_head[32 x 64] = sum over (t, sequence)  dz[t-1, seq, 32]^T  *  h_{t-1}[t, seq, 64]
+//     [dW_head | . | db_head]^T [96 x NHz] = sum over (t, sequence)  [h_{t-1} | x_t (column 31 = 1)]^T  *  dz[t-1, seq, NHz]
 //
-// on the same h slabs (the head acts on h_t, i.e. the slab that step t+1 loads as h_{t-1}).  The contraction
+// on the same h slabs (the head acts on h_t, i.e. the slab that step t+1 loads as h_{t-1}); the ones column
+// yields the head bias gradient, the other x rows are computed and ignored.  The contraction
 // index is the sequence, which is the row index of every RI32 stream: a (t, group, 32-feature block) slab,
 // [32 rows][32 floats] = 4 KB, is bit-for-bit the MN-major SWIZZLE_128B_BASE32B UMMA operand tile for K = 32
 // (the only MN-major layout kind::tf32 takes), so operands go HBM -> shared memory with plain bulk async
@@ -29,8 +30,9 @@
 // shared-memory-bandwidth bound (SS-mode MMAs read ~7 KB per 48-cycle instruction).
 //
 // Stage layout: A part = [dz block | dG blocks 0..7] (36 KB), B part = [h block 0 | h block 1 | x block] (12 KB).
-// The head MMA uses M = 128 starting at the dz block (its rows 32.. are dG columns: computed and ignored).
-// TMEM: chain D = gate columns 0..127 -> [0,96), 128..255 -> [96,192), head -> [192,256); running sum S = D + 256.
+// The head MMA takes the stage's B part as its A operand (M = 128: rows 96.. are whatever follows in shared memory,
+// computed and ignored) and the first NHz = 16 or 32 columns of the dz block as its B operand.
+// TMEM: chain D = gate columns 0..127 -> [0,96), 128..255 -> [96,192), head^T -> [192,192+NHz); running sum S = D + 256.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <stdlib.h>
@@ -48,7 +50,7 @@ constexpr int kABytes = 9 * kBlk;           // dz block + 8 dG blocks
 constexpr int kBBytes = 3 * kBlk;           // h (2 blocks) | x (1)
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kND = 96;                     // main D columns: [0,64) dW_hh, [64,95) dW_ih, 95 db
-constexpr int kNHd = 64;                    // head D columns (h only)
+constexpr int kHeadRows = 128;              // head^T accumulator rows kept per CTA (64 h units, 32 x columns incl. ones, 32 junk)
 constexpr int kH64 = 64;
 constexpr uint32_t kColHeadD = 192;
 
@@ -57,8 +59,9 @@ struct TcWgradArgs {
   const float* h;     // RI32 F = 64
   const float* x;     // RI32 F = 32
   const float* dz;    // RI32 F = 32, valid for t >= dz_t0 (null: no head)
-  float* partial;     // [grid][256][kND] then [grid][32][kNHd]
+  float* partial;     // [grid][256][kND] then [grid][kHeadRows][32]
   int64_t T, G, dz_t0;
+  int NHz;            // head columns rounded up to 16 (MMA N of the head part)
   int raw_hi;         // 1: landed words are the hi operand; 0: write the rounded hi back in place
 };
 
@@ -66,7 +69,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* smem_raw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   uint8_t* s_lo = smem_raw + kWgStages * kStageBytes;          // [A_lo (dz | dG halves) | B_lo[0] | B_lo[1]]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lo + kABytes + 2 * kBBytes);
+  // (+ one block of slack: the head MMA's lo A operand reads 4 blocks starting at a 3-block B_lo buffer)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lo + kABytes + 2 * kBBytes + kBlk);
   uint64_t* bar_full = bars;                       // [stages] producer (tx bytes) -> converters
   uint64_t* bar_raw_free = bars + kWgStages;       // [stages] MMA commit -> producer
   uint64_t* bar_conv = bars + 2 * kWgStages;       // [2] converters -> MMA, per half of the gate columns
@@ -120,7 +124,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
     // =========================== MMA issuer =====================================================
     if (lane == 0) {
       const uint32_t lo_a = smem_u32(s_lo);
-      const uint32_t idesc = idesc_tf32(128, kND, 1, 1), idesc_h = idesc_tf32(128, kNHd, 1, 1);
+      const uint32_t idesc = idesc_tf32(128, kND, 1, 1), idesc_h = idesc_tf32(128, a.NHz, 1, 1);
       bool head_open = false;                       // the head accumulator already holds a term of this chain
       for (int64_t i = 0; i < n_my; ++i) {
         const int s = (int)(i % kWgStages);
@@ -147,11 +151,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
               mma_tf32_ss(d, a_hi, b_hi, idesc, 1);
             }
           }
-          if (hf == 0 && has_dz(t)) {              // head: A = [dz | dG block 0] (rows 32.. ignored), B = h blocks
+          if (hf == 0 && has_dz(t)) {              // head^T: A = [h0 | h1 | x | junk] (the B part), B = dz block
 #pragma unroll
             for (int kb = 0; kb < 4; ++kb) {
-              const uint64_t b_hi = smem_desc_mn32(hi_b + kb * 1024, kBlk, 512), b_lo = smem_desc_mn32(lo_b + kb * 1024, kBlk, 512);
-              const uint64_t a_hi = smem_desc_mn32(hi_a + kb * 1024, kBlk, 512), a_lo = smem_desc_mn32(lo_a + kb * 1024, kBlk, 512);
+              const uint64_t a_hi = smem_desc_mn32(hi_b + kb * 1024, kBlk, 512), a_lo = smem_desc_mn32(lo_b + kb * 1024, kBlk, 512);
+              const uint64_t b_hi = smem_desc_mn32(hi_a + kb * 1024, kBlk, 512), b_lo = smem_desc_mn32(lo_a + kb * 1024, kBlk, 512);
               mma_tf32_ss(tmem + kColHeadD, a_lo, b_hi, idesc_h, head_open || kb > 0);
               mma_tf32_ss(tmem + kColHeadD, a_hi, b_lo, idesc_h, 1);
               mma_tf32_ss(tmem + kColHeadD, a_hi, b_hi, idesc_h, 1);
@@ -171,12 +175,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
     const int hf = ct >> 7;                                   // drain: warps 2-5 own half 0, warps 6-9 half 1
     const uint32_t lane_tm = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t dcol = kND * hf;                           // this thread's main columns [dcol, dcol + 96)
-    const uint32_t hcol = kColHeadD + 32 * hf;                // and its half of the head columns
+    const uint32_t hcol = kColHeadD;                          // head^T columns (drained by the half-0 threads)
     // S = 0
     {
       uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       for (int c = 0; c < kND; c += 8) tmem_st8(lane_tm + 256 + dcol + c, z);
-      for (int c = 0; c < 32; c += 8) tmem_st8(lane_tm + 256 + hcol + c, z);
+      if (hf == 0) for (int c = 0; c < 32; c += 8) tmem_st8(lane_tm + 256 + hcol + c, z);
       tmem_st_wait();
     }
     auto add16 = [&](uint32_t col) {                          // S[col .. col+16) += D[col .. col+16)
@@ -195,7 +199,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
 #pragma unroll 1
         for (int c = 0; c < kND; c += 16) add16(dcol + c);
       }
-      if (head_any) { add16(hcol); add16(hcol + 16); }
+      if (head_any && hf == 0) { add16(hcol); if (a.NHz > 16) add16(hcol + 16); }
       tmem_st_wait();
       tc_fence_before();
     };
@@ -247,6 +251,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
       if (dzb) for (int e = ct; e < kBlk4; e += kWgConv) split4(e, false);                                  // dz(t-1)
       if (main) {                                                                                          // x(t); row r's unit 3 sits at unit 3 ^ (r & 3)
         for (int e = ct; e < kBlk4; e += kWgConv) split4(kA4 + 2 * kBlk4 + e, (e & 7) == 2 * (3 ^ ((e >> 3) & 3)) + 1);
+      } else {                                                                                             // slot t = T: no x, only the ones column
+        for (int e = ct; e < kBlk4; e += kWgConv) {
+          const bool one_w = (e & 7) == 2 * (3 ^ ((e >> 3) & 3)) + 1;
+          raw[kA4 + 2 * kBlk4 + e] = make_float4(0.f, 0.f, 0.f, one_w ? 1.f : 0.f);
+          lo_b4[2 * kBlk4 + e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
       if (t > 0) {
         for (int e = ct; e < 2 * kBlk4; e += kWgConv) split4(kA4 + e, false);                               // h(t-1)
@@ -289,10 +299,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
         *reinterpret_cast<float4*>(dst + c + j) =
             make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
     }
-    if (head && (warp & 3) == 0) {                           // head rows = TMEM lanes 0..31
-      float* dsth = a.partial + (int64_t)gridDim.x * 256 * kND + ((int64_t)blockIdx.x * 32 + lane) * kNHd + 32 * hf;
+    if (head && hf == 0) {                                   // head^T row (h unit / x column) = TMEM lane
+      float* dsth = a.partial + (int64_t)gridDim.x * 256 * kND + ((int64_t)blockIdx.x * kHeadRows + (warp & 3) * 32 + lane) * 32;
 #pragma unroll 1
-      for (int c = 0; c < 32; c += 16) {
+      for (int c = 0; c < a.NHz; c += 16) {
         uint32_t v[16];
         tmem_ld16(lane_tm + 256 + hcol + c, v);
         tmem_ld_wait();
@@ -309,10 +319,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
 }
 
 // partial [n_part][256][kND] -> dw_hh [256][64], dw_ih [256][I], db [256] (row = g*64 + u from n = 4u + g);
-// head partial [n_part][32][64] -> dw_head [C][64]
+// head partial [n_part][kHeadRows][32] (transposed: row = h unit k, row 95 = ones) -> dw_head [C][64], db_head [C]
 __global__ void lstm_tc_wgrad_finish_kernel(const float* __restrict__ partial, int n_part, int I, int C,
                                             float* __restrict__ dw_ih, float* __restrict__ dw_hh, float* __restrict__ db,
-                                            float* __restrict__ dw_head) {
+                                            float* __restrict__ dw_head, float* __restrict__ db_head) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e < 256 * kND) {
     const int n = e / kND, col = e - n * kND;
@@ -324,12 +334,15 @@ __global__ void lstm_tc_wgrad_finish_kernel(const float* __restrict__ partial, i
     else if (col < kH64 + I) dw_ih[row * I + (col - kH64)] = acc;
     else db[row] = acc;
   } else if (dw_head != nullptr) {
-    const int eh = e - 256 * kND;
-    if (eh >= C * kNHd) return;
-    const float* ph = partial + (int64_t)n_part * 256 * kND;
+    const int eh = e - 256 * kND;                   // (c, k) with k = 64: the bias gradient
+    if (eh >= C * (kH64 + 1)) return;
+    const int c = eh / (kH64 + 1), k = eh - c * (kH64 + 1);
+    const int row = k < kH64 ? k : kND - 1;
+    const float* ph = partial + (int64_t)n_part * 256 * kND + row * 32 + c;
     float acc = 0.f;
-    for (int p = 0; p < n_part; ++p) acc += __ldg(ph + (int64_t)p * 32 * kNHd + eh);
-    dw_head[eh] = acc;
+    for (int p = 0; p < n_part; ++p) acc += __ldg(ph + (int64_t)p * kHeadRows * 32);
+    if (k < kH64) dw_head[c * kH64 + k] = acc;
+    else if (db_head) db_head[c] = acc;
   }
 }
 
@@ -337,7 +350,7 @@ static int wg_grid(int64_t slots) { return (int)std::min<int64_t>(sm_count(), sl
 
 int64_t lstm_tc_wgrad_workspace(int64_t B, int64_t T, int64_t I) {
   (void)B; (void)T; (void)I;
-  return sizeof(float) * (256 * kND + 32 * kNHd) * std::max<int64_t>(sm_count(), 1);
+  return sizeof(float) * (256 * kND + kHeadRows * 32) * std::max<int64_t>(sm_count(), 1);
 }
 
 int lstm_tc_wgrad(const float* dG, const float* h_seq, const float* x_ri, int64_t B, int64_t T, int64_t I, int64_t IP,
@@ -358,15 +371,16 @@ int lstm_tc_wgrad(const float* dG, const float* h_seq, const float* x_ri, int64_
     HY_REQUIRE(aligned16(head->dz), HY2DL_ERR_ALIGN, "hy2dl_lstm_wgrad: head dz is not 16-byte aligned");
     a.dz = head->dz; a.dz_t0 = head->t0; C = head->n_columns;
   }
+  a.NHz = C <= 16 ? 16 : 32;
   static const int raw_hi = [] { const char* e = getenv("HY2DL_WG_RAWHI"); return e ? atoi(e) : 1; }();   // 0: write the rounded hi back in place
   a.raw_hi = raw_hi;
-  const size_t smem = (size_t)kWgStages * kStageBytes + kABytes + 2 * kBBytes + 128 + 1024;
+  const size_t smem = (size_t)kWgStages * kStageBytes + kABytes + 2 * kBBytes + kBlk + 128 + 1024;
   const int grid = wg_grid((T + (head ? 1 : 0)) * a.G);
   cudaFuncSetAttribute(lstm_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   lstm_tc_wgrad_kernel<<<grid, kWgThreads, smem, s>>>(a);
-  const int n_out = 256 * kND + (head ? C * kNHd : 0);
+  const int n_out = 256 * kND + (head ? C * (kH64 + 1) : 0);
   lstm_tc_wgrad_finish_kernel<<<(n_out + 255) / 256, 256, 0, s>>>(a.partial, grid, (int)I, C, dw_ih, dw_hh, db,
-                                                                 head ? head->dw : nullptr);
+                                                                 head ? head->dw : nullptr, head ? head->db : nullptr);
   HY_LAUNCH_CHECK();
   return HY2DL_OK;
 }

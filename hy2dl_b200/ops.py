@@ -315,21 +315,21 @@ class LstmHeadFunction(torch.autograd.Function):
         layout, dev = ctx.layout, xT.device
         dpar_sim = dpar_sim.contiguous()
         # BPTT with the head adjoint dz * W_head accumulated by the kernel's own MMAs (no dh_seq exists); the kernel
-        # also leaves dz (RI32) for the weight-gradient GEMM and reduces the head bias gradient
+        # also leaves dz (RI32) for the weight-gradient GEMM
         G = xT.shape[1]
         dz = torch.empty(T, G, 1, 32, 32, dtype=torch.float32, device=dev)
         dw_head = torch.empty_like(w_head)
         db_head = torch.empty(w_head.shape[0], dtype=torch.float32, device=dev)
-        hb = _lib.HeadBwd(ptr(w_head), C.pointer(layout.pm), ptr(par_sim), ptr(dpar_sim), ptr(dz), ptr(db_head))
+        hb = _lib.HeadBwd(ptr(w_head), C.pointer(layout.pm), ptr(par_sim), ptr(dpar_sim), ptr(dz))
         ws_b = _ws(_lib.WS_LSTM_BWD, B, T, I, H, dev, precision)
         dG = gates   # in place
         call("hy2dl_lstm_bwd", B, T, H, ptr(w_hh), ptr(gates), ptr(c_seq), None, layout.pm.warmup, None, ptr(dG),
              ptr(ws_b), ws_b.numel(), precision, C.byref(hb), stream())
-        # all weight gradients in one GEMM over the tape: dW_ih, dW_hh, db and dW_head
+        # all weight gradients in one GEMM over the tape: dW_ih, dW_hh, db, dW_head and db_head
         dw_ih = torch.empty(4 * H, I, dtype=torch.float32, device=dev)
         dw_hh = torch.empty(4 * H, H, dtype=torch.float32, device=dev)
         db = torch.empty(4 * H, dtype=torch.float32, device=dev)
-        hw = _lib.HeadWgrad(ptr(dz), layout.pm.warmup, w_head.shape[0], ptr(dw_head))
+        hw = _lib.HeadWgrad(ptr(dz), layout.pm.warmup, w_head.shape[0], ptr(dw_head), ptr(db_head))
         ws_w = _ws(_lib.WS_LSTM_WGRAD, B, T, I, H, dev, precision)
         call("hy2dl_lstm_wgrad", ptr(dG), ptr(h_seq), ptr(xT), B, T, I, IP, H, ptr(dw_ih), ptr(dw_hh), ptr(db),
              ptr(ws_w), ws_w.numel(), precision, C.byref(hw), stream())

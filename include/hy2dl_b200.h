@@ -115,23 +115,23 @@ typedef struct {
  * hidden state is dz * W_head with dz formed in the kernel from dpar_sim (gradient of par_sim) and par_sim,
  * added to the recurrent term by the same tensor-core accumulation -- no dh_seq buffer exists.
  * dz (RI32, F = 32: [T][ceil(B/32)][32][32], steps >= warmup written, columns >= C untouched) feeds
- * hy2dl_lstm_wgrad's head part; db [C] receives the head bias gradient.  Both may be NULL, in which case
- * the head's weight and bias gradients come from hy2dl_head_map_bwd with dh_seq = NULL. */
+ * hy2dl_lstm_wgrad's head part.  It may be NULL, in which case the head's weight and bias gradients come from
+ * hy2dl_head_map_bwd with dh_seq = NULL. */
 typedef struct {
   const float* w;          /* [C][H] */
   const hy2dl_parmap* pm;
   const float* par_sim;
   const float* dpar_sim;
   float* dz;               /* out, nullable */
-  float* db;               /* out, nullable */
 } hy2dl_head_bwd;
-/* Optional head part of hy2dl_lstm_wgrad: dw [C][H] = sum_t dz_t^T h_t over the steps t >= t0, on the h slabs the
- * kernel loads anyway. */
+/* Optional head part of hy2dl_lstm_wgrad: dw [C][H] = sum_t dz_t^T h_t and db [C] = sum_t dz_t over the steps
+ * t >= t0, on the h slabs the kernel loads anyway. */
 typedef struct {
   const float* dz;         /* as written by hy2dl_lstm_bwd */
   int64_t t0;              /* first step with a head gradient (= warmup) */
   int32_t n_columns;       /* C <= 32 */
   float* dw;               /* [C][H] out */
+  float* db;               /* [C] out, nullable */
 } hy2dl_head_wgrad;
 
 /* ---- LSTM (replaces torch.nn.LSTM at modelzoo/cudalstm.py:50 and hybrid.py:92; one layer,
