@@ -818,8 +818,8 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
       float* dz_lo = dz_hi + NH * kRows;
       // batches of 16 items per thread: all loads of a batch are issued before the first use (one HBM latency
       // per batch instead of one per item)
-#pragma unroll
-      for (int bb = 0; bb < 2; ++bb) {
+#pragma unroll 1
+      for (int bb = 0; bb < 3; ++bb) {             // 3 x 16 x 96 >= 128 rows x 32 columns
         const int e0 = dt + bb * 16 * kDzThreads;
         if (e0 >= n_items) break;
         float val[16], dp[16];

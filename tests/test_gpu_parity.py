@@ -275,7 +275,9 @@ def test_lstm_vs_oracle(dev, B, T, I, H, precision):
     ("hbv", 9, 120, 50, 64, 16, ["BETA", "BETAET"], "fp32"),
     ("shm", 33, 48, 24, 128, 4, ["kf"], "fp32"),
     ("shm", 64, 365, 182, 64, 1, ["dd", "f_thr", "sumax", "beta", "perc", "kf", "ki", "kb"], "tf32x3"),
-    ("shm", 45, 48, 24, 64, 4, ["kf", "beta"], "tf32x3"),
+    ("shm", 45, 48, 24, 64, 4, ["kf", "beta"], "tf32x3"),            # 34 head columns: unfused head kernels on the RI32 streams
+    ("shm", 70, 60, 37, 64, 3, ["kf", "beta", "sumax"], "tf32x3"),   # 26 head columns: fused head, 32-column MMA variants
+    ("shm", 33, 40, 3, 64, 2, [], "tf32x3"),                         # 18 columns, all static, three simulated steps
 ])
 def test_hybrid_vs_oracle(dev, model_key, B, T, n_last, H, m, dyn, precision):
     from hy2dl_b200.aux_functions import nse_basin_averaged
@@ -320,10 +322,11 @@ def test_hybrid_vs_oracle(dev, model_key, B, T, n_last, H, m, dyn, precision):
     assert np.nanmax(np.abs(a - b) / (1 + np.abs(b))) < 1e-3
 
 
-def test_inference_no_grad_and_eval(dev):
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_inference_no_grad_and_eval(dev, precision):
     """Forward under no_grad (the notebooks' test loop) takes the tape-free path and matches."""
     g = golden("hybrid_shm_c2")
-    model = build_hybrid(g, dev).eval()
+    model = build_hybrid(g, dev, precision).eval()
     with torch.no_grad():
         pred = model(x_lstm=cu(g["x_lstm"], dev), x_conceptual=cu(g["x_conceptual"], dev))
     assert_close(npy(pred["y_hat"]), g["y_hat"], what="y_hat", **TOL)
