@@ -23,10 +23,12 @@ def install_flat_aliases() -> None:
     """
     from . import aux_functions, modelzoo
     from .aux_functions import functions_evaluation, functions_training
-    from .modelzoo import baseconceptualmodel, cudalstm, hbv, hybrid, shm, uh_routing
+    from .modelzoo import baseconceptualmodel, cudalstm, hbv, hybrid, nonsense, shm, uh_routing
+    # the package attribute `modelzoo.linear_reservoir` is the class (same name as its module, as in the reference)
+    linear_reservoir = _sys.modules[__name__ + ".modelzoo.linear_reservoir"]
     for name, mod in {
         "cudalstm": cudalstm, "hybrid": hybrid, "shm": shm, "hbv": hbv, "uh_routing": uh_routing,
-        "baseconceptualmodel": baseconceptualmodel, "functions_training": functions_training,
-        "functions_evaluation": functions_evaluation,
+        "baseconceptualmodel": baseconceptualmodel, "linear_reservoir": linear_reservoir, "nonsense": nonsense,
+        "functions_training": functions_training, "functions_evaluation": functions_evaluation,
     }.items():
         _sys.modules[name] = mod

@@ -1,9 +1,10 @@
-// K3: per-series conceptual bucket models (SHM, HBV) stepped through time, and their hand-derived
+// K3: per-series conceptual bucket models (SHM, HBV, linear reservoir, NonSense) stepped through time, and their hand-derived
 // adjoints.  One thread owns one series n = b*m + j (sample b, ensemble member j) for all steps;
 // every load/store at a step is a contiguous run over n (time-major planes), i.e. fully coalesced.
 // HBM-bound integer-free stream work: no tensor cores here by design.
 //
-// Reference semantics: modelzoo/shm.py:74-93,135-182 and modelzoo/hbv.py:73-86,127-188; PyTorch
+// Reference semantics: modelzoo/shm.py:74-93,135-182, modelzoo/hbv.py:73-86,127-188,
+// modelzoo/linear_reservoir.py:64-92 and modelzoo/nonsense.py:82-168; PyTorch
 // sub-gradient conventions for min/max/clamp/pow are reproduced (see common.cuh and SURVEY.md 7).
 #include "common.cuh"
 #include "conceptual_models.cuh"
@@ -43,9 +44,10 @@ __global__ void __launch_bounds__(kBlock) conceptual_fwd_kernel(ConceptualArgs a
   const int j = (int)(nn - b * a.m);
   const bool pow2 = (a.m & (a.m - 1)) == 0 && a.m <= 32;
 
-  float s[kNS], p[M::NP];
+  constexpr int NS = M::NS;   // planes NS..4 of the states buffer are not touched
+  float s[NS], p[M::NP];
 #pragma unroll
-  for (int k = 0; k < kNS; ++k) s[k] = a.init ? a.init[k * a.N + nn] : M::kInit;
+  for (int k = 0; k < NS; ++k) s[k] = a.init ? a.init[k * a.N + nn] : M::init(k);
 #pragma unroll
   for (int k = 0; k < M::NP; ++k) p[k] = a.par[k] ? __ldg(a.par[k] + nn) : 0.f;  // static value / t = 0
 
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(kBlock) conceptual_fwd_kernel(ConceptualArgs a
     if (live) {
       float* st = a.states + t * kNS * a.N + n;
 #pragma unroll
-      for (int k = 0; k < kNS; ++k) st[k * a.N] = s[k];
+      for (int k = 0; k < NS; ++k) st[k * a.N] = s[k];
     }
     // member mean (shm.py:182, hbv.py:188)
     float qs = qm;
@@ -97,16 +99,17 @@ __global__ void __launch_bounds__(kBlock) conceptual_bwd_kernel(ConceptualArgs a
   const int64_t b = n / a.m;
   const float inv_m = 1.f / (float)a.m;
 
-  float g[kNS], gacc[M::NP], p[M::NP];
+  constexpr int NS = M::NS;
+  float g[NS], gacc[M::NP], p[M::NP];
 #pragma unroll
-  for (int k = 0; k < kNS; ++k) g[k] = 0.f;
+  for (int k = 0; k < NS; ++k) g[k] = 0.f;
 #pragma unroll
   for (int k = 0; k < M::NP; ++k) { gacc[k] = 0.f; p[k] = a.par[k] ? __ldg(a.par[k] + n) : 0.f; }
 
   // inputs of one step: forcings, dynamic parameters, the state BEFORE the step, incoming gradients.  The
   // next (earlier) step's inputs are requested before this step's adjoint chain starts, so their HBM latency
   // hides behind ~100 dependent flops (one thread per series leaves nothing else to hide it with).
-  struct In { float P, E, Tm, gq, p[M::NP], s[kNS], ds[kNS]; };
+  struct In { float P, E, Tm, gq, p[M::NP], s[NS], ds[NS]; };
   auto load = [&](int64_t t, In& in) {
     const float* f = a.forc + (a.t0 + t) * 3 * a.B + b;
     in.P = __ldg(f); in.E = __ldg(f + a.B); in.Tm = __ldg(f + 2 * a.B);
@@ -115,13 +118,13 @@ __global__ void __launch_bounds__(kBlock) conceptual_bwd_kernel(ConceptualArgs a
     if (t > 0) {
       const float* st = a.states + (t - 1) * kNS * a.N + n;
 #pragma unroll
-      for (int k = 0; k < kNS; ++k) in.s[k] = __ldg(st + k * a.N);
+      for (int k = 0; k < NS; ++k) in.s[k] = __ldg(st + k * a.N);
     } else {
 #pragma unroll
-      for (int k = 0; k < kNS; ++k) in.s[k] = a.init ? a.init[k * a.N + n] : M::kInit;
+      for (int k = 0; k < NS; ++k) in.s[k] = a.init ? a.init[k * a.N + n] : M::init(k);
     }
 #pragma unroll
-    for (int k = 0; k < kNS; ++k) in.ds[k] = a.dstates ? __ldg(a.dstates + (t * kNS + k) * a.N + n) : 0.f;
+    for (int k = 0; k < NS; ++k) in.ds[k] = a.dstates ? __ldg(a.dstates + (t * kNS + k) * a.N + n) : 0.f;
     in.gq = __ldg(a.dq + t * a.B + b) * inv_m;
   };
   In cur, nxt;
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(kBlock) conceptual_bwd_kernel(ConceptualArgs a
   for (int64_t t = a.Tn - 1; t >= 0; --t) {
     if (t > 0) load(t - 1, nxt);
 #pragma unroll
-    for (int k = 0; k < kNS; ++k) g[k] += cur.ds[k];
+    for (int k = 0; k < NS; ++k) g[k] += cur.ds[k];
     float gp[M::NP];
     M::adjoint(cur.s, cur.p, cur.P, cur.E, cur.Tm, a.has_betaet != 0, g, cur.gq, gp);
 #pragma unroll
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(kBlock) conceptual_bwd_kernel(ConceptualArgs a
     if (a.dpar[k] && !a.ts[k]) a.dpar[k][n] = gacc[k];
   if (a.dinit) {
 #pragma unroll
-    for (int k = 0; k < kNS; ++k) a.dinit[k * a.N + n] = g[k];
+    for (int k = 0; k < NS; ++k) a.dinit[k * a.N + n] = g[k];
   }
 }
 
@@ -157,17 +160,36 @@ __global__ void pack_forcing_kernel(const float* __restrict__ xc, int64_t B, int
   if (i >= B * T) return;
   const int64_t t = i / B, b = i - t * B;
   const float* r = xc + (b * T + t) * nc;
-  const float tm = (nc == 4) ? (r[2] + r[3]) / 2.f : r[2];
+  const float tm = (nc == 4) ? (r[2] + r[3]) / 2.f : (nc == 3 ? r[2] : 0.f);  // nc == 2: P and ET only (linear reservoir)
   float* o = forc + t * 3 * B + b;
   o[0] = r[0];
   o[B] = r[1];
   o[2 * B] = tm;
 }
 
+static int n_par_of(int model) {
+  switch (model) {
+    case HY2DL_MODEL_SHM: return SHM::NP;
+    case HY2DL_MODEL_HBV: return HBV::NP;
+    case HY2DL_MODEL_LINRES: return LinRes::NP;
+    case HY2DL_MODEL_NONSENSE: return NonSense::NP;
+    default: return 0;
+  }
+}
+
+// runs `stmt` with M bound to the model's step/adjoint struct
+#define HY_MODEL_DISPATCH(model, stmt)                                       \
+  switch (model) {                                                           \
+    case HY2DL_MODEL_SHM: { using M = SHM; stmt; } break;                    \
+    case HY2DL_MODEL_HBV: { using M = HBV; stmt; } break;                    \
+    case HY2DL_MODEL_LINRES: { using M = LinRes; stmt; } break;              \
+    default: { using M = NonSense; stmt; } break;                            \
+  }
+
 static int fill_args(ConceptualArgs& a, int model, const float* forc, int64_t B, int64_t t0, int64_t Tn, int64_t m,
                      const float* const* par, const int64_t* tstride, const float* init) {
-  const int np = model == HY2DL_MODEL_SHM ? SHM::NP : HBV::NP;
-  HY_REQUIRE(model == HY2DL_MODEL_SHM || model == HY2DL_MODEL_HBV, HY2DL_ERR_SHAPE, "conceptual: unknown model %d", model);
+  const int np = n_par_of(model);
+  HY_REQUIRE(np > 0, HY2DL_ERR_SHAPE, "conceptual: unknown model %d", model);
   HY_REQUIRE(B > 0 && Tn > 0 && t0 >= 0 && m > 0 && m <= kBlock, HY2DL_ERR_SHAPE,
              "conceptual: bad sizes B=%lld t0=%lld Tn=%lld m=%lld (m <= %d)", (long long)B, (long long)t0,
              (long long)Tn, (long long)m, kBlock);
@@ -193,7 +215,7 @@ static int fill_args(ConceptualArgs& a, int model, const float* forc, int64_t B,
 using namespace hy2dl;
 
 extern "C" int hy2dl_pack_forcing(const float* xc, int64_t B, int64_t T, int64_t nc, float* forc, hy2dl_stream_t stream) {
-  HY_REQUIRE(nc == 3 || nc == 4, HY2DL_ERR_SHAPE, "hy2dl_pack_forcing: nc must be 3 or 4, got %lld", (long long)nc);
+  HY_REQUIRE(nc >= 2 && nc <= 4, HY2DL_ERR_SHAPE, "hy2dl_pack_forcing: nc must be 2, 3 or 4, got %lld", (long long)nc);
   HY_REQUIRE(B > 0 && T > 0, HY2DL_ERR_SHAPE, "hy2dl_pack_forcing: empty input");
   HY_NONNULL(xc); HY_NONNULL(forc);
   const int64_t n = B * T;
@@ -212,8 +234,7 @@ extern "C" int hy2dl_conceptual_fwd(int model, const float* forc, int64_t B, int
   a.states = states; a.q = q;
   const int tpb = (int)((kBlock / m) * m);
   const unsigned grid = (unsigned)cdiv(a.N, tpb);
-  if (model == HY2DL_MODEL_SHM) conceptual_fwd_kernel<SHM><<<grid, kBlock, 0, (cudaStream_t)stream>>>(a, tpb);
-  else conceptual_fwd_kernel<HBV><<<grid, kBlock, 0, (cudaStream_t)stream>>>(a, tpb);
+  HY_MODEL_DISPATCH(model, (conceptual_fwd_kernel<M><<<grid, kBlock, 0, (cudaStream_t)stream>>>(a, tpb)));
   HY_LAUNCH_CHECK();
   return HY2DL_OK;
 }
@@ -227,14 +248,13 @@ extern "C" int hy2dl_conceptual_bwd(int model, const float* forc, int64_t B, int
   if (rc) return rc;
   HY_NONNULL(states); HY_NONNULL(dq);
   a.states = const_cast<float*>(states); a.dq = dq; a.dstates = dstates; a.dinit = dinit;
-  const int np = model == HY2DL_MODEL_SHM ? SHM::NP : HBV::NP;
+  const int np = n_par_of(model);
   for (int k = 0; k < np; ++k) {
     HY_REQUIRE(dpar[k] != nullptr || a.par[k] == nullptr, HY2DL_ERR_ALIGN, "hy2dl_conceptual_bwd: dpar[%d] is null", k);
     a.dpar[k] = dpar[k];
   }
   const unsigned grid = (unsigned)cdiv(a.N, kBlock);
-  if (model == HY2DL_MODEL_SHM) conceptual_bwd_kernel<SHM><<<grid, kBlock, 0, (cudaStream_t)stream>>>(a);
-  else conceptual_bwd_kernel<HBV><<<grid, kBlock, 0, (cudaStream_t)stream>>>(a);
+  HY_MODEL_DISPATCH(model, (conceptual_bwd_kernel<M><<<grid, kBlock, 0, (cudaStream_t)stream>>>(a)));
   HY_LAUNCH_CHECK();
   return HY2DL_OK;
 }

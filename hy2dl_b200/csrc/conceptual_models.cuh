@@ -1,9 +1,11 @@
-// Step functions and hand-derived adjoints of the SHM and HBV bucket models.
+// Step functions and hand-derived adjoints of the bucket models (SHM, HBV, linear reservoir, NonSense).
 // Plain C++ (no CUDA intrinsics) so that the very same code is compiled into the K3 kernels
 // (conceptual.cu) and into the host-side test harness (tests/host/conceptual_host.cpp), which
 // checks the adjoint algebra against the reference's autograd on the CPU-only build box.
 //
-// Reference semantics: modelzoo/shm.py:135-182, modelzoo/hbv.py:127-188.
+// Reference semantics: modelzoo/shm.py:135-182, modelzoo/hbv.py:127-188, modelzoo/linear_reservoir.py:77-92,
+// modelzoo/nonsense.py:82-168.  Every model declares NP parameters, NS <= HY2DL_N_STATES storages (planes
+// 0..NS-1 of the states buffer, in the order of the reference's _initial_states dict) and their defaults.
 #pragma once
 #include <math.h>
 
@@ -33,8 +35,9 @@ HY_HD float pow_dexp(float base, float ex, float res) {
 // ------------------------------------------------------------------------------------------------
 struct SHM {
   static constexpr int NP = 8;
+  static constexpr int NS = 5;   // ss sf su si sb
   enum { DD, FTHR, SUMAX, BETA, PERC, KF, KI, KB };
-  static constexpr float kInit = 0.001f;
+  HY_HD static float init(int) { return 0.001f; }
   static constexpr float klu = 0.90f;
 
   // forward step: s[] is updated in place, returns member outflow
@@ -158,8 +161,9 @@ struct SHM {
 // ------------------------------------------------------------------------------------------------
 struct HBV {
   static constexpr int NP = 13;
+  static constexpr int NS = 5;   // SNOWPACK MELTWATER SM SUZ SLZ
   enum { BETA, FC, K0, K1, K2, LP, PERC, UZL, TT, CFMAX, CFR, CWH, BETAET };
-  static constexpr float kInit = 0.001f;
+  HY_HD static float init(int) { return 0.001f; }
 
   HY_HD static float step(float* s, const float* p, float P, float E, float Tm, bool has_bet) {
     const bool cold = Tm < p[TT];
@@ -309,6 +313,136 @@ struct HBV {
     gTT -= gm0 * p[CFMAX];
     gp[CFMAX] = gCFMAX;
     gp[TT] = gTT;
+  }
+};
+
+// sub-gradient of max(0, x) written as torch.maximum(zero, x): ties split 1/2 - 1/2
+HY_HD float w_pos(float x) { return x > 0.f ? 1.f : (x == 0.f ? 0.5f : 0.f); }
+
+// ------------------------------------------------------------------------------------------------
+// linear reservoir (modelzoo/linear_reservoir.py:77-92): one storage, uses P and ET only
+// ------------------------------------------------------------------------------------------------
+struct LinRes {
+  static constexpr int NP = 2;
+  static constexpr int NS = 1;   // si
+  enum { KI, AUXET };
+  HY_HD static float init(int) { return 0.001f; }
+
+  HY_HD static float step(float* s, const float* p, float P, float E, float, bool) {
+    const float d = (s[0] + P) - E * p[AUXET];
+    const float s1 = fmaxf(0.f, d);
+    const float qi = s1 * p[KI];
+    s[0] = s1 - qi;
+    return qi;
+  }
+
+  HY_HD static void adjoint(const float* s, const float* p, float P, float E, float, bool, float* g, float gq,
+                            float* gp) {
+    const float d = (s[0] + P) - E * p[AUXET];
+    const float s1 = fmaxf(0.f, d);
+    const float g_qi = gq - g[0];
+    const float g_s1 = g[0] + g_qi * p[KI];
+    gp[KI] = g_qi * s1;
+    const float g_d = g_s1 * w_pos(d);
+    gp[AUXET] = -g_d * E;
+    g[0] = g_d;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// NonSense (modelzoo/nonsense.py:82-168): snow -> baseflow -> interflow -> unsaturated zone -> outlet.
+// Reservoir constants divide (qb = sb / kb); the outflow is the unsaturated-zone outflow alone.
+// ------------------------------------------------------------------------------------------------
+struct NonSense {
+  static constexpr int NP = 5;
+  static constexpr int NS = 4;   // ss su si sb  (nonsense.py:172)
+  enum { DD, SUMAX, BETA, KI, KB };
+  enum { SS, SU, SI, SB };
+  static constexpr float klu = 0.90f;
+  HY_HD static float init(int k) { return k == SS ? 0.f : (k == SU ? 5.f : (k == SI ? 10.f : 15.f)); }
+
+  HY_HD static float step(float* s, const float* p, float P, float E, float Tm, bool) {
+    const bool cold = Tm < 0.f;
+    const float mp = cold ? 0.f : Tm * p[DD];
+    const float rain = cold ? 0.f : P, snowf = cold ? P : 0.f;
+    const float qs = fminf(s[SS], mp);
+    s[SS] = s[SS] - qs + snowf;
+    const float qsp = qs + rain;
+    const float sb1 = s[SB] + qsp;
+    const float qb = sb1 / p[KB];
+    s[SB] = sb1 - qb;
+    const float si1 = s[SI] + qb;
+    const float qi = si1 / p[KI];
+    s[SI] = si1 - qi;
+    const float psi = powf(s[SU] / p[SUMAX], p[BETA]);
+    const float su_t = s[SU] + qi * (1.f - psi);
+    const float su1 = fminf(su_t, p[SUMAX]);
+    const float qu = qi * psi + fmaxf(0.f, su_t - p[SUMAX]);
+    const float kth = (su1 <= 0.8f * p[SUMAX]) ? su1 / p[SUMAX] : 1.f;
+    s[SU] = fmaxf(0.f, su1 - E * klu * kth);
+    return qu;
+  }
+
+  HY_HD static void adjoint(const float* s, const float* p, float P, float E, float Tm, bool, float* g, float gq,
+                            float* gp) {
+    // ---- recompute the forward intermediates
+    const bool cold = Tm < 0.f;
+    const float mp = cold ? 0.f : Tm * p[DD];
+    const float rain = cold ? 0.f : P;
+    const float qs = fminf(s[SS], mp);
+    const float sb1 = s[SB] + (qs + rain);
+    const float qb = sb1 / p[KB];
+    const float si1 = s[SI] + qb;
+    const float qi = si1 / p[KI];
+    const float r = s[SU] / p[SUMAX];
+    const float psi = powf(r, p[BETA]);
+    const float su_t = s[SU] + qi * (1.f - psi);
+    const float su1 = fminf(su_t, p[SUMAX]);
+    const float ovx = su_t - p[SUMAX];
+    const bool wet = su1 <= 0.8f * p[SUMAX];
+    const float kth = wet ? su1 / p[SUMAX] : 1.f;
+    const float d = su1 - E * klu * kth;
+    // ---- evapotranspiration: su2 = max(0, d); the wilting point enters the comparison only
+    const float g_d = g[SU] * w_pos(d);
+    float g_su1 = g_d;
+    float g_smax = 0.f;
+    if (wet) {
+      const float g_kth = -g_d * E * klu;
+      g_su1 += g_kth / p[SUMAX];
+      g_smax -= g_kth * su1 / (p[SUMAX] * p[SUMAX]);
+    }
+    // ---- unsaturated zone (its outflow is the model outflow)
+    float g_qi = gq * psi;
+    float g_psi = gq * qi;
+    const float g_ovx = gq * w_pos(ovx);
+    float g_su_t = g_ovx;
+    g_smax -= g_ovx;
+    g_su_t += g_su1 * w_lt(su_t, p[SUMAX]);
+    g_smax += g_su1 * w_lt(p[SUMAX], su_t);
+    float g_su = g_su_t;
+    g_qi += g_su_t * (1.f - psi);
+    g_psi -= g_su_t * qi;
+    const float g_r = g_psi * pow_dbase(r, p[BETA]);
+    gp[BETA] = g_psi * pow_dexp(r, p[BETA], psi);
+    g_su += g_r / p[SUMAX];
+    g_smax -= g_r * s[SU] / (p[SUMAX] * p[SUMAX]);
+    gp[SUMAX] = g_smax;
+    g[SU] = g_su;
+    // ---- interflow: qi = si1 / ki, si' = si1 - qi
+    g_qi -= g[SI];
+    const float g_si1 = g[SI] + g_qi / p[KI];
+    gp[KI] = -g_qi * (qi / p[KI]);      // torch: -grad * ((self / other) / other)
+    g[SI] = g_si1;
+    // ---- baseflow: qb = sb1 / kb, sb' = sb1 - qb
+    const float g_qb = g_si1 - g[SB];
+    const float g_sb1 = g[SB] + g_qb / p[KB];
+    gp[KB] = -g_qb * (qb / p[KB]);
+    g[SB] = g_sb1;
+    // ---- snow
+    const float g_qs = g_sb1 - g[SS];
+    g[SS] = g[SS] + g_qs * w_lt(s[SS], mp);
+    const float g_mp = g_qs * w_lt(mp, s[SS]);
+    gp[DD] = cold ? 0.f : g_mp * Tm;
   }
 };
 

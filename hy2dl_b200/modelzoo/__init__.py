@@ -4,8 +4,10 @@ from .baseconceptualmodel import BaseConceptualModel
 from .cudalstm import CudaLSTM
 from .hbv import HBV
 from .hybrid import Hybrid
+from .linear_reservoir import linear_reservoir
 from .lstm import LSTM
+from .nonsense import NonSense
 from .shm import SHM
 from .uh_routing import UH_routing
 
-__all__ = ["BaseConceptualModel", "CudaLSTM", "HBV", "Hybrid", "LSTM", "SHM", "UH_routing"]
+__all__ = ["BaseConceptualModel", "CudaLSTM", "HBV", "Hybrid", "LSTM", "NonSense", "SHM", "UH_routing", "linear_reservoir"]

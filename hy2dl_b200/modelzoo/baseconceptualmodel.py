@@ -14,6 +14,7 @@ class BaseConceptualModel(nn.Module):
     """Abstract base: subclasses provide `parameter_ranges`, `_initial_states` and `_model_id`."""
 
     _model_id: Optional[int] = None  # HY2DL_MODEL_* of the CUDA implementation
+    _forcing_columns: Optional[int] = None  # leading columns of x_conceptual the model reads (None: all, 3 or 4)
 
     def __init__(self):
         super().__init__()
@@ -53,9 +54,18 @@ class BaseConceptualModel(nn.Module):
         init = None
         if initial_states is not None:
             init = torch.stack([initial_states[k].reshape(B * m) for k in self._initial_states])
-        forc = ops.pack_forcing(x_conceptual)
+        forc = ops.pack_forcing(self._forcing(x_conceptual))
         states, q = ops.conceptual(forc, par_flat, init, self._model_id, B, m, 0, T, offs, dynamic)
         return self._result(states, q, parameters, B, m)
+
+    def _forcing(self, x_conceptual: torch.Tensor) -> torch.Tensor:
+        """The columns of x_conceptual the model reads (SHM/HBV: all three or four)."""
+        n = self._forcing_columns
+        if n is None:
+            return x_conceptual
+        if x_conceptual.shape[2] < n:
+            raise ValueError(f"{type(self).__name__} needs {n} conceptual input columns, got {x_conceptual.shape[2]}")
+        return x_conceptual[:, :, :n]
 
     def _result(self, states, q, parameters, B: int, m: int):
         T = q.shape[0]

@@ -43,7 +43,7 @@ class Hybrid(nn.Module):
                                                  parameter_type=self.conceptual_dynamic_parameterization)
         if getattr(self.conceptual_model, "_model_id", None) is None:
             raise NotImplementedError(
-                f"{type(self.conceptual_model).__name__} has no hy2dl_b200 CUDA implementation (SHM and HBV do)")
+                f"{type(self.conceptual_model).__name__} has no hy2dl_b200 CUDA implementation (SHM, HBV, linear_reservoir and NonSense do)")
         self.n_conceptual_model_params = len(self.conceptual_model.parameter_ranges) * self.n_conceptual_models
         if routing_model:
             self.routing_model = routing_model()
@@ -69,11 +69,12 @@ class Hybrid(nn.Module):
         return self._layouts[key]
 
     def forward(self, x_lstm: torch.Tensor, x_conceptual: torch.Tensor):
-        """x_lstm [B,T,input_size_lstm], x_conceptual [B,T,3|4] (GPU, fp32) -> prediction dict with
+        """x_lstm [B,T,input_size_lstm], x_conceptual [B,T,2|3|4] (GPU, fp32) -> prediction dict with
         y_hat [B,T_sim,1], parameters / internal_states {name: [B,T_sim,m]}, final_states {name: [B,m]}."""
         if x_lstm.shape[:2] != x_conceptual.shape[:2]:
             raise ValueError("x_lstm and x_conceptual must share batch and time dimensions")
-        return self.forward_native(ops.pack_x(x_lstm, self.lstm.layout), ops.pack_forcing(x_conceptual))
+        return self.forward_native(ops.pack_x(x_lstm, self.lstm.layout),
+                                   ops.pack_forcing(self.conceptual_model._forcing(x_conceptual)))
 
     def forward_native(self, xT: torch.Tensor, forc: torch.Tensor):
         """Same as forward() for inputs already in native layout (xT [T,B,IP] or RI32, forc [T,3,B]), as

@@ -90,7 +90,7 @@ def pack_x(x: torch.Tensor, layout: str = "rowmajor") -> torch.Tensor:
 
 
 def pack_forcing(xc: torch.Tensor) -> torch.Tensor:
-    """[B,T,3|4] -> native [T,3,B] (P, PET, Tmean)."""
+    """[B,T,2|3|4] -> native [T,3,B] (P, PET, Tmean; two columns: temperature plane zero)."""
     require_cuda(xc, "x_conceptual")
     xc = xc.detach().contiguous()
     B, T, nc = xc.shape
@@ -398,7 +398,7 @@ class ConceptualFunction(torch.autograd.Function):
         dptrs = [None if o is None else dbase + 4 * o for o in offs]
         dq = torch.zeros(Tn, B, dtype=torch.float32, device=dev) if dq is None else dq.contiguous()
         dstates = None if dstates is None else dstates.contiguous()
-        dinit = torch.empty_like(init) if (init is not None and ctx.needs_input_grad[2]) else None
+        dinit = torch.zeros_like(init) if (init is not None and ctx.needs_input_grad[2]) else None
         call("hy2dl_conceptual_bwd", model, ptr(forc), B, t0, Tn, m, _ptr_array(ptrs), _i64_array(ts), ptr(init),
              ptr(states), ptr(dq), ptr(dstates), _ptr_array(dptrs), ptr(dinit), stream())
         return None, dpar, dinit, None, None, None, None, None, None, None

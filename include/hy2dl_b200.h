@@ -65,8 +65,11 @@ typedef void* hy2dl_stream_t; /* cudaStream_t */
 /* conceptual models */
 #define HY2DL_MODEL_SHM 0 /* 8 parameters: dd f_thr sumax beta perc kf ki kb     (modelzoo/shm.py:193-204) */
 #define HY2DL_MODEL_HBV 1 /* 13 parameters: BETA FC K0 K1 K2 LP PERC UZL TT CFMAX CFR CWH BETAET (hbv.py:199-215) */
+#define HY2DL_MODEL_LINRES 2   /* 2 parameters: ki aux_ET; 1 storage si            (modelzoo/linear_reservoir.py:99-108) */
+#define HY2DL_MODEL_NONSENSE 3 /* 5 parameters: dd sumax beta ki kb; 4 storages ss su si sb (modelzoo/nonsense.py:170-176) */
 #define HY2DL_MAX_PAR 16
-#define HY2DL_N_STATES 5
+#define HY2DL_N_STATES 5 /* planes of the states / init buffers; a model with fewer storages uses planes 0..NS-1 and
+                            never reads or writes the others */
 
 /* workspace kinds for hy2dl_workspace_bytes */
 #define HY2DL_WS_LSTM_FWD 0
@@ -81,8 +84,8 @@ int64_t hy2dl_workspace_bytes(int kind, int64_t B, int64_t T, int64_t I, int64_t
 
 /* ---- layout packing --------------------------------------------------------------------------
  * x [B][T][I] (reference batch-first layout, modelzoo/cudalstm.py:34, hybrid.py:72) -> xT [T][B][IP].
- * xc [B][T][nc], nc = 3 (P, PET, T) or 4 (P, PET, Tmax, Tmin -> mean; shm.py:74-80, hbv.py:70-77)
- *    -> forc [T][3][B].
+ * xc [B][T][nc], nc = 3 (P, PET, T), 4 (P, PET, Tmax, Tmin -> mean; shm.py:74-80, hbv.py:70-77) or 2 (P, PET;
+ *    temperature plane zero -- linear_reservoir.py:79-80 reads nothing else)  -> forc [T][3][B].
  * layout = HY2DL_LAYOUT_RI32: xT is written as RI32 (rows >= B of the last group zero filled). */
 int hy2dl_pack_x(const float* x, int64_t B, int64_t T, int64_t I, int64_t IP, float* xT, int layout, hy2dl_stream_t stream);
 int hy2dl_pack_forcing(const float* xc, int64_t B, int64_t T, int64_t nc, float* forc, hy2dl_stream_t stream);
@@ -174,12 +177,12 @@ int hy2dl_head_map_bwd(const float* h_seq, const float* par_sim, const float* dp
 /* ---- conceptual models (replace SHM.forward shm.py:135-182, HBV.forward hbv.py:127-188) --------
  * par[p] / tstride[p]: device pointer of parameter p's plane and its stride in floats between
  * time steps (N for dynamic, 0 for static).  HBV: par[12] (BETAET) may be NULL (hbv.py:157-162).
- * init [5][N] or NULL (model defaults 0.001).  Steps simulated: forc rows t0 .. t0+Tn-1. */
+ * init [5][N] or NULL (model defaults: 0.001; NonSense ss 0, su 5, si 10, sb 15).  Steps simulated: forc rows t0 .. t0+Tn-1. */
 int hy2dl_conceptual_fwd(int model, const float* forc, int64_t B, int64_t t0, int64_t Tn, int64_t m,
                          const float* const* par, const int64_t* tstride, const float* init,
                          float* states, float* q, hy2dl_stream_t stream);
 /* Adjoint. dq [Tn][B] (gradient of q), dstates [Tn][5][N] or NULL.  dpar[p] has par[p]'s shape
- * (overwritten); dinit [5][N] or NULL. */
+ * (overwritten); dinit [5][N] or NULL (planes beyond the model's storages are left untouched). */
 int hy2dl_conceptual_bwd(int model, const float* forc, int64_t B, int64_t t0, int64_t Tn, int64_t m,
                          const float* const* par, const int64_t* tstride, const float* init,
                          const float* states, const float* dq, const float* dstates,

@@ -12,6 +12,8 @@ Reference lines each function follows (paths relative to /root/reference/Hy2DL):
   map_parameters ............ modelzoo/baseconceptualmodel.py:53-76
   shm_run ................... modelzoo/shm.py:69-93 (pre-loop), :135-182 (step), :189-204 (constants)
   hbv_run ................... modelzoo/hbv.py:70-86 (pre-loop), :127-188 (step), :195-215 (constants)
+  linres_run ................ modelzoo/linear_reservoir.py:64-92 (step), :99-108 (constants)
+  nonsense_run .............. modelzoo/nonsense.py:72-94 (pre-loop), :128-168 (step), :170-176 (constants)
   uh_route .................. modelzoo/uh_routing.py:42-44, :64-74, :92-109, :111-113
   hybrid_forward ............ modelzoo/hybrid.py:62-117
   nse_basin_averaged ........ aux_functions/functions_training.py:32-41
@@ -55,12 +57,22 @@ HBV_RANGES = OrderedDict(
 HBV_STATES = ("SNOWPACK", "MELTWATER", "SM", "SUZ", "SLZ")
 HBV_INIT = 0.001
 
+LINRES_RANGES = OrderedDict(ki=(0.002, 1.0), aux_ET=(0.0, 1.5))
+LINRES_STATES = ("si",)
+LINRES_INIT = 0.001
+
+NONSENSE_RANGES = OrderedDict(dd=(0.0, 10.0), sumax=(20.0, 700.0), beta=(1.0, 6.0), ki=(1.0, 100.0), kb=(10.0, 1000.0))
+NONSENSE_STATES = ("ss", "su", "si", "sb")
+NONSENSE_INIT = {"ss": 0.0, "su": 5.0, "si": 10.0, "sb": 15.0}
+
 UH_RANGES = OrderedDict(alpha=(0.0, 2.9), beta=(0.0, 6.5))
 UH_LEN = 15
 
 MODEL_TABLE = {
     "shm": (SHM_RANGES, SHM_STATES, SHM_INIT),
     "hbv": (HBV_RANGES, HBV_STATES, HBV_INIT),
+    "linear_reservoir": (LINRES_RANGES, LINRES_STATES, LINRES_INIT),
+    "nonsense": (NONSENSE_RANGES, NONSENSE_STATES, NONSENSE_INIT),
 }
 
 
@@ -135,7 +147,7 @@ def _forcings(xc, m):
 def _start_states(names, init, value, B, m, like):
     if init is not None:
         return [init[n] for n in names]
-    return [like.new_full((B, m), value) for _ in names]
+    return [like.new_full((B, m), value[n] if isinstance(value, dict) else value) for n in names]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -250,7 +262,78 @@ def hbv_run(xc, par: Dict[str, torch.Tensor], n_models: int = 1, init: Optional[
     }
 
 
-RUNNERS = {"shm": shm_run, "hbv": hbv_run}
+# ----------------------------------------------------------------------------------------------
+# linear reservoir, NonSense
+# ----------------------------------------------------------------------------------------------
+def _pack_result(q, tape, par):
+    states = {n: torch.stack(v, dim=1) for n, v in tape.items()}
+    return {
+        "y_hat": torch.stack(q, dim=1).unsqueeze(2),
+        "parameters": par,
+        "internal_states": states,
+        "final_states": {n: s[:, -1, :] for n, s in states.items()},
+    }
+
+
+def linres_run(xc, par: Dict[str, torch.Tensor], n_models: int = 1, init: Optional[Dict] = None):
+    B, T, _ = xc.shape
+    m = n_models
+    zero = xc.new_zeros(())
+    (si,) = _start_states(LINRES_STATES, init, LINRES_INIT, B, m, xc)
+    tape, q = {"si": []}, []
+    for j in range(T):
+        p = xc[:, j, 0:1].expand(-1, m)
+        et = xc[:, j, 1:2].expand(-1, m)
+        si = torch.maximum(zero, (si + p) - et * par["aux_ET"][:, j])
+        qi = si * par["ki"][:, j]
+        si = si - qi
+        tape["si"].append(si)
+        q.append(qi.mean(dim=1))
+    return _pack_result(q, tape, par)
+
+
+def nonsense_run(xc, par: Dict[str, torch.Tensor], n_models: int = 1, init: Optional[Dict] = None):
+    """n_models must be 1: the reference stores the [B, m] outflow in a [B, 1] slot (nonsense.py:163)."""
+    B, T, _ = xc.shape
+    m = n_models
+    assert m == 1, "NonSense: the reference supports a single member"
+    P = xc[:, :, 0:1].expand(-1, -1, m)
+    E = xc[:, :, 1:2].expand(-1, -1, m)
+    Tm = xc[:, :, 2:3].expand(-1, -1, m)          # column 2 as is, also with four columns (nonsense.py:80)
+    cold = Tm < 0
+    zero = xc.new_zeros(())
+    melt_pot = torch.where(cold, zero, Tm * par["dd"])
+    rain = torch.where(cold, zero, P)
+    snowfall = torch.where(cold, P, zero)
+    pwp = 0.8 * par["sumax"]
+    klu = 0.90
+    ss, su, si, sb = _start_states(NONSENSE_STATES, init, NONSENSE_INIT, B, m, xc)
+    tape = {n: [] for n in NONSENSE_STATES}
+    q = []
+    for j in range(T):
+        smax, beta = par["sumax"][:, j], par["beta"][:, j]
+        qs = torch.minimum(ss, melt_pot[:, j])
+        ss = ss - qs + snowfall[:, j]
+        qsp = qs + rain[:, j]
+        sb = sb + qsp
+        qb = sb / par["kb"][:, j]
+        sb = sb - qb
+        si = si + qb
+        qi = si / par["ki"][:, j]
+        si = si - qi
+        psi = (su / smax) ** beta
+        su_t = su + qi * (1 - psi)
+        su = torch.minimum(su_t, smax)
+        qu = qi * psi + torch.maximum(zero, su_t - smax)
+        kth = torch.where(su <= pwp[:, j], su / smax, torch.ones_like(su))
+        su = torch.maximum(zero, su - E[:, j] * klu * kth)
+        for n, v in zip(NONSENSE_STATES, (ss, su, si, sb)):
+            tape[n].append(v)
+        q.append(qu.mean(dim=1))
+    return _pack_result(q, tape, par)
+
+
+RUNNERS = {"shm": shm_run, "hbv": hbv_run, "linear_reservoir": linres_run, "nonsense": nonsense_run}
 
 
 # ----------------------------------------------------------------------------------------------

@@ -20,6 +20,17 @@ def golden(name):
     return dict(np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False))
 
 
+DIRECT_CASES = ["shm_direct", "shm_direct_static4", "hbv_direct", "hbv_direct_nobetaet", "linres_direct",
+                "linres_direct_static", "nonsense_direct", "nonsense_direct_static"]
+HYBRID_CASES = ["hybrid_shm_c2", "hybrid_shm_mixed", "hybrid_hbv_c4", "hybrid_hbv_norouting", "hybrid_nonsense",
+                "hybrid_linres"]
+
+
+def bucket_of(name):
+    """Oracle model key of a *_direct golden file."""
+    return {"shm": "shm", "hbv": "hbv", "linres": "linear_reservoir", "nonsense": "nonsense"}[name.split("_")[0]]
+
+
 def tt(a, dtype=torch.float32, grad=False):
     x = torch.tensor(np.asarray(a), dtype=dtype)
     return x.requires_grad_(grad)

@@ -2,7 +2,7 @@
 
 Run in the build container only (the GPU box has no /root/reference):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case_name ...]      # no names: every case
 
 Every file stores the seeded inputs (or the seeds that regenerate them through
 `hy2dl_b200.synthetic`), and the reference's outputs and autograd gradients in fp32 on the host
@@ -27,6 +27,8 @@ from cudalstm import CudaLSTM  # noqa: E402
 from functions_training import nse_basin_averaged, weighted_rmse  # noqa: E402
 from hbv import HBV  # noqa: E402
 from hybrid import Hybrid  # noqa: E402
+from linear_reservoir import linear_reservoir  # noqa: E402
+from nonsense import NonSense  # noqa: E402
 from shm import SHM  # noqa: E402
 from uh_routing import UH_routing  # noqa: E402
 
@@ -279,24 +281,39 @@ def case_train_steps():
 
 
 if __name__ == "__main__":
-    torch.manual_seed(0)
-    case_cudalstm("cudalstm_c1", "gb", B=4, T=365, H=64, wseed=1, store_full_grads=True)
-    case_cudalstm("cudalstm_c3", "us_lstm", B=2, T=120, H=256, wseed=2, store_full_grads=False)
-    case_hybrid("hybrid_shm_c2", "gb", SHM, "shm", B=4, T=365, n_last=182, H=64, m=1,
-                dynamic=["dd", "f_thr", "sumax", "beta", "perc", "kf", "ki", "kb"], wseed=3, loss_kind="nse")
-    case_hybrid("hybrid_shm_mixed", "us", SHM, "shm", B=3, T=90, n_last=40, H=64, m=3,
-                dynamic=["dd", "beta", "ki"], wseed=4, loss_kind="wrmse")
-    case_hybrid("hybrid_hbv_c4", "us", HBV, "hbv", B=3, T=140, n_last=70, H=64, m=16,
-                dynamic=["BETA", "BETAET"], wseed=5, loss_kind="wrmse")
-    case_hybrid("hybrid_hbv_norouting", "gb", HBV, "hbv", B=3, T=80, n_last=30, H=128, m=2,
-                dynamic=["TT", "FC", "K1", "CFMAX"], wseed=6, loss_kind="nse", routing=False)
-    case_direct("shm_direct", SHM, lambda mdl: mdl.parameter_ranges, B=6, T=120, m=2, ncols=3)
-    case_direct("shm_direct_static4", SHM, lambda mdl: mdl.parameter_ranges, B=5, T=60, m=1, ncols=4,
-                dynamic_all=False)
-    case_direct("hbv_direct", HBV, lambda mdl: mdl.parameter_ranges, B=6, T=120, m=2, ncols=4)
-    case_direct("hbv_direct_nobetaet", HBV, lambda mdl: mdl.parameter_ranges, B=5, T=60, m=1, ncols=3,
-                dynamic_all=False, drop=("BETAET",))
-    case_uh()
-    case_losses()
-    case_sampler()
-    case_train_steps()
+    R = lambda mdl: mdl.parameter_ranges
+    CASES = {
+        "cudalstm_c1": lambda n: case_cudalstm(n, "gb", B=4, T=365, H=64, wseed=1, store_full_grads=True),
+        "cudalstm_c3": lambda n: case_cudalstm(n, "us_lstm", B=2, T=120, H=256, wseed=2, store_full_grads=False),
+        "hybrid_shm_c2": lambda n: case_hybrid(
+            n, "gb", SHM, "shm", B=4, T=365, n_last=182, H=64, m=1,
+            dynamic=["dd", "f_thr", "sumax", "beta", "perc", "kf", "ki", "kb"], wseed=3, loss_kind="nse"),
+        "hybrid_shm_mixed": lambda n: case_hybrid(n, "us", SHM, "shm", B=3, T=90, n_last=40, H=64, m=3,
+                                                  dynamic=["dd", "beta", "ki"], wseed=4, loss_kind="wrmse"),
+        "hybrid_hbv_c4": lambda n: case_hybrid(n, "us", HBV, "hbv", B=3, T=140, n_last=70, H=64, m=16,
+                                               dynamic=["BETA", "BETAET"], wseed=5, loss_kind="wrmse"),
+        "hybrid_hbv_norouting": lambda n: case_hybrid(n, "gb", HBV, "hbv", B=3, T=80, n_last=30, H=128, m=2,
+                                                      dynamic=["TT", "FC", "K1", "CFMAX"], wseed=6, loss_kind="nse",
+                                                      routing=False),
+        "hybrid_nonsense": lambda n: case_hybrid(n, "gb", NonSense, "nonsense", B=4, T=120, n_last=60, H=64, m=1,
+                                                 dynamic=["dd", "sumax", "beta", "ki", "kb"], wseed=7, loss_kind="nse"),
+        "hybrid_linres": lambda n: case_hybrid(n, "gb", linear_reservoir, "linear_reservoir", B=3, T=100, n_last=45,
+                                               H=64, m=4, dynamic=["ki"], wseed=8, loss_kind="wrmse", routing=False),
+        "shm_direct": lambda n: case_direct(n, SHM, R, B=6, T=120, m=2, ncols=3),
+        "shm_direct_static4": lambda n: case_direct(n, SHM, R, B=5, T=60, m=1, ncols=4, dynamic_all=False),
+        "hbv_direct": lambda n: case_direct(n, HBV, R, B=6, T=120, m=2, ncols=4),
+        "hbv_direct_nobetaet": lambda n: case_direct(n, HBV, R, B=5, T=60, m=1, ncols=3, dynamic_all=False,
+                                                     drop=("BETAET",)),
+        "linres_direct": lambda n: case_direct(n, linear_reservoir, R, B=6, T=120, m=3, ncols=3),
+        "linres_direct_static": lambda n: case_direct(n, linear_reservoir, R, B=5, T=60, m=1, ncols=3,
+                                                      dynamic_all=False),
+        "nonsense_direct": lambda n: case_direct(n, NonSense, R, B=7, T=120, m=1, ncols=3),
+        "nonsense_direct_static": lambda n: case_direct(n, NonSense, R, B=5, T=60, m=1, ncols=3, dynamic_all=False),
+        "uh_direct": lambda n: case_uh(),
+        "losses": lambda n: case_losses(),
+        "sampler": lambda n: case_sampler(),
+        "train_steps": lambda n: case_train_steps(),
+    }
+    for name in (sys.argv[1:] or CASES):
+        torch.manual_seed(0)
+        CASES[name](name)

@@ -10,7 +10,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from _util import ROOT, assert_close, golden
+from _util import DIRECT_CASES, ROOT, assert_close, bucket_of, golden
 
 SRC = os.path.join(ROOT, "tests", "host", "conceptual_host.cpp")
 LIB = os.path.join(ROOT, "tests", "host", "_build", "libconceptual_host.so")
@@ -18,6 +18,10 @@ SHM_NAMES = ["dd", "f_thr", "sumax", "beta", "perc", "kf", "ki", "kb"]
 HBV_NAMES = ["BETA", "FC", "K0", "K1", "K2", "LP", "PERC", "UZL", "TT", "CFMAX", "CFR", "CWH", "BETAET"]
 SHM_STATES = ["ss", "sf", "su", "si", "sb"]
 HBV_STATES = ["SNOWPACK", "MELTWATER", "SM", "SUZ", "SLZ"]
+# model id (include/hy2dl_b200.h HY2DL_MODEL_*), parameter order, storage order
+MODELS = {"shm": (0, SHM_NAMES, SHM_STATES), "hbv": (1, HBV_NAMES, HBV_STATES),
+          "linear_reservoir": (2, ["ki", "aux_ET"], ["si"]),
+          "nonsense": (3, ["dd", "sumax", "beta", "ki", "kb"], ["ss", "su", "si", "sb"])}
 
 
 @pytest.fixture(scope="module")
@@ -31,12 +35,12 @@ def fp(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-@pytest.mark.parametrize("name", ["shm_direct", "shm_direct_static4", "hbv_direct", "hbv_direct_nobetaet"])
+@pytest.mark.parametrize("name", DIRECT_CASES)
 def test_step_and_adjoint_match_reference(host, name):
     g = golden(name)
     B, T, m, ncols, dyn = [int(v) for v in g["meta"]]
-    model = 0 if name.startswith("shm") else 1
-    names, snames = (SHM_NAMES, SHM_STATES) if model == 0 else (HBV_NAMES, HBV_STATES)
+    model, names, snames = MODELS[bucket_of(name)]
+    NS = len(snames)
     N = B * m
     xc = g["x_conceptual"]
     tm = (xc[:, :, 2] + xc[:, :, 3]) / 2 if ncols == 4 else xc[:, :, 2]
@@ -59,11 +63,11 @@ def test_step_and_adjoint_match_reference(host, name):
     dstates = np.ascontiguousarray(
         np.stack([g["ws." + s].transpose(1, 0, 2).reshape(T, N) for s in snames], axis=1), dtype=np.float32)
     dq = np.ascontiguousarray(g["wq"][:, :, 0].T, dtype=np.float32)
-    states = np.zeros((T, 5, N), dtype=np.float32)
+    states = np.zeros((T, NS, N), dtype=np.float32)
     q = np.zeros((T, B), dtype=np.float32)
-    dinit = np.zeros((5, N), dtype=np.float32)
+    dinit = np.zeros((NS, N), dtype=np.float32)
     host.conceptual_host(model, C.c_int64(B), C.c_int64(T), C.c_int64(m), fp(forc), P, TS, fp(init),
-                         int("param.BETAET" in g or model == 0), fp(states), fp(q), fp(dq), fp(dstates), DP, fp(dinit))
+                         int("param.BETAET" in g or model != 1), fp(states), fp(q), fp(dq), fp(dstates), DP, fp(dinit))
     tol = dict(rtol=1e-4, atol=1e-6)
     assert_close(q.T[:, :, None], g["y_hat"], what="y_hat", **tol)
     for i, s in enumerate(snames):

@@ -76,10 +76,19 @@ def test_flat_aliases_resolve_reference_import_names():
     from hybrid import Hybrid  # noqa: F401
     from shm import SHM  # noqa: F401
     from functions_training import nse_basin_averaged  # noqa: F401
+    from linear_reservoir import linear_reservoir  # noqa: F401
+    from nonsense import NonSense
     import sys
     for k in ("hybrid", "shm", "hbv", "cudalstm", "uh_routing", "baseconceptualmodel", "functions_training",
-              "functions_evaluation"):
+              "functions_evaluation", "linear_reservoir", "nonsense"):
         sys.modules.pop(k, None)
+    # constants of the added bucket models (nonsense.py:170-176, linear_reservoir.py:99-108)
+    ns = NonSense(n_models=1, parameter_type=["ki"])
+    assert list(ns.parameter_ranges) == ["dd", "sumax", "beta", "ki", "kb"] and ns.parameter_type["ki"] == "dynamic"
+    assert ns._initial_states == {"ss": 0.0, "su": 5.0, "si": 10.0, "sb": 15.0}
+    assert linear_reservoir(n_models=3)._initial_states == {"si": 0.001}
+    with pytest.raises(ValueError):
+        NonSense(n_models=2)     # the reference's [batch, 1] output slot cannot hold two members (nonsense.py:163)
 
 
 def test_valid_window_flags_match_reference():

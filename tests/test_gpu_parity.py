@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from _util import O, PARAM_KEYS, assert_close, golden, oracle_hybrid, tt, weights
+from _util import DIRECT_CASES, O, PARAM_KEYS, assert_close, bucket_of, golden, oracle_hybrid, tt, weights
 
 pytestmark = pytest.mark.gpu
 
@@ -51,20 +51,20 @@ def test_pack_layouts(dev):
         xr = ops.pack_x(cu(x, dev), "ri32")                                      # always 32 columns wide
         x32 = torch.zeros(T, B, 32, device=dev); x32[:, :, :I] = cu(x, dev).permute(1, 0, 2)
         assert torch.equal(xr, ops.to_ri32(x32))
-    for nc in (3, 4):
+    for nc in (2, 3, 4):
         xc = rng.normal(size=(7, 11, nc)).astype(np.float32)
         f = npy(ops.pack_forcing(cu(xc, dev)))
-        tm = (xc[:, :, 2] + xc[:, :, 3]) / 2 if nc == 4 else xc[:, :, 2]
+        tm = (xc[:, :, 2] + xc[:, :, 3]) / 2 if nc == 4 else (xc[:, :, 2] if nc == 3 else 0 * xc[:, :, 0])
         assert np.array_equal(f[:, 0], xc[:, :, 0].T) and np.array_equal(f[:, 1], xc[:, :, 1].T)
         assert np.array_equal(f[:, 2], tm.T)
 
 
-@pytest.mark.parametrize("name", ["shm_direct", "shm_direct_static4", "hbv_direct", "hbv_direct_nobetaet"])
+@pytest.mark.parametrize("name", DIRECT_CASES)
 def test_bucket_models_direct(dev, name):
-    from hy2dl_b200.modelzoo import HBV, SHM
+    from hy2dl_b200.modelzoo import HBV, SHM, NonSense, linear_reservoir
     g = golden(name)
     B, T, m, ncols, dyn = [int(v) for v in g["meta"]]
-    model = (SHM if name.startswith("shm") else HBV)(n_models=m)
+    model = {"shm": SHM, "hbv": HBV, "linear_reservoir": linear_reservoir, "nonsense": NonSense}[bucket_of(name)](n_models=m)
     leaves = {k: cu(g["param." + k], dev, True) for k in model.parameter_ranges if "param." + k in g}
     pars = {k: (v if dyn else v.expand(-1, T, -1)) for k, v in leaves.items()}
     init = {k: cu(g["init." + k], dev, True) for k in model._initial_states}
@@ -175,9 +175,9 @@ def test_cudalstm_golden(dev, name, precision):
 
 
 def build_hybrid(g, dev, precision="fp32"):
-    from hy2dl_b200.modelzoo import HBV, SHM, Hybrid, UH_routing
+    from hy2dl_b200.modelzoo import HBV, SHM, Hybrid, NonSense, UH_routing, linear_reservoir
     B, T, n_last, I, H, m, wseed, routing = [int(v) for v in g["meta"]]
-    cls = {"shm": SHM, "hbv": HBV}[str(g["model"])]
+    cls = {"shm": SHM, "hbv": HBV, "nonsense": NonSense, "linear_reservoir": linear_reservoir}[str(g["model"])]
     hp = {"input_size_lstm": I, "hidden_size": H, "no_of_layers": 1, "seq_length": T, "predict_last_n": n_last,
           "n_conceptual_models": m, "conceptual_dynamic_parameterization": [str(s) for s in g["dynamic"]],
           "precision": precision}
@@ -187,7 +187,9 @@ def build_hybrid(g, dev, precision="fp32"):
 
 @pytest.mark.parametrize("name,precision", [("hybrid_shm_c2", "fp32"), ("hybrid_shm_mixed", "fp32"), ("hybrid_hbv_c4", "fp32"),
                                             ("hybrid_hbv_norouting", "fp32"), ("hybrid_shm_c2", "tf32x3"),
-                                            ("hybrid_shm_mixed", "tf32x3")])
+                                            ("hybrid_shm_mixed", "tf32x3"), ("hybrid_nonsense", "fp32"),
+                                            ("hybrid_nonsense", "tf32x3"), ("hybrid_linres", "fp32"),
+                                            ("hybrid_linres", "tf32x3")])
 def test_hybrid_golden(dev, name, precision):
     from hy2dl_b200.aux_functions import nse_basin_averaged, weighted_rmse
     g = golden(name)
@@ -278,12 +280,16 @@ def test_lstm_vs_oracle(dev, B, T, I, H, precision):
     ("shm", 45, 48, 24, 64, 4, ["kf", "beta"], "tf32x3"),            # 34 head columns: unfused head kernels on the RI32 streams
     ("shm", 70, 60, 37, 64, 3, ["kf", "beta", "sumax"], "tf32x3"),   # 26 head columns: fused head, 32-column MMA variants
     ("shm", 33, 40, 3, 64, 2, [], "tf32x3"),                         # 18 columns, all static, three simulated steps
+    ("nonsense", 40, 90, 45, 64, 1, ["dd", "sumax", "beta", "ki", "kb"], "fp32"),
+    ("nonsense", 300, 365, 182, 64, 1, ["ki", "kb"], "tf32x3"),      # 7 head columns, 4 storages
+    ("linear_reservoir", 21, 70, 30, 128, 5, ["aux_ET"], "fp32"),
+    ("linear_reservoir", 130, 120, 60, 64, 8, ["ki", "aux_ET"], "tf32x3"),   # 18 head columns, 1 storage, 8 members
 ])
 def test_hybrid_vs_oracle(dev, model_key, B, T, n_last, H, m, dyn, precision):
     from hy2dl_b200.aux_functions import nse_basin_averaged
-    from hy2dl_b200.modelzoo import HBV, SHM, Hybrid, UH_routing
+    from hy2dl_b200.modelzoo import HBV, SHM, Hybrid, NonSense, UH_routing, linear_reservoir
     from hy2dl_b200.synthetic import lstm_weights, make_basins
-    shape = "gb" if model_key == "shm" else "us"
+    shape = "us" if model_key == "hbv" else "gb"
     data = make_basins(shape, n_basins=8, n_rows=T + 10, seed=5)
     rng = np.random.default_rng(B)
     I = data.x_d.shape[2] + data.x_s.shape[1]
@@ -292,7 +298,7 @@ def test_hybrid_vs_oracle(dev, model_key, B, T, n_last, H, m, dyn, precision):
     xc = np.stack([data.x_conc[b, :T] for b in bi]).astype(np.float32)
     yo = np.stack([data.y_obs[b, T - n_last:T] for b in bi]).astype(np.float32)
     sd = np.repeat(rng.uniform(0.5, 2.0, (B, 1, 1)).astype(np.float32), n_last, axis=1)
-    cls = {"shm": SHM, "hbv": HBV}[model_key]
+    cls = {"shm": SHM, "hbv": HBV, "nonsense": NonSense, "linear_reservoir": linear_reservoir}[model_key]
     hp = {"input_size_lstm": I, "hidden_size": H, "no_of_layers": 1, "seq_length": T, "predict_last_n": n_last,
           "n_conceptual_models": m, "conceptual_dynamic_parameterization": dyn, "precision": precision}
     model = Hybrid(hp, conceptual_model=cls, routing_model=UH_routing)
@@ -330,6 +336,43 @@ def test_inference_no_grad_and_eval(dev, precision):
     with torch.no_grad():
         pred = model(x_lstm=cu(g["x_lstm"], dev), x_conceptual=cu(g["x_conceptual"], dev))
     assert_close(npy(pred["y_hat"]), g["y_hat"], what="y_hat", **TOL)
+
+
+@pytest.mark.parametrize("model_key,precision", [("shm", "fp32"), ("shm", "tf32x3"), ("hbv", "fp32")])
+def test_whole_period_inference(dev, model_key, precision):
+    """The notebooks' evaluation: one sample per basin spanning the whole test period (thousands of steps, far
+    longer than seq_length), warm-up fixed by the hyper-parameters (hybrid.py:39,95-108).  Discharge rtol 1e-4 of
+    the series' peak and basin NSE within 1e-3 of the fp64 oracle."""
+    from hy2dl_b200.aux_functions import nse
+    from hy2dl_b200.modelzoo import HBV, SHM, Hybrid, UH_routing
+    from hy2dl_b200.synthetic import lstm_weights, make_basins
+    B, T, H = 6, 2500, 64
+    data = make_basins("gb" if model_key == "shm" else "us", n_basins=B, n_rows=T, seed=23)
+    rng = np.random.default_rng(2)
+    I = data.x_d.shape[2] + data.x_s.shape[1]
+    xl = rng.normal(0, 1, (B, T, I)).astype(np.float32)
+    xc = data.x_conc[:, :T].astype(np.float32)
+    dyn = ["dd", "f_thr", "sumax", "beta", "perc", "kf", "ki", "kb"] if model_key == "shm" else ["BETA", "K1", "TT"]
+    hp = {"input_size_lstm": I, "hidden_size": H, "no_of_layers": 1, "seq_length": 730, "predict_last_n": 365,
+          "n_conceptual_models": 1, "conceptual_dynamic_parameterization": dyn, "precision": precision}
+    model = Hybrid(hp, conceptual_model=SHM if model_key == "shm" else HBV, routing_model=UH_routing)
+    w = lstm_weights(I, H, model.linear.out_features, seed=29)
+    model.load_state_dict({k: torch.tensor(v) for k, v in w.items()})
+    model = model.to(dev).eval()
+    with torch.no_grad():
+        pred = model(x_lstm=cu(xl, dev), x_conceptual=cu(xc, dev))
+        wd = {k: tt(v, torch.float64) for k, v in w.items()}
+        ref = O.hybrid_forward(wd, tt(xl, torch.float64), tt(xc, torch.float64), model=model_key, n_models=1,
+                               dynamic=dyn, warmup=365)
+    y, yr = npy(pred["y_hat"]), ref["y_hat"].numpy()
+    assert y.shape == (B, T - 365, 1)
+    assert_close(y, yr, what="y_hat", **TOL)
+    for k, v in pred["final_states"].items():
+        assert_close(npy(v), ref["final_states"][k].numpy(), what="final " + k, **TOL)
+    yo = data.y_obs[:, 365:T, 0]
+    a = nse({i: {"y_sim": y[i, :, 0], "y_obs": yo[i]} for i in range(B)}, average=False)
+    b = nse({i: {"y_sim": yr[i, :, 0], "y_obs": yo[i]} for i in range(B)}, average=False)
+    assert np.nanmax(np.abs(a - b) / (1 + np.abs(b))) < 1e-3
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32x3"])

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from _util import O, PARAM_KEYS, assert_close, golden, oracle_hybrid, tt, weights
+from _util import DIRECT_CASES, HYBRID_CASES, O, PARAM_KEYS, assert_close, bucket_of, golden, oracle_hybrid, tt, weights
 
 F32 = dict(rtol=2e-5, atol=1e-7)
 F64 = dict(rtol=3e-4, atol=1e-6)
@@ -43,7 +43,7 @@ def test_cudalstm_library_path_matches_cell_loop():
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, F32), (torch.float64, F64)])
-@pytest.mark.parametrize("name", ["hybrid_shm_c2", "hybrid_shm_mixed", "hybrid_hbv_c4", "hybrid_hbv_norouting"])
+@pytest.mark.parametrize("name", HYBRID_CASES)
 def test_hybrid(name, dtype, tol):
     g = golden(name)
     w, pred, loss = oracle_hybrid(g, dtype)
@@ -60,11 +60,11 @@ def test_hybrid(name, dtype, tol):
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, F32), (torch.float64, F64)])
-@pytest.mark.parametrize("name", ["shm_direct", "shm_direct_static4", "hbv_direct", "hbv_direct_nobetaet"])
+@pytest.mark.parametrize("name", DIRECT_CASES)
 def test_bucket_direct(name, dtype, tol):
     g = golden(name)
     B, T, m, ncols, dyn = [int(v) for v in g["meta"]]
-    model = "shm" if name.startswith("shm") else "hbv"
+    model = bucket_of(name)
     ranges, states, _ = O.MODEL_TABLE[model]
     leaves = {k: tt(g["param." + k], dtype, True) for k in ranges if "param." + k in g}
     pars = {k: (v if dyn else v.expand(-1, T, -1)) for k, v in leaves.items()}
