@@ -75,6 +75,7 @@ _SIGNATURES = {
     "hy2dl_loss_nse_finish": (i32, [p_f, p_f, p_f, i64, p_f, p_f, p_f, p_f, p_f]),
     "hy2dl_loss_wrmse_reduce": (i32, [p_f, p_f, i64, p_f, p_f]),
     "hy2dl_loss_wrmse_finish": (i32, [p_f, p_f, i64, p_f, p_f, p_f, p_f, p_f]),
+    "hy2dl_nse_basins": (i32, [p_f, p_f, i64, i64, p_f, p_f]),
     "hy2dl_window_gather": (i32, [p_f] * 8 + [i64] * 7 + [p_f] * 4 + [i32, p_f]),
     "hy2dl_grad_sqnorm": (i32, [p_f, i64, p_f, p_f]),
     "hy2dl_clip_adam": (i32, [p_f, p_f, p_f, p_f, i64, p_f, C.c_float, C.c_float, p_f, C.c_float, C.c_float, C.c_float,

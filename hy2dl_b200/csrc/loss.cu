@@ -145,3 +145,64 @@ extern "C" int hy2dl_loss_wrmse_finish(const float* y_sim, const float* y_obs, i
   HY_LAUNCH_CHECK();
   return HY2DL_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// evaluation: per-basin Nash-Sutcliffe efficiency of whole-period series on the device
+// (aux_functions/functions_evaluation.py:28-48).  y_sim, y_obs are time-major [T][B] (the native layout of
+// the discharge the hybrid chain produces); a block owns 32 neighbouring series and 8 time phases, so every
+// load is a full 128-byte line.  Two passes (mean of the valid observations, then the two sums of squares),
+// float64 accumulation like the reference's numpy arithmetic.
+// ------------------------------------------------------------------------------------------------
+namespace hy2dl {
+
+constexpr int kEvalPhases = 8;
+
+__global__ void __launch_bounds__(32 * kEvalPhases) nse_basins_kernel(const float* __restrict__ ys, const float* __restrict__ yo,
+                                                                      int64_t T, int64_t B, double* __restrict__ out) {
+  __shared__ double sm[2][kEvalPhases][32];
+  const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5;
+  const int64_t b = (int64_t)blockIdx.x * 32 + lane;
+  const bool live = b < B;
+  double so = 0.0, n = 0.0;
+  if (live)
+    for (int64_t t = ph; t < T; t += kEvalPhases) {
+      const float s = ys[t * B + b], o = yo[t * B + b];
+      if (s == s && o == o) { so += (double)o; n += 1.0; }
+    }
+  sm[0][ph][lane] = so; sm[1][ph][lane] = n;
+  __syncthreads();
+  so = 0.0; n = 0.0;
+#pragma unroll
+  for (int k = 0; k < kEvalPhases; ++k) { so += sm[0][k][lane]; n += sm[1][k][lane]; }
+  __syncthreads();
+  const double mean = n > 0.0 ? so / n : 0.0;
+  double sse = 0.0, sso = 0.0;
+  if (live)
+    for (int64_t t = ph; t < T; t += kEvalPhases) {
+      const float s = ys[t * B + b], o = yo[t * B + b];
+      if (s == s && o == o) {
+        const double e = (double)s - (double)o, d = (double)o - mean;
+        sse += e * e; sso += d * d;
+      }
+    }
+  sm[0][ph][lane] = sse; sm[1][ph][lane] = sso;
+  __syncthreads();
+  if (ph == 0 && live) {
+    sse = 0.0; sso = 0.0;
+#pragma unroll
+    for (int k = 0; k < kEvalPhases; ++k) { sse += sm[0][k][lane]; sso += sm[1][k][lane]; }
+    out[b] = n > 1.0 ? 1.0 - sse / sso : nan("");     // fewer than two valid pairs: NaN (functions_evaluation.py:45-48)
+  }
+}
+
+}  // namespace hy2dl
+
+extern "C" int hy2dl_nse_basins(const float* y_sim, const float* y_obs, int64_t T, int64_t B, double* nse,
+                                hy2dl_stream_t stream) {
+  HY_REQUIRE(T > 0 && B > 0, HY2DL_ERR_SHAPE, "hy2dl_nse_basins: empty input");
+  HY_NONNULL(y_sim); HY_NONNULL(y_obs); HY_NONNULL(nse);
+  nse_basins_kernel<<<(unsigned)cdiv(B, 32), 32 * kEvalPhases, 0, (cudaStream_t)stream>>>(y_sim, y_obs, T, B, nse);
+  HY_LAUNCH_CHECK();
+  return HY2DL_OK;
+}

@@ -209,6 +209,11 @@ int hy2dl_loss_wrmse_reduce(const float* y_sim, const float* y_obs, int64_t n, f
 int hy2dl_loss_wrmse_finish(const float* y_sim, const float* y_obs, int64_t n, const float* acc,
                             const float* gscale, float* loss, float* dy, hy2dl_stream_t stream);
 
+/* ---- evaluation metric on the device (replaces the per-basin loop of aux_functions/functions_evaluation.py:28-48
+ * for series that are already resident): y_sim, y_obs time-major [T][B], NaN in either = pair skipped;
+ * nse [B] float64, NaN where fewer than two valid pairs remain. */
+int hy2dl_nse_basins(const float* y_sim, const float* y_obs, int64_t T, int64_t B, double* nse, hy2dl_stream_t stream);
+
 /* ---- GPU-resident sliding-window sampler (replaces BaseDataset.__getitem__ + collate,
  * datasetzoo/basedataset.py:168-195).  Resident series are the concatenation of all basins:
  * x_d [R][nd], x_conc [R][nc] (or NULL), y_obs [R], x_s [nb][ns] (or NULL), basin_std [nb],

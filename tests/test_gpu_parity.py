@@ -373,6 +373,32 @@ def test_whole_period_inference(dev, model_key, precision):
     a = nse({i: {"y_sim": y[i, :, 0], "y_obs": yo[i]} for i in range(B)}, average=False)
     b = nse({i: {"y_sim": yr[i, :, 0], "y_obs": yo[i]} for i in range(B)}, average=False)
     assert np.nanmax(np.abs(a - b) / (1 + np.abs(b))) < 1e-3
+    # the same metric evaluated on the device from the resident series
+    from hy2dl_b200.aux_functions import nse_device
+    dev_nse = npy(nse_device(pred["y_hat"], cu(yo, dev), average=False))
+    assert_close(dev_nse, a, rtol=1e-9, atol=1e-12, what="device NSE vs host NSE of the same series")
+
+
+def test_nse_device_edge_cases(dev):
+    """NaN in either series drops the pair; fewer than two valid pairs give NaN (functions_evaluation.py:35-48);
+    ragged basin counts (not a multiple of the 32-series block) and the nan-median."""
+    from hy2dl_b200.aux_functions import nse, nse_device
+    rng = np.random.default_rng(4)
+    B, T = 45, 1234
+    sim = rng.gamma(1.0, 1.0, (B, T)).astype(np.float32)
+    obs = (sim + rng.normal(0, 0.5, (B, T))).astype(np.float32)
+    obs[rng.random((B, T)) < 0.05] = np.nan
+    sim[3, 100:140] = np.nan
+    obs[7] = np.nan                    # no observation at all
+    obs[9, 1:] = np.nan                # a single valid pair
+    frames = {i: {"y_sim": sim[i], "y_obs": obs[i]} for i in range(B)}
+    ref = nse(frames, average=False)
+    got = npy(nse_device(cu(sim, dev).unsqueeze(2), cu(obs, dev).unsqueeze(2), average=False))
+    assert np.isnan(got[7]) and np.isnan(got[9]) and np.isnan(ref[7]) and np.isnan(ref[9])
+    assert_close(got, ref, rtol=1e-9, atol=1e-12, what="per-basin NSE")
+    assert_close(nse_device(cu(sim, dev), cu(obs, dev)).item(), nse(frames), rtol=1e-9, what="median NSE")
+    with pytest.raises(RuntimeError):
+        nse_device(torch.zeros(2, 5), torch.zeros(2, 5))
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
