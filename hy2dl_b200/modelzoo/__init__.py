@@ -6,8 +6,9 @@ from .hbv import HBV
 from .hybrid import Hybrid
 from .linear_reservoir import linear_reservoir
 from .lstm import LSTM
+from .mflstm import MFLSTM
 from .nonsense import NonSense
 from .shm import SHM
 from .uh_routing import UH_routing
 
-__all__ = ["BaseConceptualModel", "CudaLSTM", "HBV", "Hybrid", "LSTM", "NonSense", "SHM", "UH_routing", "linear_reservoir"]
+__all__ = ["BaseConceptualModel", "CudaLSTM", "HBV", "Hybrid", "LSTM", "MFLSTM", "NonSense", "SHM", "UH_routing", "linear_reservoir"]

@@ -14,6 +14,7 @@ Reference lines each function follows (paths relative to /root/reference/Hy2DL):
   hbv_run ................... modelzoo/hbv.py:70-86 (pre-loop), :127-188 (step), :195-215 (constants)
   linres_run ................ modelzoo/linear_reservoir.py:64-92 (step), :99-108 (constants)
   nonsense_run .............. modelzoo/nonsense.py:72-94 (pre-loop), :128-168 (step), :170-176 (constants)
+  mflstm_forward ............ NO REFERENCE CODE: this project's own definition, parity unpinned
   uh_route .................. modelzoo/uh_routing.py:42-44, :64-74, :92-109, :111-113
   hybrid_forward ............ modelzoo/hybrid.py:62-117
   nse_basin_averaged ........ aux_functions/functions_training.py:32-41
@@ -116,6 +117,33 @@ def cudalstm_forward(w: Dict[str, torch.Tensor], x, library: bool = False):
 # ----------------------------------------------------------------------------------------------
 # head output -> conceptual parameters
 # ----------------------------------------------------------------------------------------------
+def mflstm_forward(w: Dict[str, torch.Tensor], x: Dict[str, torch.Tensor], columns: Dict[str, Sequence[int]],
+                   flag_column: Dict[str, int], predict_last_n: int):
+    """Multi-frequency LSTM -- PARITY UNPINNED: the reference snapshot has no such model, so
+    this restates the project's own definition (hy2dl_b200/modelzoo/mflstm.py) in its natural form: one cell,
+    stretches processed oldest first, every frequency with its own input projection W_f = W_ih[:, columns[f]] and
+    bias offset W_ih[:, flag_column[f]], shared recurrent weights, zero initial state, Linear head on the last steps.
+    x = {freq: [B, n_steps, n_inputs]} in processing order."""
+    w_ih, w_hh = w["lstm.weight_ih_l0"], w["lstm.weight_hh_l0"]
+    bias = w["lstm.bias_ih_l0"] + w["lstm.bias_hh_l0"]
+    first = next(iter(x.values()))
+    B, H = first.shape[0], w_hh.shape[1]
+    h = first.new_zeros(B, H)
+    c = first.new_zeros(B, H)
+    hs = []
+    for f, xf in x.items():
+        w_f = w_ih[:, list(columns[f])]
+        b_f = bias + (w_ih[:, flag_column[f]] if f in flag_column else 0)
+        for t in range(xf.shape[1]):
+            z = xf[:, t] @ w_f.t() + h @ w_hh.t() + b_f
+            i, fg, g, o = z.chunk(4, dim=1)
+            c = torch.sigmoid(fg) * c + torch.sigmoid(i) * torch.tanh(g)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            hs.append(h)
+    out = torch.stack(hs[-predict_last_n:], dim=1)
+    return out @ w["linear.weight"].t() + w["linear.bias"]
+
+
 def map_parameters(z, ranges: "OrderedDict[str, Tuple[float, float]]", dynamic: Sequence[str],
                    n_models: int, warmup: int):
     """z [B,T,P*m] (parameter index slow, member index fast) -> (warm-up dict, simulation dict)."""

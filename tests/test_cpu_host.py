@@ -175,3 +175,28 @@ def test_data_parallel_equals_single_process_with_unequal_nan_counts():
     mp.spawn(_dp_worker, args=(2, port, ret), nprocs=2, join=True)
     assert_close(ret["loss"], loss.item(), rtol=1e-12, what="DP loss")
     assert_close(ret["grad"], single, rtol=1e-10, what="DP gradient")
+
+
+def test_mflstm_block_packing_equals_per_frequency_projections():
+    """The multi-frequency model's block layout of the inputs (host logic of modelzoo/mflstm.py) turns one packed
+    W_ih into per-frequency projections: the plain cell loop on the packed input equals the natural per-frequency
+    form of the oracle.  (Parity of this model is unpinned: the reference snapshot has no such model.)"""
+    from hy2dl_b200.modelzoo import MFLSTM
+    from hy2dl_b200.synthetic import lstm_weights
+    hp = {"input_size_lstm": {"1D": 5, "1h": 6}, "seq_length": {"1D": 7, "1h": 9}, "n_shared_inputs": 2,
+          "hidden_size": 64, "no_of_layers": 1, "predict_last_n": 4}
+    m = MFLSTM(hp)
+    assert m.input_size_total == 3 + 4 + 2 + 1 and m.flag_column == {"1h": 9}
+    assert m.columns == {"1D": [0, 1, 2, 7, 8], "1h": [3, 4, 5, 6, 7, 8]}
+    rng = np.random.default_rng(0)
+    x = {f: torch.tensor(rng.normal(size=(3, hp["seq_length"][f], hp["input_size_lstm"][f]))) for f in ("1D", "1h")}
+    wd = weights(m.input_size_total, 64, 1, 1, torch.float64, grad=False)
+    a = O.mflstm_forward(wd, x, m.columns, m.flag_column, 4)
+    h = O.lstm_cell_sequence(m.pack(x), wd["lstm.weight_ih_l0"], wd["lstm.weight_hh_l0"], wd["lstm.bias_ih_l0"],
+                             wd["lstm.bias_hh_l0"])
+    b = h[:, -4:] @ wd["linear.weight"].t() + wd["linear.bias"]
+    assert_close(a, b, rtol=1e-13, what="packed vs per-frequency")
+    with pytest.raises(ValueError):
+        m.pack({"1D": x["1D"], "1h": x["1h"][:, :5]})
+    with pytest.raises(ValueError):
+        MFLSTM({**hp, "predict_last_n": 10})

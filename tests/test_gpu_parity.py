@@ -379,6 +379,36 @@ def test_whole_period_inference(dev, model_key, precision):
     assert_close(dev_nse, a, rtol=1e-9, atol=1e-12, what="device NSE vs host NSE of the same series")
 
 
+@pytest.mark.parametrize("B,H,precision,n_dyn,n_static", [(40, 64, "tf32x3", 3, 22), (9, 128, "fp32", 11, 27)])
+def test_mflstm_vs_own_oracle(dev, B, H, precision, n_dyn, n_static):
+    """Multi-frequency LSTM (365 daily + 336 hourly steps, last 24 hours predicted).  PARITY UNPINNED: no reference
+    implementation exists in the snapshot; the check is against this project's own fp64 restatement of the
+    definition (per-frequency projections, shared cell), forward rtol 1e-4 and gradients rtol 2e-4."""
+    from hy2dl_b200.modelzoo import MFLSTM
+    from hy2dl_b200.synthetic import lstm_weights
+    rng = np.random.default_rng(B)
+    hp = {"input_size_lstm": {"1D": 3 + n_static, "1h": n_dyn + n_static}, "seq_length": {"1D": 365, "1h": 336},
+          "n_shared_inputs": n_static, "hidden_size": H, "no_of_layers": 1, "predict_last_n": 24,
+          "drop_out_rate": 0.0, "precision": precision}
+    model = MFLSTM(hp)
+    I = model.input_size_total
+    assert I == 3 + n_dyn + n_static + 1
+    w = lstm_weights(I, H, 1, seed=31)
+    model.load_state_dict({k: torch.tensor(v) for k, v in w.items()})
+    model = model.to(dev)
+    x = {f: rng.normal(0, 1, (B, hp["seq_length"][f], hp["input_size_lstm"][f])).astype(np.float32) for f in ("1D", "1h")}
+    wy = rng.normal(0, 1, (B, 24, 1)).astype(np.float32)
+    y = model({f: cu(v, dev) for f, v in x.items()})["y_hat"]
+    (y * cu(wy, dev)).sum().backward()
+    wd = {k: tt(v, torch.float64, True) for k, v in w.items()}
+    ref = O.mflstm_forward(wd, {f: tt(v, torch.float64) for f, v in x.items()}, model.columns, model.flag_column, 24)
+    (ref * tt(wy, torch.float64)).sum().backward()
+    assert y.shape == (B, 24, 1)
+    assert_close(npy(y), ref.detach().numpy(), what="y_hat", **TOL)
+    for k, p in model.named_parameters():
+        assert_close(npy(p.grad), wd[k].grad.numpy(), what="grad " + k, rtol=2e-4, atol=1e-7)
+
+
 def test_nse_device_edge_cases(dev):
     """NaN in either series drops the pair; fewer than two valid pairs give NaN (functions_evaluation.py:35-48);
     ragged basin counts (not a multiple of the 32-series block) and the nan-median."""
