@@ -14,7 +14,7 @@ class CudaLSTM(nn.Module):
     """LSTM -> last hidden state -> Dropout -> Linear(H, 1); returns {"y_hat": [B, 1]}.
 
     Hyper-parameter keys read: input_size_lstm, hidden_size, no_of_layers, drop_out_rate
-    (cudalstm.py:18-26); optional extra key "precision" ("fp32" | "tf32x3" | "bf16").
+    (cudalstm.py:18-26); optional extra key "precision" ("fp32" | "tf32x3").
     State-dict keys: lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0,
     linear.weight, linear.bias.
     """

@@ -56,7 +56,7 @@ typedef void* hy2dl_stream_t; /* cudaStream_t */
 /* precision of the recurrent / projection matmuls */
 #define HY2DL_PREC_FP32 0   /* CUDA-core FMA, fp32-exact (parity path, rtol 1e-4)            */
 #define HY2DL_PREC_TF32X3 1 /* tcgen05 kind::tf32, 3-term split (fp32-class accuracy)         */
-#define HY2DL_PREC_BF16 2   /* tcgen05 kind::f16 bf16 operands, fp32 accumulate (throughput)  */
+#define HY2DL_PREC_BF16 2   /* reserved (kind::f16 single pass, looser tolerance): not built, calls return ERR_SHAPE */
 
 /* layout of the LSTM-side streams handled by the packing / sampler / head functions */
 #define HY2DL_LAYOUT_ROWMAJOR 0 /* [T][B][F]                                                      */
