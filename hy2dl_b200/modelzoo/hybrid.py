@@ -105,7 +105,13 @@ class Hybrid(nn.Module):
         # simulation (hybrid.py:104-108)
         s_offs = [pm.sim_off[k] for k in range(n_par)]
         s_dyn = [bool(pm.dynamic[k]) for k in range(n_par)]
-        states, q = ops.conceptual(forc, par_sim, init, cm._model_id, B, m, warmup, T_sim, s_offs, s_dyn)
+        if self.n_routing_params > 0:
+            # the routing parameters leave par_sim through the same autograd node (see ConceptualFunction)
+            r_off, beta_off = pm.sim_off[n_par], pm.sim_off[n_par + 1] - pm.sim_off[n_par]
+            states, q, routing = ops.conceptual_routing(forc, par_sim, init, cm._model_id, B, m, warmup, T_sim, s_offs,
+                                                        s_dyn, (r_off, beta_off + B))
+        else:
+            states, q = ops.conceptual(forc, par_sim, init, cm._model_id, B, m, warmup, T_sim, s_offs, s_dyn)
 
         parameters = {}
         for k, name in enumerate(layout.names):
@@ -114,6 +120,5 @@ class Hybrid(nn.Module):
                                 else plane.view(B, 1, m).expand(B, T_sim, m))
         pred = cm._result(states, q, parameters, B, m)
         if self.n_routing_params > 0:
-            alpha, beta = layout.plane(par_sim, n_par), layout.plane(par_sim, n_par + 1)
-            pred["y_hat"] = ops.uh_route(q, alpha, beta).t().unsqueeze(2)
+            pred["y_hat"] = ops.uh_route_packed(q, routing, beta_off).t().unsqueeze(2)
         return pred

@@ -361,11 +361,17 @@ class ConceptualFunction(torch.autograd.Function):
     """Bucket model over forcing rows [t0, t0+Tn).
 
     par_flat: flat buffer, parameter k's plane at offs[k] (None: parameter absent), dynamic[k] says
-    whether the plane is [Tn,N] or [N].  Returns (states [Tn,5,N], q [Tn,B]).
+    whether the plane is [Tn,N] or [N].  Returns (states [Tn,5,N], q [Tn,B], routing).
+
+    `routing_span` = (offset, length) of the routing parameters inside par_flat, or None: they are handed on as a
+    small copy (third output) and their gradient is written back into this function's own gradient of par_flat.
+    Slicing the big buffer in autograd instead would cost a zero-filled full-size gradient and a full-size add per
+    slice (2 x 110 MB fills and 2 x 330 MB adds per step at the benchmark batch).
     """
 
     @staticmethod
-    def forward(ctx, forc, par_flat, init, model: int, B: int, m: int, t0: int, Tn: int, offs, dynamic):
+    def forward(ctx, forc, par_flat, init, model: int, B: int, m: int, t0: int, Tn: int, offs, dynamic,
+                routing_span=None):
         require_cuda(forc, "forcing"); require_cuda(par_flat, "parameters")
         dev = forc.device
         N = B * m
@@ -381,13 +387,16 @@ class ConceptualFunction(torch.autograd.Function):
         call("hy2dl_conceptual_fwd", model, ptr(forc), B, t0, Tn, m, _ptr_array(ptrs), _i64_array(ts), ptr(init),
              ptr(states), ptr(q), stream())
         ctx.save_for_backward(forc, par_flat, init, states)
-        ctx.meta = (model, B, m, t0, Tn, tuple(offs), tuple(dynamic))
-        return states, q
+        ctx.meta = (model, B, m, t0, Tn, tuple(offs), tuple(dynamic), routing_span)
+        routing = None
+        if routing_span is not None:
+            routing = par_flat.detach()[routing_span[0]:routing_span[0] + routing_span[1]].clone()
+        return states, q, routing
 
     @staticmethod
-    def backward(ctx, dstates, dq):
+    def backward(ctx, dstates, dq, drouting):
         forc, par_flat, init, states = ctx.saved_tensors
-        model, B, m, t0, Tn, offs, dynamic = ctx.meta
+        model, B, m, t0, Tn, offs, dynamic, routing_span = ctx.meta
         dev = forc.device
         N = B * m
         base = par_flat.data_ptr()
@@ -401,11 +410,19 @@ class ConceptualFunction(torch.autograd.Function):
         dinit = torch.zeros_like(init) if (init is not None and ctx.needs_input_grad[2]) else None
         call("hy2dl_conceptual_bwd", model, ptr(forc), B, t0, Tn, m, _ptr_array(ptrs), _i64_array(ts), ptr(init),
              ptr(states), ptr(dq), ptr(dstates), _ptr_array(dptrs), ptr(dinit), stream())
-        return None, dpar, dinit, None, None, None, None, None, None, None
+        if drouting is not None:
+            dpar[routing_span[0]:routing_span[0] + routing_span[1]] = drouting
+        return None, dpar, dinit, None, None, None, None, None, None, None, None
 
 
 def conceptual(forc, par_flat, init, model: int, B: int, m: int, t0: int, Tn: int, offs, dynamic):
-    return ConceptualFunction.apply(forc, par_flat, init, model, B, m, t0, Tn, offs, dynamic)
+    states, q, _ = ConceptualFunction.apply(forc, par_flat, init, model, B, m, t0, Tn, offs, dynamic, None)
+    return states, q
+
+
+def conceptual_routing(forc, par_flat, init, model: int, B: int, m: int, t0: int, Tn: int, offs, dynamic, routing_span):
+    """As `conceptual`, additionally returning the routing-parameter span of par_flat as its own small tensor."""
+    return ConceptualFunction.apply(forc, par_flat, init, model, B, m, t0, Tn, offs, dynamic, routing_span)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -439,6 +456,39 @@ class UHFunction(torch.autograd.Function):
 
 def uh_route(q, alpha, beta):
     return UHFunction.apply(q, alpha, beta)
+
+
+class UHPackedFunction(torch.autograd.Function):
+    """q [T,B] and one tensor holding alpha at [0,B) and beta at [beta_off, beta_off+B) -> routed y [T,B]; the two
+    gradients are written straight into one gradient tensor of the same shape (no slicing in autograd)."""
+
+    @staticmethod
+    def forward(ctx, q, ab, beta_off: int):
+        require_cuda(q, "discharge"); require_cuda(ab, "routing parameters")
+        T, B = q.shape
+        q, ab = q.contiguous(), ab.contiguous()
+        uh = torch.empty(15, B, dtype=torch.float32, device=q.device)
+        y = torch.empty_like(q)
+        call("hy2dl_uh_fwd", ptr(q), ptr(ab), ab.data_ptr() + 4 * beta_off, B, T, ptr(uh), ptr(y), stream())
+        ctx.save_for_backward(q, ab, uh)
+        ctx.beta_off = beta_off
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        q, ab, uh = ctx.saved_tensors
+        T, B = q.shape
+        off = ctx.beta_off
+        dy = dy.contiguous()
+        dq = torch.empty_like(q)
+        dab = torch.zeros_like(ab) if ab.numel() != 2 * B else torch.empty_like(ab)   # padding between the planes stays zero
+        call("hy2dl_uh_bwd", ptr(q), ptr(ab), ab.data_ptr() + 4 * off, ptr(uh), ptr(dy), B, T, ptr(dq), ptr(dab),
+             dab.data_ptr() + 4 * off, stream())
+        return dq, dab, None
+
+
+def uh_route_packed(q, ab, beta_off: int):
+    return UHPackedFunction.apply(q, ab, beta_off)
 
 
 # --------------------------------------------------------------------------------------------------
