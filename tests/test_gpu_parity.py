@@ -379,6 +379,56 @@ def test_whole_period_inference(dev, model_key, precision):
     assert_close(dev_nse, a, rtol=1e-9, atol=1e-12, what="device NSE vs host NSE of the same series")
 
 
+def test_full_size_batch_properties(dev):
+    """BASELINE.json configs[1] at the benchmark's full per-GPU batch (18 944 sequences x 365 steps, tcgen05 path), where
+    the fp64 oracle cannot run the whole batch: (1) sequences are independent, so the discharge of the first 256
+    sequences equals, bit for bit, what a batch of only those 256 gives; (2) a random subset of 48 sequences matches the
+    fp64 oracle (rtol 1e-4); (3) gradients of a linear functional are additive over a split of the batch into halves
+    (rtol 2e-5: only the summation order differs)."""
+    from hy2dl_b200.modelzoo import SHM, Hybrid, UH_routing
+    from hy2dl_b200.synthetic import lstm_weights, make_basins
+    B, T, n_last, H, nb = 18944, 365, 182, 64, 37
+    data = make_basins("gb", n_basins=nb, n_rows=T + 300, seed=8)
+    I = data.x_d.shape[2] + data.x_s.shape[1]
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    xl = torch.randn(B, T, I, device=dev, generator=g)
+    bi = torch.randint(0, nb, (B,), device=dev, generator=g)
+    st = torch.randint(0, 300, (B,), device=dev, generator=g)
+    xc_all = cu(data.x_conc, dev)                                                    # [nb, rows, 3]
+    idx = st[:, None] + torch.arange(T, device=dev)[None, :]
+    xc = xc_all[bi[:, None], idx]                                                    # [B, T, 3]
+    wy = torch.randn(B, n_last, 1, device=dev, generator=g)
+    dyn = ["dd", "f_thr", "sumax", "beta", "perc", "kf", "ki", "kb"]
+    hp = {"input_size_lstm": I, "hidden_size": H, "no_of_layers": 1, "seq_length": T, "predict_last_n": n_last,
+          "n_conceptual_models": 1, "conceptual_dynamic_parameterization": dyn, "precision": "tf32x3"}
+    model = Hybrid(hp, conceptual_model=SHM, routing_model=UH_routing)
+    w = lstm_weights(I, H, model.linear.out_features, seed=41)
+    model.load_state_dict({k: torch.tensor(v) for k, v in w.items()})
+    model = model.to(dev)
+
+    def run(rows):
+        model.zero_grad()
+        y = model(x_lstm=xl[rows], x_conceptual=xc[rows])["y_hat"]
+        (y * wy[rows]).sum().backward()
+        return y.detach(), {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+
+    y_full, g_full = run(slice(0, B))
+    assert torch.isfinite(y_full).all()
+    y_small, _ = run(slice(0, 256))
+    assert torch.equal(y_full[:256], y_small), "sequences are not independent of their batch"
+    y_a, g_a = run(slice(0, B // 2))
+    y_b, g_b = run(slice(B // 2, B))
+    assert torch.equal(y_full[:B // 2], y_a) and torch.equal(y_full[B // 2:], y_b)
+    for k in g_full:
+        assert_close(npy(g_a[k] + g_b[k]), npy(g_full[k]), rtol=2e-5, atol=1e-6, what="additivity of grad " + k)
+    pick = torch.randperm(B, device=dev, generator=g)[:48]
+    wd = {k: tt(v, torch.float64) for k, v in w.items()}
+    with torch.no_grad():
+        ref = O.hybrid_forward(wd, tt(npy(xl[pick]), torch.float64), tt(npy(xc[pick]), torch.float64), model="shm",
+                               n_models=1, dynamic=dyn, warmup=T - n_last)
+    assert_close(npy(y_full[pick]), ref["y_hat"].numpy(), what="subset vs fp64 oracle", **TOL)
+
+
 @pytest.mark.parametrize("B,H,precision,n_dyn,n_static", [(40, 64, "tf32x3", 3, 22), (9, 128, "fp32", 11, 27)])
 def test_mflstm_vs_own_oracle(dev, B, H, precision, n_dyn, n_static):
     """Multi-frequency LSTM (365 daily + 336 hourly steps, last 24 hours predicted).  PARITY UNPINNED: no reference
