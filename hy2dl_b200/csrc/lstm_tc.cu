@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(128 * NSETS + 32, 1) lstm_tc_fwd_kernel(TcFwdA
     }
   } else {
     // =========================== MMA issuer (one thread) ======================================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t whi = smem_u32(s_whi), wlo = smem_u32(s_wlo);
       const uint32_t sbo = 128;                    // K-major no-swizzle: 8-row groups 128 B apart
       const int KS = K / 8;
@@ -744,7 +744,7 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
       }
     }
   } else if (warp == kBwdRowWarps) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = idesc_tf32(kRows, kH, 0, 0);
       const uint32_t whi = smem_u32(s_whi), wlo = smem_u32(s_wlo);
       const uint32_t lbo = kH * 16, sbo = 128;

@@ -26,8 +26,15 @@
 //
 // Warp roles (320 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer, warps 2-9 = split converters +
 // accumulator drain + epilogue.  3 raw stages (48 KB each) + A_lo + 2 x B_lo.  The pipeline unit is half a slab
-// (128 gate columns): while the tensor core works on one half the converters split the next.  The kernel is
-// shared-memory-bandwidth bound (SS-mode MMAs read ~7 KB per 48-cycle instruction).
+// (128 gate columns): while the tensor core works on one half the converters split the next.
+//
+// Measured (B = 18944, T = 365, no head): 2.23 ms = 4.4 TB/s.  The MMA warp issues under `elect_one()`: guarded by
+// `lane == 0` the same loop paid an ELECT + 4 x R2UR.BROADCAST waterfall per tcgen05.mma (divergent code cannot use
+// the uniform datapath) and the kernel ran 2.69 ms, issue-bound at ~130 cycles per 48-cycle MMA.  Timing
+// experiments on that version: hi*hi MMAs only 2.01 ms, no dG split 2.57 ms, both 1.68 ms (88 % of HBM peak = the
+// floor of this pipeline).  A variant with dG^T transposed through registers into TMEM (TS-mode MMAs, no dG lo image
+// in shared memory, running sum in global memory) measured the same 2.20 ms and was dropped; K-major instead of
+// MN-major descriptors made no difference either (MN-major kind::tf32 operands are not slower).
 //
 // Stage layout: A part = [dz block | dG blocks 0..7] (36 KB), B part = [h block 0 | h block 1 | x block] (12 KB).
 // The head MMA takes the stage's B part as its A operand (M = 128: rows 96.. are whatever follows in shared memory,
@@ -101,7 +108,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
 
   if (warp == 0) {
     // =========================== producer ======================================================
-    if (lane == 0) {
+    if (elect_one()) {
       for (int64_t i = 0; i < n_my; ++i) {
         const int s = (int)(i % kWgStages);
         int64_t t, g;
@@ -122,7 +129,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
     __syncwarp();
   } else if (warp == 1) {
     // =========================== MMA issuer =====================================================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t lo_a = smem_u32(s_lo);
       const uint32_t idesc = idesc_tf32(128, kND, 1, 1), idesc_h = idesc_tf32(128, a.NHz, 1, 1);
       bool head_open = false;                       // the head accumulator already holds a term of this chain

@@ -54,6 +54,15 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
   }
 }
 
+// One lane of a fully converged warp.  Code under `if (elect_one())` is what the compiler recognises as a
+// single-thread region: operands of tcgen05.mma / commit stay in uniform registers, where a region guarded by
+// `lane == 0` is divergent code and pays an ELECT + 4 x R2UR.BROADCAST waterfall per MMA instruction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- proxies / fences ------------------------------------------------------------------------
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
