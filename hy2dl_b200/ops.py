@@ -102,6 +102,16 @@ def pack_forcing(xc: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------------
 # LSTM
 # --------------------------------------------------------------------------------------------------
+def _consume_tape(ctx) -> None:
+    """BPTT overwrites the gate tape with dG in place (it is 2/3 of the tape: a copy would cost 7 GB per step at the
+    benchmark batch), so a graph can be back-propagated once; a second pass (retain_graph=True) must fail loudly
+    instead of reading gradients where it expects activations."""
+    if getattr(ctx, "tape_consumed", False):
+        raise RuntimeError("hy2dl_b200: this LSTM graph was already back-propagated; its tape is overwritten in place "
+                           "(retain_graph / double backward are not supported) -- run the forward pass again")
+    ctx.tape_consumed = True
+
+
 class LstmFunction(torch.autograd.Function):
     """h_seq and h_last [B,H] from xT; one layer, h0 = c0 = 0.
 
@@ -157,6 +167,7 @@ class LstmFunction(torch.autograd.Function):
             dh_last = dh_last.contiguous()
         if dh_seq is None and dh_last is None:
             return (None,) * 10
+        _consume_tape(ctx)
         ws_b = _ws(_lib.WS_LSTM_BWD, B, T, I, H, dev, precision)
         # dG overwrites the gate tape in place (the kernel reads each element before writing it)
         dG = gates
@@ -314,6 +325,7 @@ class LstmHeadFunction(torch.autograd.Function):
         B, T, I, IP, H, precision = ctx.meta
         layout, dev = ctx.layout, xT.device
         dpar_sim = dpar_sim.contiguous()
+        _consume_tape(ctx)
         # BPTT with the head adjoint dz * W_head accumulated by the kernel's own MMAs (no dh_seq exists); the kernel
         # also leaves dz (RI32) for the weight-gradient GEMM
         G = xT.shape[1]

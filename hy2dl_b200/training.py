@@ -42,11 +42,13 @@ class FusedClipAdam:
         self.flat = torch.zeros(self.n, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(self.n, dtype=torch.float32, device=dev)
         off = 0
+        self._grad_views = []
         for p, sz in zip(self.params, sizes):
             view = self.flat[off:off + p.numel()].view_as(p)
             view.copy_(p.data)
             p.data = view
             p.grad = self.grad[off:off + p.numel()].view_as(p)
+            self._grad_views.append(p.grad)
             off += sz
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
@@ -61,8 +63,22 @@ class FusedClipAdam:
 
     def zero_grad(self):
         self.grad.zero_()
+        self._relink()
+
+    def _relink(self):
+        """`model.zero_grad()` (set_to_none) or an optimiser-agnostic training loop can detach a parameter's .grad from
+        the flat buffer; pick such gradients up (host-side identity checks only) so that step() never updates from a
+        stale buffer."""
+        for p, view in zip(self.params, self._grad_views):
+            if p.grad is not view:
+                if p.grad is None:
+                    view.zero_()
+                else:
+                    view.copy_(p.grad)
+                p.grad = view
 
     def step(self):
+        self._relink()
         if self.group is not None:
             import torch.distributed as dist
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=None if self.group == "world" else self.group)

@@ -526,6 +526,38 @@ def test_trainer_native_path_matches_api_path(dev, precision):
 # ------------------------------------------------------------------------------------------------
 # error behaviour: no silent fallback
 # ------------------------------------------------------------------------------------------------
+def test_fused_optimizer_survives_model_zero_grad(dev):
+    """torch's `model.zero_grad()` sets .grad to None, which unlinks the parameters from the optimiser's flat gradient
+    buffer; the next step must still see the new gradients (same update as with the optimiser's own zero_grad)."""
+    from hy2dl_b200.training import FusedClipAdam
+    g = golden("hybrid_shm_mixed")
+    outs = []
+    for use_model_zero_grad in (False, True):
+        model = build_hybrid(g, dev, "fp32")
+        opt = FusedClipAdam(model.parameters(), lr=1e-2, max_norm=1.0)
+        for _ in range(2):
+            model.zero_grad() if use_model_zero_grad else opt.zero_grad()
+            pred = model(x_lstm=cu(g["x_lstm"], dev), x_conceptual=cu(g["x_conceptual"], dev))
+            pred["y_hat"].square().mean().backward()
+            opt.step()
+        outs.append({k: npy(v) for k, v in model.state_dict().items()})
+    for k in outs[0]:     # not bit-equal: the fp32 weight-gradient GEMM combines its split-K partials with atomics
+        assert_close(outs[1][k], outs[0][k], rtol=1e-5, atol=1e-7, what=k)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_second_backward_raises(dev, precision):
+    """The BPTT kernels turn the gate tape into dG in place; a second backward over the same graph must raise
+    rather than return gradients computed from an overwritten tape."""
+    g = golden("hybrid_shm_c2")
+    model = build_hybrid(g, dev, precision)
+    pred = model(x_lstm=cu(g["x_lstm"], dev), x_conceptual=cu(g["x_conceptual"], dev))
+    loss = pred["y_hat"].sum()
+    loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="already back-propagated"):
+        loss.backward()
+
+
 def test_cpu_tensor_raises(dev):
     from hy2dl_b200.modelzoo import CudaLSTM
     model = CudaLSTM({"input_size_lstm": 8, "hidden_size": 64, "no_of_layers": 1, "drop_out_rate": 0.0})
