@@ -16,6 +16,7 @@
 // Reference semantics: torch.nn.LSTM, one layer, h0 = c0 = 0 (modelzoo/cudalstm.py:43-50,
 // hybrid.py:84-92; equations torch/nn/modules/rnn.py:842-847; weight layout :935-941).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace hy2dl {
 
@@ -590,8 +591,22 @@ int lstm_fp32_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const floa
   return HY2DL_OK;
 }
 
+// tensor-core GEMM on the same row-major tapes (lstm_wgrad_rm_tc.cu), H = 128 / 256
+namespace tc {
+bool lstm_wgrad_rm_tc_supported(int64_t H);
+int64_t lstm_wgrad_rm_tc_workspace(int64_t H, int64_t I);
+int lstm_wgrad_rm_tc(const float* dG, const float* h_seq, const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H,
+                     float* dw_ih, float* dw_hh, float* db, void* ws, int64_t ws_bytes, cudaStream_t s);
+}  // namespace tc
+// HY2DL_FP32_WGRAD=fma keeps the CUDA-core GEMM below for every H (comparison / fallback for debugging)
+static bool use_rm_tc(int64_t H) {
+  static const bool fma_only = [] { const char* e = getenv("HY2DL_FP32_WGRAD"); return e && e[0] == 'f'; }();
+  return !fma_only && tc::lstm_wgrad_rm_tc_supported(H);
+}
+
 int lstm_fp32_wgrad(const float* dG, const float* h_seq, const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
                     int64_t H, float* dw_ih, float* dw_hh, float* db, void* ws, int64_t ws_bytes, cudaStream_t s) {
+  if (use_rm_tc(H)) return tc::lstm_wgrad_rm_tc(dG, h_seq, xT, B, T, I, IP, H, dw_ih, dw_hh, db, ws, ws_bytes, s);
   const int64_t need = lstm_fp32_workspace(HY2DL_WS_LSTM_WGRAD, B, T, I, H);
   HY_REQUIRE(ws != nullptr && ws_bytes >= need, HY2DL_ERR_WORKSPACE, "hy2dl_lstm_wgrad: workspace %lld < %lld bytes",
              (long long)ws_bytes, (long long)need);
@@ -615,6 +630,7 @@ int64_t lstm_fp32_workspace(int kind, int64_t B, int64_t T, int64_t I, int64_t H
   if (kind == HY2DL_WS_LSTM_FWD) return sizeof(float) * ((IP + H) * 4 * H + 4 * H);
   if (kind == HY2DL_WS_LSTM_BWD) return 16;
   if (kind == HY2DL_WS_LSTM_WGRAD) {
+    if (use_rm_tc(H)) return tc::lstm_wgrad_rm_tc_workspace(H, I);
     const int M = (int)(4 * H), NP = (int)round_up(H + IP + 1, 128);
     return sizeof(float) * (int64_t)wgrad_splits(T * B, M, NP) * M * NP;
   }

@@ -1,0 +1,298 @@
+// Weight gradients of the fp32 (row-major tape) recurrent path on the tensor cores, H = 128 / 256:
+//   dW[4H x (H + I + 1)] = sum over rows r = (t, b) of dG[r][:]^T * [h_{t-1}[b] | x_t[b] | 1]
+// i.e. dW_hh, dW_ih and db in one time-parallel GEMM whose contraction index is the flattened (t, b) row.
+// The forward / BPTT kernels of this path are CUDA-core kernels (lstm_fp32.cu); their weight-gradient GEMM was a
+// third of the step (67.7 ms of 188 ms at H = 256, B = 9472, T = 365: 30 TFLOP/s of fp32 FMA).  This kernel is the
+// tcgen05 pipeline of lstm_tc_wgrad.cu (3-term TF32 split, MN-major SWIZZLE_128B_BASE32B operands, chained TMEM
+// accumulators with a round-to-nearest running sum because the tensor core's fp32 accumulation truncates) fed from
+// the row-major tapes [T*B][4H], [T*B][H], [T*B][IP] instead of RI32 slabs:
+//   * the output is cut into tiles of 256 gate rows x 96 feature columns (3 blocks of 32); tile type (mt, nt) is
+//     owned by `parts` CTAs that share its 32-row slabs round-robin, so all 148 SMs work and every CTA keeps its
+//     tile in TMEM for the whole kernel;
+//   * the converter threads themselves copy a slab two iterations ahead with 16-byte cp.async (zero-fill for rows
+//     before t = 0, rows past the end and feature columns past IP) straight into the swizzled operand image: thread
+//     ct owns chunk (row ct/8, 16-byte column ct%8) of each of the 11 blocks, so its addresses are loop constants;
+//     completion is tracked by an mbarrier (cp.async.mbarrier.arrive.noinc).  A single producer warp computing 88
+//     chunk addresses per lane and slab made the kernel producer-bound (49 ms instead of 13 at H = 256);
+//   * the ones column for the bias gradient is feature H + I, patched by the converter warps.
+// Gate columns keep this path's order n = g*H + u, which is the row order of dW, so no permutation is needed.
+// Deterministic: per-CTA sums are combined in a fixed order by the finish kernel.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace hy2dl {
+namespace tc {
+
+namespace {
+constexpr int kThreads = 320;               // warp 0 idle, warp 1 MMA issuer, warps 2-9 loaders / converters / drain
+constexpr int kStages = 3;
+constexpr int kConv = 256;
+constexpr int kChain = 8;                   // slabs accumulated in TMEM before a drain (96 MMAs per accumulator)
+constexpr int kBlk = 4096;                  // one [32 rows][32 floats] block
+constexpr int kBlk4 = kBlk / 16;
+constexpr int kABytes = 8 * kBlk;           // 256 gate columns
+constexpr int kBBytes = 3 * kBlk;           // 96 feature columns
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kND = 96;
+constexpr int kChunks = kStageBytes / 16;   // 16-byte copies per slab (2816)
+
+struct Args {
+  const float* dG;    // [R][4H], column g*H + u
+  const float* h;     // [R][H]; the h operand of row r is h[r - B] (zero for r < B)
+  const float* x;     // [R][IP]
+  float* partial;     // [parts][MT*NT][256][kND]
+  int64_t R, B;
+  int H, I, IP, MT, NT, parts;
+};
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
+  const int n = valid ? 16 : 0;             // src-size 0: the 16 destination bytes are zero-filled, src is not read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {   // arrives on bar when this thread's prior cp.async are done
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1) lstm_wgrad_rm_tc_kernel(Args a) {
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  uint8_t* smem_raw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_lo = smem_raw + kStages * kStageBytes;             // [A_lo | B_lo[0] | B_lo[1]]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lo + kABytes + 2 * kBBytes);
+  uint64_t* bar_full = bars;                        // [stages] cp.async completion of all converter threads
+  uint64_t* bar_raw_free = bars + kStages;          // (unused slots)
+  uint64_t* bar_conv = bars + 2 * kStages;          // [2] converters -> MMA, per half of the gate columns
+  uint64_t* bar_lo_free = bar_conv + 2;             // [2] MMA commit -> converters, per half
+  uint64_t* bar_done = bar_conv + 4;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_conv + 5);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int TT = a.MT * a.NT;
+  const int tt = blockIdx.x % TT, part = blockIdx.x / TT;
+  const int mt = tt / a.NT, nt = tt - mt * a.NT;
+  const int64_t n_slabs = (a.R + 31) / 32;
+  const int64_t n_my = part < n_slabs ? (n_slabs - part + a.parts - 1) / a.parts : 0;   // slabs part, part + parts, ...
+  const int HB = a.H / 32;                           // feature blocks: [0, HB) h, then x blocks, then nothing
+  const int ones_f = a.H + a.I;                      // feature index of the ones column
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(bar_full + s, kConv);
+    for (int hf = 0; hf < 2; ++hf) { mbar_init(bar_conv + hf, kConv); mbar_init(bar_lo_free + hf, 1); }
+    mbar_init(bar_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(s_tmem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp == 0) {
+    // idle: the loads are issued by the converter threads
+  } else if (warp == 1) {
+    // =========================== MMA issuer =====================================================
+    if (elect_one()) {
+      const uint32_t lo_a = smem_u32(s_lo);
+      const uint32_t idesc = idesc_tf32(128, kND, 1, 1);
+      for (int64_t i = 0; i < n_my; ++i) {
+        const int s = (int)(i % kStages);
+        const uint32_t hi_a = smem_u32(smem_raw + s * kStageBytes), hi_b = hi_a + kABytes;
+        const uint32_t lo_b = lo_a + kABytes + (uint32_t)(i & 1) * kBBytes;
+        const bool first = (i % kChain) == 0;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          mbar_wait(bar_conv + hf, (uint32_t)(i & 1));
+          tc_fence_after();
+          const uint32_t d = tmem + kND * hf;
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) {
+            const uint64_t b_hi = smem_desc_mn32(hi_b + kb * 1024, kBlk, 512), b_lo = smem_desc_mn32(lo_b + kb * 1024, kBlk, 512);
+            const uint64_t a_hi = smem_desc_mn32(hi_a + hf * 4 * kBlk + kb * 1024, kBlk, 512);
+            const uint64_t a_lo = smem_desc_mn32(lo_a + hf * 4 * kBlk + kb * 1024, kBlk, 512);
+            mma_tf32_ss(d, a_lo, b_hi, idesc, !(first && kb == 0));
+            mma_tf32_ss(d, a_hi, b_lo, idesc, 1);
+            mma_tf32_ss(d, a_hi, b_hi, idesc, 1);
+          }
+          mma_commit(bar_lo_free + hf);
+        }
+      }
+      mma_commit(bar_done);
+    }
+    __syncwarp();
+  } else {
+    // =========================== converters, drain, epilogue ====================================
+    const int ct = tid - 64;
+    const int hf = ct >> 7;
+    const uint32_t lane_tm = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t dcol = kND * hf;
+    {
+      uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int c = 0; c < kND; c += 8) tmem_st8(lane_tm + 256 + dcol + c, z);
+      tmem_st_wait();
+    }
+    auto drain = [&]() {                                     // S += D, round to nearest, in registers
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < kND; c += 16) {
+        uint32_t d[16], sacc[16];
+        tmem_ld16(lane_tm + dcol + c, d);
+        tmem_ld16(lane_tm + 256 + dcol + c, sacc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sacc[j] = __float_as_uint(__uint_as_float(sacc[j]) + __uint_as_float(d[j]));
+        tmem_st8(lane_tm + 256 + dcol + c, *reinterpret_cast<uint32_t(*)[8]>(&sacc[0]));
+        tmem_st8(lane_tm + 256 + dcol + c + 8, *reinterpret_cast<uint32_t(*)[8]>(&sacc[8]));
+      }
+      tmem_st_wait();
+      tc_fence_before();
+    };
+    // where the ones column sits in this CTA's B part (block, float4 within the block row, component), if at all
+    const int ones_blk = ones_f / 32 - 3 * nt;               // block of the B part (0..2) or outside
+    const int ones_col = ones_f & 31;
+    // loads: this thread's chunk of every block of slab j -> stage j % kStages
+    const int lrow = ct >> 3, lch = ct & 7;
+    const uint32_t ldst = (uint32_t)(lrow * 128 + ((((lch >> 1) ^ (lrow & 3)) << 5) | ((lch & 1) << 4)));
+    const int F4 = 4 * a.H;
+    auto load_slab = [&](int64_t j) {
+      const int s = (int)(j % kStages);
+      if (j < n_my) {
+        const int64_t r = (part + j * a.parts) * 32 + lrow;
+        const bool in = r < a.R;
+        const uint32_t st = smem_u32(smem_raw + s * kStageBytes) + ldst;
+        const float* g = a.dG + r * F4 + 256 * mt + 4 * lch;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cp_async16_zfill(st + k * kBlk, in ? g + 32 * k : a.dG, in);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int fb = 3 * nt + k;
+          const float* src;
+          bool valid = in;
+          if (fb < HB) {
+            valid = valid && r >= a.B;
+            src = a.h + (r - a.B) * a.H + 32 * fb + 4 * lch;
+          } else {
+            const int col = 32 * (fb - HB) + 4 * lch;
+            valid = valid && col < a.IP;
+            src = a.x + r * a.IP + col;
+          }
+          cp_async16_zfill(st + (8 + k) * kBlk, valid ? src : a.dG, valid);
+        }
+      }
+      cp_async_arrive(bar_full + s);     // also for j >= n_my: nobody waits for those phases
+    };
+    load_slab(0);
+    load_slab(1);
+    float4* lo_a4 = reinterpret_cast<float4*>(s_lo);
+    for (int64_t i = 0; i < n_my; ++i) {
+      const int s = (int)(i % kStages);
+      float4* raw = reinterpret_cast<float4*>(smem_raw + s * kStageBytes);
+      float4* lo_b4 = reinterpret_cast<float4*>(s_lo + kABytes + (i & 1) * kBBytes);
+      constexpr int kA4 = kABytes / 16;
+      auto split4 = [&](int e) {                             // lo = v - trunc(v); the landed words are the hi operand
+        float4 v = raw[e];
+        if (e >= kA4) {
+          const int eb = e - kA4, blk = eb / kBlk4, w = eb - blk * kBlk4, row = w >> 3, pos = w & 7;
+          // float4 `pos` of row `row` holds features 8 ((pos >> 1) ^ (row & 3)) + 4 (pos & 1) .. + 3 of the block
+          if (blk == ones_blk && (((pos >> 1) ^ (row & 3)) * 8 + (pos & 1) * 4) == (ones_col & ~3)) {
+            const int k = ones_col & 3;
+            if (k == 0) v.x = 1.f; else if (k == 1) v.y = 1.f; else if (k == 2) v.z = 1.f; else v.w = 1.f;
+            raw[e] = v;
+          }
+        }
+        const float4 hv = make_float4(__uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u),
+                                      __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+        float4* lo = e < kA4 ? lo_a4 + e : lo_b4 + (e - kA4);
+        *lo = make_float4(v.x - hv.x, v.y - hv.y, v.z - hv.z, v.w - hv.w);
+      };
+      mbar_wait(bar_full + s, (uint32_t)((i / kStages) & 1));
+      // ---- half 0: the B operand (shared by both halves) and gate columns [0, 128)
+      if (i > 0) mbar_wait(bar_lo_free + 0, (uint32_t)((i - 1) & 1));
+      if (i > 0 && (i % kChain) == 0) {
+        mbar_wait(bar_lo_free + 1, (uint32_t)((i - 1) & 1));
+        drain();
+      }
+      for (int e = ct; e < 3 * kBlk4; e += kConv) split4(kA4 + e);
+#pragma unroll 4
+      for (int e = ct; e < 4 * kBlk4; e += kConv) split4(e);
+      fence_async_smem();
+      mbar_arrive(bar_conv + 0);
+      // ---- half 1: gate columns [128, 256)
+      if (i > 0) mbar_wait(bar_lo_free + 1, (uint32_t)((i - 1) & 1));
+      load_slab(i + 2);      // its stage held slab i - 1, whose MMAs (hi operands) have just been seen to retire
+#pragma unroll 4
+      for (int e = ct; e < 4 * kBlk4; e += kConv) split4(4 * kBlk4 + e);
+      fence_async_smem();
+      mbar_arrive(bar_conv + 1);
+    }
+    mbar_wait(bar_done, 0);
+    if (n_my > 0) drain();
+    tc_fence_after();
+    const int row = hf * 128 + (warp & 3) * 32 + lane;
+    float* dst = a.partial + (((int64_t)part * TT + tt) * 256 + row) * kND;
+#pragma unroll 1
+    for (int c = 0; c < kND; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(lane_tm + 256 + dcol + c, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(dst + c + j) =
+            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// partial [parts][MT*NT][256][96] -> dw_hh [4H][H], dw_ih [4H][I], db [4H]
+__global__ void lstm_wgrad_rm_tc_finish_kernel(const float* __restrict__ partial, int parts, int MT, int NT, int H, int I,
+                                               float* __restrict__ dw_ih, float* __restrict__ dw_hh, float* __restrict__ db) {
+  const int nf = H + I + 1;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)4 * H * nf) return;
+  const int n = (int)(e / nf), f = (int)(e - (int64_t)n * nf);
+  const int mt = n >> 8, nt = f / kND, TT = MT * NT;
+  const float* p = partial + (((int64_t)(mt * NT + nt)) * 256 + (n & 255)) * kND + (f - nt * kND);
+  float acc = 0.f;
+  for (int q = 0; q < parts; ++q) acc += __ldg(p + (int64_t)q * TT * 256 * kND);
+  if (f < H) dw_hh[(int64_t)n * H + f] = acc;
+  else if (f < H + I) dw_ih[(int64_t)n * I + (f - H)] = acc;
+  else db[n] = acc;
+}
+
+static void rm_tc_shape(int64_t H, int64_t I, int& MT, int& NT, int& parts) {
+  MT = (int)(4 * H / 256);
+  NT = (int)cdiv(H + I + 1, (int64_t)kND);
+  parts = std::max(1, sm_count() / (MT * NT));
+}
+
+bool lstm_wgrad_rm_tc_supported(int64_t H) { return H == 128 || H == 256; }
+
+int64_t lstm_wgrad_rm_tc_workspace(int64_t H, int64_t I) {
+  int MT, NT, parts;
+  rm_tc_shape(H, I, MT, NT, parts);
+  return sizeof(float) * (int64_t)parts * MT * NT * 256 * kND;
+}
+
+int lstm_wgrad_rm_tc(const float* dG, const float* h_seq, const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H,
+                     float* dw_ih, float* dw_hh, float* db, void* ws, int64_t ws_bytes, cudaStream_t s) {
+  const int64_t need = lstm_wgrad_rm_tc_workspace(H, I);
+  HY_REQUIRE(ws != nullptr && ws_bytes >= need, HY2DL_ERR_WORKSPACE, "hy2dl_lstm_wgrad: workspace %lld < %lld bytes",
+             (long long)ws_bytes, (long long)need);
+  Args a{};
+  a.dG = dG; a.h = h_seq; a.x = xT; a.partial = reinterpret_cast<float*>(ws);
+  a.R = T * B; a.B = B; a.H = (int)H; a.I = (int)I; a.IP = (int)IP;
+  rm_tc_shape(H, I, a.MT, a.NT, a.parts);
+  const size_t smem = (size_t)kStages * kStageBytes + kABytes + 2 * kBBytes + 128 + 1024;
+  cudaFuncSetAttribute(lstm_wgrad_rm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  lstm_wgrad_rm_tc_kernel<<<a.MT * a.NT * a.parts, kThreads, smem, s>>>(a);
+  const int64_t n_out = 4 * H * (H + I + 1);
+  lstm_wgrad_rm_tc_finish_kernel<<<(unsigned)cdiv(n_out, (int64_t)256), 256, 0, s>>>(a.partial, a.parts, a.MT, a.NT, (int)H, (int)I,
+                                                                                 dw_ih, dw_hh, db);
+  HY_LAUNCH_CHECK();
+  return HY2DL_OK;
+}
+
+}  // namespace tc
+}  // namespace hy2dl
