@@ -167,3 +167,32 @@ def test_tc_wgrad_shapes(B, T, I):
     assert_close(dwi.cpu().numpy(), np.einsum("tbm,tbi->mi", d, x[:, :, :I].astype(np.float64)), rtol=2e-6, what="dW_ih")
     assert_close(dwh.cpu().numpy(), np.einsum("tbm,tbk->mk", d, hprev), rtol=2e-6, atol=1e-30, what="dW_hh")
     assert_close(dbb.cpu().numpy(), d.sum((0, 1)), rtol=2e-6, what="db")
+
+
+@pytest.mark.parametrize("B,T,I,H", [(3, 5, 8, 128), (40, 7, 64, 256), (33, 3, 32, 128), (64, 2, 16, 256), (700, 9, 41, 256),
+                                     (1, 1, 31, 128)])
+def test_rowmajor_tc_wgrad_shapes(B, T, I, H):
+    """Weight gradients of the fp32 path for H = 128 / 256 (tcgen05 GEMM on the row-major tapes): input sizes whose
+    ones column falls into the zero-filled padding (I a multiple of 8, I = 64), fewer slabs than CTAs per tile type,
+    ragged last slab; checked against an fp64 contraction (rtol 4e-6: the chained tensor-core accumulation carries a
+    flat truncation bias of about -2e-6, see lstm_tc_wgrad.cu)."""
+    from hy2dl_b200 import _lib, ops
+    dev = torch.device("cuda:0")
+    IP = (I + 7) // 8 * 8
+    rng = np.random.default_rng(B + I)
+    dG = rng.normal(0, 1, (T, B, 4 * H)).astype(np.float32)       # columns g*H + u
+    h = rng.normal(0, 1, (T, B, H)).astype(np.float32)
+    x = np.zeros((T, B, IP), np.float32); x[:, :, :I] = rng.normal(0, 1, (T, B, I))
+    cu = lambda a: torch.tensor(a, device=dev)
+    dwi = torch.full((4 * H, I), np.nan, device=dev); dwh = torch.full((4 * H, H), np.nan, device=dev)
+    dbb = torch.full((4 * H,), np.nan, device=dev)
+    ws = ops._ws(_lib.WS_LSTM_WGRAD, B, T, I, H, dev, _lib.PREC_FP32)
+    args = [cu(a) for a in (dG, h, x)]
+    _lib.call("hy2dl_lstm_wgrad", *[a.data_ptr() for a in args], B, T, I, IP, H, dwi.data_ptr(), dwh.data_ptr(),
+              dbb.data_ptr(), ws.data_ptr(), ws.numel(), _lib.PREC_FP32, None, _lib.stream())
+    torch.cuda.synchronize()
+    d = dG.astype(np.float64)
+    hprev = np.concatenate([np.zeros_like(h[:1]), h[:-1]]).astype(np.float64)
+    assert_close(dwi.cpu().numpy(), np.einsum("tbm,tbi->mi", d, x[:, :, :I].astype(np.float64)), rtol=4e-6, what="dW_ih")
+    assert_close(dwh.cpu().numpy(), np.einsum("tbm,tbk->mk", d, hprev), rtol=4e-6, atol=1e-30, what="dW_hh")
+    assert_close(dbb.cpu().numpy(), d.sum((0, 1)), rtol=4e-6, what="db")
