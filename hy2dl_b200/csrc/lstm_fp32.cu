@@ -565,9 +565,20 @@ static int wgrad_splits(int64_t R, int M, int NP) {
 
 int64_t lstm_fp32_workspace(int kind, int64_t B, int64_t T, int64_t I, int64_t H);
 
+// tensor-core forward with streamed weights on the same row-major tapes (lstm_rm_tc_fwd.cu), H = 128 / 256
+namespace tc {
+bool lstm_rm_tc_fwd_supported(int64_t I, int64_t H);
+int64_t lstm_rm_tc_fwd_workspace(int64_t B, int64_t I, int64_t H);
+int lstm_rm_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H, const float* w_ih, const float* w_hh,
+                   const float* b_ih, const float* b_hh, float* h_seq, float* c_seq, float* gates, float* h_last, void* ws,
+                   int64_t ws_bytes, cudaStream_t s);
+}  // namespace tc
+
 int lstm_fp32_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H, const float* w_ih,
                   const float* w_hh, const float* b_ih, const float* b_hh, float* h_seq, float* c_seq, float* gates,
                   float* h_last, void* ws, int64_t ws_bytes, cudaStream_t s) {
+  if (tc::lstm_rm_tc_fwd_supported(I, H))
+    return tc::lstm_rm_tc_fwd(xT, B, T, I, IP, H, w_ih, w_hh, b_ih, b_hh, h_seq, c_seq, gates, h_last, ws, ws_bytes, s);
   const int64_t need = lstm_fp32_workspace(HY2DL_WS_LSTM_FWD, B, T, I, H);
   HY_REQUIRE(ws != nullptr && ws_bytes >= need, HY2DL_ERR_WORKSPACE, "hy2dl_lstm_fwd: workspace %lld < %lld bytes",
              (long long)ws_bytes, (long long)need);
@@ -627,7 +638,10 @@ int lstm_fp32_wgrad(const float* dG, const float* h_seq, const float* xT, int64_
 
 int64_t lstm_fp32_workspace(int kind, int64_t B, int64_t T, int64_t I, int64_t H) {
   const int64_t IP = round_up(I, 8);
-  if (kind == HY2DL_WS_LSTM_FWD) return sizeof(float) * ((IP + H) * 4 * H + 4 * H);
+  if (kind == HY2DL_WS_LSTM_FWD) {
+    if (tc::lstm_rm_tc_fwd_supported(I, H)) return tc::lstm_rm_tc_fwd_workspace(B, I, H);
+    return sizeof(float) * ((IP + H) * 4 * H + 4 * H);
+  }
   if (kind == HY2DL_WS_LSTM_BWD) return 16;
   if (kind == HY2DL_WS_LSTM_WGRAD) {
     if (use_rm_tc(H)) return tc::lstm_wgrad_rm_tc_workspace(H, I);

@@ -1,0 +1,367 @@
+// Recurrent LSTM forward on the tensor cores for H = 128 / 256 (row-major tapes of the fp32 path).
+//
+// For H = 64 the packed weights (196 KB hi + lo) stay in shared memory and the A operand [x | h] (hi + lo) in TMEM
+// (lstm_tc.cu).  Neither fits here: [W_ih | W_hh] hi + lo is 2.4 MB at H = 256, and [x | h] hi + lo for 128 sequences
+// is 2 x 288 TMEM columns > 512 (295 KB in shared memory).  This kernel therefore
+//   * keeps the h part of A_hi in TMEM (H columns, TS-mode MMAs for hi*hi and hi*lo), the x part of A_hi and all of
+//     A_lo in shared memory (K-major images, SS-mode MMAs);
+//   * streams the packed weights every step from L2 through a ring of 8 KB bulk copies (one copy = one K step of 8
+//     rows x 128 gate columns, hi | lo), chunk after chunk of 32 hidden units.  N = 128 per MMA matters: a first
+//     version with 32-column chunks ran 60+ cycles per MMA where 16 were budgeted (small-N MMAs pay a fixed cost);
+//   * gives a chunk two 128-column accumulators -- one for the 2/3 of the MMAs that are correction terms (2^-11 of the
+//     result, so the truncating tensor-core accumulation costs them nothing) and one for the hi*hi MMAs, whose mean
+//     truncation bias is compensated in the packed weights.  That fills TMEM (H + 256 columns), so the accumulators
+//     are single buffered: the row threads pull their 64 sums into registers first and release the pair before they
+//     start on the activations;
+//   * keeps no recurrent state in registers: the row thread re-reads c_{t-1} and, at the end of the step, its own
+//     h_t values from the tape it has just written (L2 hits) to rebuild A for the next step.  A row is owned by
+//     two threads (TMEM lane = row; the two warps of a lane quarter split every chunk's 32 units 16 | 16), and a
+//     thread only ever re-reads what it wrote itself, so no CTA-wide synchronisation is needed inside a step.
+// One CTA = 128 sequences for all T steps; 10 warps: 8 row warps, the MMA issuer, the bulk-copy producer.
+// Per step the tensor core needs 128 x 4H x K x 3 / 2048 cycles (55 k at H = 256) while 2.4 MB of weights cross
+// L2 -> shared memory per CTA: at a full wave of 148 CTAs the L2 stream, not the tensor pipe, bounds the step.
+//
+// Semantics: torch.nn.LSTM, one layer, h0 = c0 = 0 (modelzoo/cudalstm.py:43-50, hybrid.py:84-92); tapes as
+// lstm_fp32.cu writes them: h_seq, c_seq [T][B][H], gates [T][B][4H] (post-activation, column g*H + u).
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <stdlib.h>
+
+namespace hy2dl {
+namespace tc {
+
+namespace {
+constexpr int kRowsF = 128;
+constexpr int kThreadsF = 320;              // warps 0-7 rows, 8 MMA issuer, 9 producer
+constexpr int kChunkN = 128;                // gate columns per chunk = 32 hidden units x 4 gates
+constexpr int kStepBytes = 8 * kChunkN * 4 * 2;    // one K step of the packed weights: hi | lo = 8 KB
+constexpr int kSliceJ = 2;                         // K steps per ring slice (one bulk copy, one commit)
+constexpr int kSliceBytes = kSliceJ * kStepBytes;
+constexpr uint32_t kColMain = 256, kColCorr = 384;
+constexpr int kMaxKX = 80;
+
+struct FwdArgs {
+  const float* x;       // [T][B][IP]
+  const float* wpk;     // packed weights [H/32 chunks][K/8 steps][hi [2][128][4] | lo [2][128][4]]
+  float* h_seq;         // [T][B][H], or two time slots only (h_pingpong)
+  float* c_seq;
+  float* gates;         // [T][B][4H] or null
+  float* h_last;        // [B][H] or null
+  int64_t B, T;
+  int H, I, IP, KX, K;  // KX = x columns incl. the ones column, rounded to 8; K = KX + H
+  int stages;           // ring depth (what shared memory allows)
+  int h_pingpong, c_pingpong;
+  int exp;              // timing experiments (HY2DL_RM_EXP): 1 no tape stores, 2 no activation math, 4 a third of the MMAs
+};
+
+// packed weight element (chunk c, K index k, column n = 4 uu + g of the chunk): rows scaled by -log2(e) (x 2 for g)
+// and the truncation compensation; k < I: W_ih, k == I: bias, k in [KX, KX + H): W_hh, else 0.
+__global__ void rm_tc_pack_w_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, const float* __restrict__ b_ih,
+                                    const float* __restrict__ b_hh, int H, int I, int KX, int K, float comp, float* __restrict__ out) {
+  const int NJ = K / 8, NC = H / 32;
+  const int64_t total = (int64_t)NC * K * kChunkN;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(e & 3), n = (int)((e >> 2) & 127), kc = (int)((e >> 9) & 1);
+    const int64_t rest = e >> 10;
+    const int J = (int)(rest % NJ), c = (int)(rest / NJ);
+    const int k = J * 8 + kc * 4 + kk, uu = n >> 2, g = n & 3, row = g * H + c * 32 + uu;
+    float v = 0.f;
+    if (k < I) v = w_ih[(int64_t)row * I + k];
+    else if (k == I) v = b_ih[row] + b_hh[row];
+    else if (k >= KX) v = w_hh[(int64_t)row * H + (k - KX)];
+    v *= (g == 2 ? -2.f : -1.f) * 1.4426950408889634f * comp;
+    uint32_t hi, lo;
+    split_tf32_rr(v, hi, lo);
+    float* dst = out + ((int64_t)c * NJ + J) * (kStepBytes / 4) + (kc * kChunkN + n) * 4 + kk;
+    dst[0] = __uint_as_float(hi);
+    dst[kStepBytes / 8] = __uint_as_float(lo);
+  }
+}
+}  // namespace
+
+__global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  uint8_t* smem_raw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  const int K = a.K, H = a.H, KX = a.KX, NS = a.stages;
+  float* s_alo = reinterpret_cast<float*>(smem_raw);                       // [K/4][128 rows][4]
+  float* s_xhi = s_alo + (size_t)K * kRowsF;                               // [KX/4][128 rows][4]
+  uint8_t* s_ring = reinterpret_cast<uint8_t*>(s_xhi + (size_t)KX * kRowsF);   // NS x 8 KB slices
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + (size_t)NS * kSliceBytes);
+  uint64_t* bar_full = bars;                       // [NS] producer -> MMA
+  uint64_t* bar_free = bars + 8;                   // [NS] MMA commit -> producer       (NS <= 8)
+  uint64_t* bar_dfull = bars + 16;                 // MMA commit -> rows: the chunk's accumulators are complete
+  uint64_t* bar_dfree = bars + 17;                 // rows -> MMA: they have been read
+  uint64_t* bar_a = bars + 18;                     // rows -> MMA: A operand of the step is in place
+  uint64_t* bar_step = bars + 19;                  // MMA commit: every MMA of the step retired, A may be rebuilt
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NC = H / 32, NJ = K / 8, JX = KX / 8;
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_free + s, 1); }
+    mbar_init(bar_dfull, 1); mbar_init(bar_dfree, 256);
+    mbar_init(bar_a, 256);
+    mbar_init(bar_step, 1);
+    mbar_fence_init();
+  }
+  if (warp == 8) tmem_alloc(s_tmem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp < 8) {
+    // =========================== row threads ===================================================
+    const int q = warp & 3, hh = warp >> 2;                       // lane quarter, which 16 of every 32 units
+    const int rloc = q * 32 + lane;
+    const int64_t b = (int64_t)blockIdx.x * kRowsF + rloc;
+    const bool live = b < a.B;
+    const uint32_t lane_tm = tmem + ((uint32_t)(q * 32) << 16);
+    float4* alo4 = reinterpret_cast<float4*>(s_alo);
+    float4* xhi4 = reinterpret_cast<float4*>(s_xhi);
+    const int64_t BH = a.B * H;
+    auto hbuf = [&](int64_t t) { return a.h_seq + (a.h_pingpong ? (t & 1) : t) * BH + b * H; };
+    auto cbuf = [&](int64_t t) { return a.c_seq + (a.c_pingpong ? (t & 1) : t) * BH + b * H; };
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto split4 = [](const float4& v, uint32_t (&hi)[4], float4& lo) {
+      uint32_t l[4];
+      split_tf32(v.x, hi[0], l[0]); split_tf32(v.y, hi[1], l[1]); split_tf32(v.z, hi[2], l[2]); split_tf32(v.w, hi[3], l[3]);
+      lo = make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]), __uint_as_float(l[2]), __uint_as_float(l[3]));
+    };
+
+    for (int64_t t = 0; t < a.T; ++t) {
+      // ---- A operand of step t: x_t (threads of half 0) and this thread's units of h_{t-1}
+      if (t > 0) {
+        mbar_wait(bar_step, (uint32_t)((t - 1) & 1));            // all MMAs of step t-1 retired
+        tc_fence_after();
+      }
+      if (hh == 0) {
+        const float* xr = a.x + (t * a.B + b) * a.IP;
+        for (int k0 = 0; k0 < KX; k0 += 4) {
+          float4 v = (live && k0 < a.IP) ? __ldg(reinterpret_cast<const float4*>(xr + k0)) : z4;
+          if ((a.I >> 2) == (k0 >> 2)) {                          // the ones column (bias) is input column I
+            const int kq = a.I & 3;
+            if (kq == 0) v.x = 1.f; else if (kq == 1) v.y = 1.f; else if (kq == 2) v.z = 1.f; else v.w = 1.f;
+          }
+          uint32_t hi[4]; float4 lo;
+          split4(v, hi, lo);
+          xhi4[(k0 >> 2) * kRowsF + rloc] = make_float4(__uint_as_float(hi[0]), __uint_as_float(hi[1]), __uint_as_float(hi[2]), __uint_as_float(hi[3]));
+          alo4[(k0 >> 2) * kRowsF + rloc] = lo;
+        }
+      }
+      {
+        const float* hp = (t > 0 && live) ? hbuf(t - 1) + 16 * hh : nullptr;
+#pragma unroll 4
+        for (int c = 0; c < NC; ++c) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {                           // 8 units: one 256-bit load, one tcgen05.st, two lo chunks
+            const int u0 = 32 * c + 16 * hh + 8 * i;
+            const f8 v = hp ? ld256(hp + 32 * c + 8 * i) : f8_zero();      // own earlier stores: coherent loads
+            uint32_t hi8[8], lo8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split_tf32(v.v[e], hi8[e], lo8[e]);
+            tmem_st8(lane_tm + u0, hi8);
+            alo4[((KX + u0) >> 2) * kRowsF + rloc] =
+                make_float4(__uint_as_float(lo8[0]), __uint_as_float(lo8[1]), __uint_as_float(lo8[2]), __uint_as_float(lo8[3]));
+            alo4[((KX + u0) >> 2) * kRowsF + kRowsF + rloc] =
+                make_float4(__uint_as_float(lo8[4]), __uint_as_float(lo8[5]), __uint_as_float(lo8[6]), __uint_as_float(lo8[7]));
+          }
+        }
+      }
+      tmem_st_wait();
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_a);
+
+      // ---- epilogue of every chunk: 16 hidden units of this row
+      const float* cprev = (t > 0 && live) ? cbuf(t - 1) + 16 * hh : nullptr;
+      float* hout = live ? hbuf(t) + 16 * hh : nullptr;
+      float* cout = live ? cbuf(t) + 16 * hh : nullptr;
+      float* gout = (live && a.gates) ? a.gates + (t * a.B + b) * 4 * H + 16 * hh : nullptr;
+      float* hlast = (live && a.h_last && t == a.T - 1) ? a.h_last + b * H + 16 * hh : nullptr;
+      for (int c = 0; c < NC; ++c) {
+        const int64_t gch = t * NC + c;
+        f8 cp[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) cp[i] = cprev ? ld256(cprev + 32 * c + 8 * i) : f8_zero();
+        mbar_wait(bar_dfull, (uint32_t)(gch & 1));
+        tc_fence_after();
+        float z[64];                                              // main + corrections, this thread's 16 units x 4 gates
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {                             // two rounds of 32 + 32 columns, one wait each
+          uint32_t zm[32], zc[32];
+          tmem_ld32(lane_tm + kColMain + 64 * hh + 32 * i, zm);
+          tmem_ld32(lane_tm + kColCorr + 64 * hh + 32 * i, zc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) z[32 * i + j] = __uint_as_float(zm[j]) + __uint_as_float(zc[j]);
+        }
+        tc_fence_before();
+        mbar_arrive(bar_dfree);                                   // the next chunk's MMAs may overwrite the pair
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {                             // 8 units per round: whole 32-byte sectors per access
+          f8 hv, cv, gi, gf, gg, go;
+#pragma unroll
+          for (int uu = 0; uu < 8; ++uu) {
+            const float* zz = z + 32 * i + 4 * uu;
+            if (a.exp & 2) { hv.v[uu] = zz[0]; cv.v[uu] = zz[1]; gi.v[uu] = zz[2]; gf.v[uu] = zz[3]; gg.v[uu] = cp[i].v[uu]; go.v[uu] = 0.f; continue; }
+            lstm_gates(zz[0], zz[1], zz[2], zz[3], gi.v[uu], gf.v[uu], gg.v[uu], go.v[uu]);
+            cv.v[uu] = fmaf(gf.v[uu], cp[i].v[uu], gi.v[uu] * gg.v[uu]);
+            hv.v[uu] = go.v[uu] * tanh_mufu(cv.v[uu]);
+          }
+          if (hout && !(a.exp & 1)) {
+            const int o = 32 * c + 8 * i;
+            st256(hout + o, hv);                                  // re-read by this thread at the end of the step
+            st256(cout + o, cv);                                  // re-read in the next step
+            if (gout) {
+              stg256(gout + o, gi);
+              stg256(gout + H + o, gf);
+              stg256(gout + 2 * H + o, gg);
+              stg256(gout + 3 * H + o, go);
+            }
+            if (hlast) stg256(hlast + o, hv);
+          }
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // =========================== MMA issuer =====================================================
+    if (elect_one()) {
+      const uint32_t idesc = idesc_tf32(kRowsF, kChunkN, 0, 0);
+      const uint32_t a_lbo = kRowsF * 16, b_lbo = kChunkN * 16, sbo = 128;
+      const uint32_t d_main = tmem + kColMain, d_corr = tmem + kColCorr;
+      // descriptors advance by constants (the address field counts 16-byte units): no per-slice rebuilding
+      const uint64_t ring_hi0 = smem_desc(smem_u32(s_ring), b_lbo, sbo), alo0 = smem_desc(smem_u32(s_alo), a_lbo, sbo);
+      const uint64_t xhi0 = smem_desc(smem_u32(s_xhi), a_lbo, sbo);
+      constexpr uint64_t kStageStep = kSliceBytes / 16, kStepStep = kStepBytes / 16, kLoOff = kStepBytes / 32, kAStep = 2 * kRowsF * 16 / 16;
+      int st = 0;                                   // ring stage and its phase parity (no 64-bit division in this loop)
+      uint32_t ph = 0;
+      uint64_t dbh = ring_hi0;
+      for (int64_t t = 0; t < a.T; ++t) {
+        mbar_wait(bar_a, (uint32_t)(t & 1));
+        tc_fence_after();
+        for (int c = 0; c < NC; ++c) {
+          const int64_t gch = t * NC + c;
+          if (gch > 0) {
+            mbar_wait(bar_dfree, (uint32_t)((gch - 1) & 1));
+            tc_fence_after();
+          }
+          uint64_t dal = alo0, dah = xhi0;
+          uint32_t ah = tmem;
+          for (int J0 = 0; J0 < NJ; J0 += kSliceJ) {
+            mbar_wait(bar_full + st, ph);
+            tc_fence_after();
+#pragma unroll
+            for (int jj = 0; jj < kSliceJ; ++jj) {
+              const int J = J0 + jj;
+              const uint64_t bh = dbh + jj * kStepStep, bl = bh + kLoOff;
+              if (a.exp & 4) { mma_tf32_ss(d_main, dal, bh, idesc, J > 0); dal += kAStep; continue; }
+              mma_tf32_ss(d_corr, dal, bh, idesc, J > 0);
+              if (J < JX) {                         // x part: A_hi from shared memory
+                mma_tf32_ss(d_corr, dah, bl, idesc, 1);
+                mma_tf32_ss(d_main, dah, bh, idesc, J > 0);
+                dah += kAStep;
+              } else {                              // h part: A_hi in TMEM columns [0, H)
+                mma_tf32_ts(d_corr, ah, bl, idesc, 1);
+                mma_tf32_ts(d_main, ah, bh, idesc, J > 0);
+                ah += 8;
+              }
+              dal += kAStep;
+            }
+            mma_commit(bar_free + st);
+            dbh += kStageStep;
+            if (++st == NS) { st = 0; ph ^= 1; dbh = ring_hi0; }
+          }
+          mma_commit(bar_dfull);
+        }
+        mma_commit(bar_step);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================== weight-slice producer ==========================================
+    if (lane == 0) {
+      const int per_step = NC * NJ / kSliceJ;
+      int st = 0;
+      uint32_t ph = 1;                              // parity of the previous use of the stage (first round: nothing to wait for)
+      bool first_round = true;
+      for (int64_t t = 0; t < a.T; ++t) {
+        const float* src = a.wpk;
+        for (int i = 0; i < per_step; ++i, src += kSliceBytes / 4) {
+          if (!first_round) mbar_wait(bar_free + st, ph);
+          mbar_arrive_expect_tx(bar_full + st, kSliceBytes);
+          bulk_g2s(s_ring + (size_t)st * kSliceBytes, src, kSliceBytes, bar_full + st);
+          if (++st == NS) { st = 0; ph ^= 1; first_round = false; }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+static void rm_fwd_shape(int64_t I, int64_t H, int& KX, int& K) {
+  KX = (int)round_up(I + 1, 8 * kSliceJ);      // a ring slice holds kSliceJ K steps: K / 8 must be a multiple of it
+  K = KX + (int)H;
+}
+// ring depth: what is left of the 227 KB after the A images
+static int rm_fwd_stages(int KX, int K) {
+  const int64_t fixed = (int64_t)(K + KX) * kRowsF * 4 + 256 + 1024;
+  static const int cap = [] { const char* e = getenv("HY2DL_RM_STAGES"); return e ? atoi(e) : 8; }();   // experiments
+  return (int)std::min<int64_t>(cap, (232448 - fixed) / kSliceBytes);
+}
+
+bool lstm_rm_tc_fwd_supported(int64_t I, int64_t H) {
+  static const bool off = [] { const char* e = getenv("HY2DL_FP32_FWD"); return e && e[0] == 'f'; }();   // "fma": CUDA-core kernel
+  if (off || !(H == 128 || H == 256)) return false;
+  int KX, K;
+  rm_fwd_shape(I, H, KX, K);
+  return KX <= kMaxKX && rm_fwd_stages(KX, K) >= 2;
+}
+
+// packed weights + (if no tape is requested) ping-pong buffers for h and c
+int64_t lstm_rm_tc_fwd_workspace(int64_t B, int64_t I, int64_t H) {
+  int KX, K;
+  rm_fwd_shape(I, H, KX, K);
+  return sizeof(float) * ((int64_t)(H / 32) * K * kChunkN * 2 + 4 * B * H) + 256;
+}
+
+int lstm_rm_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H, const float* w_ih, const float* w_hh,
+                   const float* b_ih, const float* b_hh, float* h_seq, float* c_seq, float* gates, float* h_last, void* ws,
+                   int64_t ws_bytes, cudaStream_t s) {
+  const int64_t need = lstm_rm_tc_fwd_workspace(B, I, H);
+  HY_REQUIRE(ws != nullptr && ws_bytes >= need, HY2DL_ERR_WORKSPACE, "hy2dl_lstm_fwd: workspace %lld < %lld bytes",
+             (long long)ws_bytes, (long long)need);
+  FwdArgs a{};
+  rm_fwd_shape(I, H, a.KX, a.K);
+  float* wpk = reinterpret_cast<float*>(ws);
+  const int64_t wfl = (int64_t)(H / 32) * a.K * kChunkN * 2;
+  float* scratch = wpk + round_up(wfl, (int64_t)64);
+  // Mean truncation bias of the hi*hi accumulator (the tensor core's fp32 accumulation rounds toward zero; the K/8
+  // MMAs of a chunk are chained).  tools/dbg_zbias.py without compensation (N(0,1) inputs, default-initialised
+  // weights): -1.22e-6 (H = 256, I = 31), -1.16e-6 (H = 256, I = 41), -5.3e-7 (H = 128, I = 31); std 5.8e-7 in all
+  // cases, as for the CUDA-core kernel.  The mean must be removed to ~1e-7: on a 701-step sequence (H = 128) the
+  // parameter-gradient error is 3.6e-4 uncompensated, 1.0e-4 with 5e-7, 2.5e-4 with 7e-7.  It depends on how the
+  // partial sums grow, i.e. mildly on the data; HY2DL_RM_COMP overrides the constant.
+  static const float comp = [] { const char* e = getenv("HY2DL_RM_COMP"); return e ? (float)atof(e) : 0.f; }();
+  const float factor = 1.f + (comp != 0.f ? comp : (H == 256 ? 1.19e-6f : 5.3e-7f));
+  rm_tc_pack_w_kernel<<<256, 256, 0, s>>>(w_ih, w_hh, b_ih, b_hh, (int)H, (int)I, a.KX, a.K, factor, wpk);
+  a.x = xT; a.wpk = wpk; a.gates = gates; a.h_last = h_last;
+  a.B = B; a.T = T; a.H = (int)H; a.I = (int)I; a.IP = (int)IP;
+  a.h_seq = h_seq ? h_seq : scratch;            a.h_pingpong = h_seq ? 0 : 1;
+  a.c_seq = c_seq ? c_seq : scratch + 2 * B * H; a.c_pingpong = c_seq ? 0 : 1;
+  a.stages = rm_fwd_stages(a.KX, a.K);
+  static const int rm_exp = [] { const char* e = getenv("HY2DL_RM_EXP"); return e ? atoi(e) : 0; }();
+  a.exp = rm_exp;
+  const size_t smem = (size_t)(a.K + a.KX) * kRowsF * 4 + (size_t)a.stages * kSliceBytes + 256 + 1024;
+  cudaFuncSetAttribute(lstm_rm_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  lstm_rm_tc_fwd_kernel<<<(unsigned)cdiv(B, (int64_t)kRowsF), kThreadsF, smem, s>>>(a);
+  HY_LAUNCH_CHECK();
+  return HY2DL_OK;
+}
+
+}  // namespace tc
+}  // namespace hy2dl

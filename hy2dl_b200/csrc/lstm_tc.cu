@@ -119,30 +119,6 @@ struct TcFwdArgs {
   HeadCols hc;
 };
 
-// One reciprocal for the four gates of a hidden unit.  The accumulator holds z' = -log2(e) z (i, f, o) and
-// -2 log2(e) z (g), bias included (see lstm_tc_pack_w_kernel).  With A = 1 + 2^zi', F = 1 + 2^zf', G = 1 + 2^zg',
-// O = 1 + 2^zo' and r = 1 / (A F G O):  i = r F G O, f = r A G O, o = r A F G, g = tanh(zg) = (2 - G) r A F O.
-// Arguments are clamped (sigmoid below -20 / tanh below -10 differ from their limits by < 4e-9) so that the
-// product stays finite.  5 MUFU (4 ex2 + rcp) instead of 8: the XU pipe is the epilogue's narrowest resource.
-__device__ __forceinline__ void lstm_gates(float zi, float zf, float zg, float zo, float& gi, float& gf, float& gg, float& go) {
-  constexpr float kClamp = 28.853900817779268f;   // 20 log2(e)
-  const float A = 1.f + fast_ex2(fminf(zi, kClamp));
-  const float F = 1.f + fast_ex2(fminf(zf, kClamp));
-  const float G = 1.f + fast_ex2(fminf(zg, kClamp));
-  const float O = 1.f + fast_ex2(fminf(zo, kClamp));
-  const float AF = A * F, GO = G * O;
-  const float r = fast_rcp(AF * GO);
-  const float rAF = r * AF, rGO = r * GO;
-  gi = rGO * F;
-  gf = rGO * A;
-  go = rAF * G;
-  gg = (2.f - G) * (rAF * O);
-}
-// tanh(x) = 1 - 2 / (1 + e^2x): 2 MUFU + 3 FMA-pipe instructions; saturates correctly at +-inf
-__device__ __forceinline__ float tanh_mufu(float x) {
-  return fmaf(-2.f, fast_rcp(1.f + fast_ex2(2.885390081777927f * x)), 1.f);
-}
-
 // NSETS = 2 or 4 sets of four row warps: set s owns hidden units [s*64/NSETS, (s+1)*64/NSETS) of all 128
 // rows (warp w of a set owns TMEM lanes / rows 32 (w & 3) ..), and the step's MMAs are issued per set
 // (N = 256/NSETS gate columns each, committed separately), so the epilogue of set s runs while the tensor

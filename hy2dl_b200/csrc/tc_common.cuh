@@ -131,6 +131,21 @@ __device__ __forceinline__ f8 ldg256(const float* p) {                    // rea
                : "l"(p));
   return r;
 }
+// coherent 256-bit load (data this thread stored earlier in the kernel: the read-only path must not be used)
+__device__ __forceinline__ f8 ld256(const float* p) {
+  f8 r;
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p)
+               : "memory");
+  return r;
+}
+// plain (write-back) 256-bit store: data that is re-read soon
+__device__ __forceinline__ void st256(float* p, const f8& r) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]),
+               "f"(r.v[3]), "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7])
+               : "memory");
+}
 __device__ __forceinline__ void stg256(float* p, const f8& r) {
   asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]),
                "f"(r.v[3]), "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7])
@@ -190,6 +205,10 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
                "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- 1-D bulk async copy global -> shared (TMA engine, no tensor map); completes on an mbarrier
@@ -217,6 +236,31 @@ __device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ft
 __device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+
+// One reciprocal for the four gates of a hidden unit.  The accumulator holds z' = -log2(e) z (i, f, o) and
+// -2 log2(e) z (g), bias included (see lstm_tc_pack_w_kernel).  With A = 1 + 2^zi', F = 1 + 2^zf', G = 1 + 2^zg',
+// O = 1 + 2^zo' and r = 1 / (A F G O):  i = r F G O, f = r A G O, o = r A F G, g = tanh(zg) = (2 - G) r A F O.
+// Arguments are clamped (sigmoid below -20 / tanh below -10 differ from their limits by < 4e-9) so that the
+// product stays finite.  5 MUFU (4 ex2 + rcp) instead of 8: the XU pipe is the epilogue's narrowest resource.
+__device__ __forceinline__ void lstm_gates(float zi, float zf, float zg, float zo, float& gi, float& gf, float& gg, float& go) {
+  constexpr float kClamp = 28.853900817779268f;   // 20 log2(e)
+  const float A = 1.f + fast_ex2(fminf(zi, kClamp));
+  const float F = 1.f + fast_ex2(fminf(zf, kClamp));
+  const float G = 1.f + fast_ex2(fminf(zg, kClamp));
+  const float O = 1.f + fast_ex2(fminf(zo, kClamp));
+  const float AF = A * F, GO = G * O;
+  const float r = fast_rcp(AF * GO);
+  const float rAF = r * AF, rGO = r * GO;
+  gi = rGO * F;
+  gf = rGO * A;
+  go = rAF * G;
+  gg = (2.f - G) * (rAF * O);
+}
+// tanh(x) = 1 - 2 / (1 + e^2x): 2 MUFU + 3 FMA-pipe instructions; saturates correctly at +-inf
+__device__ __forceinline__ float tanh_mufu(float x) {
+  return fmaf(-2.f, fast_rcp(1.f + fast_ex2(2.885390081777927f * x)), 1.f);
+}
+
 
 }  // namespace tc
 }  // namespace hy2dl

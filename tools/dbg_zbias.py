@@ -7,7 +7,10 @@ import numpy as np, torch
 from hy2dl_b200 import _lib, ops
 from hy2dl_b200.synthetic import lstm_weights
 dev = torch.device("cuda:0")
-B, T, I, H = 4096, 2, 25, 64
+# usage: python tools/dbg_zbias.py [H] [I]   (H = 128 / 256: the fp32 API path = streamed-weights tensor-core forward)
+H = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+I = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+B, T = 4096, 2
 rng = np.random.default_rng(5)
 x = rng.normal(0, 1, (B, T, I)).astype(np.float32)
 w = lstm_weights(I, H, 1, seed=4)
@@ -16,10 +19,10 @@ wd = [cu(w[k]) for k in ("lstm.weight_ih_l0", "lstm.weight_hh_l0", "lstm.bias_ih
 G = (B + 31) // 32
 W_ih, W_hh = w["lstm.weight_ih_l0"].astype(np.float64), w["lstm.weight_hh_l0"].astype(np.float64)
 b = (w["lstm.bias_ih_l0"].astype(np.float64) + w["lstm.bias_hh_l0"].astype(np.float64))
-for prec, name in ((_lib.PREC_FP32, "fp32"), (_lib.PREC_TF32X3, "tf32x3")):
+for prec, name in (((_lib.PREC_FP32, "fp32"), (_lib.PREC_TF32X3, "tf32x3")) if H == 64 else ((_lib.PREC_FP32, "fp32 API, H=%d" % H),)):
     ri = prec == _lib.PREC_TF32X3
     x_in = ops.pack_x(cu(x), "ri32" if ri else "rowmajor")
-    IPx = 32 if ri else 32
+    IPx = 32 if ri else (I + 7) // 8 * 8
     Bp = G * 32 if ri else B
     h = torch.zeros(T, Bp, H, device=dev); c = torch.zeros(T, Bp, H, device=dev); g = torch.zeros(T, Bp, 4 * H, device=dev)
     hl = torch.zeros(B, H, device=dev)
