@@ -6,7 +6,7 @@ int lstm_fp32_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, 
                   const float* w_hh, const float* b_ih, const float* b_hh, float* h_seq, float* c_seq, float* gates,
                   float* h_last, void* ws, int64_t ws_bytes, cudaStream_t s);
 int lstm_fp32_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const float* gates, const float* c_seq,
-                  const float* dh_seq, int64_t dh_t0, const float* dh_last, float* dG, cudaStream_t s);
+                  const float* dh_seq, int64_t dh_t0, const float* dh_last, float* dG, void* ws, int64_t ws_bytes, cudaStream_t s);
 int lstm_fp32_wgrad(const float* dG, const float* h_seq, const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
                     int64_t H, float* dw_ih, float* dw_hh, float* db, void* ws, int64_t ws_bytes, cudaStream_t s);
 int64_t lstm_fp32_workspace(int kind, int64_t B, int64_t T, int64_t I, int64_t H);
@@ -87,7 +87,7 @@ extern "C" int hy2dl_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh
     return tc::lstm_tc_bwd(B, T, w_hh, gates, c_seq, dh_seq, dh_t0, dh_last, dG, ws, ws_bytes, head, (cudaStream_t)stream);
   }
   HY_REQUIRE(precision == HY2DL_PREC_FP32, HY2DL_ERR_SHAPE, "hy2dl_lstm_bwd: precision %d not built", precision);
-  return lstm_fp32_bwd(B, T, H, w_hh, gates, c_seq, dh_seq, dh_t0, dh_last, dG, (cudaStream_t)stream);
+  return lstm_fp32_bwd(B, T, H, w_hh, gates, c_seq, dh_seq, dh_t0, dh_last, dG, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int hy2dl_lstm_wgrad(const float* dG, const float* h_seq, const float* xT, int64_t B, int64_t T, int64_t I,

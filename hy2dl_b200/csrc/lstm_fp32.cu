@@ -565,7 +565,9 @@ static int wgrad_splits(int64_t R, int M, int NP) {
 
 int64_t lstm_fp32_workspace(int kind, int64_t B, int64_t T, int64_t I, int64_t H);
 
-// tensor-core forward with streamed weights on the same row-major tapes (lstm_rm_tc_fwd.cu), H = 128 / 256
+// H = 128 / 256: the tensor-core chain (lstm_rm_tc_fwd.cu, lstm_rm_tc_bwd.cu, lstm_wgrad_rm_tc.cu).  Its tapes c_seq and
+// gates / dG are stored in the blocked RB8 layout (tc_common.cuh), so the three kernels are selected together:
+// HY2DL_FP32_TC=0 switches the whole chain back to the CUDA-core kernels of this file (row-major tapes).
 namespace tc {
 bool lstm_rm_tc_fwd_supported(int64_t I, int64_t H);
 int64_t lstm_rm_tc_fwd_workspace(int64_t B, int64_t I, int64_t H);
@@ -574,10 +576,19 @@ int lstm_rm_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
                    int64_t ws_bytes, cudaStream_t s);
 }  // namespace tc
 
+namespace tc {
+bool lstm_rm_tc_bwd_supported(int64_t H);
+bool lstm_wgrad_rm_tc_supported(int64_t H);
+}  // namespace tc
+static bool rm_tc_chain(int64_t I, int64_t H) {
+  static const bool off = [] { const char* e = getenv("HY2DL_FP32_TC"); return e && e[0] == '0'; }();
+  return !off && tc::lstm_rm_tc_fwd_supported(I, H) && tc::lstm_rm_tc_bwd_supported(H) && tc::lstm_wgrad_rm_tc_supported(H);
+}
+
 int lstm_fp32_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H, const float* w_ih,
                   const float* w_hh, const float* b_ih, const float* b_hh, float* h_seq, float* c_seq, float* gates,
                   float* h_last, void* ws, int64_t ws_bytes, cudaStream_t s) {
-  if (tc::lstm_rm_tc_fwd_supported(I, H))
+  if (rm_tc_chain(I, H))
     return tc::lstm_rm_tc_fwd(xT, B, T, I, IP, H, w_ih, w_hh, b_ih, b_hh, h_seq, c_seq, gates, h_last, ws, ws_bytes, s);
   const int64_t need = lstm_fp32_workspace(HY2DL_WS_LSTM_FWD, B, T, I, H);
   HY_REQUIRE(ws != nullptr && ws_bytes >= need, HY2DL_ERR_WORKSPACE, "hy2dl_lstm_fwd: workspace %lld < %lld bytes",
@@ -593,8 +604,18 @@ int lstm_fp32_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, 
   return HY2DL_OK;
 }
 
+// tensor-core BPTT with streamed W_hh on the same row-major tapes (lstm_rm_tc_bwd.cu), H = 128 / 256
+namespace tc {
+bool lstm_rm_tc_bwd_supported(int64_t H);
+int64_t lstm_rm_tc_bwd_workspace(int64_t B, int64_t H);
+int lstm_rm_tc_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const float* gates, const float* c_seq, const float* dh_seq,
+                   int64_t dh_t0, const float* dh_last, float* dG, void* ws, int64_t ws_bytes, cudaStream_t s);
+}  // namespace tc
+
 int lstm_fp32_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const float* gates, const float* c_seq,
-                  const float* dh_seq, int64_t dh_t0, const float* dh_last, float* dG, cudaStream_t s) {
+                  const float* dh_seq, int64_t dh_t0, const float* dh_last, float* dG, void* ws, int64_t ws_bytes, cudaStream_t s) {
+  if (rm_tc_chain(8, H))     // the chain's condition on the input size (I <= 64) holds for every accepted call
+    return tc::lstm_rm_tc_bwd(B, T, H, w_hh, gates, c_seq, dh_seq, dh_t0, dh_last, dG, ws, ws_bytes, s);
   LstmBwdArgs a{w_hh, gates, c_seq, dh_seq, dh_last, dG, B, T, dh_t0};
   const int spt = pick_spt(B);
   HY_DISPATCH_H_SPT(H, spt, launch_bwd, a, s);
@@ -609,15 +630,10 @@ int64_t lstm_wgrad_rm_tc_workspace(int64_t H, int64_t I);
 int lstm_wgrad_rm_tc(const float* dG, const float* h_seq, const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H,
                      float* dw_ih, float* dw_hh, float* db, void* ws, int64_t ws_bytes, cudaStream_t s);
 }  // namespace tc
-// HY2DL_FP32_WGRAD=fma keeps the CUDA-core GEMM below for every H (comparison / fallback for debugging)
-static bool use_rm_tc(int64_t H) {
-  static const bool fma_only = [] { const char* e = getenv("HY2DL_FP32_WGRAD"); return e && e[0] == 'f'; }();
-  return !fma_only && tc::lstm_wgrad_rm_tc_supported(H);
-}
 
 int lstm_fp32_wgrad(const float* dG, const float* h_seq, const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
                     int64_t H, float* dw_ih, float* dw_hh, float* db, void* ws, int64_t ws_bytes, cudaStream_t s) {
-  if (use_rm_tc(H)) return tc::lstm_wgrad_rm_tc(dG, h_seq, xT, B, T, I, IP, H, dw_ih, dw_hh, db, ws, ws_bytes, s);
+  if (rm_tc_chain(I, H)) return tc::lstm_wgrad_rm_tc(dG, h_seq, xT, B, T, I, IP, H, dw_ih, dw_hh, db, ws, ws_bytes, s);
   const int64_t need = lstm_fp32_workspace(HY2DL_WS_LSTM_WGRAD, B, T, I, H);
   HY_REQUIRE(ws != nullptr && ws_bytes >= need, HY2DL_ERR_WORKSPACE, "hy2dl_lstm_wgrad: workspace %lld < %lld bytes",
              (long long)ws_bytes, (long long)need);
@@ -639,12 +655,12 @@ int lstm_fp32_wgrad(const float* dG, const float* h_seq, const float* xT, int64_
 int64_t lstm_fp32_workspace(int kind, int64_t B, int64_t T, int64_t I, int64_t H) {
   const int64_t IP = round_up(I, 8);
   if (kind == HY2DL_WS_LSTM_FWD) {
-    if (tc::lstm_rm_tc_fwd_supported(I, H)) return tc::lstm_rm_tc_fwd_workspace(B, I, H);
+    if (rm_tc_chain(I, H)) return tc::lstm_rm_tc_fwd_workspace(B, I, H);
     return sizeof(float) * ((IP + H) * 4 * H + 4 * H);
   }
-  if (kind == HY2DL_WS_LSTM_BWD) return 16;
+  if (kind == HY2DL_WS_LSTM_BWD) return rm_tc_chain(I, H) ? tc::lstm_rm_tc_bwd_workspace(B, H) : 16;
   if (kind == HY2DL_WS_LSTM_WGRAD) {
-    if (use_rm_tc(H)) return tc::lstm_wgrad_rm_tc_workspace(H, I);
+    if (rm_tc_chain(I, H)) return tc::lstm_wgrad_rm_tc_workspace(H, I);
     const int M = (int)(4 * H), NP = (int)round_up(H + IP + 1, 128);
     return sizeof(float) * (int64_t)wgrad_splits(T * B, M, NP) * M * NP;
   }

@@ -22,7 +22,8 @@
 // L2 -> shared memory per CTA: at a full wave of 148 CTAs the L2 stream, not the tensor pipe, bounds the step.
 //
 // Semantics: torch.nn.LSTM, one layer, h0 = c0 = 0 (modelzoo/cudalstm.py:43-50, hybrid.py:84-92); tapes as
-// lstm_fp32.cu writes them: h_seq, c_seq [T][B][H], gates [T][B][4H] (post-activation, column g*H + u).
+// h_seq [T][B][H] row-major (it is an API output); c_seq and gates (post-activation, column g*H + u) are tapes only
+// this chain reads and are stored in the RB8 layout (tc_common.cuh), T x ceil(B/32)*32 rows.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <stdlib.h>
@@ -35,7 +36,7 @@ constexpr int kRowsF = 128;
 constexpr int kThreadsF = 320;              // warps 0-7 rows, 8 MMA issuer, 9 producer
 constexpr int kChunkN = 128;                // gate columns per chunk = 32 hidden units x 4 gates
 constexpr int kStepBytes = 8 * kChunkN * 4 * 2;    // one K step of the packed weights: hi | lo = 8 KB
-constexpr int kSliceJ = 2;                         // K steps per ring slice (one bulk copy, one commit)
+constexpr int kSliceJ = 1;                         // K steps per ring slice (one bulk copy, one commit); 2 measured the same
 constexpr int kSliceBytes = kSliceJ * kStepBytes;
 constexpr uint32_t kColMain = 256, kColCorr = 384;
 constexpr int kMaxKX = 80;
@@ -121,7 +122,8 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
     float4* xhi4 = reinterpret_cast<float4*>(s_xhi);
     const int64_t BH = a.B * H;
     auto hbuf = [&](int64_t t) { return a.h_seq + (a.h_pingpong ? (t & 1) : t) * BH + b * H; };
-    auto cbuf = [&](int64_t t) { return a.c_seq + (a.c_pingpong ? (t & 1) : t) * BH + b * H; };
+    const int64_t G = (a.B + 31) >> 5;
+    auto cbuf = [&](int64_t t) { return a.c_seq + rb8_off(a.c_pingpong ? (t & 1) : t, G, b, H, 2 * hh); };   // RB8, block 2 hh
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     auto split4 = [](const float4& v, uint32_t (&hi)[4], float4& lo) {
       uint32_t l[4];
@@ -174,16 +176,16 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
       mbar_arrive(bar_a);
 
       // ---- epilogue of every chunk: 16 hidden units of this row
-      const float* cprev = (t > 0 && live) ? cbuf(t - 1) + 16 * hh : nullptr;
+      const float* cprev = (t > 0 && live) ? cbuf(t - 1) : nullptr;
       float* hout = live ? hbuf(t) + 16 * hh : nullptr;
-      float* cout = live ? cbuf(t) + 16 * hh : nullptr;
-      float* gout = (live && a.gates) ? a.gates + (t * a.B + b) * 4 * H + 16 * hh : nullptr;
+      float* cout = live ? cbuf(t) : nullptr;
+      float* gout = (live && a.gates) ? a.gates + rb8_off(t, G, b, 4 * H, 2 * hh) : nullptr;            // RB8, F = 4H
       float* hlast = (live && a.h_last && t == a.T - 1) ? a.h_last + b * H + 16 * hh : nullptr;
       for (int c = 0; c < NC; ++c) {
         const int64_t gch = t * NC + c;
         f8 cp[2];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) cp[i] = cprev ? ld256(cprev + 32 * c + 8 * i) : f8_zero();
+        for (int i = 0; i < 2; ++i) cp[i] = cprev ? ld256(cprev + (4 * c + i) * 256) : f8_zero();
         mbar_wait(bar_dfull, (uint32_t)(gch & 1));
         tc_fence_after();
         float z[64];                                              // main + corrections, this thread's 16 units x 4 gates
@@ -212,12 +214,13 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
           if (hout && !(a.exp & 1)) {
             const int o = 32 * c + 8 * i;
             st256(hout + o, hv);                                  // re-read by this thread at the end of the step
-            st256(cout + o, cv);                                  // re-read in the next step
+            const int blk = (4 * c + i) * 256;                    // unit block (32 c + 16 hh + 8 i) / 8 relative to block 2 hh
+            st256(cout + blk, cv);                                // re-read in the next step
             if (gout) {
-              stg256(gout + o, gi);
-              stg256(gout + H + o, gf);
-              stg256(gout + 2 * H + o, gg);
-              stg256(gout + 3 * H + o, go);
+              stg256(gout + blk, gi);
+              stg256(gout + (H / 8) * 256 + blk, gf);
+              stg256(gout + 2 * (H / 8) * 256 + blk, gg);
+              stg256(gout + 3 * (H / 8) * 256 + blk, go);
             }
             if (hlast) stg256(hlast + o, hv);
           }
@@ -315,8 +318,7 @@ static int rm_fwd_stages(int KX, int K) {
 }
 
 bool lstm_rm_tc_fwd_supported(int64_t I, int64_t H) {
-  static const bool off = [] { const char* e = getenv("HY2DL_FP32_FWD"); return e && e[0] == 'f'; }();   // "fma": CUDA-core kernel
-  if (off || !(H == 128 || H == 256)) return false;
+  if (!(H == 128 || H == 256)) return false;
   int KX, K;
   rm_fwd_shape(I, H, KX, K);
   return KX <= kMaxKX && rm_fwd_stages(KX, K) >= 2;
@@ -326,7 +328,7 @@ bool lstm_rm_tc_fwd_supported(int64_t I, int64_t H) {
 int64_t lstm_rm_tc_fwd_workspace(int64_t B, int64_t I, int64_t H) {
   int KX, K;
   rm_fwd_shape(I, H, KX, K);
-  return sizeof(float) * ((int64_t)(H / 32) * K * kChunkN * 2 + 4 * B * H) + 256;
+  return sizeof(float) * ((int64_t)(H / 32) * K * kChunkN * 2 + 4 * round_up(B, (int64_t)32) * H) + 256;
 }
 
 int lstm_rm_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H, const float* w_ih, const float* w_hh,
@@ -352,7 +354,7 @@ int lstm_rm_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
   a.x = xT; a.wpk = wpk; a.gates = gates; a.h_last = h_last;
   a.B = B; a.T = T; a.H = (int)H; a.I = (int)I; a.IP = (int)IP;
   a.h_seq = h_seq ? h_seq : scratch;            a.h_pingpong = h_seq ? 0 : 1;
-  a.c_seq = c_seq ? c_seq : scratch + 2 * B * H; a.c_pingpong = c_seq ? 0 : 1;
+  a.c_seq = c_seq ? c_seq : scratch + 2 * round_up(B, (int64_t)32) * H; a.c_pingpong = c_seq ? 0 : 1;
   a.stages = rm_fwd_stages(a.KX, a.K);
   static const int rm_exp = [] { const char* e = getenv("HY2DL_RM_EXP"); return e ? atoi(e) : 0; }();
   a.exp = rm_exp;

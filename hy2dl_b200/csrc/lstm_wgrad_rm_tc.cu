@@ -5,7 +5,8 @@
 // third of the step (67.7 ms of 188 ms at H = 256, B = 9472, T = 365: 30 TFLOP/s of fp32 FMA).  This kernel is the
 // tcgen05 pipeline of lstm_tc_wgrad.cu (3-term TF32 split, MN-major SWIZZLE_128B_BASE32B operands, chained TMEM
 // accumulators with a round-to-nearest running sum because the tensor core's fp32 accumulation truncates) fed from
-// the row-major tapes [T*B][4H], [T*B][H], [T*B][IP] instead of RI32 slabs:
+// this chain's tapes -- dG in the RB8 layout [T][ceil(B/32)][4H/8][32 rows][8] (tc_common.cuh), h_seq [T][B][H] and xT
+// [T][B][IP] row-major -- instead of RI32 slabs; a slab is the 32 sequences of one (t, group):
 //   * the output is cut into tiles of 256 gate rows x 96 feature columns (3 blocks of 32); tile type (mt, nt) is
 //     owned by `parts` CTAs that share its 32-row slabs round-robin, so all 148 SMs work and every CTA keeps its
 //     tile in TMEM for the whole kernel;
@@ -37,11 +38,11 @@ constexpr int kND = 96;
 constexpr int kChunks = kStageBytes / 16;   // 16-byte copies per slab (2816)
 
 struct Args {
-  const float* dG;    // [R][4H], column g*H + u
-  const float* h;     // [R][H]; the h operand of row r is h[r - B] (zero for r < B)
-  const float* x;     // [R][IP]
+  const float* dG;    // RB8, F = 4H, column g*H + u
+  const float* h;     // [T][B][H]; the h operand of (t, b) is h[t-1][b] (zero for t = 0)
+  const float* x;     // [T][B][IP]
   float* partial;     // [parts][MT*NT][256][kND]
-  int64_t R, B;
+  int64_t T, B, G;
   int H, I, IP, MT, NT, parts;
 };
 
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_wgrad_rm_tc_kernel(Args a) {
   const int TT = a.MT * a.NT;
   const int tt = blockIdx.x % TT, part = blockIdx.x / TT;
   const int mt = tt / a.NT, nt = tt - mt * a.NT;
-  const int64_t n_slabs = (a.R + 31) / 32;
+  const int64_t n_slabs = a.T * a.G;
   const int64_t n_my = part < n_slabs ? (n_slabs - part + a.parts - 1) / a.parts : 0;   // slabs part, part + parts, ...
   const int HB = a.H / 32;                           // feature blocks: [0, HB) h, then x blocks, then nothing
   const int ones_f = a.H + a.I;                      // feature index of the ones column
@@ -156,19 +157,22 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_wgrad_rm_tc_kernel(Args a) {
     auto load_slab = [&](int64_t j) {
       const int s = (int)(j % kStages);
       if (j < n_my) {
-        const int64_t r = (part + j * a.parts) * 32 + lrow;
-        const bool in = r < a.R;
+        const int64_t slab = part + j * a.parts, t = slab / a.G, grp = slab - t * a.G;
+        const int64_t b = grp * 32 + lrow;
+        const bool in = b < a.B;
+        const int64_t r = t * a.B + b;                 // row of the row-major streams
         const uint32_t st = smem_u32(smem_raw + s * kStageBytes) + ldst;
-        const float* g = a.dG + r * F4 + 256 * mt + 4 * lch;
+        // RB8: 8-float block (256 mt + 32 k) / 8 + lch / 2 of sequence lrow, 16-byte half lch & 1
+        const float* g = a.dG + ((slab * (F4 >> 3) + 32 * mt + (lch >> 1)) * 256 + lrow * 8 + (lch & 1) * 4);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) cp_async16_zfill(st + k * kBlk, in ? g + 32 * k : a.dG, in);
+        for (int k = 0; k < 8; ++k) cp_async16_zfill(st + k * kBlk, in ? g + 4 * k * 256 : a.dG, in);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           const int fb = 3 * nt + k;
           const float* src;
           bool valid = in;
           if (fb < HB) {
-            valid = valid && r >= a.B;
+            valid = valid && t > 0;
             src = a.h + (r - a.B) * a.H + 32 * fb + 4 * lch;
           } else {
             const int col = 32 * (fb - HB) + 4 * lch;
@@ -282,7 +286,7 @@ int lstm_wgrad_rm_tc(const float* dG, const float* h_seq, const float* xT, int64
              (long long)ws_bytes, (long long)need);
   Args a{};
   a.dG = dG; a.h = h_seq; a.x = xT; a.partial = reinterpret_cast<float*>(ws);
-  a.R = T * B; a.B = B; a.H = (int)H; a.I = (int)I; a.IP = (int)IP;
+  a.T = T; a.B = B; a.G = cdiv(B, (int64_t)32); a.H = (int)H; a.I = (int)I; a.IP = (int)IP;
   rm_tc_shape(H, I, a.MT, a.NT, a.parts);
   const size_t smem = (size_t)kStages * kStageBytes + kABytes + 2 * kBBytes + 128 + 1024;
   cudaFuncSetAttribute(lstm_wgrad_rm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -123,6 +123,14 @@ __device__ __forceinline__ void ri32_st(float4* base, int64_t t, int64_t G, int6
 __device__ __forceinline__ int64_t ri32_unit(int64_t t, int64_t G, int64_t gidx, int FB, int U, int row) {
   return ((t * G + gidx) * FB + (U >> 2)) * 1024 + row * 32 + (((U & 3) ^ (row & 3)) << 3);
 }
+// ---- RB8 tape layout of the H = 128 / 256 tensor-core chain: [t][G = ceil(B/32)][F/8][32 rows][8 floats].
+// The row-owning threads of those kernels (TMEM lane = sequence) move 8 floats = one 32-byte sector per access; in a
+// row-major tape the 32 lanes of a warp then touch 32 different lines (the LSU serialises them: the first version of
+// the BPTT kernel spent 34 of 52 ms on tape accesses), here they touch one contiguous 1 KB run.  Float offset of
+// the 8-float block `blk` of sequence b at step t; the next block of the same sequence is 256 floats further.
+__host__ __device__ __forceinline__ int64_t rb8_off(int64_t t, int64_t G, int64_t b, int F, int blk) {
+  return ((t * G + (b >> 5)) * (F >> 3) + blk) * 256 + (b & 31) * 8;
+}
 struct f8 { float v[8]; };
 __device__ __forceinline__ f8 ldg256(const float* p) {                    // read-only path, 32-byte aligned
   f8 r;

@@ -141,8 +141,11 @@ class LstmFunction(torch.autograd.Function):
         w_ih, w_hh, b_ih, b_hh = (t.detach().contiguous() for t in (w_ih, w_hh, b_ih, b_hh))
         h_seq = seq(H) if (want_seq or need_grad) else None
         h_last = torch.empty(B, H, dtype=torch.float32, device=dev)
-        c_seq = seq(H) if need_grad else None
-        gates = seq(4 * H) if need_grad else None
+        # c_seq and gates are tapes only the kernels read; the H = 128 / 256 tensor-core chain stores them blocked by
+        # 32 sequences (include/hy2dl_b200.h, "RB8"), so they hold whole groups of rows
+        tape = seq if (ri or H < 128) else (lambda F: torch.empty(T, (B + 31) // 32 * 32, F, dtype=torch.float32, device=dev))
+        c_seq = tape(H) if need_grad else None
+        gates = tape(4 * H) if need_grad else None
         ws = _ws(_lib.WS_LSTM_FWD, B, T, I, H, dev, precision)
         call("hy2dl_lstm_fwd", ptr(xT), B, T, I, IP, H, ptr(w_ih), ptr(w_hh), ptr(b_ih), ptr(b_hh), ptr(h_seq),
              ptr(c_seq), ptr(gates), ptr(h_last), ptr(ws), ws.numel(), precision, None, stream())

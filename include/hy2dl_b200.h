@@ -140,7 +140,11 @@ typedef struct {
 /* ---- LSTM (replaces torch.nn.LSTM at modelzoo/cudalstm.py:50 and hybrid.py:92; one layer,
  * unidirectional, h0 = c0 = 0, gate order i|f|g|o as torch/nn/modules/rnn.py:935-941) -------------
  * Weights come in PyTorch layout: w_ih [4H][I], w_hh [4H][H], b_ih [4H], b_hh [4H].
- * Tape outputs may be NULL (inference): c_seq, gates; h_seq may be NULL if only h_last is wanted. */
+ * Tape outputs may be NULL (inference): c_seq, gates; h_seq may be NULL if only h_last is wanted.
+ * c_seq, gates and dG are tapes that only hy2dl_lstm_bwd / hy2dl_lstm_wgrad read back: their layout is the forward
+ * kernel's choice.  Row-major precisions, H = 64: [T][B][H] and [T][B][4][H].  Row-major precisions, H = 128 / 256
+ * (tensor-core chain, unless HY2DL_FP32_TC=0): "RB8" = [T][ceil(B/32)][F/8][32 sequences][8 floats], F = H or 4H --
+ * allocate T * ceil(B/32)*32 * F floats for them. */
 int hy2dl_lstm_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H,
                    const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
                    float* h_seq, float* c_seq, float* gates, float* h_last,

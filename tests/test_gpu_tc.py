@@ -187,7 +187,11 @@ def test_rowmajor_tc_wgrad_shapes(B, T, I, H):
     dwi = torch.full((4 * H, I), np.nan, device=dev); dwh = torch.full((4 * H, H), np.nan, device=dev)
     dbb = torch.full((4 * H,), np.nan, device=dev)
     ws = ops._ws(_lib.WS_LSTM_WGRAD, B, T, I, H, dev, _lib.PREC_FP32)
-    args = [cu(a) for a in (dG, h, x)]
+    # the gate-gradient tape of this chain is blocked: [T][ceil(B/32)][4H/8][32 sequences][8]  (RB8)
+    G = (B + 31) // 32
+    dG_p = np.zeros((T, G * 32, 4 * H), np.float32); dG_p[:, :B] = dG
+    dG_rb8 = np.ascontiguousarray(dG_p.reshape(T, G, 32, 4 * H // 8, 8).transpose(0, 1, 3, 2, 4))
+    args = [cu(a) for a in (dG_rb8, h, x)]
     _lib.call("hy2dl_lstm_wgrad", *[a.data_ptr() for a in args], B, T, I, IP, H, dwi.data_ptr(), dwh.data_ptr(),
               dbb.data_ptr(), ws.data_ptr(), ws.numel(), _lib.PREC_FP32, None, _lib.stream())
     torch.cuda.synchronize()
