@@ -44,14 +44,15 @@ constexpr int kMaxKX = 80;
 struct FwdArgs {
   const float* x;       // [T][B][IP]
   const float* wpk;     // packed weights [H/32 chunks][K/8 steps][hi [2][128][4] | lo [2][128][4]]
-  float* h_seq;         // [T][B][H], or two time slots only (h_pingpong)
+  float* h_seq;         // [T][B][H] row-major API output, or null
+  float* h_own;         // RB8 [2 slots][ceil(B/32)*32][H]: h of the last two steps, what the row threads re-read
   float* c_seq;
   float* gates;         // [T][B][4H] or null
   float* h_last;        // [B][H] or null
   int64_t B, T;
   int H, I, IP, KX, K;  // KX = x columns incl. the ones column, rounded to 8; K = KX + H
   int stages;           // ring depth (what shared memory allows)
-  int h_pingpong, c_pingpong;
+  int c_pingpong;
   int exp;              // timing experiments (HY2DL_RM_EXP): 1 no tape stores, 2 no activation math, 4 a third of the MMAs
 };
 
@@ -121,8 +122,8 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
     float4* alo4 = reinterpret_cast<float4*>(s_alo);
     float4* xhi4 = reinterpret_cast<float4*>(s_xhi);
     const int64_t BH = a.B * H;
-    auto hbuf = [&](int64_t t) { return a.h_seq + (a.h_pingpong ? (t & 1) : t) * BH + b * H; };
     const int64_t G = (a.B + 31) >> 5;
+    auto hown = [&](int64_t t) { return a.h_own + rb8_off(t & 1, G, b, H, 2 * hh); };                        // RB8, block 2 hh
     auto cbuf = [&](int64_t t) { return a.c_seq + rb8_off(a.c_pingpong ? (t & 1) : t, G, b, H, 2 * hh); };   // RB8, block 2 hh
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     auto split4 = [](const float4& v, uint32_t (&hi)[4], float4& lo) {
@@ -152,13 +153,13 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
         }
       }
       {
-        const float* hp = (t > 0 && live) ? hbuf(t - 1) + 16 * hh : nullptr;
+        const float* hp = (t > 0 && live) ? hown(t - 1) : nullptr;
 #pragma unroll 4
         for (int c = 0; c < NC; ++c) {
 #pragma unroll
           for (int i = 0; i < 2; ++i) {                           // 8 units: one 256-bit load, one tcgen05.st, two lo chunks
             const int u0 = 32 * c + 16 * hh + 8 * i;
-            const f8 v = hp ? ld256(hp + 32 * c + 8 * i) : f8_zero();      // own earlier stores: coherent loads
+            const f8 v = hp ? ld256(hp + (4 * c + i) * 256) : f8_zero();    // own earlier stores: coherent loads
             uint32_t hi8[8], lo8[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) split_tf32(v.v[e], hi8[e], lo8[e]);
@@ -177,7 +178,8 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
 
       // ---- epilogue of every chunk: 16 hidden units of this row
       const float* cprev = (t > 0 && live) ? cbuf(t - 1) : nullptr;
-      float* hout = live ? hbuf(t) + 16 * hh : nullptr;
+      float* hout = (live && a.h_seq) ? a.h_seq + t * BH + b * H + 16 * hh : nullptr;      // row-major API output
+      float* hself = live ? hown(t) : nullptr;
       float* cout = live ? cbuf(t) : nullptr;
       float* gout = (live && a.gates) ? a.gates + rb8_off(t, G, b, 4 * H, 2 * hh) : nullptr;            // RB8, F = 4H
       float* hlast = (live && a.h_last && t == a.T - 1) ? a.h_last + b * H + 16 * hh : nullptr;
@@ -211,10 +213,11 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
             cv.v[uu] = fmaf(gf.v[uu], cp[i].v[uu], gi.v[uu] * gg.v[uu]);
             hv.v[uu] = go.v[uu] * tanh_mufu(cv.v[uu]);
           }
-          if (hout && !(a.exp & 1)) {
+          if (hself && !(a.exp & 1)) {
             const int o = 32 * c + 8 * i;
-            st256(hout + o, hv);                                  // re-read by this thread at the end of the step
             const int blk = (4 * c + i) * 256;                    // unit block (32 c + 16 hh + 8 i) / 8 relative to block 2 hh
+            st256(hself + blk, hv);                               // re-read by this thread at the end of the step
+            if (hout) stg256(hout + o, hv);
             st256(cout + blk, cv);                                // re-read in the next step
             if (gout) {
               stg256(gout + blk, gi);
@@ -328,7 +331,7 @@ bool lstm_rm_tc_fwd_supported(int64_t I, int64_t H) {
 int64_t lstm_rm_tc_fwd_workspace(int64_t B, int64_t I, int64_t H) {
   int KX, K;
   rm_fwd_shape(I, H, KX, K);
-  return sizeof(float) * ((int64_t)(H / 32) * K * kChunkN * 2 + 4 * round_up(B, (int64_t)32) * H) + 256;
+  return sizeof(float) * ((int64_t)(H / 32) * K * kChunkN * 2 + 4 * round_up(B, (int64_t)32) * H) + 256;   // weights + h_own + c ping-pong
 }
 
 int lstm_rm_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H, const float* w_ih, const float* w_hh,
@@ -353,7 +356,7 @@ int lstm_rm_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
   rm_tc_pack_w_kernel<<<256, 256, 0, s>>>(w_ih, w_hh, b_ih, b_hh, (int)H, (int)I, a.KX, a.K, factor, wpk);
   a.x = xT; a.wpk = wpk; a.gates = gates; a.h_last = h_last;
   a.B = B; a.T = T; a.H = (int)H; a.I = (int)I; a.IP = (int)IP;
-  a.h_seq = h_seq ? h_seq : scratch;            a.h_pingpong = h_seq ? 0 : 1;
+  a.h_seq = h_seq; a.h_own = scratch;
   a.c_seq = c_seq ? c_seq : scratch + 2 * round_up(B, (int64_t)32) * H; a.c_pingpong = c_seq ? 0 : 1;
   a.stages = rm_fwd_stages(a.KX, a.K);
   static const int rm_exp = [] { const char* e = getenv("HY2DL_RM_EXP"); return e ? atoi(e) : 0; }();
