@@ -13,10 +13,10 @@
 //     core multiplies chunk c;
 //   * W_hh (hi | lo, 2 MB at H = 256) is streamed every step from L2 through a ring of 16 KB bulk copies (one K step);
 //   * the hi*hi accumulator is only trusted for 4 chunks (32 chained MMAs: the accumulation truncates, and a bias in
-//     dh_rec compounds over the recurrence): after every 4 chunks the row threads write main + corrections as that
-//     group's partial sum of dh_rec to global scratch (L2 resident; the partials are added, round to nearest, when
-//     the next step loads its dh) and the next group starts by overwriting the accumulators; the group's mean bias
-//     is compensated in the packed weights;
+//     dh_rec compounds over the recurrence): after every 4 chunks the row threads add main + corrections into the
+//     dh_rec buffer in global scratch (round to nearest; 3 x [B][H] of scratch in all, which stays L2 resident --
+//     one buffer per group made 78 MB and went to DRAM) and the next group starts by overwriting the accumulators;
+//     the group's mean bias is compensated in the packed weights;
 //   * dc and dh live in global scratch ([B][H] each, two time slots for dh), not in shared memory or registers.
 // A row is owned by two threads (TMEM lane = row; the two warps of a lane quarter take 8 | 8 of a chunk's 16 units);
 // a thread only re-reads scratch it wrote itself.  10 warps: 8 row warps, the MMA issuer, the bulk-copy producer.
@@ -46,7 +46,7 @@ struct BwdArgs {
   const float* dh_last; // [B][H] or null
   float* dG;            // [T][B][4H], may alias gates
   float* dc;            // scratch [B][H], zero-initialised
-  float* dh;            // scratch [2 time slots][H/64 groups][B][H], zero-initialised: the groups' partial sums of dh_rec
+  float* dh;            // scratch RB8 [2 time slots][B][H], zero-initialised: dh_rec, accumulated group by group
   int64_t B, T, dh_t0;
   int H, stages;
   int exp;              // timing experiments (HY2DL_RMB_EXP): 1 hi*hi MMAs only, 2 no accumulator pull, 4 no tape traffic
@@ -121,8 +121,8 @@ __global__ void __launch_bounds__(kThreadsB, 1) lstm_rm_tc_bwd_kernel(BwdArgs a)
     for (int64_t s = 0; s < a.T; ++s) {
       const int64_t t = a.T - 1 - s;
       // dh_rec(t) = sum of the group partials written during the previous step; dh_rec(t-1) is written group by group
-      const float* dh_rd = a.dh + (s & 1) * n_groups * GH + rb8_off(0, G, b, H, hh);
-      float* dh_wr = a.dh + ((s + 1) & 1) * n_groups * GH + rb8_off(0, G, b, H, hh);
+      const float* dh_rd = a.dh + (s & 1) * GH + rb8_off(0, G, b, H, hh);
+      float* dh_wr = a.dh + ((s + 1) & 1) * GH + rb8_off(0, G, b, H, hh);
       const float* gp = a.gates + rb8_off(t, G, b, 4 * H, hh);
       float* dgp = a.dG + rb8_off(t, G, b, 4 * H, hh);
       const float* ctp = a.c_seq + rb8_off(t, G, b, H, hh);
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) lstm_rm_tc_bwd_kernel(BwdArgs a)
         tp.ct = ld256(ctp + ob);
         if (cpp) tp.cp = ld256(cpp + ob);
         tp.dc = ld256(dcp + ob);
-        for (int g = 0; g < n_groups; ++g) { const f8 e = ld256(dh_rd + g * GH + ob); for (int k = 0; k < 8; ++k) tp.dh.v[k] += e.v[k]; }
+        tp.dh = ld256(dh_rd + ob);
         if (dhe) { const f8 e = ld256(dhe + o); for (int k = 0; k < 8; ++k) tp.dh.v[k] += e.v[k]; }
         if (dhl) { const f8 e = ld256(dhl + o); for (int k = 0; k < 8; ++k) tp.dh.v[k] += e.v[k]; }
       };
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) lstm_rm_tc_bwd_kernel(BwdArgs a)
       auto pull = [&](int g) {                     // group g of this step: main + corrections -> its partial of dh_rec(t-1)
         mbar_wait(bar_group, (uint32_t)(ggr & 1));
         tc_fence_after();
-        float* dst = dh_wr + g * GH;
+        float* dst = dh_wr;                        // one buffer per time slot: 3 x [B][H] of scratch stay L2 resident
 #pragma unroll 4
         for (int u0 = 8 * hh; u0 < ((a.exp & 2) ? 0 : H); u0 += 16) {  // this thread's columns: units with (u >> 3) & 1 == hh
           uint32_t zm[8], zc[8];
@@ -197,7 +197,11 @@ __global__ void __launch_bounds__(kThreadsB, 1) lstm_rm_tc_bwd_kernel(BwdArgs a)
           f8 acc;
 #pragma unroll
           for (int k = 0; k < 8; ++k) acc.v[k] = __uint_as_float(zm[k]) + __uint_as_float(zc[k]);
-          if (live) st256(dst + (u0 >> 4) * 512, acc);      // unit block u0 / 8 = 2 (u0 / 16) + hh
+          if (live) {                                        // unit block u0 / 8 = 2 (u0 / 16) + hh
+            float* p = dst + (u0 >> 4) * 512;
+            if (g > 0) { const f8 old = ld256(p); for (int k = 0; k < 8; ++k) acc.v[k] += old.v[k]; }
+            st256(p, acc);
+          }
         }
         tc_fence_before();
         mbar_arrive(bar_pulled);
@@ -296,9 +300,9 @@ bool lstm_rm_tc_bwd_supported(int64_t H) {
   return H == 128 || H == 256;
 }
 
-// packed W_hh (hi | lo) + dc [B][H] + dh [2][H/64][B][H]
+// packed W_hh (hi | lo) + dc [B][H] + dh [2][B][H]
 int64_t lstm_rm_tc_bwd_workspace(int64_t B, int64_t H) {
-  return sizeof(float) * (8 * H * H + (1 + 2 * (H / 64)) * round_up(B, (int64_t)32) * H) + 256;
+  return sizeof(float) * (8 * H * H + 3 * round_up(B, (int64_t)32) * H) + 256;
 }
 
 int lstm_rm_tc_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const float* gates, const float* c_seq, const float* dh_seq,
@@ -316,7 +320,7 @@ int lstm_rm_tc_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const flo
   static const float comp = [] { const char* e = getenv("HY2DL_RM_BCOMP"); return e ? (float)atof(e) : 5e-7f; }();
   rm_tc_pack_whh_kernel<<<256, 256, 0, s>>>(w_hh, (int)H, 1.f + comp, wpk);
   const int64_t Bp = round_up(B, (int64_t)32);
-  cudaMemsetAsync(scratch, 0, sizeof(float) * (1 + 2 * (H / 64)) * Bp * H, s);
+  cudaMemsetAsync(scratch, 0, sizeof(float) * 3 * Bp * H, s);
   a.wpk = wpk; a.gates = gates; a.c_seq = c_seq; a.dh_seq = dh_seq; a.dh_last = dh_last; a.dG = dG;
   a.dc = scratch; a.dh = scratch + Bp * H;
   a.B = B; a.T = T; a.dh_t0 = dh_t0; a.H = (int)H;
