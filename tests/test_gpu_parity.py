@@ -248,7 +248,11 @@ def test_train_steps_golden(dev):
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,T,I,H,precision", [(256, 365, 25, 64, "fp32"), (37, 50, 31, 256, "fp32"), (5, 33, 7, 128, "fp32"),
                                                 (70, 40, 41, 64, "fp32"), (256, 365, 25, 64, "tf32x3"), (70, 40, 31, 64, "tf32x3"),
-                                                (5, 33, 7, 64, "tf32x3")])
+                                                (5, 33, 7, 64, "tf32x3"),
+                                                # H = 128 / 256 tensor-core chain (streamed weights, blocked tapes): a single step, the
+                                                # widest input (ones column in its own K step), two tiles with a ragged second one
+                                                (1, 1, 3, 128, "fp32"), (130, 3, 64, 256, "fp32"), (33, 2, 8, 128, "fp32"),
+                                                (200, 120, 31, 256, "fp32")])
 def test_lstm_vs_oracle(dev, B, T, I, H, precision):
     from hy2dl_b200.modelzoo import LSTM
     from hy2dl_b200.synthetic import lstm_weights
