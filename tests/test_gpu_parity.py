@@ -174,6 +174,18 @@ def test_cudalstm_golden(dev, name, precision):
         assert_close(got, ref, what="grad " + k, **GTOL)
 
 
+def test_cudalstm_h256_inference_without_tapes(dev):
+    """H = 256 under no_grad: no h_seq / c_seq / gates buffers are passed, the streamed-weights forward keeps the last
+    two steps of h and c in its workspace; same y_hat as the reference (golden C3)."""
+    from hy2dl_b200.modelzoo import CudaLSTM
+    g = golden("cudalstm_c3")
+    B, T, I, H, wseed = [int(v) for v in g["meta"]]
+    model = load(CudaLSTM({"input_size_lstm": I, "hidden_size": H, "no_of_layers": 1, "drop_out_rate": 0.0}), I, H, 1, wseed, dev).eval()
+    with torch.no_grad():
+        y = model(cu(g["x_lstm"], dev))["y_hat"]
+    assert_close(npy(y), g["y_hat"], what="y_hat", **TOL)
+
+
 def build_hybrid(g, dev, precision="fp32"):
     from hy2dl_b200.modelzoo import HBV, SHM, Hybrid, NonSense, UH_routing, linear_reservoir
     B, T, n_last, I, H, m, wseed, routing = [int(v) for v in g["meta"]]
