@@ -18,6 +18,8 @@
 //     one buffer per group made 78 MB and went to DRAM) and the next group starts by overwriting the accumulators;
 //     the group's mean bias is compensated in the packed weights;
 //   * dc and dh live in global scratch ([B][H] each, two time slots for dh), not in shared memory or registers.
+// Timing experiments on the row-major-tape version (H = 256, B = 256, 52.1 ms): hi*hi MMAs only 50.7 ms, no accumulator
+// pull 46.0 ms, no tape traffic 18.1 ms -- the row-strided sector accesses were the cost, hence the RB8 tapes.
 // A row is owned by two threads (TMEM lane = row; the two warps of a lane quarter take 8 | 8 of a chunk's 16 units);
 // a thread only re-reads scratch it wrote itself.  10 warps: 8 row warps, the MMA issuer, the bulk-copy producer.
 //
@@ -49,7 +51,6 @@ struct BwdArgs {
   float* dh;            // scratch RB8 [2 time slots][B][H], zero-initialised: dh_rec, accumulated group by group
   int64_t B, T, dh_t0;
   int H, stages;
-  int exp;              // timing experiments (HY2DL_RMB_EXP): 1 hi*hi MMAs only, 2 no accumulator pull, 4 no tape traffic
 };
 
 // packed element (chunk c, K step j = 2 g + half, kc, k_out n, kk): W_hh[g*H + 16 c + 8 half + 4 kc + kk][n]
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) lstm_rm_tc_bwd_kernel(BwdArgs a)
         const int o = kUnitsC * c;                 // row-major offset of the chunk (units o + 8 hh ..)
         const int ob = 2 * c * 256;                // RB8 offset of unit block 2 c (+ hh in the base pointers)
         tp.gi = tp.gf = tp.gg = tp.go = tp.ct = tp.cp = tp.dh = tp.dc = f8_zero();
-        if (!live || (a.exp & 4)) return;
+        if (!live) return;
         tp.gi = ld256(gp + ob); tp.gf = ld256(gp + HB * 256 + ob); tp.gg = ld256(gp + 2 * HB * 256 + ob); tp.go = ld256(gp + 3 * HB * 256 + ob);
         tp.ct = ld256(ctp + ob);
         if (cpp) tp.cp = ld256(cpp + ob);
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) lstm_rm_tc_bwd_kernel(BwdArgs a)
           dg.v[k] = dct * tp.gi.v[k] * (1.f - tp.gg.v[k] * tp.gg.v[k]);
           dcn.v[k] = dct * tp.gf.v[k];
         }
-        if (live && !(a.exp & 4)) {
+        if (live) {
           stg256(dgp + ob, di); stg256(dgp + HB * 256 + ob, df); stg256(dgp + 2 * HB * 256 + ob, dg); stg256(dgp + 3 * HB * 256 + ob, dO);
           st256(dcp + ob, dcn);
         }
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) lstm_rm_tc_bwd_kernel(BwdArgs a)
         tc_fence_after();
         float* dst = dh_wr;                        // one buffer per time slot: 3 x [B][H] of scratch stay L2 resident
 #pragma unroll 4
-        for (int u0 = 8 * hh; u0 < ((a.exp & 2) ? 0 : H); u0 += 16) {  // this thread's columns: units with (u >> 3) & 1 == hh
+        for (int u0 = 8 * hh; u0 < H; u0 += 16) {  // this thread's columns: units with (u >> 3) & 1 == hh
           uint32_t zm[8], zc[8];
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                        : "=r"(zm[0]), "=r"(zm[1]), "=r"(zm[2]), "=r"(zm[3]), "=r"(zm[4]), "=r"(zm[5]), "=r"(zm[6]), "=r"(zm[7])
@@ -250,10 +251,8 @@ __global__ void __launch_bounds__(kThreadsB, 1) lstm_rm_tc_bwd_kernel(BwdArgs a)
             tc_fence_after();
             const uint64_t bl = dbh + kBLo;
             const uint32_t acc = !(open && j == 0);
-            if (!(a.exp & 1)) {
-              mma_tf32_ss(d_corr, dal, dbh, idesc, acc);
-              mma_tf32_ss(d_corr, dah, bl, idesc, 1);
-            }
+            mma_tf32_ss(d_corr, dal, dbh, idesc, acc);
+            mma_tf32_ss(d_corr, dah, bl, idesc, 1);
             mma_tf32_ss(d_main, dah, dbh, idesc, acc);
             dah += kAStep; dal += kAStep;
             mma_commit(bar_free + st);
@@ -325,8 +324,6 @@ int lstm_rm_tc_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const flo
   a.dc = scratch; a.dh = scratch + Bp * H;
   a.B = B; a.T = T; a.dh_t0 = dh_t0; a.H = (int)H;
   a.stages = rm_bwd_stages(H);
-  static const int rmb_exp = [] { const char* e = getenv("HY2DL_RMB_EXP"); return e ? atoi(e) : 0; }();
-  a.exp = rmb_exp;
   const size_t smem = (size_t)2 * kABufBytes + (size_t)a.stages * (2 * H * 4 * 4 * 2) + 256 + 1024;
   cudaFuncSetAttribute(lstm_rm_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   lstm_rm_tc_bwd_kernel<<<(unsigned)cdiv(B, (int64_t)kRowsB), kThreadsB, smem, s>>>(a);

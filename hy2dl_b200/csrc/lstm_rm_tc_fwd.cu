@@ -17,6 +17,9 @@
 //     h_t values from the tape it has just written (L2 hits) to rebuild A for the next step.  A row is owned by
 //     two threads (TMEM lane = row; the two warps of a lane quarter split every chunk's 32 units 16 | 16), and a
 //     thread only ever re-reads what it wrote itself, so no CTA-wide synchronisation is needed inside a step.
+// Timing experiments on the first complete version (H = 256, B = 256, 30.8 ms): without tape stores 20.7 ms (they
+// were row-strided 16-byte stores then; whole sectors now), without the activation arithmetic 30.6 ms, a third of
+// the MMAs 27.1 ms, all three 12.3 ms; ring depth 2 / 4 / 8 and one or two K steps per commit: no difference.
 // One CTA = 128 sequences for all T steps; 10 warps: 8 row warps, the MMA issuer, the bulk-copy producer.
 // Per step the tensor core needs 128 x 4H x K x 3 / 2048 cycles (55 k at H = 256) while 2.4 MB of weights cross
 // L2 -> shared memory per CTA: at a full wave of 148 CTAs the L2 stream, not the tensor pipe, bounds the step.
@@ -53,7 +56,6 @@ struct FwdArgs {
   int H, I, IP, KX, K;  // KX = x columns incl. the ones column, rounded to 8; K = KX + H
   int stages;           // ring depth (what shared memory allows)
   int c_pingpong;
-  int exp;              // timing experiments (HY2DL_RM_EXP): 1 no tape stores, 2 no activation math, 4 a third of the MMAs
 };
 
 // packed weight element (chunk c, K index k, column n = 4 uu + g of the chunk): rows scaled by -log2(e) (x 2 for g)
@@ -208,12 +210,11 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
 #pragma unroll
           for (int uu = 0; uu < 8; ++uu) {
             const float* zz = z + 32 * i + 4 * uu;
-            if (a.exp & 2) { hv.v[uu] = zz[0]; cv.v[uu] = zz[1]; gi.v[uu] = zz[2]; gf.v[uu] = zz[3]; gg.v[uu] = cp[i].v[uu]; go.v[uu] = 0.f; continue; }
             lstm_gates(zz[0], zz[1], zz[2], zz[3], gi.v[uu], gf.v[uu], gg.v[uu], go.v[uu]);
             cv.v[uu] = fmaf(gf.v[uu], cp[i].v[uu], gi.v[uu] * gg.v[uu]);
             hv.v[uu] = go.v[uu] * tanh_mufu(cv.v[uu]);
           }
-          if (hself && !(a.exp & 1)) {
+          if (hself) {
             const int o = 32 * c + 8 * i;
             const int blk = (4 * c + i) * 256;                    // unit block (32 c + 16 hh + 8 i) / 8 relative to block 2 hh
             st256(hself + blk, hv);                               // re-read by this thread at the end of the step
@@ -261,7 +262,6 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
             for (int jj = 0; jj < kSliceJ; ++jj) {
               const int J = J0 + jj;
               const uint64_t bh = dbh + jj * kStepStep, bl = bh + kLoOff;
-              if (a.exp & 4) { mma_tf32_ss(d_main, dal, bh, idesc, J > 0); dal += kAStep; continue; }
               mma_tf32_ss(d_corr, dal, bh, idesc, J > 0);
               if (J < JX) {                         // x part: A_hi from shared memory
                 mma_tf32_ss(d_corr, dah, bl, idesc, 1);
@@ -316,8 +316,7 @@ static void rm_fwd_shape(int64_t I, int64_t H, int& KX, int& K) {
 // ring depth: what is left of the 227 KB after the A images
 static int rm_fwd_stages(int KX, int K) {
   const int64_t fixed = (int64_t)(K + KX) * kRowsF * 4 + 256 + 1024;
-  static const int cap = [] { const char* e = getenv("HY2DL_RM_STAGES"); return e ? atoi(e) : 8; }();   // experiments
-  return (int)std::min<int64_t>(cap, (232448 - fixed) / kSliceBytes);
+  return (int)std::min<int64_t>(8, (232448 - fixed) / kSliceBytes);   // 2, 4 and 8 stages measured the same
 }
 
 bool lstm_rm_tc_fwd_supported(int64_t I, int64_t H) {
@@ -359,8 +358,6 @@ int lstm_rm_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
   a.h_seq = h_seq; a.h_own = scratch;
   a.c_seq = c_seq ? c_seq : scratch + 2 * round_up(B, (int64_t)32) * H; a.c_pingpong = c_seq ? 0 : 1;
   a.stages = rm_fwd_stages(a.KX, a.K);
-  static const int rm_exp = [] { const char* e = getenv("HY2DL_RM_EXP"); return e ? atoi(e) : 0; }();
-  a.exp = rm_exp;
   const size_t smem = (size_t)(a.K + a.KX) * kRowsF * 4 + (size_t)a.stages * kSliceBytes + 256 + 1024;
   cudaFuncSetAttribute(lstm_rm_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   lstm_rm_tc_fwd_kernel<<<(unsigned)cdiv(B, (int64_t)kRowsF), kThreadsF, smem, s>>>(a);
