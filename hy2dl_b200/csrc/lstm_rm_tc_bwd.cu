@@ -314,7 +314,7 @@ int lstm_rm_tc_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const flo
   float* scratch = wpk + 8 * H * H;
   // mean truncation bias of a group's hi*hi accumulator (kGroup chunks x 8 = 32 chained MMAs).  The gate gradients
   // have random signs, so the partial sums grow like a random walk and the bias is smaller than in the forward
-  // kernel: parameter-gradient error vs the fp64 oracle (H = 256, T = 365) 4.1e-5 / 4.0e-5 / 4.3e-5 / 4.6e-5 for a
+  // kernel: parameter-gradient error vs an fp64 evaluation (H = 256, T = 365) 4.1e-5 / 4.0e-5 / 4.3e-5 / 4.6e-5 for a
   // compensation of 0 / 5e-7 / 1.1e-6 / 1.7e-6 (CUDA-core chain: 2.0e-5).  HY2DL_RM_BCOMP overrides.
   static const float comp = [] { const char* e = getenv("HY2DL_RM_BCOMP"); return e ? (float)atof(e) : 5e-7f; }();
   rm_tc_pack_whh_kernel<<<256, 256, 0, s>>>(w_hh, (int)H, 1.f + comp, wpk);

@@ -14,7 +14,7 @@ class CudaLSTM(nn.Module):
     """LSTM -> last hidden state -> Dropout -> Linear(H, 1); returns {"y_hat": [B, 1]}.
 
     Hyper-parameter keys read: input_size_lstm, hidden_size, no_of_layers, drop_out_rate
-    (cudalstm.py:18-26); optional extra key "precision" ("fp32" | "tf32x3").
+    (cudalstm.py:18-26); optional extra key "precision" ("auto" default | "fp32" | "tf32x3", see LSTM).
     State-dict keys: lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0,
     linear.weight, linear.bias.
     """
@@ -25,7 +25,7 @@ class CudaLSTM(nn.Module):
         self.hidden_size = hyperparameters["hidden_size"]
         self.num_layers = hyperparameters["no_of_layers"]
         self.lstm = LSTM(input_size=self.input_size_lstm, hidden_size=self.hidden_size, batch_first=True,
-                         num_layers=self.num_layers, precision=hyperparameters.get("precision", "fp32"))
+                         num_layers=self.num_layers, precision=hyperparameters.get("precision", "auto"))
         self.dropout = torch.nn.Dropout(hyperparameters["drop_out_rate"])
         self.linear = nn.Linear(in_features=self.hidden_size, out_features=1)
 

@@ -20,7 +20,7 @@ from .lstm import LSTM
 
 class Hybrid(nn.Module):
     """hyperparameters keys: input_size_lstm, hidden_size, no_of_layers, seq_length, predict_last_n,
-    n_conceptual_models, conceptual_dynamic_parameterization (hybrid.py:32-46); optional "precision".
+    n_conceptual_models, conceptual_dynamic_parameterization (hybrid.py:32-46); optional "precision" ("auto" default, see LSTM).
     `conceptual_model` / `routing_model` are passed as classes, as in the reference (hybrid.py:47-53).
     """
 
@@ -35,7 +35,7 @@ class Hybrid(nn.Module):
         self.warmup_period = self.seq_length - self.predict_last_n
 
         self.lstm = LSTM(input_size=self.input_size_lstm, hidden_size=self.hidden_size, batch_first=True,
-                         num_layers=self.num_layers, precision=hyperparameters.get("precision", "fp32"))
+                         num_layers=self.num_layers, precision=hyperparameters.get("precision", "auto"))
 
         self.n_conceptual_models = hyperparameters["n_conceptual_models"]
         self.conceptual_dynamic_parameterization = hyperparameters["conceptual_dynamic_parameterization"]

@@ -65,7 +65,7 @@ class MFLSTM(nn.Module):
             self.columns[f] += shared
         self.input_size_total = col
         self.lstm = LSTM(input_size=col, hidden_size=self.hidden_size, batch_first=True,
-                         num_layers=hyperparameters["no_of_layers"], precision=hyperparameters.get("precision", "fp32"))
+                         num_layers=hyperparameters["no_of_layers"], precision=hyperparameters.get("precision", "auto"))
         self.dropout = nn.Dropout(hyperparameters.get("drop_out_rate", 0.0))
         self.linear = nn.Linear(in_features=self.hidden_size, out_features=1)
 

@@ -200,3 +200,16 @@ def test_mflstm_block_packing_equals_per_frequency_projections():
         m.pack({"1D": x["1D"], "1h": x["1h"][:, :5]})
     with pytest.raises(ValueError):
         MFLSTM({**hp, "predict_last_n": 10})
+
+
+def test_default_precision_resolution():
+    """`precision` is optional: the default picks the tensor-core path with resident weights where it exists (H = 64,
+    input_size <= 31) and the fp32 API path otherwise; unknown names are rejected."""
+    from hy2dl_b200.modelzoo import LSTM, CudaLSTM
+    assert LSTM(25, 64).precision == "tf32x3" and LSTM(25, 64).layout == "ri32"
+    assert LSTM(41, 64).precision == "fp32" and LSTM(31, 256).precision == "fp32" and LSTM(31, 256).layout == "rowmajor"
+    assert LSTM(25, 64, precision="fp32").precision == "fp32"
+    hp = {"input_size_lstm": 25, "hidden_size": 64, "no_of_layers": 1, "drop_out_rate": 0.0}
+    assert CudaLSTM(hp).lstm.precision == "tf32x3" and CudaLSTM({**hp, "precision": "fp32"}).lstm.precision == "fp32"
+    with pytest.raises(ValueError):
+        LSTM(25, 64, precision="fp16")

@@ -237,7 +237,7 @@ def test_train_steps_golden(dev):
     g = golden("train_steps")
     B, T, n_last, I, H, m, wseed = [int(v) for v in g["meta"]]
     hp = {"input_size_lstm": I, "hidden_size": H, "no_of_layers": 1, "seq_length": T, "predict_last_n": n_last,
-          "n_conceptual_models": m, "conceptual_dynamic_parameterization": ["dd", "kf", "beta"]}
+          "n_conceptual_models": m, "conceptual_dynamic_parameterization": ["dd", "kf", "beta"], "precision": "fp32"}
     model = load(Hybrid(hp, conceptual_model=SHM, routing_model=UH_routing), I, H, 8 * m + 2, wseed, dev)
     opt = FusedClipAdam(model.parameters(), lr=1e-3, max_norm=1.0)
     for step in range(3):
