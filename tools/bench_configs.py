@@ -20,6 +20,7 @@ CONFIGS = {
     "c2": ("gb", "shm", 64, 1, ["dd", "f_thr", "sumax", "beta", "perc", "kf", "ki", "kb"], "nse", 182, "tf32x3",
            (256, 18944)),
     "c3": ("us_lstm", "cudalstm", 256, 0, [], "nse", 1, "fp32", (256, 9472, 18944)),
+    "c3_h128": ("us_lstm", "cudalstm", 128, 0, [], "nse", 1, "fp32", (256, 18944)),   # the notebook's own hidden size
     "c4": ("us", "hbv", 256, 16, ["BETA", "BETAET"], "wrmse", 182, "fp32", (256, 9472, 18944)),
     "nonsense": ("gb", "nonsense", 64, 1, ["dd", "sumax", "beta", "ki", "kb"], "nse", 182, "tf32x3", (256, 18944)),
 }
