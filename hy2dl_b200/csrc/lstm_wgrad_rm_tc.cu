@@ -7,7 +7,8 @@
 // accumulators with a round-to-nearest running sum because the tensor core's fp32 accumulation truncates) fed from
 // this chain's tapes -- dG in the RB8 layout [T][ceil(B/32)][4H/8][32 rows][8] (tc_common.cuh), h_seq [T][B][H] and xT
 // [T][B][IP] row-major -- instead of RI32 slabs; a slab is the 32 sequences of one (t, group):
-//   * the output is cut into tiles of 256 gate rows x 96 feature columns (3 blocks of 32); tile type (mt, nt) is
+//   * the output is cut into tiles of 256 gate rows x 96 or 128 feature columns (3 or 4 blocks of 32, whichever
+//     needs fewer tiles); tile type (mt, nt) is
 //     owned by `parts` CTAs that share its 32-row slabs round-robin, so all 148 SMs work and every CTA keeps its
 //     tile in TMEM for the whole kernel;
 //   * the converter threads themselves copy a slab two iterations ahead with 16-byte cp.async (zero-fill for rows
@@ -32,18 +33,15 @@ constexpr int kChain = 8;                   // slabs accumulated in TMEM before 
 constexpr int kBlk = 4096;                  // one [32 rows][32 floats] block
 constexpr int kBlk4 = kBlk / 16;
 constexpr int kABytes = 8 * kBlk;           // 256 gate columns
-constexpr int kBBytes = 3 * kBlk;           // 96 feature columns
-constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kND = 96;
-constexpr int kChunks = kStageBytes / 16;   // 16-byte copies per slab (2816)
+// feature columns per tile: NB = 3 or 4 blocks of 32 (N = 96 / 128), whichever needs fewer tiles for H + I + 1 columns
 
 struct Args {
   const float* dG;    // RB8, F = 4H, column g*H + u
   const float* h;     // [T][B][H]; the h operand of (t, b) is h[t-1][b] (zero for t = 0)
   const float* x;     // [T][B][IP]
-  float* partial;     // [parts][MT*NT][256][kND]
+  float* partial;     // [parts][MT*NT][256][32 NB]
   int64_t T, B, G;
-  int H, I, IP, MT, NT, parts;
+  int H, I, IP, MT, NT, NB, parts;
 };
 
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
@@ -58,8 +56,9 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {   // arrives on
 __global__ void __launch_bounds__(kThreads, 1) lstm_wgrad_rm_tc_kernel(Args a) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* smem_raw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_lo = smem_raw + kStages * kStageBytes;             // [A_lo | B_lo[0] | B_lo[1]]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lo + kABytes + 2 * kBBytes);
+  const int NB = a.NB, ND = 32 * NB, bbytes = NB * kBlk, stage_bytes = kABytes + bbytes;
+  uint8_t* s_lo = smem_raw + kStages * stage_bytes;              // [A_lo | B_lo[0] | B_lo[1]]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lo + kABytes + 2 * bbytes);
   uint64_t* bar_full = bars;                        // [stages] cp.async completion of all converter threads
   uint64_t* bar_raw_free = bars + kStages;          // (unused slots)
   uint64_t* bar_conv = bars + 2 * kStages;          // [2] converters -> MMA, per half of the gate columns
@@ -94,17 +93,17 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_wgrad_rm_tc_kernel(Args a) {
     // =========================== MMA issuer =====================================================
     if (elect_one()) {
       const uint32_t lo_a = smem_u32(s_lo);
-      const uint32_t idesc = idesc_tf32(128, kND, 1, 1);
+      const uint32_t idesc = idesc_tf32(128, ND, 1, 1);
       for (int64_t i = 0; i < n_my; ++i) {
         const int s = (int)(i % kStages);
-        const uint32_t hi_a = smem_u32(smem_raw + s * kStageBytes), hi_b = hi_a + kABytes;
-        const uint32_t lo_b = lo_a + kABytes + (uint32_t)(i & 1) * kBBytes;
+        const uint32_t hi_a = smem_u32(smem_raw + s * stage_bytes), hi_b = hi_a + kABytes;
+        const uint32_t lo_b = lo_a + kABytes + (uint32_t)(i & 1) * bbytes;
         const bool first = (i % kChain) == 0;
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           mbar_wait(bar_conv + hf, (uint32_t)(i & 1));
           tc_fence_after();
-          const uint32_t d = tmem + kND * hf;
+          const uint32_t d = tmem + ND * hf;
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb) {
             const uint64_t b_hi = smem_desc_mn32(hi_b + kb * 1024, kBlk, 512), b_lo = smem_desc_mn32(lo_b + kb * 1024, kBlk, 512);
@@ -125,16 +124,16 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_wgrad_rm_tc_kernel(Args a) {
     const int ct = tid - 64;
     const int hf = ct >> 7;
     const uint32_t lane_tm = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t dcol = kND * hf;
+    const uint32_t dcol = ND * hf;
     {
       uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int c = 0; c < kND; c += 8) tmem_st8(lane_tm + 256 + dcol + c, z);
+      for (int c = 0; c < ND; c += 8) tmem_st8(lane_tm + 256 + dcol + c, z);
       tmem_st_wait();
     }
     auto drain = [&]() {                                     // S += D, round to nearest, in registers
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < kND; c += 16) {
+      for (int c = 0; c < ND; c += 16) {
         uint32_t d[16], sacc[16];
         tmem_ld16(lane_tm + dcol + c, d);
         tmem_ld16(lane_tm + 256 + dcol + c, sacc);
@@ -148,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_wgrad_rm_tc_kernel(Args a) {
       tc_fence_before();
     };
     // where the ones column sits in this CTA's B part (block, float4 within the block row, component), if at all
-    const int ones_blk = ones_f / 32 - 3 * nt;               // block of the B part (0..2) or outside
+    const int ones_blk = ones_f / 32 - NB * nt;              // block of the B part (0 .. NB-1) or outside
     const int ones_col = ones_f & 31;
     // loads: this thread's chunk of every block of slab j -> stage j % kStages
     const int lrow = ct >> 3, lch = ct & 7;
@@ -161,14 +160,14 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_wgrad_rm_tc_kernel(Args a) {
         const int64_t b = grp * 32 + lrow;
         const bool in = b < a.B;
         const int64_t r = t * a.B + b;                 // row of the row-major streams
-        const uint32_t st = smem_u32(smem_raw + s * kStageBytes) + ldst;
+        const uint32_t st = smem_u32(smem_raw + s * stage_bytes) + ldst;
         // RB8: 8-float block (256 mt + 32 k) / 8 + lch / 2 of sequence lrow, 16-byte half lch & 1
         const float* g = a.dG + ((slab * (F4 >> 3) + 32 * mt + (lch >> 1)) * 256 + lrow * 8 + (lch & 1) * 4);
 #pragma unroll
         for (int k = 0; k < 8; ++k) cp_async16_zfill(st + k * kBlk, in ? g + 4 * k * 256 : a.dG, in);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int fb = 3 * nt + k;
+        for (int k = 0; k < NB; ++k) {
+          const int fb = NB * nt + k;
           const float* src;
           bool valid = in;
           if (fb < HB) {
@@ -189,8 +188,8 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_wgrad_rm_tc_kernel(Args a) {
     float4* lo_a4 = reinterpret_cast<float4*>(s_lo);
     for (int64_t i = 0; i < n_my; ++i) {
       const int s = (int)(i % kStages);
-      float4* raw = reinterpret_cast<float4*>(smem_raw + s * kStageBytes);
-      float4* lo_b4 = reinterpret_cast<float4*>(s_lo + kABytes + (i & 1) * kBBytes);
+      float4* raw = reinterpret_cast<float4*>(smem_raw + s * stage_bytes);
+      float4* lo_b4 = reinterpret_cast<float4*>(s_lo + kABytes + (i & 1) * bbytes);
       constexpr int kA4 = kABytes / 16;
       auto split4 = [&](int e) {                             // lo = v - trunc(v); the landed words are the hi operand
         float4 v = raw[e];
@@ -215,7 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_wgrad_rm_tc_kernel(Args a) {
         mbar_wait(bar_lo_free + 1, (uint32_t)((i - 1) & 1));
         drain();
       }
-      for (int e = ct; e < 3 * kBlk4; e += kConv) split4(kA4 + e);
+      for (int e = ct; e < NB * kBlk4; e += kConv) split4(kA4 + e);
 #pragma unroll 4
       for (int e = ct; e < 4 * kBlk4; e += kConv) split4(e);
       fence_async_smem();
@@ -232,9 +231,9 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_wgrad_rm_tc_kernel(Args a) {
     if (n_my > 0) drain();
     tc_fence_after();
     const int row = hf * 128 + (warp & 3) * 32 + lane;
-    float* dst = a.partial + (((int64_t)part * TT + tt) * 256 + row) * kND;
+    float* dst = a.partial + (((int64_t)part * TT + tt) * 256 + row) * ND;
 #pragma unroll 1
-    for (int c = 0; c < kND; c += 16) {
+    for (int c = 0; c < ND; c += 16) {
       uint32_t v[16];
       tmem_ld16(lane_tm + 256 + dcol + c, v);
       tmem_ld_wait();
@@ -250,33 +249,35 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_wgrad_rm_tc_kernel(Args a) {
 }
 
 // partial [parts][MT*NT][256][96] -> dw_hh [4H][H], dw_ih [4H][I], db [4H]
-__global__ void lstm_wgrad_rm_tc_finish_kernel(const float* __restrict__ partial, int parts, int MT, int NT, int H, int I,
+__global__ void lstm_wgrad_rm_tc_finish_kernel(const float* __restrict__ partial, int parts, int MT, int NT, int ND, int H, int I,
                                                float* __restrict__ dw_ih, float* __restrict__ dw_hh, float* __restrict__ db) {
   const int nf = H + I + 1;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (int64_t)4 * H * nf) return;
   const int n = (int)(e / nf), f = (int)(e - (int64_t)n * nf);
-  const int mt = n >> 8, nt = f / kND, TT = MT * NT;
-  const float* p = partial + (((int64_t)(mt * NT + nt)) * 256 + (n & 255)) * kND + (f - nt * kND);
+  const int mt = n >> 8, nt = f / ND, TT = MT * NT;
+  const float* p = partial + (((int64_t)(mt * NT + nt)) * 256 + (n & 255)) * ND + (f - nt * ND);
   float acc = 0.f;
-  for (int q = 0; q < parts; ++q) acc += __ldg(p + (int64_t)q * TT * 256 * kND);
+  for (int q = 0; q < parts; ++q) acc += __ldg(p + (int64_t)q * TT * 256 * ND);
   if (f < H) dw_hh[(int64_t)n * H + f] = acc;
   else if (f < H + I) dw_ih[(int64_t)n * I + (f - H)] = acc;
   else db[n] = acc;
 }
 
-static void rm_tc_shape(int64_t H, int64_t I, int& MT, int& NT, int& parts) {
+static void rm_tc_shape(int64_t H, int64_t I, int& MT, int& NT, int& NB, int& parts) {
   MT = (int)(4 * H / 256);
-  NT = (int)cdiv(H + I + 1, (int64_t)kND);
+  const int64_t blocks = cdiv(H + I + 1, (int64_t)32);
+  NB = cdiv(blocks, (int64_t)4) < cdiv(blocks, (int64_t)3) ? 4 : 3;
+  NT = (int)cdiv(blocks, (int64_t)NB);
   parts = std::max(1, sm_count() / (MT * NT));
 }
 
 bool lstm_wgrad_rm_tc_supported(int64_t H) { return H == 128 || H == 256; }
 
 int64_t lstm_wgrad_rm_tc_workspace(int64_t H, int64_t I) {
-  int MT, NT, parts;
-  rm_tc_shape(H, I, MT, NT, parts);
-  return sizeof(float) * (int64_t)parts * MT * NT * 256 * kND;
+  int MT, NT, NB, parts;
+  rm_tc_shape(H, I, MT, NT, NB, parts);
+  return sizeof(float) * (int64_t)parts * MT * NT * 256 * 32 * NB;
 }
 
 int lstm_wgrad_rm_tc(const float* dG, const float* h_seq, const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H,
@@ -287,12 +288,13 @@ int lstm_wgrad_rm_tc(const float* dG, const float* h_seq, const float* xT, int64
   Args a{};
   a.dG = dG; a.h = h_seq; a.x = xT; a.partial = reinterpret_cast<float*>(ws);
   a.T = T; a.B = B; a.G = cdiv(B, (int64_t)32); a.H = (int)H; a.I = (int)I; a.IP = (int)IP;
-  rm_tc_shape(H, I, a.MT, a.NT, a.parts);
-  const size_t smem = (size_t)kStages * kStageBytes + kABytes + 2 * kBBytes + 128 + 1024;
+  rm_tc_shape(H, I, a.MT, a.NT, a.NB, a.parts);
+  const size_t bbytes = (size_t)a.NB * kBlk;
+  const size_t smem = (size_t)kStages * (kABytes + bbytes) + kABytes + 2 * bbytes + 128 + 1024;
   cudaFuncSetAttribute(lstm_wgrad_rm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   lstm_wgrad_rm_tc_kernel<<<a.MT * a.NT * a.parts, kThreads, smem, s>>>(a);
   const int64_t n_out = 4 * H * (H + I + 1);
-  lstm_wgrad_rm_tc_finish_kernel<<<(unsigned)cdiv(n_out, (int64_t)256), 256, 0, s>>>(a.partial, a.parts, a.MT, a.NT, (int)H, (int)I,
+  lstm_wgrad_rm_tc_finish_kernel<<<(unsigned)cdiv(n_out, (int64_t)256), 256, 0, s>>>(a.partial, a.parts, a.MT, a.NT, 32 * a.NB, (int)H, (int)I,
                                                                                  dw_ih, dw_hh, db);
   HY_LAUNCH_CHECK();
   return HY2DL_OK;
