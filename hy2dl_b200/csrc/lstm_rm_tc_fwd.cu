@@ -14,7 +14,7 @@
 //     are single buffered: the row threads pull their 64 sums into registers first and release the pair before they
 //     start on the activations;
 //   * keeps no recurrent state in registers: the row thread re-reads c_{t-1} and, at the end of the step, its own
-//     h_t values from the tape it has just written (L2 hits) to rebuild A for the next step.  A row is owned by
+//     h_t values from a two-slot scratch it has just written (L2 hits) to rebuild A for the next step.  A row is owned by
 //     two threads (TMEM lane = row; the two warps of a lane quarter split every chunk's 32 units 16 | 16), and a
 //     thread only ever re-reads what it wrote itself, so no CTA-wide synchronisation is needed inside a step.
 // Timing experiments on the first complete version (H = 256, B = 256, 30.8 ms): without tape stores 20.7 ms (they
@@ -49,8 +49,8 @@ struct FwdArgs {
   const float* wpk;     // packed weights [H/32 chunks][K/8 steps][hi [2][128][4] | lo [2][128][4]]
   float* h_seq;         // [T][B][H] row-major API output, or null
   float* h_own;         // RB8 [2 slots][ceil(B/32)*32][H]: h of the last two steps, what the row threads re-read
-  float* c_seq;
-  float* gates;         // [T][B][4H] or null
+  float* c_seq;         // RB8 tape [T][..][H], or two slots of scratch (c_pingpong)
+  float* gates;         // RB8 tape, F = 4H, or null
   float* h_last;        // [B][H] or null
   int64_t B, T;
   int H, I, IP, KX, K;  // KX = x columns incl. the ones column, rounded to 8; K = KX + H
