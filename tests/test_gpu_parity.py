@@ -574,6 +574,41 @@ def test_second_backward_raises(dev, precision):
         loss.backward()
 
 
+def test_cuda_core_fallback_for_large_hidden_sizes(dev):
+    """HY2DL_FP32_TC=0 switches H = 128 / 256 back to the CUDA-core kernels with row-major tapes.  The switch is read once
+    per process, so the check runs in a child process: same oracle comparison as test_lstm_vs_oracle (rtol 1e-4)."""
+    import os
+    import subprocess
+    import sys
+    code = """
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np, torch
+from _util import O, tt, assert_close
+from hy2dl_b200.modelzoo import LSTM
+from hy2dl_b200.synthetic import lstm_weights
+dev = torch.device("cuda:0")
+for B, T, I, H in ((37, 40, 31, 256), (5, 33, 7, 128)):
+    rng = np.random.default_rng(B + T)
+    x = rng.normal(0, 1, (B, T, I)).astype(np.float32); gh = rng.normal(0, 1, (B, T, H)).astype(np.float32)
+    w = lstm_weights(I, H, 1, seed=9)
+    lstm = LSTM(I, H, precision="fp32").to(dev)
+    lstm.load_state_dict({k[5:]: torch.tensor(v) for k, v in w.items() if k.startswith("lstm.")})
+    out, _ = lstm(torch.tensor(x, device=dev))
+    (out * torch.tensor(gh, device=dev)).sum().backward()
+    wd = {k: tt(v, torch.float64, True) for k, v in w.items() if k.startswith("lstm.")}
+    ref = O.lstm_cell_sequence(tt(x, torch.float64), wd["lstm.weight_ih_l0"], wd["lstm.weight_hh_l0"], wd["lstm.bias_ih_l0"], wd["lstm.bias_hh_l0"])
+    (ref * tt(gh, torch.float64)).sum().backward()
+    assert_close(out.detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-4, atol=1e-6, what="h_seq")
+    for k, p in lstm.named_parameters():
+        assert_close(p.grad.cpu().numpy(), wd["lstm." + k].grad.numpy(), rtol=1e-4, atol=1e-6, what="grad " + k)
+print("fallback ok")
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, HY2DL_FP32_TC="0")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "fallback ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_cpu_tensor_raises(dev):
     from hy2dl_b200.modelzoo import CudaLSTM
     model = CudaLSTM({"input_size_lstm": 8, "hidden_size": 64, "no_of_layers": 1, "drop_out_rate": 0.0})
