@@ -213,3 +213,21 @@ def test_default_precision_resolution():
     assert CudaLSTM(hp).lstm.precision == "tf32x3" and CudaLSTM({**hp, "precision": "fp32"}).lstm.precision == "fp32"
     with pytest.raises(ValueError):
         LSTM(25, 64, precision="fp16")
+
+
+def test_bench_contract_constants():
+    """bench.py measures BASELINE.json's metric on configs[1]; its algorithmic-byte model is SURVEY.md section 8(d)'s
+    (C2: about 1.230 MB per sequence, LSTM part 4 T (2 I + 12 H) = 1.194 MB) and every C-ABI call it times has bytes."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    assert bench.METRIC.split(" at ")[0] in base["metric"]
+    ab = bench.algo_bytes()
+    assert 4 * 365 * (2 * 25 + 12 * 64) == 1_194_280
+    assert abs(ab["total"] - 1.230e6) < 0.01e6
+    assert ab["hy2dl_lstm_fwd"] + ab["hy2dl_lstm_bwd"] + ab["hy2dl_lstm_wgrad"] == 1_194_280
+    hp = bench.hyper()
+    assert hp["hidden_size"] == 64 and hp["seq_length"] == 365 and hp["predict_last_n"] == 182
