@@ -23,8 +23,8 @@ for prec, name in (((_lib.PREC_FP32, "fp32"), (_lib.PREC_TF32X3, "tf32x3")) if H
     ri = prec == _lib.PREC_TF32X3
     x_in = ops.pack_x(cu(x), "ri32" if ri else "rowmajor")
     IPx = 32 if ri else (I + 7) // 8 * 8
-    Bp = G * 32 if ri else B
-    h = torch.zeros(T, Bp, H, device=dev); c = torch.zeros(T, Bp, H, device=dev); g = torch.zeros(T, Bp, 4 * H, device=dev)
+    Bp = G * 32 if (ri or H >= 128) else B       # RI32 / RB8 tapes hold whole groups of 32 sequences
+    h = torch.zeros(T, Bp if ri else B, H, device=dev); c = torch.zeros(T, Bp, H, device=dev); g = torch.zeros(T, Bp, 4 * H, device=dev)
     hl = torch.zeros(B, H, device=dev)
     ws = ops._ws(_lib.WS_LSTM_FWD, B, T, I, H, dev, prec)
     _lib.call("hy2dl_lstm_fwd", x_in.data_ptr(), B, T, I, IPx, H, *[t.data_ptr() for t in wd], h.data_ptr(), c.data_ptr(),
@@ -33,6 +33,8 @@ for prec, name in (((_lib.PREC_FP32, "fp32"), (_lib.PREC_TF32X3, "tf32x3")) if H
     if ri:
         h = ops.from_ri32(h.view(T, G, H // 32, 32, 32), B)
         g = ops.from_ri32(g.view(T, G, 4 * H // 32, 32, 32), B).reshape(T, B, H, 4).permute(0, 1, 3, 2).reshape(T, B, 4 * H)
+    if not ri and H >= 128:      # RB8 [T][G][4H/8][32][8] -> row-major [T][B][4H]
+        g = g.view(T, G, 4 * H // 8, 32, 8).permute(0, 1, 3, 2, 4).reshape(T, G * 32, 4 * H)[:, :B]
     h0 = h[0].cpu().double().numpy(); g1 = g[1].cpu().double().numpy()
     z_ref = x[:, 1].astype(np.float64) @ W_ih.T + h0 @ W_hh.T + b
     z_k = np.empty_like(z_ref)
