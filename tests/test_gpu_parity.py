@@ -288,6 +288,34 @@ def test_lstm_vs_oracle(dev, B, T, I, H, precision):
         assert_close(npy(p.grad), wd["lstm." + k].grad.numpy(), what="grad " + k, **TOL)
 
 
+def test_large_hidden_chain_random_shapes(dev):
+    """Twelve seeded random (H, input size, batch, length) combinations of the H = 128 / 256 tensor-core chain against
+    the fp64 oracle: every input width 1..64 class (ones column position, K padding), ragged 32-sequence groups and
+    128-row tiles, gradient through the whole sequence and optionally through h_n.  rtol 1e-4."""
+    from hy2dl_b200.modelzoo import LSTM
+    from hy2dl_b200.synthetic import lstm_weights
+    pick = np.random.default_rng(7)
+    for case in range(12):
+        H = int(pick.choice([128, 256])); I = int(pick.integers(1, 65)); B = int(pick.integers(1, 300)); T = int(pick.integers(1, 40))
+        want_last = bool(pick.integers(0, 2))
+        rng = np.random.default_rng(case)
+        x = rng.normal(0, 1, (B, T, I)).astype(np.float32)
+        gh = rng.normal(0, 1, (B, T, H)).astype(np.float32)
+        w = lstm_weights(I, H, 1, seed=case)
+        lstm = LSTM(I, H, precision="fp32").to(dev)
+        lstm.load_state_dict({k[5:]: torch.tensor(v) for k, v in w.items() if k.startswith("lstm.")})
+        out, (hn, _) = lstm(cu(x, dev))
+        ((out * cu(gh, dev)).sum() + (hn.sum() if want_last else 0)).backward()
+        wd = {k: tt(v, torch.float64, True) for k, v in w.items() if k.startswith("lstm.")}
+        ref = O.lstm_cell_sequence(tt(x, torch.float64), wd["lstm.weight_ih_l0"], wd["lstm.weight_hh_l0"],
+                                   wd["lstm.bias_ih_l0"], wd["lstm.bias_hh_l0"])
+        ((ref * tt(gh, torch.float64)).sum() + (ref[:, -1].sum() if want_last else 0)).backward()
+        tag = f"H={H} I={I} B={B} T={T}"
+        assert_close(npy(out), ref.detach().numpy(), what="h_seq " + tag, **TOL)
+        for k, p in lstm.named_parameters():
+            assert_close(npy(p.grad), wd["lstm." + k].grad.numpy(), what=f"grad {k} " + tag, **TOL)
+
+
 @pytest.mark.parametrize("model_key,B,T,n_last,H,m,dyn,precision", [
     ("shm", 64, 365, 182, 64, 1, ["dd", "f_thr", "sumax", "beta", "perc", "kf", "ki", "kb"], "fp32"),
     ("hbv", 9, 120, 50, 64, 16, ["BETA", "BETAET"], "fp32"),
