@@ -288,6 +288,50 @@ def test_lstm_vs_oracle(dev, B, T, I, H, precision):
         assert_close(npy(p.grad), wd["lstm." + k].grad.numpy(), what="grad " + k, **TOL)
 
 
+def test_hybrid_random_configurations(dev):
+    """Twelve seeded random hybrids (bucket model, members, which parameters are dynamic, routing on / off, batch,
+    lengths, input size; default precision, so fused and unfused heads both occur) against the fp64 oracle:
+    discharge and every parameter gradient, rtol 1e-4.  (32 such cases fuzzed offline: worst error 5.6e-6.)"""
+    from hy2dl_b200.aux_functions import nse_basin_averaged
+    from hy2dl_b200.modelzoo import HBV, SHM, Hybrid, NonSense, UH_routing, linear_reservoir
+    from hy2dl_b200.synthetic import lstm_weights, make_basins
+    models = {"shm": SHM, "hbv": HBV, "nonsense": NonSense, "linear_reservoir": linear_reservoir}
+    pick = np.random.default_rng(11)
+    for case in range(12):
+        key = str(pick.choice(list(models)))
+        cls = models[key]
+        m = 1 if key == "nonsense" else int(pick.integers(1, 5))
+        names = list(cls(n_models=1).parameter_ranges)
+        dyn = [n for n in names if pick.random() < 0.4]
+        routing = bool(pick.integers(0, 2))
+        B, T = int(pick.integers(1, 200)), int(pick.integers(6, 80))
+        n_last, I = int(pick.integers(2, T - 1)), int(pick.integers(3, 32))
+        data = make_basins("us" if key == "hbv" else "gb", n_basins=5, n_rows=T + 5, seed=case)
+        rng = np.random.default_rng(case)
+        xl = rng.normal(0, 1, (B, T, I)).astype(np.float32)
+        bi = rng.integers(0, 5, B)
+        xc = np.stack([data.x_conc[b, :T] for b in bi]).astype(np.float32)
+        yo = np.stack([data.y_obs[b, T - n_last:T] for b in bi]).astype(np.float32)
+        yo[0, 0, 0] = 1.0                                      # at least one valid target
+        sd = np.repeat(rng.uniform(0.5, 2.0, (B, 1, 1)).astype(np.float32), n_last, axis=1)
+        hp = {"input_size_lstm": I, "hidden_size": 64, "no_of_layers": 1, "seq_length": T, "predict_last_n": n_last,
+              "n_conceptual_models": m, "conceptual_dynamic_parameterization": dyn}
+        model = Hybrid(hp, conceptual_model=cls, routing_model=UH_routing if routing else None)
+        w = lstm_weights(I, 64, model.linear.out_features, seed=case + 100)
+        model.load_state_dict({k: torch.tensor(v) for k, v in w.items()})
+        model = model.to(dev)
+        pred = model(x_lstm=cu(xl, dev), x_conceptual=cu(xc, dev))
+        nse_basin_averaged(y_sim=pred["y_hat"], y_obs=cu(yo, dev), per_basin_target_std=cu(sd, dev)).backward()
+        wd = {k: tt(v, torch.float64, True) for k, v in w.items()}
+        ref = O.hybrid_forward(wd, tt(xl, torch.float64), tt(xc, torch.float64), model=key, n_models=m, dynamic=dyn,
+                               warmup=T - n_last, routing=routing)
+        O.nse_basin_averaged(ref["y_hat"], tt(yo, torch.float64), tt(sd, torch.float64)).backward()
+        tag = f"{key} m={m} dyn={dyn} routing={routing} B={B} T={T} n_last={n_last} I={I}"
+        assert_close(npy(pred["y_hat"]), ref["y_hat"].detach().numpy(), what="y_hat " + tag, **TOL)
+        for k, p in model.named_parameters():
+            assert_close(npy(p.grad), wd[k].grad.numpy(), what=f"grad {k} " + tag, rtol=1e-4, atol=1e-7)
+
+
 def test_large_hidden_chain_random_shapes(dev):
     """Twelve seeded random (H, input size, batch, length) combinations of the H = 128 / 256 tensor-core chain against
     the fp64 oracle: every input width 1..64 class (ones column position, K padding), ragged 32-sequence groups and
