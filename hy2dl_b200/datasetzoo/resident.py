@@ -76,8 +76,14 @@ class ResidentDataset:
     def __init__(self, x_d: np.ndarray, y_obs: np.ndarray, sequence_length: int, predict_last_n: int = 1,
                  x_s: Optional[np.ndarray] = None, x_conc: Optional[np.ndarray] = None, device="cuda",
                  check_nan: bool = True, basins: Optional[Sequence[int]] = None):
-        if basins is not None:  # data-parallel shard: this rank's basins only
-            basins = np.asarray(basins)
+        # Data-parallel shard (`basins` = this rank's basins): the windows and the resident series are the shard's,
+        # but the scaler is a GLOBAL statistic (basedataset.py:233-245 stacks every basin) -- every rank must
+        # standardise with the same numbers or N ranks no longer reproduce the single-process batch.  So the full
+        # arrays stay referenced for calculate_global_statistics() and only the shard is uploaded.
+        self._full = (x_d, x_s, y_obs)
+        self.basins = None if basins is None else np.asarray(basins)
+        if basins is not None:
+            basins = self.basins
             x_d, y_obs = x_d[basins], y_obs[basins]
             x_s = None if x_s is None else x_s[basins]
             x_conc = None if x_conc is None else x_conc[basins]
@@ -110,15 +116,74 @@ class ResidentDataset:
         self.basin_std = np.array([np.nanstd(self._y[b]) for b in range(self.nb)], dtype=np.float32)
 
     def calculate_global_statistics(self):
-        gx = self._x_d.reshape(-1, self.nd)
+        """Global mean / std over ALL basins handed to the constructor (not only this rank's shard)."""
+        full_x_d, full_x_s, full_y = self._full
+        gx = full_x_d.reshape(-1, self.nd)
         self.scaler["x_d_mean"] = np.nanmean(gx, axis=0).astype(np.float32)
         self.scaler["x_d_std"] = np.nanstd(gx, axis=0).astype(np.float32)
-        gy = self._y.reshape(-1, self._y.shape[2])
+        gy = full_y.reshape(-1, full_y.shape[2])
         self.scaler["y_mean"] = np.nanmean(gy, axis=0).astype(np.float32)
         self.scaler["y_std"] = np.nanstd(gy, axis=0).astype(np.float32)
-        if self._x_s is not None:
-            self.scaler["x_s_mean"] = self._x_s.mean(axis=0).astype(np.float32)
-            self.scaler["x_s_std"] = self._x_s.std(axis=0, ddof=1).astype(np.float32)
+        if full_x_s is not None:
+            self.scaler["x_s_mean"] = full_x_s.mean(axis=0).astype(np.float32)
+            self.scaler["x_s_std"] = full_x_s.std(axis=0, ddof=1).astype(np.float32)
+
+    def set_scaler(self, scaler: Dict[str, np.ndarray]):
+        """Use a scaler computed elsewhere (validation / test sets reuse the training scaler; a rank that was only
+        given its own shard's arrays receives the global one)."""
+        self.scaler = {k: np.asarray(v.numpy() if hasattr(v, "numpy") else v, dtype=np.float32) for k, v in scaler.items()}
+
+    # ---- the reference's dataset object as the source --------------------------------------------
+    @classmethod
+    def from_reference(cls, dataset, device="cuda", basins: Optional[Sequence[int]] = None) -> "ResidentDataset":
+        """Build the resident sampler from a constructed reference `BaseDataset` (any datasetzoo subclass;
+        datasetzoo/basedataset.py:56-163): the notebooks' dataset cell stays as it is and this is the one added line.
+
+        Takes the per-basin tensors `sequence_data[basin]["x_d" | "y_obs" | "x_conceptual" | "x_s"]` (:147-163) *in
+        the state they are in* -- call it after `calculate_basin_std()`, `calculate_global_statistics()` and
+        `standardize_data()` exactly as the notebooks do (LSTM_CAMELS_GB.ipynb: training-set cell) -- together with
+        the dataset's own `valid_entities` (so sample k here is `dataset[k]` there), `basin_std` and `scaler`, and
+        uploads them.  All basins of a BaseDataset share one date range (:129-131), so the series are rectangular.
+        `basins`: optional list of positions in `resident.basin_ids` to keep (data-parallel shard).
+        """
+        ids = [b for b in dataset.entities_ids if b in dataset.sequence_data]
+        if not ids:
+            raise ValueError("the reference dataset holds no basin with a valid sample")
+        if basins is not None:
+            ids = [ids[int(k)] for k in basins]
+        sd = dataset.sequence_data
+        npy = lambda t: t.detach().cpu().numpy().astype(np.float32)
+        x_d = np.stack([npy(sd[b]["x_d"]) for b in ids])
+        y = np.stack([npy(sd[b]["y_obs"]) for b in ids])
+        if y.shape[2] != 1:
+            raise NotImplementedError("hy2dl_b200 handles a single target variable, as every reference experiment does")
+        x_s = np.stack([npy(sd[b]["x_s"]) for b in ids]) if "x_s" in sd[ids[0]] else None
+        x_c = np.stack([npy(sd[b]["x_conceptual"]) for b in ids]) if "x_conceptual" in sd[ids[0]] else None
+        self = cls.__new__(cls)
+        self.sequence_length, self.predict_last_n = dataset.sequence_length, dataset.predict_last_n
+        self.nb, self.nr, self.nd = x_d.shape
+        self.ns = 0 if x_s is None else x_s.shape[1]
+        self.nc = 0 if x_c is None else x_c.shape[2]
+        self.input_size = self.nd + self.ns
+        self.IP = round_up(self.input_size, 8)
+        self.device = torch.device(device)
+        self._x_d, self._x_s, self._x_conc, self._y = x_d, x_s, x_c, y
+        self._full = (x_d, x_s, y)
+        self.basins = None
+        self.basin_ids = list(ids)
+        pos = {b: k for k, b in enumerate(ids)}
+        self.valid_entities = np.array([(pos[b], i) for b, i in dataset.valid_entities if b in pos],
+                                       dtype=np.int64).reshape(-1, 2)
+        self.scaler = {}
+        if dataset.scaler:
+            self.set_scaler(dataset.scaler)
+        self.basin_std = np.array([float(dataset.basin_std[b]) if b in dataset.basin_std else 0.0 for b in ids],
+                                  dtype=np.float32)
+        self._resident = False
+        self.layout = "rowmajor"
+        if self.device.type == "cuda":
+            self.to_device_raw()        # the tensors are already in the state the notebook left them in
+        return self
 
     def standardize_data(self, standardize_output: bool = True):
         """Standardise and move everything to the GPU (call once, after the statistics)."""

@@ -36,5 +36,5 @@ class CudaLSTM(nn.Module):
     def forward_native(self, xT: torch.Tensor, B: int = None):
         """xT: [T, B, IP] (or RI32 with B given) as written by the GPU-resident sampler."""
         _, h_last = self.lstm.run_native(xT, want_seq=False, B=B)
-        out = self.dropout(h_last)  # PyTorch's op on [B, H]: RNG semantics stay PyTorch's
+        out = self.dropout(h_last[:, :self.hidden_size])  # PyTorch's op on [B, H]: RNG semantics stay PyTorch's
         return {"y_hat": self.linear(out)}

@@ -90,11 +90,11 @@ class Hybrid(nn.Module):
         # LSTM over all T steps; only steps >= warmup receive gradient from the head
         if self.lstm.precision == "tf32x3" and self.linear.out_features <= ops.FUSED_HEAD_MAX_COLUMNS:
             # LSTM + head in one kernel: the hidden sequence is only written as the BPTT tape
-            par_sim, par_warm = ops.lstm_head(xT, *self.lstm.weights(), self.linear.weight, self.linear.bias,
-                                              self.input_size_lstm, layout)
+            par_sim, par_warm = ops.lstm_head(xT, *self.lstm.kernel_weights(), self.lstm.pad_head(self.linear.weight),
+                                              self.linear.bias, self.input_size_lstm, layout)
         else:
             h_seq, _ = self.lstm.run_native(xT, dh_t0=warmup, want_seq=True, B=B)
-            par_sim, par_warm = ops.head_map(h_seq, self.linear.weight, self.linear.bias, layout)
+            par_sim, par_warm = ops.head_map(h_seq, self.lstm.pad_head(self.linear.weight), self.linear.bias, layout)
 
         # warm-up: frozen parameters, no gradient (hybrid.py:99-102)
         with torch.no_grad():

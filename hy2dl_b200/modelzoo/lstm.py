@@ -30,13 +30,24 @@ class LSTM(nn.Module):
         if not batch_first:
             raise NotImplementedError("hy2dl_b200.LSTM is batch_first only, as the reference uses it")
         self.input_size, self.hidden_size, self.num_layers, self.batch_first = input_size, hidden_size, 1, True
+        # The reference takes any sizes (cudalstm.py:18-24).  The kernels are built for 64 / 128 / 256 hidden units:
+        # other sizes run zero-padded to the next of those (exact: a padded unit has z = 0 for every gate, hence
+        # i = f = o = 1/2, g = 0, c = h = 0 for all t, and feeds zero columns of W_hh), see kernel_weights().
+        if not (1 <= hidden_size <= 256):
+            raise ValueError(f"hy2dl_b200.LSTM: hidden_size must be in [1, 256] (got {hidden_size})")
+        if not (1 <= input_size <= 64):
+            raise ValueError(f"hy2dl_b200.LSTM: input_size must be in [1, 64] (got {input_size})")
+        self.kernel_hidden = 64 if hidden_size <= 64 else (128 if hidden_size <= 128 else 256)
         # "auto": the fastest kernels that meet the fp32 tolerances (rtol 1e-4) for this shape -- the tcgen05 path with
         # resident weights ("tf32x3": H = 64, input_size <= 31); otherwise "fp32", which is the streamed-weights tcgen05
         # chain for H = 128 / 256 and the CUDA-core kernels for H = 64 with wider inputs
         if precision == "auto":
-            precision = "tf32x3" if (hidden_size == 64 and input_size <= 31) else "fp32"
+            precision = "tf32x3" if (self.kernel_hidden == 64 and input_size <= 31) else "fp32"
         if precision not in ops.PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(ops.PRECISIONS)} or 'auto', got '{precision}'")
+        if precision == "tf32x3" and not (self.kernel_hidden == 64 and input_size <= 31):
+            raise ValueError("hy2dl_b200.LSTM: precision 'tf32x3' (weights resident on chip) takes hidden_size <= 64 and "
+                             f"input_size <= 31 (got {hidden_size}, {input_size}); use 'auto' or 'fp32'")
         self.precision = precision
         H = hidden_size
         self.weight_ih_l0 = nn.Parameter(torch.empty(4 * H, input_size))
@@ -53,6 +64,24 @@ class LSTM(nn.Module):
     def weights(self):
         return self.weight_ih_l0, self.weight_hh_l0, self.bias_ih_l0, self.bias_hh_l0
 
+    def kernel_weights(self):
+        """The four parameters at the kernels' hidden size HK = kernel_hidden: unit u of gate g sits at row
+        g*HK + u, padded rows / columns are zero.  Differentiable torch indexing on the (small) weights, so the
+        gradients of the padded tensors flow back to the real parameters."""
+        H, HK = self.hidden_size, self.kernel_hidden
+        if H == HK:
+            return self.weights()
+        w_ih, w_hh, b_ih, b_hh = self.weights()
+        pad_rows = lambda w: torch.nn.functional.pad(w.view(4, H, -1), (0, 0, 0, HK - H)).reshape(4 * HK, -1)
+        w_ih_p = pad_rows(w_ih)
+        w_hh_p = torch.nn.functional.pad(pad_rows(w_hh), (0, HK - H))
+        return w_ih_p, w_hh_p, pad_rows(b_ih.view(-1, 1)).view(-1), pad_rows(b_hh.view(-1, 1)).view(-1)
+
+    def pad_head(self, w_head: torch.Tensor) -> torch.Tensor:
+        """A Linear(H, C) weight [C, H] at the kernels' hidden size [C, HK] (zero columns for the padded units)."""
+        H, HK = self.hidden_size, self.kernel_hidden
+        return w_head if H == HK else torch.nn.functional.pad(w_head, (0, HK - H))
+
     @property
     def layout(self) -> str:
         """Layout of the native streams this module reads and writes ("rowmajor" | "ri32")."""
@@ -61,21 +90,29 @@ class LSTM(nn.Module):
     def run_native(self, xT: torch.Tensor, dh_t0: int = 0, want_seq: bool = True, B: Optional[int] = None):
         """xT: native input ([T,B,IP], or RI32 for precision tf32x3 with B given) ->
         (h_seq in the same layout or empty, h_last [B,H])."""
-        return ops.lstm(xT, *self.weights(), self.input_size, dh_t0, want_seq, self.precision, B)
+        h_seq, h_last = ops.lstm(xT, *self.kernel_weights(), self.input_size, dh_t0, want_seq, self.precision, B)
+        return h_seq, h_last
 
     def forward(self, x: torch.Tensor, hx: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
         """nn.LSTM-compatible call: x [B,T,I] -> (out [B,T,H], (h_n [1,B,H], c_n=None)).
 
-        The initial state is zero, which is the only way the reference ever calls it
-        (cudalstm.py:43-50); `hx` is accepted for signature compatibility and not read.
+        The initial state is zero, which is the only way the reference ever calls it (cudalstm.py:43-50,
+        hybrid.py:84-92: explicit zero tensors).  `hx` may therefore be None or all-zero tensors; anything else
+        raises instead of being silently ignored.  c_n is not produced by the kernels (no reference caller reads it).
         """
         if x.dim() != 3 or x.shape[2] != self.input_size:
             raise ValueError(f"expected x of shape [B, T, {self.input_size}], got {tuple(x.shape)}")
-        B = x.shape[0]
+        if hx is not None:
+            if not (isinstance(hx, (tuple, list)) and len(hx) == 2):
+                raise ValueError("hx must be a (h_0, c_0) pair")
+            if any(bool(t.detach().ne(0).any()) for t in hx):
+                raise NotImplementedError("hy2dl_b200.LSTM starts from h_0 = c_0 = 0 (as every reference model does); "
+                                          "a non-zero initial state is not supported")
+        B, H = x.shape[0], self.hidden_size
         h_seq, h_last = self.run_native(ops.pack_x(x, self.layout), B=B)
         if ops.is_ri32(h_seq):
             h_seq = ops.from_ri32(h_seq, B)
-        return h_seq.permute(1, 0, 2), (h_last.unsqueeze(0), None)
+        return h_seq[:, :, :H].permute(1, 0, 2), (h_last[:, :H].unsqueeze(0), None)
 
     def extra_repr(self) -> str:
         return f"{self.input_size}, {self.hidden_size}, batch_first=True, precision={self.precision}"

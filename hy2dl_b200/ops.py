@@ -16,7 +16,7 @@ import torch
 from . import _lib
 from ._lib import ParMap, call, ptr, require_cuda, stream
 
-PRECISIONS = {"fp32": _lib.PREC_FP32, "tf32x3": _lib.PREC_TF32X3, "bf16": _lib.PREC_BF16}
+PRECISIONS = {"fp32": _lib.PREC_FP32, "tf32x3": _lib.PREC_TF32X3}
 
 
 def round_up(a: int, b: int) -> int:
@@ -138,6 +138,7 @@ class LstmFunction(torch.autograd.Function):
             T, B, IP = xT.shape
             seq = lambda F: torch.empty(T, B, F, dtype=torch.float32, device=dev)
         need_grad = any(ctx.needs_input_grad[1:5])
+        ctx.set_materialize_grads(False)     # an unused output (h_seq or h_last) arrives as None, not as a zero tensor
         w_ih, w_hh, b_ih, b_hh = (t.detach().contiguous() for t in (w_ih, w_hh, b_ih, b_hh))
         h_seq = seq(H) if (want_seq or need_grad) else None
         h_last = torch.empty(B, H, dtype=torch.float32, device=dev)
@@ -265,10 +266,13 @@ class HeadMapFunction(torch.autograd.Function):
         ctx.save_for_backward(h_seq, w_c, par_sim)
         ctx.layout = layout
         ctx.mark_non_differentiable(par_warm)
+        ctx.set_materialize_grads(False)
         return par_sim, par_warm
 
     @staticmethod
     def backward(ctx, dpar_sim, _dpar_warm):
+        if dpar_sim is None:
+            return None, None, None, None
         h_seq, w, par_sim = ctx.saved_tensors
         layout = ctx.layout
         T, B, H = h_seq.shape[0], layout.B, w.shape[1]
@@ -320,10 +324,13 @@ class LstmHeadFunction(torch.autograd.Function):
         ctx.meta = (B, T, I, IP, H, precision)
         ctx.layout = layout
         ctx.mark_non_differentiable(par_warm)
+        ctx.set_materialize_grads(False)
         return par_sim, par_warm
 
     @staticmethod
     def backward(ctx, dpar_sim, _dpar_warm):
+        if dpar_sim is None:
+            return (None,) * 9
         xT, w_hh, w_head, h_seq, c_seq, gates, par_sim = ctx.saved_tensors
         B, T, I, IP, H, precision = ctx.meta
         layout, dev = ctx.layout, xT.device
@@ -402,6 +409,9 @@ class ConceptualFunction(torch.autograd.Function):
         call("hy2dl_conceptual_fwd", model, ptr(forc), B, t0, Tn, m, _ptr_array(ptrs), _i64_array(ts), ptr(init),
              ptr(states), ptr(q), stream())
         ctx.save_for_backward(forc, par_flat, init, states)
+        # the hybrid never differentiates the storages: without this, autograd hands the adjoint kernel a zero-filled
+        # [Tn,5,N] tensor (17 M floats at the benchmark batch: one fill launch plus five extra plane reads per step)
+        ctx.set_materialize_grads(False)
         ctx.meta = (model, B, m, t0, Tn, tuple(offs), tuple(dynamic), routing_span)
         routing = None
         if routing_span is not None:
@@ -412,6 +422,8 @@ class ConceptualFunction(torch.autograd.Function):
     def backward(ctx, dstates, dq, drouting):
         forc, par_flat, init, states = ctx.saved_tensors
         model, B, m, t0, Tn, offs, dynamic, routing_span = ctx.meta
+        if dstates is None and dq is None and drouting is None:
+            return (None,) * 11
         dev = forc.device
         N = B * m
         base = par_flat.data_ptr()

@@ -163,11 +163,25 @@ class Trainer:
         n_batches = n // batch_size
         if max_updates is not None:
             n_batches = min(n_batches, max_updates)
+        n_batches = common_step_count(n_batches, self.group, self.dataset.device)
         total = torch.zeros((), dtype=torch.float32, device=self.dataset.device)
         self.model.train()
         for i in range(n_batches):
             total += self.step(order[i * batch_size:(i + 1) * batch_size])
         return total / max(n_batches, 1)
+
+
+def common_step_count(n_local: int, group, device) -> int:
+    """Every step issues collectives (loss partial sums, flat gradient), so all ranks of a data-parallel group must
+    run the SAME number of steps.  Ranks own different basins and NaN filtering leaves them different window counts:
+    the epoch length is the minimum over the group (drop-last on the shortest shard).  One small
+    all-reduce per epoch; group=None: single process, nothing to do."""
+    if group is None:
+        return n_local
+    import torch.distributed as dist
+    t = torch.tensor([n_local], dtype=torch.int64, device=device if dist.get_backend() == "nccl" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=None if group == "world" else group)
+    return int(t.item())
 
 
 def shard_basins(n_basins: int, rank: int, world: int):

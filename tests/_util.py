@@ -22,8 +22,21 @@ def golden(name):
 
 DIRECT_CASES = ["shm_direct", "shm_direct_static4", "hbv_direct", "hbv_direct_nobetaet", "linres_direct",
                 "linres_direct_static", "nonsense_direct", "nonsense_direct_static"]
-HYBRID_CASES = ["hybrid_shm_c2", "hybrid_shm_mixed", "hybrid_hbv_c4", "hybrid_hbv_norouting", "hybrid_nonsense",
-                "hybrid_linres"]
+HYBRID_CASES = ["hybrid_shm_c2", "hybrid_shm_mixed", "hybrid_hbv_h64", "hybrid_hbv_norouting", "hybrid_nonsense",
+                "hybrid_linres", "hybrid_hbv_c4", "hybrid_hbv_c4_t730"]
+CUDALSTM_CASES = ["cudalstm_c1", "cudalstm_c3", "cudalstm_c3_full", "cudalstm_c3_h128", "cudalstm_c3_trained",
+                  "cudalstm_h100"]
+
+
+def cudalstm_weights_np(g):
+    """numpy state dict of a cudalstm_* golden file (meta = B, T, I, H, wseed[, trained])."""
+    meta = [int(v) for v in g["meta"]]
+    B, T, I, H, wseed = meta[:5]
+    w = lstm_weights(I, H, 1, seed=wseed)
+    if len(meta) > 5 and meta[5]:            # "trained-like" weights: make_golden.trained_like
+        for k in ("lstm.weight_ih_l0", "lstm.weight_hh_l0"):
+            w[k] = (w[k] * 1.5).astype(np.float32)
+    return w
 
 
 def bucket_of(name):
@@ -65,12 +78,42 @@ def rel_err(a, b):
     return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-30))
 
 
+# Every comparison is also recorded element-wise (tests/conftest.py writes the list to
+# gpurun_out/parity_report.json at the end of the session): `frac_outside` is the share of elements with
+# |a-b| > rtol*|b| + 1e-6*max|b|, i.e. outside numpy.allclose(rtol, atol = 1e-6 * scale) -- the figure a
+# tensor-level bound hides for small-magnitude elements (low flows, tiny gradients).
+PARITY_LOG = []
+_current_test = [""]
+# hard element-wise gate on top of the tensor-level one: at most this share of the elements may be outside
+# |a-b| <= 10*rtol*|b| + 1e-5*max|b|  (a value that is 1e-5 of the tensor's scale is below the fp32 noise of
+# the reference's own recurrence; see test_oracle_golden's fp32-vs-fp64 spread)
+ELEMENTWISE_MAX_FRAC = 1e-3
+
+
 def assert_close(a, b, rtol, atol=0.0, what=""):
-    """max |a-b| <= atol + rtol * max|b|  (tensor-level relative tolerance; stated in each test)."""
+    """max |a-b| <= atol + rtol * max|b|  (tensor-level relative tolerance; stated in each test),
+    plus the element-wise gate above; both figures are logged."""
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    if isinstance(b, torch.Tensor):
+        b = b.detach().cpu().numpy()
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
     assert np.isnan(a).sum() == np.isnan(b).sum(), f"{what}: NaN pattern differs"
-    err = np.nanmax(np.abs(a - b)) if a.size else 0.0
-    lim = atol + rtol * (np.nanmax(np.abs(b)) if b.size else 0.0)
-    assert err <= lim, f"{what}: max abs err {err:.3e} > {lim:.3e} (rtol {rtol}, scale {np.nanmax(np.abs(b)):.3e})"
+    if not a.size:
+        return
+    scale = np.nanmax(np.abs(b))
+    d = np.abs(a - b)
+    err = np.nanmax(d)
+    lim = atol + rtol * scale
+    ok = ~np.isnan(d)
+    n = max(int(ok.sum()), 1)
+    frac_outside = float((d[ok] > rtol * np.abs(b[ok]) + 1e-6 * scale).sum()) / n
+    frac_gate = float((d[ok] > 10 * rtol * np.abs(b[ok]) + 1e-5 * scale + atol).sum()) / n
+    PARITY_LOG.append({"test": _current_test[0], "what": what, "n": int(a.size), "rtol": rtol, "scale": float(scale),
+                       "max_err_over_scale": float(err / (scale + 1e-300)), "frac_outside_elementwise": frac_outside,
+                       "frac_outside_gate": frac_gate})
+    assert err <= lim, f"{what}: max abs err {err:.3e} > {lim:.3e} (rtol {rtol}, scale {scale:.3e})"
+    assert frac_gate <= ELEMENTWISE_MAX_FRAC, (f"{what}: {frac_gate:.2e} of the elements are outside "
+                                               f"|a-b| <= {10 * rtol:g}|b| + 1e-5*scale")

@@ -17,3 +17,32 @@ def cuda_lib():
     """The C-ABI library, loaded; GPU tests fail loudly if it is missing."""
     from hy2dl_b200 import _lib
     return _lib.load()
+
+
+@pytest.fixture(autouse=True)
+def _name_parity_records(request):
+    import _util
+    _util._current_test[0] = request.node.nodeid
+    yield
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Element-wise parity figures of every comparison made in this session (tests/_util.assert_close)."""
+    try:
+        import json
+        import _util
+        if not _util.PARITY_LOG:
+            return
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        gpu = any("gpu" in (r["test"] or "") for r in _util.PARITY_LOG)
+        worst = sorted(_util.PARITY_LOG, key=lambda r: -r["frac_outside_elementwise"])[:40]
+        summary = {"comparisons": len(_util.PARITY_LOG),
+                   "with_any_element_outside_allclose": sum(r["frac_outside_elementwise"] > 0 for r in _util.PARITY_LOG),
+                   "worst_frac_outside_elementwise": worst[0]["frac_outside_elementwise"],
+                   "worst_max_err_over_scale": max(r["max_err_over_scale"] for r in _util.PARITY_LOG),
+                   "worst": worst}
+        with open(os.path.join(out, "parity_report_gpu.json" if gpu else "parity_report_cpu.json"), "w") as f:
+            json.dump(summary, f, indent=1)
+    except Exception as e:  # a report must never fail the suite
+        print("parity report not written:", e)

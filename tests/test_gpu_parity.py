@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from _util import DIRECT_CASES, O, PARAM_KEYS, assert_close, bucket_of, golden, oracle_hybrid, tt, weights
+from _util import DIRECT_CASES, O, PARAM_KEYS, cudalstm_weights_np, assert_close, bucket_of, golden, oracle_hybrid, tt, weights
 
 pytestmark = pytest.mark.gpu
 
@@ -153,14 +153,20 @@ def test_sampler_gather(dev):
 # ------------------------------------------------------------------------------------------------
 # model-level cases against the reference's golden vectors
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name,precision", [("cudalstm_c1", "fp32"), ("cudalstm_c3", "fp32"), ("cudalstm_c1", "tf32x3")])
+@pytest.mark.parametrize("name,precision", [
+    ("cudalstm_c1", "fp32"), ("cudalstm_c3", "fp32"), ("cudalstm_c1", "tf32x3"),
+    # BASELINE configs[2] at its real shape (T = 365, H = 256 and the notebook's own H = 128), full gradients;
+    # the same with trained-like weights (recurrent and input matrices x 3, forget-gate bias 3); an arbitrary
+    # hidden size (H = 100: zero-padded to 128 at weight-pack time)
+    ("cudalstm_c3_full", "auto"), ("cudalstm_c3_h128", "auto"), ("cudalstm_c3_trained", "auto"), ("cudalstm_h100", "auto")])
 def test_cudalstm_golden(dev, name, precision):
     from hy2dl_b200.aux_functions import nse_basin_averaged
     from hy2dl_b200.modelzoo import CudaLSTM
     g = golden(name)
-    B, T, I, H, wseed = [int(v) for v in g["meta"]]
-    model = load(CudaLSTM({"input_size_lstm": I, "hidden_size": H, "no_of_layers": 1, "drop_out_rate": 0.0,
-                           "precision": precision}), I, H, 1, wseed, dev)
+    B, T, I, H, wseed = [int(v) for v in g["meta"]][:5]
+    model = CudaLSTM({"input_size_lstm": I, "hidden_size": H, "no_of_layers": 1, "drop_out_rate": 0.0, "precision": precision})
+    model.load_state_dict({k: torch.tensor(v) for k, v in cudalstm_weights_np(g).items()})
+    model = model.to(dev)
     y = model(cu(g["x_lstm"], dev))["y_hat"]
     loss = nse_basin_averaged(y_sim=y, y_obs=cu(g["y_obs"], dev), per_basin_target_std=cu(g["basin_std"], dev))
     loss.backward()
@@ -179,7 +185,7 @@ def test_cudalstm_h256_inference_without_tapes(dev):
     two steps of h and c in its workspace; same y_hat as the reference (golden C3)."""
     from hy2dl_b200.modelzoo import CudaLSTM
     g = golden("cudalstm_c3")
-    B, T, I, H, wseed = [int(v) for v in g["meta"]]
+    B, T, I, H, wseed = [int(v) for v in g["meta"]][:5]
     model = load(CudaLSTM({"input_size_lstm": I, "hidden_size": H, "no_of_layers": 1, "drop_out_rate": 0.0}), I, H, 1, wseed, dev).eval()
     with torch.no_grad():
         y = model(cu(g["x_lstm"], dev))["y_hat"]
@@ -197,7 +203,10 @@ def build_hybrid(g, dev, precision="fp32"):
     return load(model, I, H, model.linear.out_features, wseed, dev)
 
 
-@pytest.mark.parametrize("name,precision", [("hybrid_shm_c2", "fp32"), ("hybrid_shm_mixed", "fp32"), ("hybrid_hbv_c4", "fp32"),
+@pytest.mark.parametrize("name,precision", [("hybrid_shm_c2", "fp32"), ("hybrid_shm_mixed", "fp32"), ("hybrid_hbv_h64", "fp32"),
+                                            # BASELINE configs[3] at its real shape: H = 256, I = 41, HBV x 16 + UH (210 head
+                                            # columns), weighted_rmse; T = 365 (183/182) and the notebook's 730 (365/365)
+                                            ("hybrid_hbv_c4", "auto"), ("hybrid_hbv_c4_t730", "auto"),
                                             ("hybrid_hbv_norouting", "fp32"), ("hybrid_shm_c2", "tf32x3"),
                                             ("hybrid_shm_mixed", "tf32x3"), ("hybrid_nonsense", "fp32"),
                                             ("hybrid_nonsense", "tf32x3"), ("hybrid_linres", "fp32"),
@@ -286,6 +295,39 @@ def test_lstm_vs_oracle(dev, B, T, I, H, precision):
     assert_close(npy(hn[0]), ref[:, -1].detach().numpy(), what="h_n", **TOL)
     for k, p in lstm.named_parameters():
         assert_close(npy(p.grad), wd["lstm." + k].grad.numpy(), what="grad " + k, **TOL)
+
+
+@pytest.mark.parametrize("B,T,I,H,wscale", [
+    (256, 365, 31, 256, 1.0),      # BASELINE configs[2]: the reference batch at the real sequence length
+    (256, 365, 31, 128, 1.0),      # the notebook's own hidden size (LSTM_CAMELS_US.ipynb:127-142)
+    (64, 730, 41, 256, 1.0),       # configs[3]'s LSTM at the notebook-native 730 steps
+    (48, 365, 31, 256, 1.5),       # trained-like weights (make_golden.trained_like: matrices x 1.5, forget bias 3)
+    (48, 365, 25, 64, 1.5),        # the same on the resident-weights H = 64 path
+    (40, 120, 20, 100, 1.0),       # arbitrary hidden size: zero-padded to 128 at weight-pack time
+    (40, 120, 20, 40, 1.0),        # ... and to 64
+])
+def test_lstm_real_shapes_vs_oracle(dev, B, T, I, H, wscale):
+    """The recurrent chain at the BASELINE shapes against the fp64 oracle: hidden sequence and every parameter
+    gradient at rtol 1e-4 (tensor level) with the element-wise figures recorded (tests/_util.assert_close)."""
+    from hy2dl_b200.modelzoo import LSTM
+    from hy2dl_b200.synthetic import lstm_weights
+    rng = np.random.default_rng(B + T + H)
+    x = rng.normal(0, 1, (B, T, I)).astype(np.float32)
+    gh = (rng.normal(0, 1, (B, T, H)) * (rng.random((B, T, 1)) < 0.5)).astype(np.float32)   # half of the steps feed a gradient
+    w = {k[5:]: v for k, v in lstm_weights(I, H, 1, seed=H + I).items() if k.startswith("lstm.")}
+    for k in ("weight_ih_l0", "weight_hh_l0"):
+        w[k] = (w[k] * wscale).astype(np.float32)
+    lstm = LSTM(I, H).to(dev)                                   # default precision: what a user gets
+    lstm.load_state_dict({k: torch.tensor(v) for k, v in w.items()})
+    out, (hn, _) = lstm(cu(x, dev))
+    assert out.shape == (B, T, H) and hn.shape == (1, B, H)
+    (out * cu(gh, dev)).sum().backward()
+    wd = {k: tt(v, torch.float64, True) for k, v in w.items()}
+    ref = O.lstm_cell_sequence(tt(x, torch.float64), wd["weight_ih_l0"], wd["weight_hh_l0"], wd["bias_ih_l0"], wd["bias_hh_l0"])
+    (ref * tt(gh, torch.float64)).sum().backward()
+    assert_close(npy(out), ref.detach().numpy(), what="h_seq", **TOL)
+    for k, p in lstm.named_parameters():
+        assert_close(npy(p.grad), wd[k].grad.numpy(), what="grad " + k, **TOL)
 
 
 def test_hybrid_random_configurations(dev):

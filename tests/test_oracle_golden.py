@@ -8,18 +8,21 @@ import numpy as np
 import pytest
 import torch
 
-from _util import DIRECT_CASES, HYBRID_CASES, O, PARAM_KEYS, assert_close, bucket_of, golden, oracle_hybrid, tt, weights
+from _util import CUDALSTM_CASES, DIRECT_CASES, HYBRID_CASES, O, cudalstm_weights_np, PARAM_KEYS, assert_close, bucket_of, golden, oracle_hybrid, tt, weights
 
 F32 = dict(rtol=2e-5, atol=1e-7)
 F64 = dict(rtol=3e-4, atol=1e-6)
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, F32), (torch.float64, F64)])
-@pytest.mark.parametrize("name", ["cudalstm_c1", "cudalstm_c3"])
+@pytest.mark.parametrize("name", CUDALSTM_CASES)
 def test_cudalstm(name, dtype, tol):
     g = golden(name)
-    B, T, I, H, wseed = [int(v) for v in g["meta"]]
-    w = weights(I, H, 1, wseed, dtype)
+    if name == "cudalstm_c3_trained":
+        # trained-like weights amplify rounding errors: two fp32 implementations (this cell loop, the reference's
+        # oneDNN kernel) differ by up to 8e-5 in the gradients, each being ~5e-5 away from fp64 (make_golden.trained_like)
+        tol = F64
+    w = {k: tt(v, dtype, True) for k, v in cudalstm_weights_np(g).items()}
     y = O.cudalstm_forward(w, tt(g["x_lstm"], dtype))
     loss = O.nse_basin_averaged(y, tt(g["y_obs"], dtype), tt(g["basin_std"], dtype))
     loss.backward()
@@ -36,7 +39,7 @@ def test_cudalstm(name, dtype, tol):
 
 def test_cudalstm_library_path_matches_cell_loop():
     g = golden("cudalstm_c1")
-    B, T, I, H, wseed = [int(v) for v in g["meta"]]
+    B, T, I, H, wseed = [int(v) for v in g["meta"]][:5]
     w = weights(I, H, 1, wseed, grad=False)
     a = O.cudalstm_forward(w, tt(g["x_lstm"]), library=True)
     assert_close(a, g["y_hat"], what="library y_hat", **F32)
