@@ -65,12 +65,14 @@ _SIGNATURES = {
     "hy2dl_lstm_wgrad": (i32, [p_f, p_f, p_f, i64, i64, i64, i64, i64, p_f, p_f, p_f, p_f, i64, i32, C.POINTER(HeadWgrad), p_f]),
     "hy2dl_parmap_layout": (i64, [C.POINTER(ParMap), i64, i64]),
     "hy2dl_head_map_fwd": (i32, [p_f, i64, i64, i64, p_f, p_f, C.POINTER(ParMap), p_f, p_f, i32, p_f]),
-    "hy2dl_head_map_bwd": (i32, [p_f, p_f, p_f, i64, i64, i64, p_f, C.POINTER(ParMap), p_f, p_f, p_f, i32, p_f]),
+    "hy2dl_head_map_bwd": (i32, [p_f, p_f, p_f, i64, i64, i64, p_f, C.POINTER(ParMap), p_f, p_f, p_f, p_f, i64, i32, p_f]),
     "hy2dl_conceptual_fwd": (i32, [i32, p_f, i64, i64, i64, i64, C.POINTER(p_f), C.POINTER(i64), p_f, p_f, p_f, p_f]),
     "hy2dl_conceptual_bwd": (i32, [i32, p_f, i64, i64, i64, i64, C.POINTER(p_f), C.POINTER(i64), p_f, p_f, p_f, p_f,
                                    C.POINTER(p_f), p_f, p_f]),
     "hy2dl_uh_fwd": (i32, [p_f, p_f, p_f, i64, i64, p_f, p_f, p_f]),
     "hy2dl_uh_bwd": (i32, [p_f, p_f, p_f, p_f, p_f, i64, i64, p_f, p_f, p_f, p_f]),
+    "hy2dl_loss_acc_floats": (i64, []),
+    "hy2dl_sqnorm_floats": (i64, []),
     "hy2dl_loss_nse_reduce": (i32, [p_f, p_f, p_f, i64, p_f, p_f]),
     "hy2dl_loss_nse_finish": (i32, [p_f, p_f, p_f, i64, p_f, p_f, p_f, p_f, p_f]),
     "hy2dl_loss_wrmse_reduce": (i32, [p_f, p_f, i64, p_f, p_f]),

@@ -41,6 +41,7 @@ struct HeadArgs {
   float* dh_seq;
   float* dw;
   float* dbias;
+  unsigned* ticket;     // bwd: ordered-accumulation ticket (zero on entry, left zero)
   int64_t B, T, H;
   int32_t m, n_par, warmup;
   int32_t accumulate_dh;
@@ -216,22 +217,46 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(HeadArgs a, HeadChun
         if (want_dh && (a.ri32 || r < nb)) a.dh_seq[o] = a.accumulate_dh ? a.dh_seq[o] + dh : dh;
       }
       if constexpr (!reg_acc) {
+        // the four row quarters add their partial sums in turn (no shared-memory atomics: fixed order)
+        for (int turn = 0; turn < 4; ++turn) {
+          if (rq == turn) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c)
-          if (c < ch.ncol) atomicAdd(dws + c * H + k, dwt[c]);
+            for (int c = 0; c < NC; ++c)
+              if (c < ch.ncol) dws[c * H + k] += dwt[c];
+          }
+          __syncthreads();
+        }
       }
     }
   }
   __syncthreads();
   if constexpr (reg_acc) {
+    for (int turn = 0; turn < 4; ++turn) {
+      if (rq == turn) {
 #pragma unroll
-    for (int c = 0; c < NC; ++c)
-      if (c < ch.ncol) atomicAdd(dws + c * H + kk, acc_dw[c]);
+        for (int c = 0; c < NC; ++c)
+          if (c < ch.ncol) dws[c * H + kk] += acc_dw[c];
+      }
+      __syncthreads();
+    }
   }
   if (tid < ch.ncol) dbs[tid] = acc_db;
+  // Blocks add their sums to dw / dbias in block order (deterministic, no floating-point atomics): block b waits
+  // for the ticket to reach b.  Blocks are dispatched in index order, so every block a waiting block depends on is
+  // already running or finished.
+  if (tid == 0) {
+    while (atomicAdd(a.ticket, 0u) != blockIdx.x) __nanosleep(64);
+    __threadfence();
+  }
   __syncthreads();
-  for (int e = tid; e < ch.ncol * H; e += kThreads) atomicAdd(a.dw + (int64_t)ch.col[e / H] * H + (e % H), dws[e]);
-  if (tid < ch.ncol) atomicAdd(a.dbias + ch.col[tid], dbs[tid]);
+  for (int e = tid; e < ch.ncol * H; e += kThreads) {
+    float* p = a.dw + (int64_t)ch.col[e / H] * H + (e % H);
+    __stcg(p, __ldcg(p) + dws[e]);
+  }
+  if (tid < ch.ncol) { float* p = a.dbias + ch.col[tid]; __stcg(p, __ldcg(p) + dbs[tid]); }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) atomicExch(a.ticket, blockIdx.x + 1 == gridDim.x ? 0u : blockIdx.x + 1);
 }
 
 static size_t head_smem(int64_t H, bool bwd) {
@@ -330,22 +355,24 @@ extern "C" int hy2dl_head_map_fwd(const float* h_seq, int64_t B, int64_t T, int6
 
 extern "C" int hy2dl_head_map_bwd(const float* h_seq, const float* par_sim, const float* dpar_sim, int64_t B, int64_t T,
                                   int64_t H, const float* w, const hy2dl_parmap* pm, float* dh_seq, float* dw,
-                                  float* dbias, int layout, hy2dl_stream_t stream) {
+                                  float* dbias, void* ws, int64_t ws_bytes, int layout, hy2dl_stream_t stream) {
   int rc = check_parmap(pm, T, "hy2dl_head_map_bwd");
   if (rc) return rc;
   HY_REQUIRE(B > 0 && H > 0 && H <= 512 && H % 64 == 0, HY2DL_ERR_SHAPE, "hy2dl_head_map_bwd: bad sizes B=%lld H=%lld (H must be a multiple of 64)", (long long)B, (long long)H);
   HY_NONNULL(h_seq); HY_NONNULL(par_sim); HY_NONNULL(dpar_sim); HY_NONNULL(w); HY_NONNULL(dw); HY_NONNULL(dbias);
+  HY_REQUIRE(ws != nullptr && ws_bytes >= 16, HY2DL_ERR_WORKSPACE, "hy2dl_head_map_bwd: needs 16 bytes of workspace");
   HeadChunk chunks[32];
   const int n = build_chunks(pm, chunks, 32);
   HY_REQUIRE(n > 0, HY2DL_ERR_SHAPE, "hy2dl_head_map_bwd: too many head columns");
   cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(ws, 0, 16, s);
   const int64_t C = (int64_t)pm->n_par * pm->n_members + pm->n_routing;
   cudaMemsetAsync(dw, 0, sizeof(float) * C * H, s);
   cudaMemsetAsync(dbias, 0, sizeof(float) * C, s);
   HeadArgs a{};
   a.h_seq = h_seq; a.w = w; a.par_sim = const_cast<float*>(par_sim);
   a.B = B; a.T = T; a.H = H; a.m = pm->n_members; a.n_par = pm->n_par; a.warmup = pm->warmup;
-  a.dpar_sim = dpar_sim; a.dh_seq = dh_seq; a.dw = dw; a.dbias = dbias;
+  a.dpar_sim = dpar_sim; a.dh_seq = dh_seq; a.dw = dw; a.dbias = dbias; a.ticket = reinterpret_cast<unsigned*>(ws);
   HY_REQUIRE(layout == HY2DL_LAYOUT_ROWMAJOR || (layout == HY2DL_LAYOUT_RI32 && H % 32 == 0), HY2DL_ERR_SHAPE,
              "hy2dl_head_map_bwd: unknown layout %d (RI32 needs H %% 32 == 0)", layout);
   a.ri32 = layout == HY2DL_LAYOUT_RI32;

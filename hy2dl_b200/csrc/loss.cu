@@ -8,9 +8,18 @@ namespace hy2dl {
 
 constexpr int kLossBlock = 256;
 
+// Deterministic grid reduction (no floating-point atomics: the reference seeds everything, functions_aux.py
+// set_random_seed, so two runs must give bit-identical weights).  acc layout, kLossAccFloats floats, zero-initialised
+// by the caller:  [0,4) the sums (written by the last block to finish), [4] arrival ticket (integer atomic, reset to 0
+// by the last block), [8 + 4 b, 8 + 4 b + NACC) the partial sums of block b.  The last block adds the partials in a
+// fixed order (lane-strided, then the xor-shuffle tree), so the result depends on the grid size only.
+constexpr int kLossMaxBlocks = 592;
+constexpr int kLossAccFloats = 8 + 4 * kLossMaxBlocks;
+
 template <int NACC>
 __device__ __forceinline__ void block_accumulate(float (&v)[NACC], float* acc) {
   __shared__ float sm[NACC][kLossBlock / 32];
+  __shared__ int is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < NACC; ++k) {
@@ -19,12 +28,31 @@ __device__ __forceinline__ void block_accumulate(float (&v)[NACC], float* acc) {
   }
   __syncthreads();
   if (warp == 0) {
+    float* mine = acc + 8 + 4 * blockIdx.x;
 #pragma unroll
     for (int k = 0; k < NACC; ++k) {
       float s = lane < kLossBlock / 32 ? sm[k][lane] : 0.f;
       s = warp_sum(s);
-      if (lane == 0) atomicAdd(acc + k, s);
+      if (lane == 0) mine[k] = s;
     }
+    if (lane == 0) {
+      __threadfence();
+      const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(acc + 4), 1u);
+      is_last = ticket == gridDim.x - 1;
+    }
+  }
+  __syncthreads();
+  if (is_last && warp == 0) {
+    __threadfence();
+    const volatile float* part = acc + 8;
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) {
+      float s = 0.f;
+      for (unsigned b = lane; b < gridDim.x; b += 32) s += part[4 * b + k];
+      s = warp_sum(s);
+      if (lane == 0) acc[k] = s;
+    }
+    if (lane == 0) *reinterpret_cast<unsigned*>(acc + 4) = 0u;
   }
 }
 
@@ -102,10 +130,12 @@ __global__ void __launch_bounds__(kLossBlock) wrmse_finish_kernel(const float* _
   }
 }
 
-static unsigned loss_grid(int64_t n) { return (unsigned)std::min<int64_t>(cdiv(n, kLossBlock), 4 * (int64_t)sm_count()); }
+static unsigned loss_grid(int64_t n) { return (unsigned)std::min<int64_t>(cdiv(n, kLossBlock), std::min<int64_t>(kLossMaxBlocks, 4 * (int64_t)sm_count())); }
 
 }  // namespace hy2dl
 using namespace hy2dl;
+
+extern "C" int64_t hy2dl_loss_acc_floats(void) { return kLossAccFloats; }
 
 extern "C" int hy2dl_loss_nse_reduce(const float* y_sim, const float* y_obs, const float* basin_std, int64_t n,
                                      float* acc, hy2dl_stream_t stream) {

@@ -8,11 +8,16 @@
 //   * streams the packed weights every step from L2 through a ring of 8 KB bulk copies (one copy = one K step of 8
 //     rows x 128 gate columns, hi | lo), chunk after chunk of 32 hidden units.  N = 128 per MMA matters: a first
 //     version with 32-column chunks ran 60+ cycles per MMA where 16 were budgeted (small-N MMAs pay a fixed cost);
-//   * gives a chunk two 128-column accumulators -- one for the 2/3 of the MMAs that are correction terms (2^-11 of the
-//     result, so the truncating tensor-core accumulation costs them nothing) and one for the hi*hi MMAs, whose mean
-//     truncation bias is compensated in the packed weights.  That fills TMEM (H + 256 columns), so the accumulators
-//     are single buffered: the row threads pull their 64 sums into registers first and release the pair before they
-//     start on the activations;
+//   * accumulates a chunk in SHORT chains.  The tensor core's fp32 accumulation truncates; the loss of a chain of L
+//     accumulating hi*hi MMAs (~0.25 * 2^-23 * L of the sum, toward zero) repeats from step to step for a slowly varying
+//     state, so it compounds linearly over the recurrence (tools/dbg_step_noise.py, tools/sim_trunc.py: one chain of
+//     K/8 = 36 gave a parameter-gradient error of 1.2e-4 on the reference golden of BASELINE configs[2], B = 8, T = 365).
+//     The K steps of a chunk are cut into splits of kSplitJ = 4: a split first issues its 8 correction MMAs
+//     (a_lo*b_hi, a_hi*b_lo: 2^-11 of the result, their truncation costs nothing) and then its 4 hi*hi MMAs into ONE
+//     128-column accumulator; the two accumulator regions of TMEM (H + 2 x 128 columns = all of it at H = 256) alternate
+//     between splits, so a region is drained by the row threads -- who add the partial sums in registers, round to
+//     nearest -- while the tensor core fills the other one.  A split's 4 weight slices stay in the ring until its hi*hi
+//     MMAs have been issued (they are read twice);
 //   * keeps no recurrent state in registers: the row thread re-reads c_{t-1} and, at the end of the step, its own
 //     h_t values from a two-slot scratch it has just written (L2 hits) to rebuild A for the next step.  A row is owned by
 //     two threads (TMEM lane = row; the two warps of a lane quarter split every chunk's 32 units 16 | 16), and a
@@ -41,7 +46,8 @@ constexpr int kChunkN = 128;                // gate columns per chunk = 32 hidde
 constexpr int kStepBytes = 8 * kChunkN * 4 * 2;    // one K step of the packed weights: hi | lo = 8 KB
 constexpr int kSliceJ = 1;                         // K steps per ring slice (one bulk copy, one commit); 2 measured the same
 constexpr int kSliceBytes = kSliceJ * kStepBytes;
-constexpr uint32_t kColMain = 256, kColCorr = 384;
+constexpr uint32_t kColAcc = 256;                   // accumulator regions [256, 384) and [384, 512), alternating between splits
+constexpr int kSplitJ = 4;                         // K steps per split = accumulating hi*hi MMAs per chain (2 if the ring is short)
 constexpr int kMaxKX = 80;
 
 struct FwdArgs {
@@ -56,6 +62,8 @@ struct FwdArgs {
   int H, I, IP, KX, K;  // KX = x columns incl. the ones column, rounded to 8; K = KX + H
   int stages;           // ring depth (what shared memory allows)
   int c_pingpong;
+  int act_sep;          // experiment: one reciprocal per gate
+  int splitj;           // K steps per split (a split's weight slices stay in the ring until its hi*hi MMAs are issued)
 };
 
 // packed weight element (chunk c, K index k, column n = 4 uu + g of the chunk): rows scaled by -log2(e) (x 2 for g)
@@ -91,19 +99,21 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
   float* s_xhi = s_alo + (size_t)K * kRowsF;                               // [KX/4][128 rows][4]
   uint8_t* s_ring = reinterpret_cast<uint8_t*>(s_xhi + (size_t)KX * kRowsF);   // NS x 8 KB slices
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + (size_t)NS * kSliceBytes);
-  uint64_t* bar_full = bars;                       // [NS] producer -> MMA
-  uint64_t* bar_free = bars + 8;                   // [NS] MMA commit -> producer       (NS <= 8)
-  uint64_t* bar_dfull = bars + 16;                 // MMA commit -> rows: the chunk's accumulators are complete
-  uint64_t* bar_dfree = bars + 17;                 // rows -> MMA: they have been read
-  uint64_t* bar_a = bars + 18;                     // rows -> MMA: A operand of the step is in place
-  uint64_t* bar_step = bars + 19;                  // MMA commit: every MMA of the step retired, A may be rebuilt
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* bar_full = bars;                       // [NS <= 8] producer -> MMA
+  uint64_t* bar_free = bars + 8;                   // [NS] MMA commit -> producer
+  uint64_t* bar_dfull = bars + 16;                 // [2] MMA commit -> rows: the split's accumulator region is complete
+  uint64_t* bar_dfree = bars + 18;                 // [2] rows -> MMA: it has been read
+  uint64_t* bar_a = bars + 20;                     // rows -> MMA: A operand of the step is in place
+  uint64_t* bar_step = bars + 21;                  // MMA commit: every MMA of the step retired, A may be rebuilt
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NC = H / 32, NJ = K / 8, JX = KX / 8;
+  const int SJ = a.splitj;
+  const int NSP = (NJ + SJ - 1) / SJ;               // splits per chunk (the last one may be shorter)
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_free + s, 1); }
-    mbar_init(bar_dfull, 1); mbar_init(bar_dfree, 256);
+    for (int r = 0; r < 2; ++r) { mbar_init(bar_dfull + r, 1); mbar_init(bar_dfree + r, 256); }
     mbar_init(bar_a, 256);
     mbar_init(bar_step, 1);
     mbar_fence_init();
@@ -190,27 +200,35 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
         f8 cp[2];
 #pragma unroll
         for (int i = 0; i < 2; ++i) cp[i] = cprev ? ld256(cprev + (4 * c + i) * 256) : f8_zero();
-        mbar_wait(bar_dfull, (uint32_t)(gch & 1));
-        tc_fence_after();
-        float z[64];                                              // main + corrections, this thread's 16 units x 4 gates
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {                             // two rounds of 32 + 32 columns, one wait each
-          uint32_t zm[32], zc[32];
-          tmem_ld32(lane_tm + kColMain + 64 * hh + 32 * i, zm);
-          tmem_ld32(lane_tm + kColCorr + 64 * hh + 32 * i, zc);
+        // partial sums of the chunk's splits, added in registers (round to nearest); see the header
+        float z[64];                                              // this thread's 16 units x 4 gates
+        for (int sp = 0; sp < NSP; ++sp) {
+          const int64_t gsp = gch * NSP + sp;                     // split counter over the whole kernel
+          const int r = (int)(gsp & 1);
+          mbar_wait(bar_dfull + r, (uint32_t)((gsp >> 1) & 1));
+          tc_fence_after();
+          uint32_t z0[32], z1[32];
+          tmem_ld32(lane_tm + kColAcc + 128 * r + 64 * hh, z0);
+          tmem_ld32(lane_tm + kColAcc + 128 * r + 64 * hh + 32, z1);
           tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(bar_dfree + r);                             // the region may be overwritten
+          if (sp == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) z[32 * i + j] = __uint_as_float(zm[j]) + __uint_as_float(zc[j]);
+            for (int j = 0; j < 32; ++j) { z[j] = __uint_as_float(z0[j]); z[32 + j] = __uint_as_float(z1[j]); }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { z[j] += __uint_as_float(z0[j]); z[32 + j] += __uint_as_float(z1[j]); }
+          }
         }
-        tc_fence_before();
-        mbar_arrive(bar_dfree);                                   // the next chunk's MMAs may overwrite the pair
 #pragma unroll
         for (int i = 0; i < 2; ++i) {                             // 8 units per round: whole 32-byte sectors per access
           f8 hv, cv, gi, gf, gg, go;
 #pragma unroll
           for (int uu = 0; uu < 8; ++uu) {
             const float* zz = z + 32 * i + 4 * uu;
-            lstm_gates(zz[0], zz[1], zz[2], zz[3], gi.v[uu], gf.v[uu], gg.v[uu], go.v[uu]);
+            if (a.act_sep) lstm_gates_sep(zz[0], zz[1], zz[2], zz[3], gi.v[uu], gf.v[uu], gg.v[uu], go.v[uu]);
+            else lstm_gates(zz[0], zz[1], zz[2], zz[3], gi.v[uu], gf.v[uu], gg.v[uu], go.v[uu]);
             cv.v[uu] = fmaf(gf.v[uu], cp[i].v[uu], gi.v[uu] * gg.v[uu]);
             hv.v[uu] = go.v[uu] * tanh_mufu(cv.v[uu]);
           }
@@ -236,49 +254,52 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
     if (elect_one()) {
       const uint32_t idesc = idesc_tf32(kRowsF, kChunkN, 0, 0);
       const uint32_t a_lbo = kRowsF * 16, b_lbo = kChunkN * 16, sbo = 128;
-      const uint32_t d_main = tmem + kColMain, d_corr = tmem + kColCorr;
+      // descriptors advance by constants (the address field counts 16-byte units): no per-slice rebuilding
       // descriptors advance by constants (the address field counts 16-byte units): no per-slice rebuilding
       const uint64_t ring_hi0 = smem_desc(smem_u32(s_ring), b_lbo, sbo), alo0 = smem_desc(smem_u32(s_alo), a_lbo, sbo);
       const uint64_t xhi0 = smem_desc(smem_u32(s_xhi), a_lbo, sbo);
-      constexpr uint64_t kStageStep = kSliceBytes / 16, kStepStep = kStepBytes / 16, kLoOff = kStepBytes / 32, kAStep = 2 * kRowsF * 16 / 16;
-      int st = 0;                                   // ring stage and its phase parity (no 64-bit division in this loop)
+      constexpr uint64_t kStageStep = kSliceBytes / 16, kLoOff = kStepBytes / 32, kAStep = 2 * kRowsF * 16 / 16;
+      int st = 0;                                   // ring stage of the split's first K step and its phase parity
       uint32_t ph = 0;
-      uint64_t dbh = ring_hi0;
+      int64_t gsp = 0;                              // split counter
       for (int64_t t = 0; t < a.T; ++t) {
         mbar_wait(bar_a, (uint32_t)(t & 1));
         tc_fence_after();
         for (int c = 0; c < NC; ++c) {
-          const int64_t gch = t * NC + c;
-          if (gch > 0) {
-            mbar_wait(bar_dfree, (uint32_t)((gch - 1) & 1));
-            tc_fence_after();
-          }
-          uint64_t dal = alo0, dah = xhi0;
-          uint32_t ah = tmem;
-          for (int J0 = 0; J0 < NJ; J0 += kSliceJ) {
-            mbar_wait(bar_full + st, ph);
-            tc_fence_after();
-#pragma unroll
-            for (int jj = 0; jj < kSliceJ; ++jj) {
-              const int J = J0 + jj;
-              const uint64_t bh = dbh + jj * kStepStep, bl = bh + kLoOff;
-              mma_tf32_ss(d_corr, dal, bh, idesc, J > 0);
-              if (J < JX) {                         // x part: A_hi from shared memory
-                mma_tf32_ss(d_corr, dah, bl, idesc, 1);
-                mma_tf32_ss(d_main, dah, bh, idesc, J > 0);
-                dah += kAStep;
-              } else {                              // h part: A_hi in TMEM columns [0, H)
-                mma_tf32_ts(d_corr, ah, bl, idesc, 1);
-                mma_tf32_ts(d_main, ah, bh, idesc, J > 0);
-                ah += 8;
-              }
-              dal += kAStep;
+          for (int Jb = 0; Jb < NJ; Jb += SJ, ++gsp) {
+            const int n = min(SJ, NJ - Jb);
+            const int r = (int)(gsp & 1);
+            const uint32_t d = tmem + kColAcc + 128 * r;
+            if (gsp >= 2) {                         // the rows have drained this region's previous split
+              mbar_wait(bar_dfree + r, (uint32_t)(((gsp >> 1) - 1) & 1));
+              tc_fence_after();
             }
-            mma_commit(bar_free + st);
-            dbh += kStageStep;
-            if (++st == NS) { st = 0; ph ^= 1; dbh = ring_hi0; }
+            // correction terms first, while the accumulator is ~2^-11 of its final size
+            for (int j = 0; j < n; ++j) {
+              const int J = Jb + j;
+              int sj = st + j; uint32_t pj = ph;
+              if (sj >= NS) { sj -= NS; pj ^= 1; }
+              mbar_wait(bar_full + sj, pj);
+              tc_fence_after();
+              const uint64_t bh = ring_hi0 + (uint64_t)sj * kStageStep, bl = bh + kLoOff;
+              mma_tf32_ss(d, alo0 + (uint64_t)J * kAStep, bh, idesc, j > 0);
+              if (J < JX) mma_tf32_ss(d, xhi0 + (uint64_t)J * kAStep, bl, idesc, 1);     // x part: A_hi from shared memory
+              else mma_tf32_ts(d, tmem + 8 * (uint32_t)(J - JX), bl, idesc, 1);           // h part: A_hi in TMEM columns [0, H)
+            }
+            // the split's hi*hi chain; a slice is released once its second reader has been issued
+            for (int j = 0; j < n; ++j) {
+              const int J = Jb + j;
+              int sj = st + j;
+              if (sj >= NS) sj -= NS;
+              const uint64_t bh = ring_hi0 + (uint64_t)sj * kStageStep;
+              if (J < JX) mma_tf32_ss(d, xhi0 + (uint64_t)J * kAStep, bh, idesc, 1);
+              else mma_tf32_ts(d, tmem + 8 * (uint32_t)(J - JX), bh, idesc, 1);
+              mma_commit(bar_free + sj);
+            }
+            mma_commit(bar_dfull + r);
+            st += n;
+            if (st >= NS) { st -= NS; ph ^= 1; }
           }
-          mma_commit(bar_dfull);
         }
         mma_commit(bar_step);
       }
@@ -323,7 +344,7 @@ bool lstm_rm_tc_fwd_supported(int64_t I, int64_t H) {
   if (!(H == 128 || H == 256)) return false;
   int KX, K;
   rm_fwd_shape(I, H, KX, K);
-  return KX <= kMaxKX && rm_fwd_stages(KX, K) >= 2;
+  return KX <= kMaxKX && rm_fwd_stages(KX, K) >= 3;
 }
 
 // packed weights + (if no tape is requested) ping-pong buffers for h and c
@@ -351,13 +372,27 @@ int lstm_rm_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
   // parameter-gradient error is 3.6e-4 uncompensated, 1.0e-4 with 5e-7, 2.5e-4 with 7e-7.  It depends on how the
   // partial sums grow, i.e. mildly on the data; HY2DL_RM_COMP overrides the constant.
   static const float comp = [] { const char* e = getenv("HY2DL_RM_COMP"); return e ? (float)atof(e) : 0.f; }();
-  const float factor = 1.f + (comp != 0.f ? comp : (H == 256 ? 1.19e-6f : 5.3e-7f));
+  // chains of kSplitJ = 4 accumulating hi*hi MMAs leave a mean truncation loss of ~1.3e-7 of the sum (0.25 * 2^-23 * 4),
+  // removed here; what remains is data dependent and an order of magnitude below fp32 rounding.
+  const float factor = 1.f + (comp != 0.f ? comp : 1.3e-7f);
   rm_tc_pack_w_kernel<<<256, 256, 0, s>>>(w_ih, w_hh, b_ih, b_hh, (int)H, (int)I, a.KX, a.K, factor, wpk);
   a.x = xT; a.wpk = wpk; a.gates = gates; a.h_last = h_last;
   a.B = B; a.T = T; a.H = (int)H; a.I = (int)I; a.IP = (int)IP;
   a.h_seq = h_seq; a.h_own = scratch;
   a.c_seq = c_seq ? c_seq : scratch + 2 * round_up(B, (int64_t)32) * H; a.c_pingpong = c_seq ? 0 : 1;
   a.stages = rm_fwd_stages(a.KX, a.K);
+  // K steps per split: its slices stay in the ring until the hi*hi pass, so it must leave the producer a free slot.
+  // Measured at H = 256, I = 31, B = 18 944, T = 365 (8 stages), forward time / parameter-gradient error vs fp64 on the
+  // reference golden of BASELINE configs[2]:  2: 44.9 ms / 2.3e-5,  4: 38.4 / 9.8e-6,  6: 35.5 / 2.2e-5,  7: 35.2 / 3.1e-5;
+  // the old kernel (one chain of 36, separate correction accumulator) 27.3 ms / 1.2e-4, cut into 2 / 3 chains with the
+  // accumulators pulled in between 31.8 ms / 4.9e-5 and 34.6 ms / 2.6e-5.  The cost is TMEM read bandwidth: every split
+  // is one more 64 KB pull of its accumulator region into registers.  (A variant with separate hi and lo rings of 4 KB
+  // slots, so that only the hi halves stay resident, measured the same: the L2 stream is not what binds here.)
+  a.splitj = a.stages >= 8 ? 6 : a.stages >= 6 ? kSplitJ : 2;
+  static const int sj_env = [] { const char* e = getenv("HY2DL_RM_SPLITJ"); return e ? atoi(e) : 0; }();
+  if (sj_env > 0 && sj_env < a.stages) a.splitj = sj_env;
+  static const int act_sep = [] { const char* e = getenv("HY2DL_RM_ACT"); return e ? atoi(e) : 0; }();
+  a.act_sep = act_sep;
   const size_t smem = (size_t)(a.K + a.KX) * kRowsF * 4 + (size_t)a.stages * kSliceBytes + 256 + 1024;
   cudaFuncSetAttribute(lstm_rm_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   lstm_rm_tc_fwd_kernel<<<(unsigned)cdiv(B, (int64_t)kRowsF), kThreadsF, smem, s>>>(a);

@@ -4,17 +4,37 @@
 
 namespace hy2dl {
 
+// Deterministic (no floating-point atomics).  out layout, kNormFloats floats, zero-initialised once by the caller:
+// [0] the squared norm (written by the last block to finish), [1] arrival ticket (integer atomic, reset by the last
+// block), [2 + b] partial sum of block b; the last block adds them in a fixed order.
+constexpr int kNormMaxBlocks = 296;
+constexpr int kNormFloats = 2 + kNormMaxBlocks;
+
 __global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g, int64_t n, float* out) {
   float v = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) v += g[i] * g[i];
   __shared__ float sm[8];
+  __shared__ int is_last;
   v = warp_sum(v);
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
   __syncthreads();
   if (threadIdx.x < 32) {
     float s = threadIdx.x < 8 ? sm[threadIdx.x] : 0.f;
     s = warp_sum(s);
-    if (threadIdx.x == 0) atomicAdd(out, s);
+    if (threadIdx.x == 0) {
+      out[2 + blockIdx.x] = s;
+      __threadfence();
+      is_last = atomicAdd(reinterpret_cast<unsigned*>(out + 1), 1u) == gridDim.x - 1;
+    }
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x < 32) {
+    __threadfence();
+    const volatile float* part = out + 2;
+    float s = 0.f;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += 32) s += part[b];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) { out[0] = s; *reinterpret_cast<unsigned*>(out + 1) = 0u; }
   }
 }
 
@@ -48,10 +68,12 @@ __global__ void bump_step_kernel(int64_t* step_count) { *step_count += 1; }
 }  // namespace hy2dl
 using namespace hy2dl;
 
+extern "C" int64_t hy2dl_sqnorm_floats(void) { return kNormFloats; }
+
 extern "C" int hy2dl_grad_sqnorm(const float* grad, int64_t n, float* norm_sq, hy2dl_stream_t stream) {
   HY_REQUIRE(n > 0, HY2DL_ERR_SHAPE, "hy2dl_grad_sqnorm: empty input");
   HY_NONNULL(grad); HY_NONNULL(norm_sq);
-  const unsigned grid = (unsigned)std::min<int64_t>(cdiv(n, 256), 2 * (int64_t)sm_count());
+  const unsigned grid = (unsigned)std::min<int64_t>(cdiv(n, 256), std::min<int64_t>(kNormMaxBlocks, 2 * (int64_t)sm_count()));
   sqnorm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(grad, n, norm_sq);
   HY_LAUNCH_CHECK();
   return HY2DL_OK;

@@ -264,6 +264,15 @@ __device__ __forceinline__ void lstm_gates(float zi, float zf, float zg, float z
   go = rAF * G;
   gg = (2.f - G) * (rAF * O);
 }
+// The same with one reciprocal per gate (8 MUFU): every gate carries the rounding of its own ex2 / rcp only, where
+// the shared reciprocal above carries the errors of all four exponentials.
+__device__ __forceinline__ void lstm_gates_sep(float zi, float zf, float zg, float zo, float& gi, float& gf, float& gg, float& go) {
+  constexpr float kClamp = 28.853900817779268f;
+  gi = fast_rcp(1.f + fast_ex2(fminf(zi, kClamp)));
+  gf = fast_rcp(1.f + fast_ex2(fminf(zf, kClamp)));
+  go = fast_rcp(1.f + fast_ex2(fminf(zo, kClamp)));
+  gg = fmaf(2.f, fast_rcp(1.f + fast_ex2(fminf(zg, 2.f * kClamp))), -1.f);
+}
 // tanh(x) = 1 - 2 / (1 + e^2x): 2 MUFU + 3 FMA-pipe instructions; saturates correctly at +-inf
 __device__ __forceinline__ float tanh_mufu(float x) {
   return fmaf(-2.f, fast_rcp(1.f + fast_ex2(2.885390081777927f * x)), 1.f);

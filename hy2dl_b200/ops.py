@@ -282,8 +282,9 @@ class HeadMapFunction(torch.autograd.Function):
         dh_seq = torch.empty_like(h_seq)  # rows < warmup stay uninitialised (dh_t0)
         dw = torch.empty_like(w)
         db = torch.empty(w.shape[0], dtype=torch.float32, device=dev)
+        ws = torch.empty(16, dtype=torch.uint8, device=dev)
         call("hy2dl_head_map_bwd", ptr(h_seq), ptr(par_sim), ptr(dpar_sim), B, T, H, ptr(w), C.byref(layout.pm),
-             ptr(dh_seq), ptr(dw), ptr(db), lay, stream())
+             ptr(dh_seq), ptr(dw), ptr(db), ptr(ws), ws.numel(), lay, stream())
         return dh_seq, dw, db, None
 
 
@@ -530,14 +531,20 @@ def _allreduce_sum(t: torch.Tensor, group):
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=None if group == "world" else group)
 
 
+def _loss_acc(device) -> torch.Tensor:
+    """Zeroed accumulator of the loss reductions: sums at [0,4), then ticket and per-block partials
+    (include/hy2dl_b200.h)."""
+    return torch.zeros(int(_lib.load().hy2dl_loss_acc_floats()), dtype=torch.float32, device=device)
+
+
 class NseLossFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y_sim, y_obs, std, group):
         require_cuda(y_sim, "y_sim"); require_cuda(y_obs, "y_obs"); require_cuda(std, "per_basin_target_std")
         n = y_sim.numel()
-        acc = torch.zeros(4, dtype=torch.float32, device=y_sim.device)
+        acc = _loss_acc(y_sim.device)
         call("hy2dl_loss_nse_reduce", ptr(y_sim), ptr(y_obs), ptr(std), n, ptr(acc), stream())
-        _allreduce_sum(acc, group)
+        _allreduce_sum(acc[:4], group)
         loss = torch.empty((), dtype=torch.float32, device=y_sim.device)
         call("hy2dl_loss_nse_finish", ptr(y_sim), ptr(y_obs), ptr(std), n, ptr(acc), None, ptr(loss), None, stream())
         ctx.save_for_backward(y_sim, y_obs, std, acc)
@@ -559,9 +566,9 @@ class WrmseLossFunction(torch.autograd.Function):
     def forward(ctx, y_sim, y_obs, group):
         require_cuda(y_sim, "y_sim"); require_cuda(y_obs, "y_obs")
         n = y_sim.numel()
-        acc = torch.zeros(4, dtype=torch.float32, device=y_sim.device)
+        acc = _loss_acc(y_sim.device)
         call("hy2dl_loss_wrmse_reduce", ptr(y_sim), ptr(y_obs), n, ptr(acc), stream())
-        _allreduce_sum(acc, group)
+        _allreduce_sum(acc[:4], group)
         loss = torch.empty((), dtype=torch.float32, device=y_sim.device)
         call("hy2dl_loss_wrmse_finish", ptr(y_sim), ptr(y_obs), n, ptr(acc), None, ptr(loss), None, stream())
         ctx.save_for_backward(y_sim, y_obs, acc)

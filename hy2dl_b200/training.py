@@ -54,7 +54,8 @@ class FusedClipAdam:
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step_count = torch.zeros((), dtype=torch.int64, device=dev)
         self.lr = torch.full((), lr, dtype=torch.float32, device=dev)
-        self.norm_sq = torch.zeros((), dtype=torch.float32, device=dev)
+        # [0] squared norm, then the reduction's ticket and per-block partial sums (include/hy2dl_b200.h)
+        self.norm_sq = torch.zeros(int(_lib.load().hy2dl_sqnorm_floats()), dtype=torch.float32, device=dev)
         self.max_norm, self.betas, self.eps, self.group = max_norm, betas, eps, group
 
     def set_lr(self, lr: float):
@@ -82,7 +83,7 @@ class FusedClipAdam:
         if self.group is not None:
             import torch.distributed as dist
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=None if self.group == "world" else self.group)
-        self.norm_sq.zero_()
+        self.norm_sq[:1].zero_()
         if self.max_norm > 0:
             call("hy2dl_grad_sqnorm", ptr(self.grad), self.n, ptr(self.norm_sq), stream())
         call("hy2dl_clip_adam", ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.n,
@@ -91,7 +92,7 @@ class FusedClipAdam:
 
     def grad_norm(self) -> torch.Tensor:
         """Pre-clip global gradient norm of the last step (device scalar)."""
-        return self.norm_sq.sqrt()
+        return self.norm_sq[0].sqrt()
 
 
 def forward_loss(model: nn.Module, batch: Batch, loss: str, group=None) -> torch.Tensor:

@@ -174,9 +174,11 @@ int hy2dl_head_map_fwd(const float* h_seq, int64_t B, int64_t T, int64_t H,
  * (the warm-up runs under no_grad, hybrid.py:99-102, so row warmup-1 and earlier get no gradient
  * and are left untouched), and overwrites dw [C][H], dbias [C].  dh_seq may be NULL: weight and bias
  * gradients only (the hidden-state gradient is then formed inside hy2dl_lstm_bwd, see hy2dl_head_bwd). */
+/* ws: >= 16 bytes of device scratch (the ticket of the fixed-order accumulation of dw / dbias over thread blocks:
+ * no floating-point atomics, bit-reproducible). */
 int hy2dl_head_map_bwd(const float* h_seq, const float* par_sim, const float* dpar_sim, int64_t B, int64_t T,
                        int64_t H, const float* w, const hy2dl_parmap* pm, float* dh_seq, float* dw, float* dbias,
-                       int layout, hy2dl_stream_t stream);
+                       void* ws, int64_t ws_bytes, int layout, hy2dl_stream_t stream);
 
 /* ---- conceptual models (replace SHM.forward shm.py:135-182, HBV.forward hbv.py:127-188) --------
  * par[p] / tstride[p]: device pointer of parameter p's plane and its stride in floats between
@@ -201,10 +203,14 @@ int hy2dl_uh_bwd(const float* q, const float* alpha, const float* beta, const fl
 
 /* ---- losses (replace aux_functions/functions_training.py:32-41 and :72-81) ----------------------
  * y_sim, y_obs, basin_std: n elements in the same order; NaN in y_obs = missing.
- * *_reduce writes partial sums to acc (NSE: {sum w*e^2, count}; wRMSE: {sum e^2, sum le^2, count});
- * acc must be zeroed by the caller and can be all-reduced across ranks before *_finish.
+ * *_reduce writes the masked sums to acc[0..3] (NSE: {sum w*e^2, count}; wRMSE: {sum e^2, sum le^2, count});
+ * acc holds hy2dl_loss_acc_floats() floats (the sums, an arrival ticket and one partial sum per thread block:
+ * the reduction uses no floating-point atomics, the last block adds the partials in a fixed order, so results
+ * are bit-reproducible); it must be zeroed by the caller ONCE (the kernel leaves the ticket at zero) and
+ * acc[0..3] can be all-reduced across ranks before *_finish.
  * *_finish writes the scalar loss and, if dy != NULL, dL/dy_sim scaled by *gscale (device scalar
  * or NULL = 1). */
+int64_t hy2dl_loss_acc_floats(void);
 int hy2dl_loss_nse_reduce(const float* y_sim, const float* y_obs, const float* basin_std, int64_t n,
                           float* acc, hy2dl_stream_t stream);
 int hy2dl_loss_nse_finish(const float* y_sim, const float* y_obs, const float* basin_std, int64_t n,
@@ -229,10 +235,13 @@ int hy2dl_window_gather(const float* x_d, const float* x_s, const float* x_conc,
                         float* xT, float* forc, float* y_win, float* std_win, int layout, hy2dl_stream_t stream);
 
 /* ---- optimiser tail on one flat buffer (replaces clip_grad_norm_(.., max_norm) + Adam.step,
- * experiments/LSTM_CAMELS_GB.ipynb:298-299).  norm_sq: device scalar, zeroed by the caller before
- * hy2dl_grad_sqnorm (can be all-reduced);  lr: device scalar (so a scheduler can change it under a
+ * experiments/LSTM_CAMELS_GB.ipynb:298-299).  norm_sq: hy2dl_sqnorm_floats() device floats, zeroed by the
+ * caller once: [0] receives the squared norm (overwritten by every hy2dl_grad_sqnorm; can be all-reduced), the
+ * rest is the arrival ticket and one partial sum per thread block (fixed-order sum, no floating-point atomics:
+ * bit-reproducible);  lr: device scalar (so a scheduler can change it under a
  * captured CUDA graph);  step_count: device int64, incremented by the kernel;  the gradient is
  * first multiplied by grad_scale (e.g. 1/world_size), then clipped to max_norm (<= 0: no clipping). */
+int64_t hy2dl_sqnorm_floats(void);
 int hy2dl_grad_sqnorm(const float* grad, int64_t n, float* norm_sq, hy2dl_stream_t stream);
 int hy2dl_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                     const float* norm_sq, float grad_scale, float max_norm, const float* lr, float beta1,

@@ -44,6 +44,22 @@ def bucket_of(name):
     return {"shm": "shm", "hbv": "hbv", "linres": "linear_reservoir", "nonsense": "nonsense"}[name.split("_")[0]]
 
 
+def camels_like_inputs(B, T, I, seed, n_dynamic=None):
+    """LSTM inputs shaped like the reference's samples (basedataset.py:174-177): a few standardised dynamic forcings
+    that vary in time and static attributes that are constant over the window.  (White noise on all I inputs makes the
+    H = 256 recurrence amplify rounding errors until fp32 itself is 4e-4 away from fp64 at T = 730.)"""
+    from hy2dl_b200.synthetic import make_basins
+    nd = n_dynamic if n_dynamic is not None else {25: 3, 31: 5, 41: 6}.get(I, min(5, I))
+    data = make_basins("us", n_basins=16, n_rows=T + 30, seed=seed)
+    rng = np.random.default_rng(seed)
+    bi = rng.integers(0, 16, B)
+    e = rng.integers(T - 1, T + 30, B)
+    xd = np.stack([data.x_d[b, i - T + 1:i + 1, :nd] for b, i in zip(bi, e)]).astype(np.float64)
+    xd = (xd - xd.mean((0, 1))) / (xd.std((0, 1)) + 1e-9)
+    xs = np.repeat(rng.normal(0, 1, (B, 1, I - nd)), T, axis=1)
+    return np.concatenate([xd, xs], axis=2).astype(np.float32)
+
+
 def tt(a, dtype=torch.float32, grad=False):
     x = torch.tensor(np.asarray(a), dtype=dtype)
     return x.requires_grad_(grad)
@@ -115,5 +131,5 @@ def assert_close(a, b, rtol, atol=0.0, what=""):
                        "max_err_over_scale": float(err / (scale + 1e-300)), "frac_outside_elementwise": frac_outside,
                        "frac_outside_gate": frac_gate})
     assert err <= lim, f"{what}: max abs err {err:.3e} > {lim:.3e} (rtol {rtol}, scale {scale:.3e})"
-    assert frac_gate <= ELEMENTWISE_MAX_FRAC, (f"{what}: {frac_gate:.2e} of the elements are outside "
-                                               f"|a-b| <= {10 * rtol:g}|b| + 1e-5*scale")
+    assert frac_gate * n <= max(1.0, ELEMENTWISE_MAX_FRAC * n), (f"{what}: {frac_gate:.2e} of the {n} elements are outside "
+                                                                 f"|a-b| <= {10 * rtol:g}|b| + 1e-5*scale")

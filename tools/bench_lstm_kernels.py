@@ -7,21 +7,22 @@ from hy2dl_b200 import _lib, ops
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--B", type=int, default=18944); ap.add_argument("--T", type=int, default=365)
-ap.add_argument("--I", type=int, default=25); ap.add_argument("--prec", default="tf32x3"); ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--I", type=int, default=25); ap.add_argument("--H", type=int, default=64); ap.add_argument("--prec", default="tf32x3"); ap.add_argument("--iters", type=int, default=3)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
-B, T, I, H = a.B, a.T, a.I, 64
+B, T, I, H = a.B, a.T, a.I, a.H
 prec = ops.PRECISIONS[a.prec]
 ri = a.prec == "tf32x3"
 IP = 32 if ri else (I + 7) // 8 * 8
 G = (B + 31) // 32
 torch.manual_seed(0)
-k = 1 / 8.0
+k = 1 / float(np.sqrt(H))
 w_ih = (torch.rand(4 * H, I, device=dev) * 2 - 1) * k; w_hh = (torch.rand(4 * H, H, device=dev) * 2 - 1) * k
 b_ih = (torch.rand(4 * H, device=dev) * 2 - 1) * k; b_hh = (torch.rand(4 * H, device=dev) * 2 - 1) * k
 seq = (lambda F: torch.empty(T, G, F // 32, 32, 32, device=dev)) if ri else (lambda F: torch.empty(T, B, F, device=dev))
 x = seq(IP); x.normal_()
-h, c, g = seq(H), seq(H), seq(4 * H)
+tape = seq if (ri or H < 128) else (lambda F: torch.empty(T, G * 32, F, device=dev))     # RB8 tapes hold whole 32-row groups
+h, c, g = seq(H), tape(H), tape(4 * H)
 dh = seq(H); dh.normal_()
 hl = torch.empty(B, H, device=dev)
 dwi = torch.empty(4 * H, I, device=dev); dwh = torch.empty(4 * H, H, device=dev); db = torch.empty(4 * H, device=dev)
