@@ -44,5 +44,10 @@ def pytest_sessionfinish(session, exitstatus):
                    "worst": worst}
         with open(os.path.join(out, "parity_report_gpu.json" if gpu else "parity_report_cpu.json"), "w") as f:
             json.dump(summary, f, indent=1)
+        # every comparison, one line each: test | what | n | rtol | max err / scale | share outside allclose | share outside the gate
+        with open(os.path.join(out, "parity_all_gpu.tsv" if gpu else "parity_all_cpu.tsv"), "w") as f:
+            for r in _util.PARITY_LOG:
+                f.write("\t".join([r["test"].split("::")[-1], r["what"], str(r["n"]), f"{r['rtol']:.1e}", f"{r['max_err_over_scale']:.2e}",
+                                   f"{r['frac_outside_elementwise']:.2e}", f"{r['frac_outside_gate']:.2e}"]) + "\n")
     except Exception as e:  # a report must never fail the suite
         print("parity report not written:", e)

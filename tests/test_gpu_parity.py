@@ -14,7 +14,7 @@ from _util import DIRECT_CASES, O, PARAM_KEYS, cudalstm_weights_np, assert_close
 pytestmark = pytest.mark.gpu
 
 TOL = dict(rtol=1e-4, atol=1e-6)
-GTOL = dict(rtol=3e-4, atol=1e-6)   # gradients vs the reference's fp32 autograd (its noise ~1e-4, see test_oracle_golden)
+GTOL = dict(rtol=1.5e-4, atol=1e-6)   # gradients vs the reference's own fp32 autograd: two fp32-class results, each up to ~7e-5 from exact arithmetic on the ill-conditioned cases (test_oracle_golden records the reference's distance to fp64)
 
 
 @pytest.fixture(scope="module")
@@ -256,8 +256,8 @@ def test_train_steps_golden(dev):
                                   per_basin_target_std=cu(g[f"step{step}.basin_std"], dev))
         loss.backward()
         opt.step()
-        assert_close(loss.item(), g["losses"][step], rtol=2e-4, what=f"loss {step}")
-        assert_close(opt.grad_norm().item(), g["norms"][step], rtol=3e-4, what=f"grad norm {step}")
+        assert_close(loss.item(), g["losses"][step], rtol=1e-4, what=f"loss {step}")
+        assert_close(opt.grad_norm().item(), g["norms"][step], rtol=1e-4, what=f"grad norm {step}")
     sd = model.state_dict()
     assert list(sd) == list(PARAM_KEYS)
     for k in PARAM_KEYS:
@@ -501,7 +501,7 @@ def test_hybrid_vs_oracle(dev, model_key, B, T, n_last, H, m, dyn, precision):
     for k, v in pred["internal_states"].items():
         assert_close(npy(v), ref["internal_states"][k].detach().numpy(), what="state " + k, **TOL)
     for k, p in model.named_parameters():
-        assert_close(npy(p.grad), wd[k].grad.numpy(), what="grad " + k, rtol=2e-4, atol=1e-7)
+        assert_close(npy(p.grad), wd[k].grad.numpy(), what="grad " + k, rtol=1e-4, atol=1e-7)
     # basin-level NSE agreement (acceptance metric, 1e-3)
     from hy2dl_b200.aux_functions import nse
     ours = {i: {"y_sim": npy(pred["y_hat"])[i, :, 0], "y_obs": yo[i, :, 0]} for i in range(B)}
@@ -638,7 +638,7 @@ def test_mflstm_vs_own_oracle(dev, B, H, precision, n_dyn, n_static):
     assert y.shape == (B, 24, 1)
     assert_close(npy(y), ref.detach().numpy(), what="y_hat", **TOL)
     for k, p in model.named_parameters():
-        assert_close(npy(p.grad), wd[k].grad.numpy(), what="grad " + k, rtol=2e-4, atol=1e-7)
+        assert_close(npy(p.grad), wd[k].grad.numpy(), what="grad " + k, rtol=2e-4, atol=1e-7)   # 701 recurrent steps; parity unpinned (no reference model)
 
 
 def test_nse_device_edge_cases(dev):
