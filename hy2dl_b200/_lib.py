@@ -72,6 +72,7 @@ _SIGNATURES = {
     "hy2dl_uh_fwd": (i32, [p_f, p_f, p_f, i64, i64, p_f, p_f, p_f]),
     "hy2dl_uh_bwd": (i32, [p_f, p_f, p_f, p_f, p_f, i64, i64, p_f, p_f, p_f, p_f]),
     "hy2dl_loss_acc_floats": (i64, []),
+    "hy2dl_head_bwd_workspace_bytes": (i64, [i64]),
     "hy2dl_sqnorm_floats": (i64, []),
     "hy2dl_loss_nse_reduce": (i32, [p_f, p_f, p_f, i64, p_f, p_f]),
     "hy2dl_loss_nse_finish": (i32, [p_f, p_f, p_f, i64, p_f, p_f, p_f, p_f, p_f]),

@@ -41,7 +41,7 @@ struct HeadArgs {
   float* dh_seq;
   float* dw;
   float* dbias;
-  unsigned* ticket;     // bwd: ordered-accumulation ticket (zero on entry, left zero)
+  float* part;          // bwd: per-block partial sums [grid][kChunk][H] | [grid][kChunk] (workspace)
   int64_t B, T, H;
   int32_t m, n_par, warmup;
   int32_t accumulate_dh;
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kThreads) head_fwd_kernel(HeadArgs a, HeadChun
 // with broadcast LDS.128 and h[r][k] with one conflict-free LDS; it produces dh[r][k] (written as whole
 // 128-byte lines) and accumulates dW[c][k] in registers across all tiles of the CTA (H = 64) or in
 // shared memory (larger H).  smem: ws[kChunk][H] | hs[32][H] | dzs[32][kChunk] | dws[kChunk][H] | dbs[kChunk]
-template <int NC, bool REG_ACC>   // NC: head columns rounded up (8, 16, 32); REG_ACC: H == 64, dW accumulators in registers
+template <int NC>   // NC: head columns of the launch rounded up (8, 16, 32)
 __global__ void __launch_bounds__(kThreads) head_bwd_kernel(HeadArgs a, HeadChunk ch) {
   extern __shared__ __align__(16) float sm[];
   const int H = (int)a.H;
@@ -128,10 +128,13 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(HeadArgs a, HeadChun
   float* dzs = hs + kRows * H;             // [kRows][kDz] (padded: conflict-free column writes, 16-byte rows)
   float* dws = dzs + kRows * kDz;          // [kChunk][H]
   float* dbs = dws + kChunk * H;           // [kChunk]
+  // thread -> (hidden column k, row slice): 256 threads = 64 columns x 4; with KB = H / 64 column blocks the four
+  // groups are KB column blocks x RS = 4 / KB row slices of 32 / RS rows.  Every thread keeps its column of W and
+  // its NC weight-gradient sums in registers for the whole kernel -- no shared-memory atomics, fixed summation order.
   const int tid = threadIdx.x, kk = tid & 63, rq = tid >> 6;
+  const int KB = H / 64, RS = 4 / KB, nrows = kRows / RS;
+  const int k = (rq % KB) * 64 + kk, r0 = (rq / KB) * nrows;
   const int64_t N = a.B * a.m;
-  const int KB = H / 64;
-  constexpr bool reg_acc = REG_ACC;
   const bool want_dh = a.dh_seq != nullptr;      // null: weight / bias gradients only
 
   for (int e = tid; e < kChunk * H; e += kThreads) {
@@ -139,9 +142,10 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(HeadArgs a, HeadChun
     dws[e] = 0.f;
   }
   if (tid < kChunk) dbs[tid] = 0.f;
-  float acc_dw[NC];
+  __syncthreads();
+  float wreg[NC], acc_dw[NC];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) acc_dw[c] = 0.f;
+  for (int c = 0; c < NC; ++c) { wreg[c] = ws[c * H + k]; acc_dw[c] = 0.f; }
   float acc_db = 0.f;
 
   const int64_t t_first = ch.is_dynamic ? a.warmup : a.T - 1;
@@ -181,83 +185,59 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(HeadArgs a, HeadChun
       for (int r = 0; r < kRows; ++r) s += dzs[r * kDz + tid];
       acc_db += s;
     }
-    for (int kb = 0; kb < KB; ++kb) {
-      const int k = kb * 64 + kk;
-      float wreg[NC];
-#pragma unroll
-      for (int c = 0; c < NC; ++c) wreg[c] = ws[c * H + k];
-      float dwt[REG_ACC ? 1 : NC];
-#pragma unroll
-      for (int c = 0; c < (REG_ACC ? 1 : NC); ++c) dwt[c] = 0.f;
 #pragma unroll 2
-      for (int rr = 0; rr < 8; ++rr) {
-        const int r = rq * 8 + rr;
-        const float hk = hs[r * H + k];
-        float dh = 0.f;
+    for (int rr = 0; rr < nrows; ++rr) {
+      const int r = r0 + rr;
+      const float hk = hs[r * H + k];
+      float dh = 0.f;
 #pragma unroll
-        for (int c4 = 0; c4 < NC; c4 += 4) {
-          {
-            const float4 d4 = *reinterpret_cast<const float4*>(dzs + r * kDz + c4);
-            dh = fmaf(d4.x, wreg[c4], dh); dh = fmaf(d4.y, wreg[c4 + 1], dh);
-            dh = fmaf(d4.z, wreg[c4 + 2], dh); dh = fmaf(d4.w, wreg[c4 + 3], dh);
-            if constexpr (reg_acc) {
-              acc_dw[c4] = fmaf(d4.x, hk, acc_dw[c4]); acc_dw[c4 + 1] = fmaf(d4.y, hk, acc_dw[c4 + 1]);
-              acc_dw[c4 + 2] = fmaf(d4.z, hk, acc_dw[c4 + 2]); acc_dw[c4 + 3] = fmaf(d4.w, hk, acc_dw[c4 + 3]);
-            } else {
-              constexpr int M = REG_ACC ? 0 : ~0;   // keeps the indices in range in the unused instantiation
-              dwt[c4 & M] = fmaf(d4.x, hk, dwt[c4 & M]); dwt[(c4 + 1) & M] = fmaf(d4.y, hk, dwt[(c4 + 1) & M]);
-              dwt[(c4 + 2) & M] = fmaf(d4.z, hk, dwt[(c4 + 2) & M]); dwt[(c4 + 3) & M] = fmaf(d4.w, hk, dwt[(c4 + 3) & M]);
-            }
-          }
-        }
-        // dh[r][k]: a warp covers 32 consecutive k of one row = one 128-byte line in either layout
-        int64_t o;
-        if (a.ri32) o = (t * tiles_b + b0 / kRows) * kRows * H + (int64_t)(k >> 5) * 1024 + r * 32 + ((((k >> 3) ^ r) & 3) << 3) + (k & 7);
-        else o = (t * a.B + b0 + r) * H + k;
-        if (want_dh && (a.ri32 || r < nb)) a.dh_seq[o] = a.accumulate_dh ? a.dh_seq[o] + dh : dh;
+      for (int c4 = 0; c4 < NC; c4 += 4) {
+        const float4 d4 = *reinterpret_cast<const float4*>(dzs + r * kDz + c4);
+        dh = fmaf(d4.x, wreg[c4], dh); dh = fmaf(d4.y, wreg[c4 + 1], dh);
+        dh = fmaf(d4.z, wreg[c4 + 2], dh); dh = fmaf(d4.w, wreg[c4 + 3], dh);
+        acc_dw[c4] = fmaf(d4.x, hk, acc_dw[c4]); acc_dw[c4 + 1] = fmaf(d4.y, hk, acc_dw[c4 + 1]);
+        acc_dw[c4 + 2] = fmaf(d4.z, hk, acc_dw[c4 + 2]); acc_dw[c4 + 3] = fmaf(d4.w, hk, acc_dw[c4 + 3]);
       }
-      if constexpr (!reg_acc) {
-        // the four row quarters add their partial sums in turn (no shared-memory atomics: fixed order)
-        for (int turn = 0; turn < 4; ++turn) {
-          if (rq == turn) {
-#pragma unroll
-            for (int c = 0; c < NC; ++c)
-              if (c < ch.ncol) dws[c * H + k] += dwt[c];
-          }
-          __syncthreads();
-        }
-      }
+      // dh[r][k]: a warp covers 32 consecutive k of one row = one 128-byte line in either layout
+      int64_t o;
+      if (a.ri32) o = (t * tiles_b + b0 / kRows) * kRows * H + (int64_t)(k >> 5) * 1024 + r * 32 + ((((k >> 3) ^ r) & 3) << 3) + (k & 7);
+      else o = (t * a.B + b0 + r) * H + k;
+      if (want_dh && (a.ri32 || r < nb)) a.dh_seq[o] = a.accumulate_dh ? a.dh_seq[o] + dh : dh;
     }
   }
   __syncthreads();
-  if constexpr (reg_acc) {
-    for (int turn = 0; turn < 4; ++turn) {
-      if (rq == turn) {
+  // the RS row slices of a column add their sums in turn (fixed order)
+  for (int turn = 0; turn < RS; ++turn) {
+    if (rq / KB == turn) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c)
-          if (c < ch.ncol) dws[c * H + kk] += acc_dw[c];
-      }
-      __syncthreads();
+      for (int c = 0; c < NC; ++c)
+        if (c < ch.ncol) dws[c * H + k] += acc_dw[c];
     }
+    __syncthreads();
   }
-  if (tid < ch.ncol) dbs[tid] = acc_db;
-  // Blocks add their sums to dw / dbias in block order (deterministic, no floating-point atomics): block b waits
-  // for the ticket to reach b.  Blocks are dispatched in index order, so every block a waiting block depends on is
-  // already running or finished.
-  if (tid == 0) {
-    while (atomicAdd(a.ticket, 0u) != blockIdx.x) __nanosleep(64);
-    __threadfence();
-  }
-  __syncthreads();
-  for (int e = tid; e < ch.ncol * H; e += kThreads) {
-    float* p = a.dw + (int64_t)ch.col[e / H] * H + (e % H);
-    __stcg(p, __ldcg(p) + dws[e]);
-  }
-  if (tid < ch.ncol) { float* p = a.dbias + ch.col[tid]; __stcg(p, __ldcg(p) + dbs[tid]); }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) atomicExch(a.ticket, blockIdx.x + 1 == gridDim.x ? 0u : blockIdx.x + 1);
+  // per-block sums -> workspace; head_bwd_finish_kernel adds them in block order (no floating-point atomics)
+  float* pw = a.part + (int64_t)blockIdx.x * kChunk * H;
+  for (int e = tid; e < ch.ncol * H; e += kThreads) pw[e] = dws[e];
+  if (tid < ch.ncol) a.part[(int64_t)gridDim.x * kChunk * H + blockIdx.x * kChunk + tid] = acc_db;
 }
+
+// dw[col[c]][k] = sum over blocks (in block order) of the partial sums; one thread per element
+__global__ void __launch_bounds__(256) head_bwd_finish_kernel(const float* __restrict__ part, int nblocks, int H, HeadChunk ch,
+                                                              float* __restrict__ dw, float* __restrict__ dbias) {
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e < ch.ncol * H) {
+    float s = 0.f;
+    for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * kChunk * H + e];
+    dw[(int64_t)ch.col[e / H] * H + (e % H)] = s;
+  } else if (e < ch.ncol * H + ch.ncol) {
+    const int c = e - ch.ncol * H;
+    float s = 0.f;
+    for (int b = 0; b < nblocks; ++b) s += part[(int64_t)nblocks * kChunk * H + b * kChunk + c];
+    dbias[ch.col[c]] = s;
+  }
+}
+
+constexpr int kHeadBwdMaxBlocks = 296;
 
 static size_t head_smem(int64_t H, bool bwd) {
   size_t f = bwd ? (size_t)kChunk * H * 2 + (size_t)kRows * H + (size_t)kRows * kDz + kChunk
@@ -353,26 +333,30 @@ extern "C" int hy2dl_head_map_fwd(const float* h_seq, int64_t B, int64_t T, int6
   return HY2DL_OK;
 }
 
+extern "C" int64_t hy2dl_head_bwd_workspace_bytes(int64_t H) {
+  return (int64_t)sizeof(float) * kHeadBwdMaxBlocks * kChunk * (H + 1);
+}
+
 extern "C" int hy2dl_head_map_bwd(const float* h_seq, const float* par_sim, const float* dpar_sim, int64_t B, int64_t T,
                                   int64_t H, const float* w, const hy2dl_parmap* pm, float* dh_seq, float* dw,
                                   float* dbias, void* ws, int64_t ws_bytes, int layout, hy2dl_stream_t stream) {
   int rc = check_parmap(pm, T, "hy2dl_head_map_bwd");
   if (rc) return rc;
-  HY_REQUIRE(B > 0 && H > 0 && H <= 512 && H % 64 == 0, HY2DL_ERR_SHAPE, "hy2dl_head_map_bwd: bad sizes B=%lld H=%lld (H must be a multiple of 64)", (long long)B, (long long)H);
+  HY_REQUIRE(B > 0 && (H == 64 || H == 128 || H == 256), HY2DL_ERR_SHAPE, "hy2dl_head_map_bwd: bad sizes B=%lld H=%lld (H must be 64, 128 or 256)", (long long)B, (long long)H);
   HY_NONNULL(h_seq); HY_NONNULL(par_sim); HY_NONNULL(dpar_sim); HY_NONNULL(w); HY_NONNULL(dw); HY_NONNULL(dbias);
-  HY_REQUIRE(ws != nullptr && ws_bytes >= 16, HY2DL_ERR_WORKSPACE, "hy2dl_head_map_bwd: needs 16 bytes of workspace");
+  HY_REQUIRE(ws != nullptr && ws_bytes >= hy2dl_head_bwd_workspace_bytes(H), HY2DL_ERR_WORKSPACE,
+             "hy2dl_head_map_bwd: workspace %lld < %lld bytes", (long long)ws_bytes, (long long)hy2dl_head_bwd_workspace_bytes(H));
   HeadChunk chunks[32];
   const int n = build_chunks(pm, chunks, 32);
   HY_REQUIRE(n > 0, HY2DL_ERR_SHAPE, "hy2dl_head_map_bwd: too many head columns");
   cudaStream_t s = (cudaStream_t)stream;
-  cudaMemsetAsync(ws, 0, 16, s);
   const int64_t C = (int64_t)pm->n_par * pm->n_members + pm->n_routing;
   cudaMemsetAsync(dw, 0, sizeof(float) * C * H, s);
   cudaMemsetAsync(dbias, 0, sizeof(float) * C, s);
   HeadArgs a{};
   a.h_seq = h_seq; a.w = w; a.par_sim = const_cast<float*>(par_sim);
   a.B = B; a.T = T; a.H = H; a.m = pm->n_members; a.n_par = pm->n_par; a.warmup = pm->warmup;
-  a.dpar_sim = dpar_sim; a.dh_seq = dh_seq; a.dw = dw; a.dbias = dbias; a.ticket = reinterpret_cast<unsigned*>(ws);
+  a.dpar_sim = dpar_sim; a.dh_seq = dh_seq; a.dw = dw; a.dbias = dbias; a.part = reinterpret_cast<float*>(ws);
   HY_REQUIRE(layout == HY2DL_LAYOUT_ROWMAJOR || (layout == HY2DL_LAYOUT_RI32 && H % 32 == 0), HY2DL_ERR_SHAPE,
              "hy2dl_head_map_bwd: unknown layout %d (RI32 needs H %% 32 == 0)", layout);
   a.ri32 = layout == HY2DL_LAYOUT_RI32;
@@ -392,17 +376,12 @@ extern "C" int hy2dl_head_map_bwd(const float* h_seq, const float* par_sim, cons
     a.accumulate_dh = chunks[i].is_dynamic ? (dyn_written ? 1 : 0) : 1;
     if (chunks[i].is_dynamic) dyn_written = true;
     const int64_t slots = chunks[i].is_dynamic ? (T - pm->warmup) : 1;
-    const unsigned grid = (unsigned)std::min<int64_t>(slots * cdiv(B, kRows), 4 * (int64_t)sm_count());
+    const unsigned grid = (unsigned)std::min<int64_t>(slots * cdiv(B, kRows), std::min<int64_t>(kHeadBwdMaxBlocks, 2 * (int64_t)sm_count()));
     const int nc = chunks[i].ncol;
-    if (H == 64) {
-      if (nc <= 8) launch(head_bwd_kernel<8, true>, grid, chunks[i]);
-      else if (nc <= 16) launch(head_bwd_kernel<16, true>, grid, chunks[i]);
-      else launch(head_bwd_kernel<32, true>, grid, chunks[i]);
-    } else {
-      if (nc <= 8) launch(head_bwd_kernel<8, false>, grid, chunks[i]);
-      else if (nc <= 16) launch(head_bwd_kernel<16, false>, grid, chunks[i]);
-      else launch(head_bwd_kernel<32, false>, grid, chunks[i]);
-    }
+    if (nc <= 8) launch(head_bwd_kernel<8>, grid, chunks[i]);
+    else if (nc <= 16) launch(head_bwd_kernel<16>, grid, chunks[i]);
+    else launch(head_bwd_kernel<32>, grid, chunks[i]);
+    head_bwd_finish_kernel<<<(unsigned)cdiv((int64_t)nc * H + nc, 256), 256, 0, s>>>(a.part, (int)grid, (int)H, chunks[i], dw, dbias);
   }
   HY_LAUNCH_CHECK();
   return HY2DL_OK;

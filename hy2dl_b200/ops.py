@@ -282,7 +282,7 @@ class HeadMapFunction(torch.autograd.Function):
         dh_seq = torch.empty_like(h_seq)  # rows < warmup stay uninitialised (dh_t0)
         dw = torch.empty_like(w)
         db = torch.empty(w.shape[0], dtype=torch.float32, device=dev)
-        ws = torch.empty(16, dtype=torch.uint8, device=dev)
+        ws = torch.empty(int(_lib.load().hy2dl_head_bwd_workspace_bytes(H)), dtype=torch.uint8, device=dev)
         call("hy2dl_head_map_bwd", ptr(h_seq), ptr(par_sim), ptr(dpar_sim), B, T, H, ptr(w), C.byref(layout.pm),
              ptr(dh_seq), ptr(dw), ptr(db), ptr(ws), ws.numel(), lay, stream())
         return dh_seq, dw, db, None

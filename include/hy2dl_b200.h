@@ -174,8 +174,9 @@ int hy2dl_head_map_fwd(const float* h_seq, int64_t B, int64_t T, int64_t H,
  * (the warm-up runs under no_grad, hybrid.py:99-102, so row warmup-1 and earlier get no gradient
  * and are left untouched), and overwrites dw [C][H], dbias [C].  dh_seq may be NULL: weight and bias
  * gradients only (the hidden-state gradient is then formed inside hy2dl_lstm_bwd, see hy2dl_head_bwd). */
-/* ws: >= 16 bytes of device scratch (the ticket of the fixed-order accumulation of dw / dbias over thread blocks:
- * no floating-point atomics, bit-reproducible). */
+/* ws: hy2dl_head_bwd_workspace_bytes(H) bytes of device scratch: per-thread-block partial sums of dw / dbias, added in
+ * block order by a finish kernel (no floating-point atomics: bit-reproducible). */
+int64_t hy2dl_head_bwd_workspace_bytes(int64_t H);
 int hy2dl_head_map_bwd(const float* h_seq, const float* par_sim, const float* dpar_sim, int64_t B, int64_t T,
                        int64_t H, const float* w, const hy2dl_parmap* pm, float* dh_seq, float* dw, float* dbias,
                        void* ws, int64_t ws_bytes, int layout, hy2dl_stream_t stream);

@@ -103,7 +103,9 @@ def lstm_library(x, w_ih, w_hh, b_ih, b_hh):
     H = w_hh.shape[1]
     h0 = x.new_zeros(1, B, H)
     c0 = x.new_zeros(1, B, H)
-    out, _, _ = torch._VF.lstm(x, (h0, c0), [w_ih, w_hh, b_ih, b_hh], True, 1, 0.0, False, False, True)
+    # train flag: cuDNN (x on a GPU: bench.py's `baseline_gpu_library` leg) only keeps its reserve space for the backward
+    # pass in training mode; with dropout 0 the flag changes no number.  The CPU path (oneDNN) is called as before.
+    out, _, _ = torch._VF.lstm(x, (h0, c0), [w_ih, w_hh, b_ih, b_hh], True, 1, 0.0, x.is_cuda, False, True)
     return out
 
 

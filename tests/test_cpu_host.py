@@ -216,8 +216,9 @@ def test_default_precision_resolution():
 
 
 def test_bench_contract_constants():
-    """bench.py measures BASELINE.json's metric on configs[1]; its algorithmic-byte model is SURVEY.md section 8(d)'s
-    (C2: about 1.230 MB per sequence, LSTM part 4 T (2 I + 12 H) = 1.194 MB) and every C-ABI call it times has bytes."""
+    """bench.py measures BASELINE.json's metric; its algorithmic byte / FLOP models are SURVEY.md section 8(d)'s for every
+    config (C1 1.194 MB, C2 about 1.230 MB, C3 4.576 MB, C4 about 4.81 MB per sequence; 45.2 / 620.5 / 635.4 MFLOP), the
+    default headline is configs[1] and every C-ABI call it times has bytes."""
     import importlib.util
     import json
     spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
@@ -225,9 +226,23 @@ def test_bench_contract_constants():
     spec.loader.exec_module(bench)
     base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
     assert bench.METRIC.split(" at ")[0] in base["metric"]
+    assert len(bench.CONFIGS) == len(base["configs"]) == 5 and bench.CFG is bench.CONFIGS["c2"]
     ab = bench.algo_bytes()
     assert 4 * 365 * (2 * 25 + 12 * 64) == 1_194_280
     assert abs(ab["total"] - 1.230e6) < 0.01e6
     assert ab["hy2dl_lstm_fwd"] + ab["hy2dl_lstm_bwd"] + ab["hy2dl_lstm_wgrad"] == 1_194_280
     hp = bench.hyper()
     assert hp["hidden_size"] == 64 and hp["seq_length"] == 365 and hp["predict_last_n"] == 182
+    C = bench.CONFIGS
+    assert bench.algo_bytes(C["c1"])["total"] == 1_194_280 + 16
+    assert bench.algo_bytes(C["c3"])["total"] == 4 * 365 * 3134 + 16 == 4_575_656
+    c4 = bench.algo_bytes(C["c4"])
+    assert c4["total"] == 4 * 365 * 3154 + 4 * 182 * 16 * 16 + 4 * 182 * 10 + 4 * 183 * 4 + 16 * 182
+    assert abs(c4["total"] - 4.81e6) < 0.01e6
+    assert c4["hy2dl_conceptual_fwd"] + c4["hy2dl_conceptual_bwd"] == 4 * 182 * 16 * 16 + 4 * 182 * 10 + 4 * 183 * 4
+    assert bench.algo_flops(C["c1"]) == 2 * 365 * 256 * 242 and abs(bench.algo_flops(C["c1"]) - 45.2e6) < 0.1e6
+    assert bench.algo_flops(C["c3"]) == 2 * 365 * 1024 * 830 and bench.algo_flops(C["c4"]) == 2 * 365 * 1024 * 850
+    for name in ("c3", "c4"):
+        hp = bench.hyper(C[name])
+        assert hp["hidden_size"] == 256
+    assert bench.hyper(C["c4"])["n_conceptual_models"] == 16 and bench.hyper(C["c4"])["conceptual_dynamic_parameterization"] == ["BETA", "BETAET"]
