@@ -64,6 +64,7 @@ struct FwdArgs {
   int c_pingpong;
   int act_sep;          // experiment: one reciprocal per gate
   int splitj;           // K steps per split (a split's weight slices stay in the ring until its hi*hi MMAs are issued)
+  int dbg;              // timing experiments (HY2DL_RM_DBG): 1 no tape stores, 2 no correction MMAs, 4 no drains but the last, 8 no A rebuild
 };
 
 // packed weight element (chunk c, K index k, column n = 4 uu + g of the chunk): rows scaled by -log2(e) (x 2 for g)
@@ -165,7 +166,8 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
         }
       }
       {
-        const float* hp = (t > 0 && live) ? hown(t - 1) : nullptr;
+        const float* hp = (t > 0 && live && !(a.dbg & 8)) ? hown(t - 1) : nullptr;
+        if (!((a.dbg & 8) && t > 1))
 #pragma unroll 4
         for (int c = 0; c < NC; ++c) {
 #pragma unroll
@@ -208,12 +210,13 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
           mbar_wait(bar_dfull + r, (uint32_t)((gsp >> 1) & 1));
           tc_fence_after();
           uint32_t z0[32], z1[32];
+          if ((a.dbg & 4) && sp != NSP - 1) { tc_fence_before(); mbar_arrive(bar_dfree + r); continue; }
           tmem_ld32(lane_tm + kColAcc + 128 * r + 64 * hh, z0);
           tmem_ld32(lane_tm + kColAcc + 128 * r + 64 * hh + 32, z1);
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(bar_dfree + r);                             // the region may be overwritten
-          if (sp == 0) {
+          if (sp == 0 || (a.dbg & 4)) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) { z[j] = __uint_as_float(z0[j]); z[32 + j] = __uint_as_float(z1[j]); }
           } else {
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
             cv.v[uu] = fmaf(gf.v[uu], cp[i].v[uu], gi.v[uu] * gg.v[uu]);
             hv.v[uu] = go.v[uu] * tanh_mufu(cv.v[uu]);
           }
-          if (hself) {
+          if (hself && !(a.dbg & 1)) {
             const int o = 32 * c + 8 * i;
             const int blk = (4 * c + i) * 256;                    // unit block (32 c + 16 hh + 8 i) / 8 relative to block 2 hh
             st256(hself + blk, hv);                               // re-read by this thread at the end of the step
@@ -282,6 +285,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
               mbar_wait(bar_full + sj, pj);
               tc_fence_after();
               const uint64_t bh = ring_hi0 + (uint64_t)sj * kStageStep, bl = bh + kLoOff;
+              if (a.dbg & 2) { if (j == 0) mma_tf32_ss(d, alo0 + (uint64_t)J * kAStep, bh, idesc, 0); continue; }
               mma_tf32_ss(d, alo0 + (uint64_t)J * kAStep, bh, idesc, j > 0);
               if (J < JX) mma_tf32_ss(d, xhi0 + (uint64_t)J * kAStep, bl, idesc, 1);     // x part: A_hi from shared memory
               else mma_tf32_ts(d, tmem + 8 * (uint32_t)(J - JX), bl, idesc, 1);           // h part: A_hi in TMEM columns [0, H)
@@ -393,6 +397,8 @@ int lstm_rm_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
   if (sj_env > 0 && sj_env < a.stages) a.splitj = sj_env;
   static const int act_sep = [] { const char* e = getenv("HY2DL_RM_ACT"); return e ? atoi(e) : 0; }();
   a.act_sep = act_sep;
+  static const int dbg = [] { const char* e = getenv("HY2DL_RM_DBG"); return e ? atoi(e) : 0; }();
+  a.dbg = dbg;
   const size_t smem = (size_t)(a.K + a.KX) * kRowsF * 4 + (size_t)a.stages * kSliceBytes + 256 + 1024;
   cudaFuncSetAttribute(lstm_rm_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   lstm_rm_tc_fwd_kernel<<<(unsigned)cdiv(B, (int64_t)kRowsF), kThreadsF, smem, s>>>(a);
