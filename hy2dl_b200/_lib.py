@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libhy2dl_b200.so")
 
 MAX_PAR = 16
 N_STATES = 5
-PREC_FP32, PREC_TF32X3, PREC_BF16 = 0, 1, 2
+PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
 MODEL_SHM, MODEL_HBV, MODEL_LINRES, MODEL_NONSENSE = 0, 1, 2, 3
 WS_LSTM_FWD, WS_LSTM_BWD, WS_LSTM_WGRAD = 0, 1, 2
 LAYOUT_ROWMAJOR, LAYOUT_RI32 = 0, 1

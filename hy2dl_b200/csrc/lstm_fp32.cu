@@ -573,7 +573,7 @@ bool lstm_rm_tc_fwd_supported(int64_t I, int64_t H);
 int64_t lstm_rm_tc_fwd_workspace(int64_t B, int64_t I, int64_t H);
 int lstm_rm_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H, const float* w_ih, const float* w_hh,
                    const float* b_ih, const float* b_hh, float* h_seq, float* c_seq, float* gates, float* h_last, void* ws,
-                   int64_t ws_bytes, cudaStream_t s);
+                   int64_t ws_bytes, int single, cudaStream_t s);
 }  // namespace tc
 
 namespace tc {
@@ -587,9 +587,11 @@ static bool rm_tc_chain(int64_t I, int64_t H) {
 
 int lstm_fp32_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H, const float* w_ih,
                   const float* w_hh, const float* b_ih, const float* b_hh, float* h_seq, float* c_seq, float* gates,
-                  float* h_last, void* ws, int64_t ws_bytes, cudaStream_t s) {
+                  float* h_last, void* ws, int64_t ws_bytes, int single, cudaStream_t s) {
   if (rm_tc_chain(I, H))
-    return tc::lstm_rm_tc_fwd(xT, B, T, I, IP, H, w_ih, w_hh, b_ih, b_hh, h_seq, c_seq, gates, h_last, ws, ws_bytes, s);
+    return tc::lstm_rm_tc_fwd(xT, B, T, I, IP, H, w_ih, w_hh, b_ih, b_hh, h_seq, c_seq, gates, h_last, ws, ws_bytes, single, s);
+  HY_REQUIRE(!single, HY2DL_ERR_SHAPE, "hy2dl_lstm_fwd: precision tf32 runs on the tensor-core kernels only (H = 64 with input_size <= 31, "
+             "H = 128 / 256); got H=%lld I=%lld", (long long)H, (long long)I);
   const int64_t need = lstm_fp32_workspace(HY2DL_WS_LSTM_FWD, B, T, I, H);
   HY_REQUIRE(ws != nullptr && ws_bytes >= need, HY2DL_ERR_WORKSPACE, "hy2dl_lstm_fwd: workspace %lld < %lld bytes",
              (long long)ws_bytes, (long long)need);
@@ -609,13 +611,15 @@ namespace tc {
 bool lstm_rm_tc_bwd_supported(int64_t H);
 int64_t lstm_rm_tc_bwd_workspace(int64_t B, int64_t H);
 int lstm_rm_tc_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const float* gates, const float* c_seq, const float* dh_seq,
-                   int64_t dh_t0, const float* dh_last, float* dG, void* ws, int64_t ws_bytes, cudaStream_t s);
+                   int64_t dh_t0, const float* dh_last, float* dG, void* ws, int64_t ws_bytes, int single, cudaStream_t s);
 }  // namespace tc
 
 int lstm_fp32_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const float* gates, const float* c_seq,
-                  const float* dh_seq, int64_t dh_t0, const float* dh_last, float* dG, void* ws, int64_t ws_bytes, cudaStream_t s) {
+                  const float* dh_seq, int64_t dh_t0, const float* dh_last, float* dG, void* ws, int64_t ws_bytes, int single,
+                  cudaStream_t s) {
   if (rm_tc_chain(8, H))     // the chain's condition on the input size (I <= 64) holds for every accepted call
-    return tc::lstm_rm_tc_bwd(B, T, H, w_hh, gates, c_seq, dh_seq, dh_t0, dh_last, dG, ws, ws_bytes, s);
+    return tc::lstm_rm_tc_bwd(B, T, H, w_hh, gates, c_seq, dh_seq, dh_t0, dh_last, dG, ws, ws_bytes, single, s);
+  HY_REQUIRE(!single, HY2DL_ERR_SHAPE, "hy2dl_lstm_bwd: precision tf32 runs on the tensor-core kernels only (H=%lld)", (long long)H);
   LstmBwdArgs a{w_hh, gates, c_seq, dh_seq, dh_last, dG, B, T, dh_t0};
   const int spt = pick_spt(B);
   HY_DISPATCH_H_SPT(H, spt, launch_bwd, a, s);
@@ -628,12 +632,13 @@ namespace tc {
 bool lstm_wgrad_rm_tc_supported(int64_t H);
 int64_t lstm_wgrad_rm_tc_workspace(int64_t H, int64_t I);
 int lstm_wgrad_rm_tc(const float* dG, const float* h_seq, const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H,
-                     float* dw_ih, float* dw_hh, float* db, void* ws, int64_t ws_bytes, cudaStream_t s);
+                     float* dw_ih, float* dw_hh, float* db, void* ws, int64_t ws_bytes, int single, cudaStream_t s);
 }  // namespace tc
 
 int lstm_fp32_wgrad(const float* dG, const float* h_seq, const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
-                    int64_t H, float* dw_ih, float* dw_hh, float* db, void* ws, int64_t ws_bytes, cudaStream_t s) {
-  if (rm_tc_chain(I, H)) return tc::lstm_wgrad_rm_tc(dG, h_seq, xT, B, T, I, IP, H, dw_ih, dw_hh, db, ws, ws_bytes, s);
+                    int64_t H, float* dw_ih, float* dw_hh, float* db, void* ws, int64_t ws_bytes, int single, cudaStream_t s) {
+  if (rm_tc_chain(I, H)) return tc::lstm_wgrad_rm_tc(dG, h_seq, xT, B, T, I, IP, H, dw_ih, dw_hh, db, ws, ws_bytes, single, s);
+  HY_REQUIRE(!single, HY2DL_ERR_SHAPE, "hy2dl_lstm_wgrad: precision tf32 runs on the tensor-core kernels only (H=%lld)", (long long)H);
   const int64_t need = lstm_fp32_workspace(HY2DL_WS_LSTM_WGRAD, B, T, I, H);
   HY_REQUIRE(ws != nullptr && ws_bytes >= need, HY2DL_ERR_WORKSPACE, "hy2dl_lstm_wgrad: workspace %lld < %lld bytes",
              (long long)ws_bytes, (long long)need);

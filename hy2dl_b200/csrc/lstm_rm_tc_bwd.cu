@@ -51,6 +51,7 @@ struct BwdArgs {
   float* dh;            // scratch RB8 [2 time slots][B][H], zero-initialised: dh_rec, accumulated group by group
   int64_t B, T, dh_t0;
   int H, stages;
+  int single;           // HY2DL_PREC_TF32: hi*hi MMAs only, only the hi half of W_hh is streamed
 };
 
 // packed element (chunk c, K step j = 2 g + half, kc, k_out n, kk): W_hh[g*H + 16 c + 8 half + 4 kc + kk][n]
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) lstm_rm_tc_bwd_kernel(BwdArgs a)
           tmem_ld_wait();
           f8 acc;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc.v[k] = __uint_as_float(zm[k]) + __uint_as_float(zc[k]);
+          for (int k = 0; k < 8; ++k) acc.v[k] = a.single ? __uint_as_float(zm[k]) : __uint_as_float(zm[k]) + __uint_as_float(zc[k]);
           if (live) {                                        // unit block u0 / 8 = 2 (u0 / 16) + hh
             float* p = dst + (u0 >> 4) * 512;
             if (g > 0) { const f8 old = ld256(p); for (int k = 0; k < 8; ++k) acc.v[k] += old.v[k]; }
@@ -251,8 +252,10 @@ __global__ void __launch_bounds__(kThreadsB, 1) lstm_rm_tc_bwd_kernel(BwdArgs a)
             tc_fence_after();
             const uint64_t bl = dbh + kBLo;
             const uint32_t acc = !(open && j == 0);
-            mma_tf32_ss(d_corr, dal, dbh, idesc, acc);
-            mma_tf32_ss(d_corr, dah, bl, idesc, 1);
+            if (!a.single) {
+              mma_tf32_ss(d_corr, dal, dbh, idesc, acc);
+              mma_tf32_ss(d_corr, dah, bl, idesc, 1);
+            }
             mma_tf32_ss(d_main, dah, dbh, idesc, acc);
             dah += kAStep; dal += kAStep;
             mma_commit(bar_free + st);
@@ -276,8 +279,9 @@ __global__ void __launch_bounds__(kThreadsB, 1) lstm_rm_tc_bwd_kernel(BwdArgs a)
         const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wpk);
         for (int i = 0; i < per_step; ++i, src += step_bytes) {
           if (!first_round) mbar_wait(bar_free + st, ph);
-          mbar_arrive_expect_tx(bar_full + st, (uint32_t)step_bytes);
-          bulk_g2s(s_ring + (size_t)st * step_bytes, src, (uint32_t)step_bytes, bar_full + st);
+          const uint32_t nbytes = a.single ? (uint32_t)step_bytes / 2 : (uint32_t)step_bytes;    // hi | lo
+          mbar_arrive_expect_tx(bar_full + st, nbytes);
+          bulk_g2s(s_ring + (size_t)st * step_bytes, src, nbytes, bar_full + st);
           if (++st == NS) { st = 0; ph ^= 1; first_round = false; }
         }
       }
@@ -305,7 +309,7 @@ int64_t lstm_rm_tc_bwd_workspace(int64_t B, int64_t H) {
 }
 
 int lstm_rm_tc_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const float* gates, const float* c_seq, const float* dh_seq,
-                   int64_t dh_t0, const float* dh_last, float* dG, void* ws, int64_t ws_bytes, cudaStream_t s) {
+                   int64_t dh_t0, const float* dh_last, float* dG, void* ws, int64_t ws_bytes, int single, cudaStream_t s) {
   const int64_t need = lstm_rm_tc_bwd_workspace(B, H);
   HY_REQUIRE(ws != nullptr && ws_bytes >= need, HY2DL_ERR_WORKSPACE, "hy2dl_lstm_bwd: workspace %lld < %lld bytes (H = %lld needs the "
              "packed W_hh and the dc / dh scratch)", (long long)ws_bytes, (long long)need, (long long)H);
@@ -322,7 +326,7 @@ int lstm_rm_tc_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const flo
   cudaMemsetAsync(scratch, 0, sizeof(float) * 3 * Bp * H, s);
   a.wpk = wpk; a.gates = gates; a.c_seq = c_seq; a.dh_seq = dh_seq; a.dh_last = dh_last; a.dG = dG;
   a.dc = scratch; a.dh = scratch + Bp * H;
-  a.B = B; a.T = T; a.dh_t0 = dh_t0; a.H = (int)H;
+  a.B = B; a.T = T; a.dh_t0 = dh_t0; a.H = (int)H; a.single = single;
   a.stages = rm_bwd_stages(H);
   const size_t smem = (size_t)2 * kABufBytes + (size_t)a.stages * (2 * H * 4 * 4 * 2) + 256 + 1024;
   cudaFuncSetAttribute(lstm_rm_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -64,6 +64,7 @@ struct FwdArgs {
   int c_pingpong;
   int act_sep;          // experiment: one reciprocal per gate
   int splitj;           // K steps per split (a split's weight slices stay in the ring until its hi*hi MMAs are issued)
+  int single;           // HY2DL_PREC_TF32: hi*hi MMAs only (one chain per chunk), only the hi half of the weights is streamed
   int dbg;              // timing experiments (HY2DL_RM_DBG): 1 no tape stores, 2 no correction MMAs, 4 no drains but the last, 8 no A rebuild
 };
 
@@ -277,6 +278,20 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
               mbar_wait(bar_dfree + r, (uint32_t)(((gsp >> 1) - 1) & 1));
               tc_fence_after();
             }
+            if (a.single) {                         // single pass: every slice is read once
+              for (int j = 0; j < n; ++j) {
+                const int J = Jb + j;
+                mbar_wait(bar_full + st, ph);
+                tc_fence_after();
+                const uint64_t bh = ring_hi0 + (uint64_t)st * kStageStep;
+                if (J < JX) mma_tf32_ss(d, xhi0 + (uint64_t)J * kAStep, bh, idesc, j > 0);
+                else mma_tf32_ts(d, tmem + 8 * (uint32_t)(J - JX), bh, idesc, j > 0);
+                mma_commit(bar_free + st);
+                if (++st == NS) { st = 0; ph ^= 1; }
+              }
+              mma_commit(bar_dfull + r);
+              continue;
+            }
             // correction terms first, while the accumulator is ~2^-11 of its final size
             for (int j = 0; j < n; ++j) {
               const int J = Jb + j;
@@ -320,8 +335,9 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
         const float* src = a.wpk;
         for (int i = 0; i < per_step; ++i, src += kSliceBytes / 4) {
           if (!first_round) mbar_wait(bar_free + st, ph);
-          mbar_arrive_expect_tx(bar_full + st, kSliceBytes);
-          bulk_g2s(s_ring + (size_t)st * kSliceBytes, src, kSliceBytes, bar_full + st);
+          const uint32_t nbytes = a.single ? kSliceBytes / 2 : kSliceBytes;        // hi | lo
+          mbar_arrive_expect_tx(bar_full + st, nbytes);
+          bulk_g2s(s_ring + (size_t)st * kSliceBytes, src, nbytes, bar_full + st);
           if (++st == NS) { st = 0; ph ^= 1; first_round = false; }
         }
       }
@@ -360,7 +376,7 @@ int64_t lstm_rm_tc_fwd_workspace(int64_t B, int64_t I, int64_t H) {
 
 int lstm_rm_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H, const float* w_ih, const float* w_hh,
                    const float* b_ih, const float* b_hh, float* h_seq, float* c_seq, float* gates, float* h_last, void* ws,
-                   int64_t ws_bytes, cudaStream_t s) {
+                   int64_t ws_bytes, int single, cudaStream_t s) {
   const int64_t need = lstm_rm_tc_fwd_workspace(B, I, H);
   HY_REQUIRE(ws != nullptr && ws_bytes >= need, HY2DL_ERR_WORKSPACE, "hy2dl_lstm_fwd: workspace %lld < %lld bytes",
              (long long)ws_bytes, (long long)need);
@@ -395,6 +411,8 @@ int lstm_rm_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
   a.splitj = a.stages >= 8 ? 6 : a.stages >= 6 ? kSplitJ : 2;
   static const int sj_env = [] { const char* e = getenv("HY2DL_RM_SPLITJ"); return e ? atoi(e) : 0; }();
   if (sj_env > 0 && sj_env < a.stages) a.splitj = sj_env;
+  a.single = single;
+  if (single) a.splitj = a.K / 8;              // one chain, one accumulator pull per chunk
   static const int act_sep = [] { const char* e = getenv("HY2DL_RM_ACT"); return e ? atoi(e) : 0; }();
   a.act_sep = act_sep;
   static const int dbg = [] { const char* e = getenv("HY2DL_RM_DBG"); return e ? atoi(e) : 0; }();

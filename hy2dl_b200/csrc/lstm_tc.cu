@@ -112,6 +112,7 @@ struct TcFwdArgs {
   float* h_last;        // row-major [B][64] (nullable)
   int64_t B, T, G;      // G = ceil(B / 32) groups
   int IP;
+  int single;           // HY2DL_PREC_TF32: single-pass TF32 (the hi*hi MMAs only), the throughput mode
   // fused head (has_head == 0: none); its weights are rows 256.. of w_hi / w_lo
   int has_head;
   float* par_sim;
@@ -353,15 +354,16 @@ __global__ void __launch_bounds__(128 * NSETS + 32, 1) lstm_tc_fwd_kernel(TcFwdA
           // all correction terms first, while the accumulator is still ~2^-11 of its final size: the
           // tensor core's fp32 accumulation loses up to an ulp of the ACCUMULATOR per MMA, so only the
           // K/8 hi*hi instructions round at full magnitude
+          if (!a.single)
+            for (int j = 0; j < KS; ++j) {
+              const uint64_t d_hi = smem_desc(whi + boff + (uint32_t)j * 2 * lbo_t, lbo_t, sbo);
+              const uint64_t d_lo = smem_desc(wlo + boff + (uint32_t)j * 2 * lbo_t, lbo_t, sbo);
+              mma_tf32_ts(d, tmem + kColAlo + 8 * j, d_hi, id, j > 0);
+              mma_tf32_ts(d, tmem + kColAhi + 8 * j, d_lo, id, 1);
+            }
           for (int j = 0; j < KS; ++j) {
             const uint64_t d_hi = smem_desc(whi + boff + (uint32_t)j * 2 * lbo_t, lbo_t, sbo);
-            const uint64_t d_lo = smem_desc(wlo + boff + (uint32_t)j * 2 * lbo_t, lbo_t, sbo);
-            mma_tf32_ts(d, tmem + kColAlo + 8 * j, d_hi, id, j > 0);
-            mma_tf32_ts(d, tmem + kColAhi + 8 * j, d_lo, id, 1);
-          }
-          for (int j = 0; j < KS; ++j) {
-            const uint64_t d_hi = smem_desc(whi + boff + (uint32_t)j * 2 * lbo_t, lbo_t, sbo);
-            mma_tf32_ts(d, tmem + kColAhi + 8 * j, d_hi, id, 1);
+            mma_tf32_ts(d, tmem + kColAhi + 8 * j, d_hi, id, !a.single || j > 0);
           }
           mma_commit(bar_done + s);
         }
@@ -370,15 +372,16 @@ __global__ void __launch_bounds__(128 * NSETS + 32, 1) lstm_tc_fwd_kernel(TcFwdA
         mbar_wait(bar_a_ready, (uint32_t)(a.T & 1));
         tc_fence_after();
         const uint32_t id = idesc_tf32(kRows, NH, 0, 0), d = tmem + kColHead, boff = (uint32_t)kN * 16;
+        if (!a.single)
+          for (int j = 0; j < KS; ++j) {
+            const uint64_t d_hi = smem_desc(whi + boff + (uint32_t)j * 2 * lbo_t, lbo_t, sbo);
+            const uint64_t d_lo = smem_desc(wlo + boff + (uint32_t)j * 2 * lbo_t, lbo_t, sbo);
+            mma_tf32_ts(d, tmem + kColAlo + 8 * j, d_hi, id, j > 0);
+            mma_tf32_ts(d, tmem + kColAhi + 8 * j, d_lo, id, 1);
+          }
         for (int j = 0; j < KS; ++j) {
           const uint64_t d_hi = smem_desc(whi + boff + (uint32_t)j * 2 * lbo_t, lbo_t, sbo);
-          const uint64_t d_lo = smem_desc(wlo + boff + (uint32_t)j * 2 * lbo_t, lbo_t, sbo);
-          mma_tf32_ts(d, tmem + kColAlo + 8 * j, d_hi, id, j > 0);
-          mma_tf32_ts(d, tmem + kColAhi + 8 * j, d_lo, id, 1);
-        }
-        for (int j = 0; j < KS; ++j) {
-          const uint64_t d_hi = smem_desc(whi + boff + (uint32_t)j * 2 * lbo_t, lbo_t, sbo);
-          mma_tf32_ts(d, tmem + kColAhi + 8 * j, d_hi, id, 1);
+          mma_tf32_ts(d, tmem + kColAhi + 8 * j, d_hi, id, !a.single || j > 0);
         }
         mma_commit(bar_head);
       }
@@ -432,7 +435,7 @@ bool lstm_tc_supported(int64_t I, int64_t H) { return H == 64 && I <= 31; }   //
 
 int lstm_tc_fwd(const float* x_ri, int64_t B, int64_t T, int64_t I, int64_t IP, const float* w_ih, const float* w_hh,
                 const float* b_ih, const float* b_hh, float* h_seq, float* c_seq, float* gates, float* h_last, void* ws,
-                int64_t ws_bytes, const hy2dl_head_fwd* head, cudaStream_t s) {
+                int64_t ws_bytes, const hy2dl_head_fwd* head, int single, cudaStream_t s) {
   const int K = (int)(IP + kH);
   const int64_t need = lstm_tc_workspace(HY2DL_WS_LSTM_FWD, B, T, I, kH);
   HY_REQUIRE(ws != nullptr && ws_bytes >= need, HY2DL_ERR_WORKSPACE, "hy2dl_lstm_fwd(tf32x3): workspace %lld < %lld bytes",
@@ -458,7 +461,7 @@ int lstm_tc_fwd(const float* x_ri, int64_t B, int64_t T, int64_t I, int64_t IP, 
   a.x = x_ri;
   a.w_hi = w_hi; a.w_lo = w_lo;
   a.h_seq = h_seq; a.c_seq = c_seq; a.gates = gates; a.h_last = h_last;
-  a.B = B; a.T = T; a.G = cdiv(B, 32); a.IP = (int)IP;
+  a.B = B; a.T = T; a.G = cdiv(B, 32); a.IP = (int)IP; a.single = single;
   const size_t smem = tc_fwd_smem(K, NH);
   static const int sets = [] { const char* e = getenv("HY2DL_FWD_SETS"); return e ? (atoi(e) == 4 ? 4 : 2) : kFwdSets; }();   // tuning knob
   if (sets == 2) {
@@ -537,6 +540,7 @@ struct TcBwdArgs {
   const float* dh_last;   // row-major [B][64] or null
   float* dG;              // RI32 F = 256; may alias gates
   int64_t B, T, G, dh_t0;
+  int single;             // HY2DL_PREC_TF32: hi*hi MMAs only
   // fused head adjoint (has_head == 0: none): dh_ext(t) = dz_t * W_head with dz from dpar_sim / par_sim
   int has_head;
   const float* wh_hi;     // [NH/4][64][4]
@@ -733,15 +737,16 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
         mbar_wait(bar_dz_full + buf, (uint32_t)((dz_i / n_dzbuf) & 1));
         tc_fence_after();
         const uint32_t a_hi = smem_u32(s_dz) + buf * dz_buf_bytes, a_lo = a_hi + dz_lo_off;
-        for (int j = 0; j < NH / 8; ++j) {
-          const uint64_t ah = smem_desc(a_hi + j * 2 * 2048, 2048, 128), al = smem_desc(a_lo + j * 2 * 2048, 2048, 128);
-          const uint64_t bh = smem_desc(hw_hi + j * 2 * lbo, lbo, sbo), bl = smem_desc(hw_lo + j * 2 * lbo, lbo, sbo);
-          mma_tf32_ss(d, al, bh, idesc, j > 0);
-          mma_tf32_ss(d, ah, bl, idesc, 1);
-        }
+        if (!a.single)
+          for (int j = 0; j < NH / 8; ++j) {
+            const uint64_t ah = smem_desc(a_hi + j * 2 * 2048, 2048, 128), al = smem_desc(a_lo + j * 2 * 2048, 2048, 128);
+            const uint64_t bh = smem_desc(hw_hi + j * 2 * lbo, lbo, sbo), bl = smem_desc(hw_lo + j * 2 * lbo, lbo, sbo);
+            mma_tf32_ss(d, al, bh, idesc, j > 0);
+            mma_tf32_ss(d, ah, bl, idesc, 1);
+          }
         for (int j = 0; j < NH / 8; ++j) {
           const uint64_t ah = smem_desc(a_hi + j * 2 * 2048, 2048, 128), bh = smem_desc(hw_hi + j * 2 * lbo, lbo, sbo);
-          mma_tf32_ss(d, ah, bh, idesc, 1);
+          mma_tf32_ss(d, ah, bh, idesc, !a.single || j > 0);
         }
         mma_commit(bar_dz_free + buf);
         ++dz_i;
@@ -761,18 +766,20 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
           if (k == 0 && has_dz) issue_dz(d);       // (the row threads have finished reading this buffer by now)
           const uint32_t abase = tmem + kColSlot0 + 128 * slot;
           const bool acc0 = k == 0 && has_dz;
+          if (!a.single) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {            // correction terms first (see header)
-            const uint32_t J = 8 * k + j;
-            const uint64_t d_hi = smem_desc(whi + J * 2 * lbo, lbo, sbo);
-            const uint64_t d_lo = smem_desc(wlo + J * 2 * lbo, lbo, sbo);
-            mma_tf32_ts(d, abase + 64 + 8 * j, d_hi, idesc, (((k & 1) | j) != 0) || acc0);
-            mma_tf32_ts(d, abase + 8 * j, d_lo, idesc, 1);
+            for (int j = 0; j < 8; ++j) {          // correction terms first (see header)
+              const uint32_t J = 8 * k + j;
+              const uint64_t d_hi = smem_desc(whi + J * 2 * lbo, lbo, sbo);
+              const uint64_t d_lo = smem_desc(wlo + J * 2 * lbo, lbo, sbo);
+              mma_tf32_ts(d, abase + 64 + 8 * j, d_hi, idesc, (((k & 1) | j) != 0) || acc0);
+              mma_tf32_ts(d, abase + 8 * j, d_lo, idesc, 1);
+            }
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint64_t d_hi = smem_desc(whi + (uint32_t)(8 * k + j) * 2 * lbo, lbo, sbo);
-            mma_tf32_ts(d, abase + 8 * j, d_hi, idesc, 1);
+            mma_tf32_ts(d, abase + 8 * j, d_hi, idesc, !a.single || (((k & 1) | j) != 0) || acc0);
           }
           mma_commit(bar_free + slot);
         }
@@ -844,7 +851,7 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
 
 int lstm_tc_bwd(int64_t B, int64_t T, const float* w_hh, const float* gates, const float* c_seq, const float* dh_seq,
                 int64_t dh_t0, const float* dh_last, float* dG, void* ws, int64_t ws_bytes, const hy2dl_head_bwd* head,
-                cudaStream_t s) {
+                int single, cudaStream_t s) {
   const int64_t need = lstm_tc_workspace(HY2DL_WS_LSTM_BWD, B, T, 1, kH);
   HY_REQUIRE(ws != nullptr && ws_bytes >= need, HY2DL_ERR_WORKSPACE, "hy2dl_lstm_bwd(tf32x3): workspace %lld < %lld bytes",
              (long long)ws_bytes, (long long)need);
@@ -854,7 +861,7 @@ int lstm_tc_bwd(int64_t B, int64_t T, const float* w_hh, const float* gates, con
   TcBwdArgs a{};
   a.w_hi = w_hi; a.w_lo = w_lo;
   a.gates = gates; a.c_seq = c_seq; a.dh_seq = dh_seq; a.dh_last = dh_last; a.dG = dG;
-  a.B = B; a.T = T; a.G = cdiv(B, 32); a.dh_t0 = dh_t0;
+  a.B = B; a.T = T; a.G = cdiv(B, 32); a.dh_t0 = dh_t0; a.single = single;
   size_t smem = (size_t)kN * kH * 4 * 2 + (size_t)kH * kRows * 4 + 128;
   int threads = kBwdThreads;
   if (head) {

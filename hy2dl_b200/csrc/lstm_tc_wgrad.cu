@@ -70,6 +70,7 @@ struct TcWgradArgs {
   int64_t T, G, dz_t0;
   int NHz;            // head columns rounded up to 16 (MMA N of the head part)
   int raw_hi;         // 1: landed words are the hi operand; 0: write the rounded hi back in place
+  int single;         // HY2DL_PREC_TF32: hi*hi MMAs only
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArgs a) {
@@ -153,9 +154,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
               const uint64_t b_hi = smem_desc_mn32(hi_b + kb * 1024, kBlk, 512), b_lo = smem_desc_mn32(lo_b + kb * 1024, kBlk, 512);
               const uint64_t a_hi = smem_desc_mn32(hi_a + kBlk + hf * 4 * kBlk + kb * 1024, kBlk, 512);
               const uint64_t a_lo = smem_desc_mn32(lo_a + kBlk + hf * 4 * kBlk + kb * 1024, kBlk, 512);
-              mma_tf32_ss(d, a_lo, b_hi, idesc, !(first && kb == 0));
-              mma_tf32_ss(d, a_hi, b_lo, idesc, 1);
-              mma_tf32_ss(d, a_hi, b_hi, idesc, 1);
+              if (!a.single) {
+                mma_tf32_ss(d, a_lo, b_hi, idesc, !(first && kb == 0));
+                mma_tf32_ss(d, a_hi, b_lo, idesc, 1);
+              }
+              mma_tf32_ss(d, a_hi, b_hi, idesc, !a.single || !(first && kb == 0));
             }
           }
           if (hf == 0 && has_dz(t)) {              // head^T: A = [h0 | h1 | x | junk] (the B part), B = dz block
@@ -163,9 +166,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
             for (int kb = 0; kb < 4; ++kb) {
               const uint64_t a_hi = smem_desc_mn32(hi_b + kb * 1024, kBlk, 512), a_lo = smem_desc_mn32(lo_b + kb * 1024, kBlk, 512);
               const uint64_t b_hi = smem_desc_mn32(hi_a + kb * 1024, kBlk, 512), b_lo = smem_desc_mn32(lo_a + kb * 1024, kBlk, 512);
-              mma_tf32_ss(tmem + kColHeadD, a_lo, b_hi, idesc_h, head_open || kb > 0);
-              mma_tf32_ss(tmem + kColHeadD, a_hi, b_lo, idesc_h, 1);
-              mma_tf32_ss(tmem + kColHeadD, a_hi, b_hi, idesc_h, 1);
+              if (!a.single) {
+                mma_tf32_ss(tmem + kColHeadD, a_lo, b_hi, idesc_h, head_open || kb > 0);
+                mma_tf32_ss(tmem + kColHeadD, a_hi, b_lo, idesc_h, 1);
+              }
+              mma_tf32_ss(tmem + kColHeadD, a_hi, b_hi, idesc_h, !a.single || head_open || kb > 0);
             }
             head_open = true;
           }
@@ -362,7 +367,7 @@ int64_t lstm_tc_wgrad_workspace(int64_t B, int64_t T, int64_t I) {
 
 int lstm_tc_wgrad(const float* dG, const float* h_seq, const float* x_ri, int64_t B, int64_t T, int64_t I, int64_t IP,
                   float* dw_ih, float* dw_hh, float* db, void* ws, int64_t ws_bytes, const hy2dl_head_wgrad* head,
-                  cudaStream_t s) {
+                  int single, cudaStream_t s) {
   const int64_t need = lstm_tc_wgrad_workspace(B, T, I);
   HY_REQUIRE(ws != nullptr && ws_bytes >= need, HY2DL_ERR_WORKSPACE, "hy2dl_lstm_wgrad(tf32x3): workspace %lld < %lld bytes",
              (long long)ws_bytes, (long long)need);
@@ -380,7 +385,7 @@ int lstm_tc_wgrad(const float* dG, const float* h_seq, const float* x_ri, int64_
   }
   a.NHz = C <= 16 ? 16 : 32;
   static const int raw_hi = [] { const char* e = getenv("HY2DL_WG_RAWHI"); return e ? atoi(e) : 1; }();   // 0: write the rounded hi back in place
-  a.raw_hi = raw_hi;
+  a.raw_hi = raw_hi; a.single = single;
   const size_t smem = (size_t)kWgStages * kStageBytes + kABytes + 2 * kBBytes + kBlk + 128 + 1024;
   const int grid = wg_grid((T + (head ? 1 : 0)) * a.G);
   cudaFuncSetAttribute(lstm_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

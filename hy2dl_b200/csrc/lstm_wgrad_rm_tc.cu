@@ -42,6 +42,7 @@ struct Args {
   float* partial;     // [parts][MT*NT][256][32 NB]
   int64_t T, B, G;
   int H, I, IP, MT, NT, NB, parts;
+  int single;         // HY2DL_PREC_TF32: hi*hi MMAs only
 };
 
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
@@ -109,9 +110,11 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_wgrad_rm_tc_kernel(Args a) {
             const uint64_t b_hi = smem_desc_mn32(hi_b + kb * 1024, kBlk, 512), b_lo = smem_desc_mn32(lo_b + kb * 1024, kBlk, 512);
             const uint64_t a_hi = smem_desc_mn32(hi_a + hf * 4 * kBlk + kb * 1024, kBlk, 512);
             const uint64_t a_lo = smem_desc_mn32(lo_a + hf * 4 * kBlk + kb * 1024, kBlk, 512);
-            mma_tf32_ss(d, a_lo, b_hi, idesc, !(first && kb == 0));
-            mma_tf32_ss(d, a_hi, b_lo, idesc, 1);
-            mma_tf32_ss(d, a_hi, b_hi, idesc, 1);
+            if (!a.single) {
+              mma_tf32_ss(d, a_lo, b_hi, idesc, !(first && kb == 0));
+              mma_tf32_ss(d, a_hi, b_lo, idesc, 1);
+            }
+            mma_tf32_ss(d, a_hi, b_hi, idesc, !a.single || !(first && kb == 0));
           }
           mma_commit(bar_lo_free + hf);
         }
@@ -281,7 +284,7 @@ int64_t lstm_wgrad_rm_tc_workspace(int64_t H, int64_t I) {
 }
 
 int lstm_wgrad_rm_tc(const float* dG, const float* h_seq, const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H,
-                     float* dw_ih, float* dw_hh, float* db, void* ws, int64_t ws_bytes, cudaStream_t s) {
+                     float* dw_ih, float* dw_hh, float* db, void* ws, int64_t ws_bytes, int single, cudaStream_t s) {
   const int64_t need = lstm_wgrad_rm_tc_workspace(H, I);
   HY_REQUIRE(ws != nullptr && ws_bytes >= need, HY2DL_ERR_WORKSPACE, "hy2dl_lstm_wgrad: workspace %lld < %lld bytes",
              (long long)ws_bytes, (long long)need);
@@ -289,6 +292,7 @@ int lstm_wgrad_rm_tc(const float* dG, const float* h_seq, const float* xT, int64
   a.dG = dG; a.h = h_seq; a.x = xT; a.partial = reinterpret_cast<float*>(ws);
   a.T = T; a.B = B; a.G = cdiv(B, (int64_t)32); a.H = (int)H; a.I = (int)I; a.IP = (int)IP;
   rm_tc_shape(H, I, a.MT, a.NT, a.NB, a.parts);
+  a.single = single;
   const size_t bbytes = (size_t)a.NB * kBlk;
   const size_t smem = (size_t)kStages * (kABytes + bbytes) + kABytes + 2 * bbytes + 128 + 1024;
   cudaFuncSetAttribute(lstm_wgrad_rm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -88,10 +88,10 @@ class Hybrid(nn.Module):
         N, T_sim = B * m, T - warmup
 
         # LSTM over all T steps; only steps >= warmup receive gradient from the head
-        if self.lstm.precision == "tf32x3" and self.linear.out_features <= ops.FUSED_HEAD_MAX_COLUMNS:
+        if self.lstm.layout == "ri32" and self.linear.out_features <= ops.FUSED_HEAD_MAX_COLUMNS:
             # LSTM + head in one kernel: the hidden sequence is only written as the BPTT tape
             par_sim, par_warm = ops.lstm_head(xT, *self.lstm.kernel_weights(), self.lstm.pad_head(self.linear.weight),
-                                              self.linear.bias, self.input_size_lstm, layout)
+                                              self.linear.bias, self.input_size_lstm, layout, self.lstm.precision)
         else:
             h_seq, _ = self.lstm.run_native(xT, dh_t0=warmup, want_seq=True, B=B)
             par_sim, par_warm = ops.head_map(h_seq, self.lstm.pad_head(self.linear.weight), self.linear.bias, layout)

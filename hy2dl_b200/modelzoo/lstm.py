@@ -40,7 +40,8 @@ class LSTM(nn.Module):
         self.kernel_hidden = 64 if hidden_size <= 64 else (128 if hidden_size <= 128 else 256)
         # "auto": the fastest kernels that meet the fp32 tolerances (rtol 1e-4) for this shape -- the tcgen05 path with
         # resident weights ("tf32x3": H = 64, input_size <= 31); otherwise "fp32", which is the streamed-weights tcgen05
-        # chain for H = 128 / 256 and the CUDA-core kernels for H = 64 with wider inputs
+        # chain for H = 128 / 256 and the CUDA-core kernels for H = 64 with wider inputs.  "tf32" is the throughput mode
+        # (single-pass TF32 operands on the same tensor-core kernels; looser, stated tolerance -- never picked by "auto")
         if precision == "auto":
             precision = "tf32x3" if (self.kernel_hidden == 64 and input_size <= 31) else "fp32"
         if precision not in ops.PRECISIONS:
@@ -48,6 +49,9 @@ class LSTM(nn.Module):
         if precision == "tf32x3" and not (self.kernel_hidden == 64 and input_size <= 31):
             raise ValueError("hy2dl_b200.LSTM: precision 'tf32x3' (weights resident on chip) takes hidden_size <= 64 and "
                              f"input_size <= 31 (got {hidden_size}, {input_size}); use 'auto' or 'fp32'")
+        if precision == "tf32" and self.kernel_hidden == 64 and input_size > 31:
+            raise ValueError("hy2dl_b200.LSTM: precision 'tf32' (throughput mode) runs on the tensor-core kernels only: hidden_size <= 64 "
+                             f"with input_size <= 31, or hidden_size in (64, 256] (got {hidden_size}, {input_size})")
         self.precision = precision
         H = hidden_size
         self.weight_ih_l0 = nn.Parameter(torch.empty(4 * H, input_size))
@@ -85,7 +89,7 @@ class LSTM(nn.Module):
     @property
     def layout(self) -> str:
         """Layout of the native streams this module reads and writes ("rowmajor" | "ri32")."""
-        return ops.layout_of(self.precision)
+        return ops.layout_of(self.precision, self.kernel_hidden)
 
     def run_native(self, xT: torch.Tensor, dh_t0: int = 0, want_seq: bool = True, B: Optional[int] = None):
         """xT: native input ([T,B,IP], or RI32 for precision tf32x3 with B given) ->

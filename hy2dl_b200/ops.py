@@ -16,7 +16,9 @@ import torch
 from . import _lib
 from ._lib import ParMap, call, ptr, require_cuda, stream
 
-PRECISIONS = {"fp32": _lib.PREC_FP32, "tf32x3": _lib.PREC_TF32X3}
+# "fp32" and "tf32x3" are the fp32-class parity paths; "tf32" is the throughput mode (the same tensor-core kernels without
+# the correction terms of the 3-term TF32 split: 10-bit operands, fp32 accumulate; include/hy2dl_b200.h)
+PRECISIONS = {"fp32": _lib.PREC_FP32, "tf32x3": _lib.PREC_TF32X3, "tf32": _lib.PREC_TF32}
 
 
 def round_up(a: int, b: int) -> int:
@@ -67,9 +69,13 @@ def is_ri32(t: torch.Tensor) -> bool:
     return t.dim() == 5
 
 
-def layout_of(precision: str) -> str:
-    """The stream layout a recurrent-kernel precision works in."""
-    return "ri32" if precision == "tf32x3" else "rowmajor"
+def layout_of(precision: str, hidden: int = 64) -> str:
+    """The stream layout a recurrent-kernel precision works in at the kernels' hidden size (64 / 128 / 256)."""
+    return "ri32" if (precision == "tf32x3" or (precision == "tf32" and hidden == 64)) else "rowmajor"
+
+
+def _ri32_family(precision: int, H: int) -> bool:
+    return precision == _lib.PREC_TF32X3 or (precision == _lib.PREC_TF32 and H == 64)
 
 
 def pack_x(x: torch.Tensor, layout: str = "rowmajor") -> torch.Tensor:
@@ -125,11 +131,11 @@ class LstmFunction(torch.autograd.Function):
     def forward(ctx, xT, w_ih, w_hh, b_ih, b_hh, I: int, dh_t0: int, want_seq: bool, precision: int, B: int):
         for n, t in (("xT", xT), ("weight_ih", w_ih), ("weight_hh", w_hh), ("bias_ih", b_ih), ("bias_hh", b_hh)):
             require_cuda(t, n)
-        ri = precision == _lib.PREC_TF32X3
-        if ri != is_ri32(xT):
-            raise RuntimeError("hy2dl_b200: precision 'tf32x3' works on RI32 inputs and the other precisions on "
-                               f"row-major ones (got a {xT.dim()}-D xT); pack / gather with layout=ops.layout_of(precision)")
         H = w_hh.shape[1]
+        ri = _ri32_family(precision, H)
+        if ri != is_ri32(xT):
+            raise RuntimeError("hy2dl_b200: the resident-weights path (H = 64, precision 'tf32x3' / 'tf32') works on RI32 inputs and "
+                               f"the others on row-major ones (got a {xT.dim()}-D xT); pack / gather with layout=ops.layout_of(precision, H)")
         dev = xT.device
         if ri:
             T, G, IP = xT.shape[0], xT.shape[1], xT.shape[2] * 32
@@ -300,13 +306,12 @@ class LstmHeadFunction(torch.autograd.Function):
     (par_sim flat planes, par_warm [P,N]).  The hidden sequence never leaves the kernels' own layout."""
 
     @staticmethod
-    def forward(ctx, xT, w_ih, w_hh, b_ih, b_hh, w_head, b_head, I: int, layout: ParLayout):
+    def forward(ctx, xT, w_ih, w_hh, b_ih, b_hh, w_head, b_head, I: int, layout: ParLayout, precision: int = _lib.PREC_TF32X3):
         for n, t in (("xT", xT), ("weight_ih", w_ih), ("weight_hh", w_hh), ("bias_ih", b_ih), ("bias_hh", b_hh),
                      ("linear.weight", w_head), ("linear.bias", b_head)):
             require_cuda(t, n)
         if not is_ri32(xT):
-            raise RuntimeError("hy2dl_b200: the fused LSTM + head path works on RI32 inputs (precision 'tf32x3')")
-        precision = _lib.PREC_TF32X3
+            raise RuntimeError("hy2dl_b200: the fused LSTM + head path works on RI32 inputs (H = 64, precision 'tf32x3' / 'tf32')")
         B, H, dev = layout.B, w_hh.shape[1], xT.device
         T, G, IP = xT.shape[0], xT.shape[1], xT.shape[2] * 32
         seq = lambda F: torch.empty(T, G, F // 32, 32, 32, dtype=torch.float32, device=dev)
@@ -331,7 +336,7 @@ class LstmHeadFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dpar_sim, _dpar_warm):
         if dpar_sim is None:
-            return (None,) * 9
+            return (None,) * 10
         xT, w_hh, w_head, h_seq, c_seq, gates, par_sim = ctx.saved_tensors
         B, T, I, IP, H, precision = ctx.meta
         layout, dev = ctx.layout, xT.device
@@ -356,11 +361,11 @@ class LstmHeadFunction(torch.autograd.Function):
         ws_w = _ws(_lib.WS_LSTM_WGRAD, B, T, I, H, dev, precision)
         call("hy2dl_lstm_wgrad", ptr(dG), ptr(h_seq), ptr(xT), B, T, I, IP, H, ptr(dw_ih), ptr(dw_hh), ptr(db),
              ptr(ws_w), ws_w.numel(), precision, C.byref(hw), stream())
-        return None, dw_ih, dw_hh, db, db.clone(), dw_head, db_head, None, None
+        return None, dw_ih, dw_hh, db, db.clone(), dw_head, db_head, None, None, None
 
 
-def lstm_head(xT, w_ih, w_hh, b_ih, b_hh, w_head, b_head, input_size: int, layout: ParLayout):
-    return LstmHeadFunction.apply(xT, w_ih, w_hh, b_ih, b_hh, w_head, b_head, input_size, layout)
+def lstm_head(xT, w_ih, w_hh, b_ih, b_hh, w_head, b_head, input_size: int, layout: ParLayout, precision: str = "tf32x3"):
+    return LstmHeadFunction.apply(xT, w_ih, w_hh, b_ih, b_hh, w_head, b_head, input_size, layout, PRECISIONS[precision])
 
 
 # --------------------------------------------------------------------------------------------------

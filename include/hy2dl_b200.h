@@ -54,9 +54,14 @@ extern "C" {
 typedef void* hy2dl_stream_t; /* cudaStream_t */
 
 /* precision of the recurrent / projection matmuls */
-#define HY2DL_PREC_FP32 0   /* CUDA-core FMA, fp32-exact (parity path, rtol 1e-4)            */
-#define HY2DL_PREC_TF32X3 1 /* tcgen05 kind::tf32, 3-term split (fp32-class accuracy)         */
-#define HY2DL_PREC_BF16 2   /* reserved (kind::f16 single pass, looser tolerance): not built, calls return ERR_SHAPE */
+#define HY2DL_PREC_FP32 0   /* fp32-class (parity path, rtol 1e-4).  H = 64: CUDA-core FMA kernels.  H = 128 / 256: tcgen05
+                             * kind::tf32 with the 3-term operand split and streamed weights (row-major streams, RB8 tapes);
+                             * HY2DL_FP32_TC=0 in the environment selects the CUDA-core kernels there as well */
+#define HY2DL_PREC_TF32X3 1 /* fp32-class: tcgen05 kind::tf32, 3-term split, weights resident on chip (H = 64, RI32 streams) */
+#define HY2DL_PREC_TF32 2   /* throughput mode: the same tensor-core kernels with the correction terms switched off (single-pass
+                             * TF32 operands, 10-bit mantissa, fp32 accumulate).  NOT the parity path: measured against fp64,
+                             * discharge ~1e-3 and gradients ~1e-2 of their scale (tests/test_gpu_parity.py::test_tf32_mode).  Streams
+                             * and tapes as TF32X3 at H = 64 and as FP32 at H = 128 / 256 */
 
 /* layout of the LSTM-side streams handled by the packing / sampler / head functions */
 #define HY2DL_LAYOUT_ROWMAJOR 0 /* [T][B][F]                                                      */
