@@ -71,7 +71,8 @@ struct FwdArgs {
 // packed weight element (chunk c, K index k, column n = 4 uu + g of the chunk): rows scaled by -log2(e) (x 2 for g)
 // and the truncation compensation; k < I: W_ih, k == I: bias, k in [KX, KX + H): W_hh, else 0.
 __global__ void rm_tc_pack_w_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, const float* __restrict__ b_ih,
-                                    const float* __restrict__ b_hh, int H, int I, int KX, int K, float comp, float* __restrict__ out) {
+                                    const float* __restrict__ b_hh, int H, int I, int KX, int K, float comp, int pair,
+                                    float* __restrict__ out) {
   const int NJ = K / 8, NC = H / 32;
   const int64_t total = (int64_t)NC * K * kChunkN;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -86,45 +87,71 @@ __global__ void rm_tc_pack_w_kernel(const float* __restrict__ w_ih, const float*
     v *= (g == 2 ? -2.f : -1.f) * 1.4426950408889634f * comp;
     uint32_t hi, lo;
     split_tf32_rr(v, hi, lo);
-    float* dst = out + ((int64_t)c * NJ + J) * (kStepBytes / 4) + (kc * kChunkN + n) * 4 + kk;
-    dst[0] = __uint_as_float(hi);
-    dst[kStepBytes / 8] = __uint_as_float(lo);
+    if (pair) {      // CTA-pair layout: per K step [rank 0: hi [2][64][4] | lo [2][64][4]] [rank 1: hi | lo]; rank r holds columns 64 r ..
+      float* dst = out + ((int64_t)c * NJ + J) * (kStepBytes / 4) + (n >> 6) * (kStepBytes / 8) + (kc * 64 + (n & 63)) * 4 + kk;
+      dst[0] = __uint_as_float(hi);
+      dst[kStepBytes / 16] = __uint_as_float(lo);
+    } else {
+      float* dst = out + ((int64_t)c * NJ + J) * (kStepBytes / 4) + (kc * kChunkN + n) * 4 + kk;
+      dst[0] = __uint_as_float(hi);
+      dst[kStepBytes / 8] = __uint_as_float(lo);
+    }
   }
 }
 }  // namespace
 
+// PAIR: the kernel runs as clusters of two CTAs on the SMs of one TPC (cta_group::2).  The leader's thread issues every MMA with
+// M = 256 -- 128 sequences from each CTA -- and each CTA streams only ITS half of every weight slice (N/2 = 64 gate columns), so
+// the L2 -> shared-memory weight stream per sequence halves (it bounds the single-CTA kernel at a full wave: 148 CTAs x 2.4 MB
+// per step).  Row threads, tapes and the accumulator hand-shake are per CTA as before; completions are multicast to both CTAs,
+// the peer's arrivals reach the leader's mbarriers through the cluster's shared-memory window.
+template <bool PAIR>
 __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* smem_raw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  const int K = a.K, H = a.H, KX = a.KX, NS = a.stages;
+  const int K = a.K, H = a.H, KX = a.KX;
+  constexpr int kSlot = PAIR ? kSliceBytes / 2 : kSliceBytes;    // bytes of one K step in THIS CTA's ring: hi | lo of its columns
+  const int NS = PAIR ? 2 * a.stages : a.stages;                 // ring slots (<= 16)
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0;
   float* s_alo = reinterpret_cast<float*>(smem_raw);                       // [K/4][128 rows][4]
   float* s_xhi = s_alo + (size_t)K * kRowsF;                               // [KX/4][128 rows][4]
-  uint8_t* s_ring = reinterpret_cast<uint8_t*>(s_xhi + (size_t)KX * kRowsF);   // NS x 8 KB slices
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + (size_t)NS * kSliceBytes);
-  uint64_t* bar_full = bars;                       // [NS <= 8] producer -> MMA
-  uint64_t* bar_free = bars + 8;                   // [NS] MMA commit -> producer
-  uint64_t* bar_dfull = bars + 16;                 // [2] MMA commit -> rows: the split's accumulator region is complete
-  uint64_t* bar_dfree = bars + 18;                 // [2] rows -> MMA: it has been read
-  uint64_t* bar_a = bars + 20;                     // rows -> MMA: A operand of the step is in place
-  uint64_t* bar_step = bars + 21;                  // MMA commit: every MMA of the step retired, A may be rebuilt
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 22);
+  uint8_t* s_ring = reinterpret_cast<uint8_t*>(s_xhi + (size_t)KX * kRowsF);   // NS slots of kSlot bytes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + (size_t)a.stages * kSliceBytes);
+  uint64_t* bar_full = bars;                       // [NS <= 16] producer (+ the peer's relay) -> MMA
+  uint64_t* bar_free = bars + 16;                  // [NS] MMA commit -> producer
+  uint64_t* bar_dfull = bars + 32;                 // [2] MMA commit -> rows: the split's accumulator region is complete
+  uint64_t* bar_dfree = bars + 34;                 // [2] rows -> MMA: it has been read
+  uint64_t* bar_a = bars + 36;                     // rows -> MMA: A operand of the step is in place
+  uint64_t* bar_step = bars + 37;                  // MMA commit: every MMA of the step retired, A may be rebuilt
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 38);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NC = H / 32, NJ = K / 8, JX = KX / 8;
   const int SJ = a.splitj;
   const int NSP = (NJ + SJ - 1) / SJ;               // splits per chunk (the last one may be shorter)
+  // arrivals: every local row thread arrives on bar_a / bar_dfree itself; the peer's eight row warps add one arrival each
+  // (lane 0, after a warp barrier) through the cluster window.  The leader's bar_full takes its own producer's
+  // arrive.expect_tx plus the peer's relay (its copy of the slice has landed).
   if (tid == 0) {
-    for (int s = 0; s < NS; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_free + s, 1); }
-    for (int r = 0; r < 2; ++r) { mbar_init(bar_dfull + r, 1); mbar_init(bar_dfree + r, 256); }
-    mbar_init(bar_a, 256);
+    const uint32_t rows_cnt = PAIR ? 256 + 8 : 256;
+    for (int s = 0; s < NS; ++s) { mbar_init(bar_full + s, (PAIR && rank == 0) ? 2 : 1); mbar_init(bar_free + s, 1); }
+    for (int r = 0; r < 2; ++r) { mbar_init(bar_dfull + r, 1); mbar_init(bar_dfree + r, rows_cnt); }
+    mbar_init(bar_a, rows_cnt);
     mbar_init(bar_step, 1);
     mbar_fence_init();
   }
-  if (warp == 8) tmem_alloc(s_tmem, 512);
+  if (warp == 8) { if (PAIR) tmem_alloc2(s_tmem, 512); else tmem_alloc(s_tmem, 512); }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync();                        // the peer's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
+  // a row thread's arrival on a barrier the MMA issuer waits for
+  auto rows_arrive = [&](uint64_t* bar) {
+    if (!PAIR || rank == 0) { mbar_arrive(bar); return; }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_remote(mapa_rank(smem_u32(bar), 0));
+  };
 
   if (warp < 8) {
     // =========================== row threads ===================================================
@@ -189,7 +216,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
       tmem_st_wait();
       fence_async_smem();
       tc_fence_before();
-      mbar_arrive(bar_a);
+      rows_arrive(bar_a);
 
       // ---- epilogue of every chunk: 16 hidden units of this row
       const float* cprev = (t > 0 && live) ? cbuf(t - 1) : nullptr;
@@ -211,12 +238,12 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
           mbar_wait(bar_dfull + r, (uint32_t)((gsp >> 1) & 1));
           tc_fence_after();
           uint32_t z0[32], z1[32];
-          if ((a.dbg & 4) && sp != NSP - 1) { tc_fence_before(); mbar_arrive(bar_dfree + r); continue; }
+          if ((a.dbg & 4) && sp != NSP - 1) { tc_fence_before(); rows_arrive(bar_dfree + r); continue; }
           tmem_ld32(lane_tm + kColAcc + 128 * r + 64 * hh, z0);
           tmem_ld32(lane_tm + kColAcc + 128 * r + 64 * hh + 32, z1);
           tmem_ld_wait();
           tc_fence_before();
-          mbar_arrive(bar_dfree + r);                             // the region may be overwritten
+          rows_arrive(bar_dfree + r);                             // the region may be overwritten
           if (sp == 0 || (a.dbg & 4)) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) { z[j] = __uint_as_float(z0[j]); z[32 + j] = __uint_as_float(z1[j]); }
@@ -254,20 +281,26 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
       }
     }
   } else if (warp == 8) {
-    // =========================== MMA issuer =====================================================
-    if (elect_one()) {
-      const uint32_t idesc = idesc_tf32(kRowsF, kChunkN, 0, 0);
-      const uint32_t a_lbo = kRowsF * 16, b_lbo = kChunkN * 16, sbo = 128;
-      // descriptors advance by constants (the address field counts 16-byte units): no per-slice rebuilding
+    // =========================== MMA issuer (the leader's, in a pair) ===========================
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc = idesc_tf32(PAIR ? 2 * kRowsF : kRowsF, kChunkN, 0, 0);
+      const uint32_t a_lbo = kRowsF * 16, b_lbo = (PAIR ? kChunkN / 2 : kChunkN) * 16, sbo = 128;
       // descriptors advance by constants (the address field counts 16-byte units): no per-slice rebuilding
       const uint64_t ring_hi0 = smem_desc(smem_u32(s_ring), b_lbo, sbo), alo0 = smem_desc(smem_u32(s_alo), a_lbo, sbo);
       const uint64_t xhi0 = smem_desc(smem_u32(s_xhi), a_lbo, sbo);
-      constexpr uint64_t kStageStep = kSliceBytes / 16, kLoOff = kStepBytes / 32, kAStep = 2 * kRowsF * 16 / 16;
+      constexpr uint64_t kStageStep = kSlot / 16, kLoOff = kSlot / 32, kAStep = 2 * kRowsF * 16 / 16;
+      auto mma_ss = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc) { if (PAIR) mma2_tf32_ss(d, ad, bd, idesc, acc); else mma_tf32_ss(d, ad, bd, idesc, acc); };
+      auto mma_ts = [&](uint32_t d, uint32_t at, uint64_t bd, uint32_t acc) { if (PAIR) mma2_tf32_ts(d, at, bd, idesc, acc); else mma_tf32_ts(d, at, bd, idesc, acc); };
+      auto commit = [&](uint64_t* bar) { if (PAIR) mma2_commit(bar); else mma_commit(bar); };
+      static_assert(true, "");
+      // (a try_wait with .acquire.cluster costs several hundred cycles per poll: 140 us per step against 42 for the plain
+      // form, measured; the plain form is what CUTLASS's ClusterBarrier uses for cluster-wide arrivals as well)
+      auto wait_rows = [&](uint64_t* bar, uint32_t par) { mbar_wait(bar, par); };
       int st = 0;                                   // ring stage of the split's first K step and its phase parity
       uint32_t ph = 0;
       int64_t gsp = 0;                              // split counter
       for (int64_t t = 0; t < a.T; ++t) {
-        mbar_wait(bar_a, (uint32_t)(t & 1));
+        wait_rows(bar_a, (uint32_t)(t & 1));
         tc_fence_after();
         for (int c = 0; c < NC; ++c) {
           for (int Jb = 0; Jb < NJ; Jb += SJ, ++gsp) {
@@ -275,21 +308,21 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
             const int r = (int)(gsp & 1);
             const uint32_t d = tmem + kColAcc + 128 * r;
             if (gsp >= 2) {                         // the rows have drained this region's previous split
-              mbar_wait(bar_dfree + r, (uint32_t)(((gsp >> 1) - 1) & 1));
+              wait_rows(bar_dfree + r, (uint32_t)(((gsp >> 1) - 1) & 1));
               tc_fence_after();
             }
             if (a.single) {                         // single pass: every slice is read once
               for (int j = 0; j < n; ++j) {
                 const int J = Jb + j;
-                mbar_wait(bar_full + st, ph);
+                wait_rows(bar_full + st, ph);
                 tc_fence_after();
                 const uint64_t bh = ring_hi0 + (uint64_t)st * kStageStep;
-                if (J < JX) mma_tf32_ss(d, xhi0 + (uint64_t)J * kAStep, bh, idesc, j > 0);
-                else mma_tf32_ts(d, tmem + 8 * (uint32_t)(J - JX), bh, idesc, j > 0);
-                mma_commit(bar_free + st);
+                if (J < JX) mma_ss(d, xhi0 + (uint64_t)J * kAStep, bh, j > 0);
+                else mma_ts(d, tmem + 8 * (uint32_t)(J - JX), bh, j > 0);
+                commit(bar_free + st);
                 if (++st == NS) { st = 0; ph ^= 1; }
               }
-              mma_commit(bar_dfull + r);
+              commit(bar_dfull + r);
               continue;
             }
             // correction terms first, while the accumulator is ~2^-11 of its final size
@@ -297,13 +330,13 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
               const int J = Jb + j;
               int sj = st + j; uint32_t pj = ph;
               if (sj >= NS) { sj -= NS; pj ^= 1; }
-              mbar_wait(bar_full + sj, pj);
+              wait_rows(bar_full + sj, pj);
               tc_fence_after();
               const uint64_t bh = ring_hi0 + (uint64_t)sj * kStageStep, bl = bh + kLoOff;
-              if (a.dbg & 2) { if (j == 0) mma_tf32_ss(d, alo0 + (uint64_t)J * kAStep, bh, idesc, 0); continue; }
-              mma_tf32_ss(d, alo0 + (uint64_t)J * kAStep, bh, idesc, j > 0);
-              if (J < JX) mma_tf32_ss(d, xhi0 + (uint64_t)J * kAStep, bl, idesc, 1);     // x part: A_hi from shared memory
-              else mma_tf32_ts(d, tmem + 8 * (uint32_t)(J - JX), bl, idesc, 1);           // h part: A_hi in TMEM columns [0, H)
+              if (a.dbg & 2) { if (j == 0) mma_ss(d, alo0 + (uint64_t)J * kAStep, bh, 0); continue; }
+              mma_ss(d, alo0 + (uint64_t)J * kAStep, bh, j > 0);
+              if (J < JX) mma_ss(d, xhi0 + (uint64_t)J * kAStep, bl, 1);     // x part: A_hi from shared memory
+              else mma_ts(d, tmem + 8 * (uint32_t)(J - JX), bl, 1);           // h part: A_hi in TMEM columns [0, H)
             }
             // the split's hi*hi chain; a slice is released once its second reader has been issued
             for (int j = 0; j < n; ++j) {
@@ -311,16 +344,28 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
               int sj = st + j;
               if (sj >= NS) sj -= NS;
               const uint64_t bh = ring_hi0 + (uint64_t)sj * kStageStep;
-              if (J < JX) mma_tf32_ss(d, xhi0 + (uint64_t)J * kAStep, bh, idesc, 1);
-              else mma_tf32_ts(d, tmem + 8 * (uint32_t)(J - JX), bh, idesc, 1);
-              mma_commit(bar_free + sj);
+              if (J < JX) mma_ss(d, xhi0 + (uint64_t)J * kAStep, bh, 1);
+              else mma_ts(d, tmem + 8 * (uint32_t)(J - JX), bh, 1);
+              commit(bar_free + sj);
             }
-            mma_commit(bar_dfull + r);
+            commit(bar_dfull + r);
             st += n;
             if (st >= NS) { st -= NS; ph ^= 1; }
           }
         }
-        mma_commit(bar_step);
+        commit(bar_step);
+      }
+    } else if (PAIR && rank == 1 && lane == 0) {
+      // =========================== the peer's relay ============================================
+      // tells the leader that this CTA's half of a weight slice has landed (a bulk copy can only signal a barrier of the
+      // CTA it writes to)
+      int st = 0;
+      uint32_t ph = 0;
+      const int64_t n_slices = a.T * NC * NJ;
+      for (int64_t i = 0; i < n_slices; ++i) {
+        mbar_wait(bar_full + st, ph);
+        mbar_arrive_remote(mapa_rank(smem_u32(bar_full + st), 0));
+        if (++st == NS) { st = 0; ph ^= 1; }
       }
     }
     __syncwarp();
@@ -331,13 +376,13 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
       int st = 0;
       uint32_t ph = 1;                              // parity of the previous use of the stage (first round: nothing to wait for)
       bool first_round = true;
+      const uint32_t nbytes = a.single ? kSlot / 2 : kSlot;        // hi | lo
       for (int64_t t = 0; t < a.T; ++t) {
-        const float* src = a.wpk;
-        for (int i = 0; i < per_step; ++i, src += kSliceBytes / 4) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wpk) + (PAIR ? rank * kSlot : 0);
+        for (int i = 0; i < per_step; ++i, src += kSliceBytes) {
           if (!first_round) mbar_wait(bar_free + st, ph);
-          const uint32_t nbytes = a.single ? kSliceBytes / 2 : kSliceBytes;        // hi | lo
           mbar_arrive_expect_tx(bar_full + st, nbytes);
-          bulk_g2s(s_ring + (size_t)st * kSliceBytes, src, nbytes, bar_full + st);
+          bulk_g2s(s_ring + (size_t)st * kSlot, src, nbytes, bar_full + st);
           if (++st == NS) { st = 0; ph ^= 1; first_round = false; }
         }
       }
@@ -346,7 +391,12 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (PAIR) {
+    cluster_sync();                                 // both CTAs are done with TMEM and with each other's barriers
+    if (warp == 8) tmem_dealloc2(tmem, 512);
+  } else if (warp == 8) {
+    tmem_dealloc(tmem, 512);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -356,7 +406,7 @@ static void rm_fwd_shape(int64_t I, int64_t H, int& KX, int& K) {
 }
 // ring depth: what is left of the 227 KB after the A images
 static int rm_fwd_stages(int KX, int K) {
-  const int64_t fixed = (int64_t)(K + KX) * kRowsF * 4 + 256 + 1024;
+  const int64_t fixed = (int64_t)(K + KX) * kRowsF * 4 + 512 + 1024;
   return (int)std::min<int64_t>(8, (232448 - fixed) / kSliceBytes);   // 2, 4 and 8 stages measured the same
 }
 
@@ -395,12 +445,16 @@ int lstm_rm_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
   // chains of kSplitJ = 4 accumulating hi*hi MMAs leave a mean truncation loss of ~1.3e-7 of the sum (0.25 * 2^-23 * 4),
   // removed here; what remains is data dependent and an order of magnitude below fp32 rounding.
   const float factor = 1.f + (comp != 0.f ? comp : 1.3e-7f);
-  rm_tc_pack_w_kernel<<<256, 256, 0, s>>>(w_ih, w_hh, b_ih, b_hh, (int)H, (int)I, a.KX, a.K, factor, wpk);
+  // CTA pairs (cta_group::2) unless switched off: HY2DL_RM_PAIR=0
+  static const bool pair = [] { const char* e = getenv("HY2DL_RM_PAIR"); return !(e && e[0] == '0'); }();
+  rm_tc_pack_w_kernel<<<256, 256, 0, s>>>(w_ih, w_hh, b_ih, b_hh, (int)H, (int)I, a.KX, a.K, factor, pair ? 1 : 0, wpk);
   a.x = xT; a.wpk = wpk; a.gates = gates; a.h_last = h_last;
   a.B = B; a.T = T; a.H = (int)H; a.I = (int)I; a.IP = (int)IP;
   a.h_seq = h_seq; a.h_own = scratch;
   a.c_seq = c_seq ? c_seq : scratch + 2 * round_up(B, (int64_t)32) * H; a.c_pingpong = c_seq ? 0 : 1;
   a.stages = rm_fwd_stages(a.KX, a.K);
+  static const int stages_env = [] { const char* e = getenv("HY2DL_RM_STAGES"); return e ? atoi(e) : 0; }();   // experiment: shallower ring
+  if (stages_env >= 3 && stages_env < a.stages) a.stages = stages_env;
   // K steps per split: its slices stay in the ring until the hi*hi pass, so it must leave the producer a free slot.
   // Measured at H = 256, I = 31, B = 18 944, T = 365 (8 stages), forward time / parameter-gradient error vs fp64 on the
   // reference golden of BASELINE configs[2]:  2: 44.9 ms / 2.3e-5,  4: 38.4 / 9.8e-6,  6: 35.5 / 2.2e-5,  7: 35.2 / 3.1e-5;
@@ -417,9 +471,23 @@ int lstm_rm_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
   a.act_sep = act_sep;
   static const int dbg = [] { const char* e = getenv("HY2DL_RM_DBG"); return e ? atoi(e) : 0; }();
   a.dbg = dbg;
-  const size_t smem = (size_t)(a.K + a.KX) * kRowsF * 4 + (size_t)a.stages * kSliceBytes + 256 + 1024;
-  cudaFuncSetAttribute(lstm_rm_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  lstm_rm_tc_fwd_kernel<<<(unsigned)cdiv(B, (int64_t)kRowsF), kThreadsF, smem, s>>>(a);
+  const size_t smem = (size_t)(a.K + a.KX) * kRowsF * 4 + (size_t)a.stages * kSliceBytes + 512 + 1024;
+  const unsigned tiles = (unsigned)cdiv(B, (int64_t)kRowsF);
+  if (pair) {
+    static const int psj_env = [] { const char* e = getenv("HY2DL_RM_PAIR_SPLITJ"); return e ? atoi(e) : 0; }();
+    if (!single && psj_env > 0 && psj_env <= 2 * a.stages - 2) a.splitj = psj_env;    // twice the slots would allow longer splits
+    cudaFuncSetAttribute(lstm_rm_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((tiles + 1) / 2 * 2); cfg.blockDim = dim3(kThreadsF); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, lstm_rm_tc_fwd_kernel<true>, a);
+  } else {
+    cudaFuncSetAttribute(lstm_rm_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lstm_rm_tc_fwd_kernel<false><<<tiles, kThreadsF, smem, s>>>(a);
+  }
   HY_LAUNCH_CHECK();
   return HY2DL_OK;
 }
