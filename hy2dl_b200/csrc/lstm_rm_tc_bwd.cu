@@ -55,7 +55,7 @@ struct BwdArgs {
 };
 
 // packed element (chunk c, K step j = 2 g + half, kc, k_out n, kk): W_hh[g*H + 16 c + 8 half + 4 kc + kk][n]
-__global__ void rm_tc_pack_whh_kernel(const float* __restrict__ w_hh, int H, float comp, float* __restrict__ out) {
+__global__ void rm_tc_pack_whh_kernel(const float* __restrict__ w_hh, int H, float comp, int pair, float* __restrict__ out) {
   const int step_floats = 2 * H * 4 * 2;                      // hi | lo of one K step
   const int64_t total = (int64_t)4 * H * H;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -67,42 +67,62 @@ __global__ void rm_tc_pack_whh_kernel(const float* __restrict__ w_hh, int H, flo
     const int row = g * H + kUnitsC * c + 8 * half + 4 * kc + kk;
     uint32_t hi, lo;
     split_tf32_rr(w_hh[(int64_t)row * H + n] * comp, hi, lo);
-    float* dst = out + ((int64_t)c * 8 + j) * step_floats + (kc * H + n) * 4 + kk;
-    dst[0] = __uint_as_float(hi);
-    dst[step_floats / 2] = __uint_as_float(lo);
+    if (pair) {    // CTA-pair layout: per K step [rank 0: hi [2][H/2][4] | lo] [rank 1: hi | lo]; rank r holds output columns r H/2 ..
+      const int hn = H / 2;
+      float* dst = out + ((int64_t)c * 8 + j) * step_floats + (n / hn) * (step_floats / 2) + (kc * hn + (n % hn)) * 4 + kk;
+      dst[0] = __uint_as_float(hi);
+      dst[step_floats / 4] = __uint_as_float(lo);
+    } else {
+      float* dst = out + ((int64_t)c * 8 + j) * step_floats + (kc * H + n) * 4 + kk;
+      dst[0] = __uint_as_float(hi);
+      dst[step_floats / 2] = __uint_as_float(lo);
+    }
   }
 }
 }  // namespace
 
+// PAIR: clusters of two CTAs (cta_group::2): the leader issues every MMA with M = 256 (128 sequences of each CTA), each CTA
+// streams only its half of every W_hh slice (H/2 output columns); see lstm_rm_tc_fwd.cu.
+template <bool PAIR>
 __global__ void __launch_bounds__(kThreadsB, 1) lstm_rm_tc_bwd_kernel(BwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* smem_raw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  const int H = a.H, NS = a.stages, NCH = H / kUnitsC;
-  const int step_bytes = 2 * H * 4 * 4 * 2;                   // one K step of packed W_hh: hi | lo (16 KB at H = 256)
+  const int H = a.H, NCH = H / kUnitsC;
+  const int NS = PAIR ? 2 * a.stages : a.stages;              // ring slots (<= 16)
+  const int full_step_bytes = 2 * H * 4 * 4 * 2;              // one K step of packed W_hh, both CTAs' columns: hi | lo (16 KB at H = 256)
+  const int step_bytes = PAIR ? full_step_bytes / 2 : full_step_bytes;   // this CTA's part = one ring slot
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0;
   uint8_t* s_a = smem_raw;                                    // [2 buffers][hi 32 KB | lo 32 KB], image [16 kc][128 rows][4]
   uint8_t* s_ring = s_a + 2 * kABufBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + (size_t)NS * step_bytes);
-  uint64_t* bar_full = bars;                       // [NS] producer -> MMA
-  uint64_t* bar_free = bars + 8;                   // [NS] MMA commit -> producer
-  uint64_t* bar_afull = bars + 16;                 // [2] rows -> MMA: A image of a chunk is in place
-  uint64_t* bar_afree = bars + 18;                 // [2] MMA commit -> rows: the chunk's MMAs retired
-  uint64_t* bar_group = bars + 20;                 // MMA commit: a group's MMAs retired, accumulators complete
-  uint64_t* bar_pulled = bars + 21;                // rows -> MMA: accumulators have been read
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 22);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + (size_t)a.stages * full_step_bytes);
+  uint64_t* bar_full = bars;                       // [NS <= 16] producer (+ the peer's relay) -> MMA
+  uint64_t* bar_free = bars + 16;                  // [NS] MMA commit -> producer
+  uint64_t* bar_afull = bars + 32;                 // [2] rows -> MMA: A image of a chunk is in place
+  uint64_t* bar_afree = bars + 34;                 // [2] MMA commit -> rows: the chunk's MMAs retired
+  uint64_t* bar_group = bars + 36;                 // MMA commit: a group's MMAs retired, accumulators complete
+  uint64_t* bar_pulled = bars + 37;                // rows -> MMA: accumulators have been read
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 38);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < NS; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_free + s, 1); }
-    for (int p = 0; p < 2; ++p) { mbar_init(bar_afull + p, 256); mbar_init(bar_afree + p, 1); }
+    const uint32_t rows_cnt = PAIR ? 256 + 8 : 256;           // + one arrival per row warp of the peer
+    for (int s = 0; s < NS; ++s) { mbar_init(bar_full + s, (PAIR && rank == 0) ? 2 : 1); mbar_init(bar_free + s, 1); }
+    for (int p = 0; p < 2; ++p) { mbar_init(bar_afull + p, rows_cnt); mbar_init(bar_afree + p, 1); }
     mbar_init(bar_group, 1);
-    mbar_init(bar_pulled, 256);
+    mbar_init(bar_pulled, rows_cnt);
     mbar_fence_init();
   }
-  if (warp == 8) tmem_alloc(s_tmem, 512);
+  if (warp == 8) { if (PAIR) tmem_alloc2(s_tmem, 512); else tmem_alloc(s_tmem, 512); }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync();
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
+  auto rows_arrive = [&](uint64_t* bar) {            // a row thread's arrival on a barrier the MMA issuer waits for
+    if (!PAIR || rank == 0) { mbar_arrive(bar); return; }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_remote(mapa_rank(smem_u32(bar), 0));
+  };
   const uint32_t col_main = 0, col_corr = (uint32_t)H;        // H = 256: [0,256) | [256,512)
 
   if (warp < 8) {
@@ -179,7 +199,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) lstm_rm_tc_bwd_kernel(BwdArgs a)
           img_lo[(kc0 + 1) * kRowsB + rloc] = make_float4(__uint_as_float(lo[4]), __uint_as_float(lo[5]), __uint_as_float(lo[6]), __uint_as_float(lo[7]));
         }
         fence_async_smem();
-        mbar_arrive(bar_afull + buf);
+        rows_arrive(bar_afull + buf);
         ++gch;
       };
       auto pull = [&](int g) {                     // group g of this step: main + corrections -> its partial of dh_rec(t-1)
@@ -206,7 +226,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) lstm_rm_tc_bwd_kernel(BwdArgs a)
           }
         }
         tc_fence_before();
-        mbar_arrive(bar_pulled);
+        rows_arrive(bar_pulled);
         ++ggr;
       };
       Tape cur, nxt;
@@ -222,15 +242,17 @@ __global__ void __launch_bounds__(kThreadsB, 1) lstm_rm_tc_bwd_kernel(BwdArgs a)
       pull(n_groups - 1);
     }
   } else if (warp == 8) {
-    // =========================== MMA issuer =====================================================
-    if (elect_one()) {
-      const uint32_t idesc = idesc_tf32(kRowsB, H, 0, 0);
-      const uint32_t a_lbo = kRowsB * 16, b_lbo = (uint32_t)H * 16, sbo = 128;
+    // =========================== MMA issuer (the leader's, in a pair) ===========================
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc = idesc_tf32(PAIR ? 2 * kRowsB : kRowsB, H, 0, 0);
+      const uint32_t a_lbo = kRowsB * 16, b_lbo = (uint32_t)(PAIR ? H / 2 : H) * 16, sbo = 128;
       const uint32_t d_main = tmem + col_main, d_corr = tmem + col_corr;
       const uint64_t ring0 = smem_desc(smem_u32(s_ring), b_lbo, sbo);
       const uint64_t a0[2] = {smem_desc(smem_u32(s_a), a_lbo, sbo), smem_desc(smem_u32(s_a + kABufBytes), a_lbo, sbo)};
       const uint64_t kStageStep = (uint64_t)step_bytes / 16, kBLo = (uint64_t)step_bytes / 32;
       constexpr uint64_t kALo = kABufBytes / 32, kAStep = 2 * kRowsB * 16 / 16;
+      auto mma_ss = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc) { if (PAIR) mma2_tf32_ss(d, ad, bd, idesc, acc); else mma_tf32_ss(d, ad, bd, idesc, acc); };
+      auto commit = [&](uint64_t* bar) { if (PAIR) mma2_commit(bar); else mma_commit(bar); };
       int st = 0;
       uint32_t ph = 0;
       uint64_t dbh = ring0;
@@ -253,18 +275,28 @@ __global__ void __launch_bounds__(kThreadsB, 1) lstm_rm_tc_bwd_kernel(BwdArgs a)
             const uint64_t bl = dbh + kBLo;
             const uint32_t acc = !(open && j == 0);
             if (!a.single) {
-              mma_tf32_ss(d_corr, dal, dbh, idesc, acc);
-              mma_tf32_ss(d_corr, dah, bl, idesc, 1);
+              mma_ss(d_corr, dal, dbh, acc);
+              mma_ss(d_corr, dah, bl, 1);
             }
-            mma_tf32_ss(d_main, dah, dbh, idesc, acc);
+            mma_ss(d_main, dah, dbh, acc);
             dah += kAStep; dal += kAStep;
-            mma_commit(bar_free + st);
+            commit(bar_free + st);
             dbh += kStageStep;
             if (++st == NS) { st = 0; ph ^= 1; dbh = ring0; }
           }
-          mma_commit(bar_afree + buf);
-          if ((c % kGroup) == kGroup - 1) { mma_commit(bar_group); ++ggr; }
+          commit(bar_afree + buf);
+          if ((c % kGroup) == kGroup - 1) { commit(bar_group); ++ggr; }
         }
+      }
+    } else if (PAIR && rank == 1 && lane == 0) {
+      // the peer's relay: tells the leader that this CTA's half of a W_hh slice has landed
+      int st = 0;
+      uint32_t ph = 0;
+      const int64_t n_slices = a.T * NCH * 8;
+      for (int64_t i = 0; i < n_slices; ++i) {
+        mbar_wait(bar_full + st, ph);
+        mbar_arrive_remote(mapa_rank(smem_u32(bar_full + st), 0));
+        if (++st == NS) { st = 0; ph ^= 1; }
       }
     }
     __syncwarp();
@@ -275,11 +307,11 @@ __global__ void __launch_bounds__(kThreadsB, 1) lstm_rm_tc_bwd_kernel(BwdArgs a)
       int st = 0;
       uint32_t ph = 1;
       bool first_round = true;
+      const uint32_t nbytes = a.single ? (uint32_t)step_bytes / 2 : (uint32_t)step_bytes;    // hi | lo
       for (int64_t s = 0; s < a.T; ++s) {
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wpk);
-        for (int i = 0; i < per_step; ++i, src += step_bytes) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wpk) + (PAIR ? rank * step_bytes : 0);
+        for (int i = 0; i < per_step; ++i, src += full_step_bytes) {
           if (!first_round) mbar_wait(bar_free + st, ph);
-          const uint32_t nbytes = a.single ? (uint32_t)step_bytes / 2 : (uint32_t)step_bytes;    // hi | lo
           mbar_arrive_expect_tx(bar_full + st, nbytes);
           bulk_g2s(s_ring + (size_t)st * step_bytes, src, nbytes, bar_full + st);
           if (++st == NS) { st = 0; ph ^= 1; first_round = false; }
@@ -290,13 +322,18 @@ __global__ void __launch_bounds__(kThreadsB, 1) lstm_rm_tc_bwd_kernel(BwdArgs a)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (PAIR) {
+    cluster_sync();
+    if (warp == 8) tmem_dealloc2(tmem, 512);
+  } else if (warp == 8) {
+    tmem_dealloc(tmem, 512);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 static int rm_bwd_stages(int64_t H) {
   const int64_t step_bytes = 2 * H * 4 * 4 * 2;
-  return (int)std::min<int64_t>(8, (232448 - 2 * kABufBytes - 256 - 1024) / step_bytes);
+  return (int)std::min<int64_t>(8, (232448 - 2 * kABufBytes - 512 - 1024) / step_bytes);
 }
 
 bool lstm_rm_tc_bwd_supported(int64_t H) {
@@ -321,16 +358,30 @@ int lstm_rm_tc_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const flo
   // kernel: parameter-gradient error vs an fp64 evaluation (H = 256, T = 365) 4.1e-5 / 4.0e-5 / 4.3e-5 / 4.6e-5 for a
   // compensation of 0 / 5e-7 / 1.1e-6 / 1.7e-6 (CUDA-core chain: 2.0e-5).  HY2DL_RM_BCOMP overrides.
   static const float comp = [] { const char* e = getenv("HY2DL_RM_BCOMP"); return e ? (float)atof(e) : 5e-7f; }();
-  rm_tc_pack_whh_kernel<<<256, 256, 0, s>>>(w_hh, (int)H, 1.f + comp, wpk);
+  // CTA pairs (HY2DL_RM_PAIR=1): parity-green, not faster (30.9 ms against 30.6 ms at H = 256; 10.4 / 9.7 at H = 128), see lstm_rm_tc_fwd.cu
+  static const bool pair = [] { const char* e = getenv("HY2DL_RM_PAIR"); return e && e[0] == '1'; }();
+  rm_tc_pack_whh_kernel<<<256, 256, 0, s>>>(w_hh, (int)H, 1.f + comp, pair ? 1 : 0, wpk);
   const int64_t Bp = round_up(B, (int64_t)32);
   cudaMemsetAsync(scratch, 0, sizeof(float) * 3 * Bp * H, s);
   a.wpk = wpk; a.gates = gates; a.c_seq = c_seq; a.dh_seq = dh_seq; a.dh_last = dh_last; a.dG = dG;
   a.dc = scratch; a.dh = scratch + Bp * H;
   a.B = B; a.T = T; a.dh_t0 = dh_t0; a.H = (int)H; a.single = single;
   a.stages = rm_bwd_stages(H);
-  const size_t smem = (size_t)2 * kABufBytes + (size_t)a.stages * (2 * H * 4 * 4 * 2) + 256 + 1024;
-  cudaFuncSetAttribute(lstm_rm_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  lstm_rm_tc_bwd_kernel<<<(unsigned)cdiv(B, (int64_t)kRowsB), kThreadsB, smem, s>>>(a);
+  const size_t smem = (size_t)2 * kABufBytes + (size_t)a.stages * (2 * H * 4 * 4 * 2) + 512 + 1024;
+  const unsigned tiles = (unsigned)cdiv(B, (int64_t)kRowsB);
+  if (pair) {
+    cudaFuncSetAttribute(lstm_rm_tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((tiles + 1) / 2 * 2); cfg.blockDim = dim3(kThreadsB); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, lstm_rm_tc_bwd_kernel<true>, a);
+  } else {
+    cudaFuncSetAttribute(lstm_rm_tc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lstm_rm_tc_bwd_kernel<false><<<tiles, kThreadsB, smem, s>>>(a);
+  }
   HY_LAUNCH_CHECK();
   return HY2DL_OK;
 }

@@ -445,8 +445,12 @@ int lstm_rm_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
   // chains of kSplitJ = 4 accumulating hi*hi MMAs leave a mean truncation loss of ~1.3e-7 of the sum (0.25 * 2^-23 * 4),
   // removed here; what remains is data dependent and an order of magnitude below fp32 rounding.
   const float factor = 1.f + (comp != 0.f ? comp : 1.3e-7f);
-  // CTA pairs (cta_group::2) unless switched off: HY2DL_RM_PAIR=0
-  static const bool pair = [] { const char* e = getenv("HY2DL_RM_PAIR"); return !(e && e[0] == '0'); }();
+  // CTA pairs (cta_group::2, M = 256): HY2DL_RM_PAIR=1.  Built, parity-green (the whole -m gpu suite passes with it) and NOT
+  // the default: at H = 256, B = 18 944, T = 365 it runs 36.4 ms against 36.8 ms single-CTA (H = 128: 12.3 / 11.8), i.e. halving
+  // the weight stream per SM buys nothing -- what bounds this kernel is the row threads' chain (accumulator pulls through the
+  // 64 B/clk TMEM read port, activations, 0.9 MB of tape stores per step and CTA), see the HY2DL_RM_DBG ablation in DESIGN.md.
+  // With twice the ring slots a pair can run longer splits (HY2DL_RM_PAIR_SPLITJ=12: 28.7 ms) at the accuracy of chains of 12.
+  static const bool pair = [] { const char* e = getenv("HY2DL_RM_PAIR"); return e && e[0] == '1'; }();
   rm_tc_pack_w_kernel<<<256, 256, 0, s>>>(w_ih, w_hh, b_ih, b_hh, (int)H, (int)I, a.KX, a.K, factor, pair ? 1 : 0, wpk);
   a.x = xT; a.wpk = wpk; a.gates = gates; a.h_last = h_last;
   a.B = B; a.T = T; a.H = (int)H; a.I = (int)I; a.IP = (int)IP;
