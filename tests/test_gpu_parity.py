@@ -150,6 +150,33 @@ def test_sampler_gather(dev):
     assert torch.equal(b2.as_reference()["x_lstm"], ref["x_lstm"])
 
 
+def test_sampler_gather_through_from_reference(dev):
+    """`ResidentDataset.from_reference(dataset)`: the route a notebook takes.  The GPU box has no reference tree, so the
+    object handed over here carries the attributes of a constructed, standardised `BaseDataset` (basedataset.py:56-163,
+    251-267) rebuilt from the sampler golden (tests/test_cpu_host.py runs the same route on the real reference class);
+    the gathered batch must equal the reference's own samples."""
+    from types import SimpleNamespace
+    from hy2dl_b200.datasetzoo import ResidentDataset
+    g = golden("sampler")
+    nb, nr, L, n_last = [int(v) for v in g["meta"]]
+    t = lambda a: torch.tensor(np.asarray(a, dtype=np.float32))
+    ids = [str(i) for i in range(nb)]
+    seq = {b: {"x_d": t((g["x_d"][k] - g["scaler_x_d_mean"]) / g["scaler_x_d_std"]), "y_obs": t(g["y_obs"][k]),
+               "x_conceptual": t(g["x_d"][k]), "x_s": t((g["x_s"][k] - g["scaler_x_s_mean"]) / g["scaler_x_s_std"])}
+           for k, b in enumerate(ids)}
+    ref_ds = SimpleNamespace(entities_ids=ids, sequence_data=seq, sequence_length=L, predict_last_n=n_last,
+                             valid_entities=[(str(b), int(i)) for b, i in g["valid_entities"]],
+                             scaler={k[7:]: t(v) for k, v in g.items() if k.startswith("scaler_")},
+                             basin_std={b: t(g["std_per_basin"][k]) for k, b in enumerate(ids)})
+    ds = ResidentDataset.from_reference(ref_ds, device=dev)
+    assert len(ds) == len(g["valid_entities"]) and ds.basin_ids == ids
+    ref = ds.gather(torch.tensor(g["pick"], device=dev)).as_reference()
+    assert_close(npy(ref["x_lstm"]), g["x_lstm"], rtol=1e-5, atol=1e-6, what="x_lstm")
+    assert_close(npy(ref["x_conceptual"]), g["x_conceptual"], rtol=0, what="x_conceptual")
+    assert_close(npy(ref["y_obs"]), g["y_win"], rtol=0, what="y window")
+    assert_close(npy(ref["basin_std"]), g["basin_std"], rtol=1e-6, what="basin_std")
+
+
 # ------------------------------------------------------------------------------------------------
 # model-level cases against the reference's golden vectors
 # ------------------------------------------------------------------------------------------------
