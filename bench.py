@@ -264,6 +264,12 @@ def port_train_steps(cfg, steps, warmup, batch=256, seed=42, device="cpu"):
             "ms_per_step": per_step * 1e3, "batch": batch}
 
 
+def run_gpu_library(args):
+    """One (config, batch) of the stated library baseline on cuda:0 (child process of the default bench line)."""
+    r = port_train_steps(CFG, max(1, min(args.steps, 3)), 1, batch=args.batch, device="cuda:0")
+    print(json.dumps({"value": r["value"], "unit": "sequences/s", "ms_per_step": r["ms_per_step"], "sample": r["sample"]}))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -683,16 +689,18 @@ def run_ours(args):
                 configs[name + "_tf32"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
             torch.cuda.empty_cache()
         # stated library baseline: the oracle port (same torch ops as the reference) on THIS GPU -- nn.LSTM -> cuDNN, the
-        # bucket loop as eager ATen ops -- i.e. what the unmodified reference does with running_device = "gpu"
+        # bucket loop as eager ATen ops -- i.e. what the unmodified reference does with running_device = "gpu".  It runs in
+        # a child process (`--impl gpu_library`), so that the process of our arm never calls into the cuDNN RNN path.
         gpu_lib = {}
         for name, batches in (("c1", (256, 16384)), ("c3", (256, 4096)), ("c2", (256,))):
             for b_ in batches:
                 try:
-                    r = port_train_steps(CONFIGS[name], 2, 1, batch=b_, device="cuda:0")
-                    gpu_lib[f"{name}_b{b_}"] = {"value": r["value"], "unit": "sequences/s", "ms_per_step": r["ms_per_step"], "sample": r["sample"]}
+                    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "gpu_library", "--config", name,
+                                          "--batch", str(b_), "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+                    js = [l for l in out.stdout.splitlines() if l.startswith("{")]
+                    gpu_lib[f"{name}_b{b_}"] = json.loads(js[-1]) if js else {"error": (out.stderr or "no output")[-200:]}
                 except Exception as ex:
                     gpu_lib[f"{name}_b{b_}"] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
-                torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:
         r = port_train_steps(cfg, 2 if cfg["H"] >= 128 else 3, 1)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -720,7 +728,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "gpu_library"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json config to measure as the headline (default c2 = configs[1])")
     ap.add_argument("--batch", type=int, default=DEFAULT_BATCH, help="sequences per GPU per step (saturating: 128-row tiles x 148 SMs)")
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x3", "tf32"],
@@ -738,6 +746,8 @@ def main():
     CFG = CONFIGS[args.config]
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "gpu_library":
+        run_gpu_library(args)
     else:
         run_ours(args)
 
