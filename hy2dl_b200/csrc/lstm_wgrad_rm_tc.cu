@@ -156,39 +156,62 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_wgrad_rm_tc_kernel(Args a) {
     const int lrow = ct >> 3, lch = ct & 7;
     const uint32_t ldst = (uint32_t)(lrow * 128 + ((((lch >> 1) ^ (lrow & 3)) << 5) | ((lch & 1) << 4)));
     const int F4 = 4 * a.H;
-    auto load_slab = [&](int64_t j) {
-      const int s = (int)(j % kStages);
-      if (j < n_my) {
-        const int64_t slab = part + j * a.parts, t = slab / a.G, grp = slab - t * a.G;
-        const int64_t b = grp * 32 + lrow;
+    // The loader threads are this kernel's critical resource (ncu source view: they are busy, not waiting), so everything
+    // that does not depend on the slab is hoisted: slab j of this CTA is (t, grp) = divmod(part + j * parts, G), advanced
+    // incrementally (a 64-bit division per slab and thread was 6 % of the kernel's samples), the per-thread offsets inside a
+    // slab are constants, and the B-part source of every block is decided once.
+    const int64_t step_t = a.parts / a.G, step_g = a.parts - step_t * a.G;       // divmod(parts, G), once
+    int64_t ld_j = 0, ld_t = part / a.G, ld_g = part - (part / a.G) * a.G;       // next slab to load
+    const int64_t g_off = ((int64_t)(32 * mt + (lch >> 1))) * 256 + lrow * 8 + (lch & 1) * 4;
+    const int64_t slab_floats = (int64_t)(F4 >> 3) * 256;                        // dG floats per (t, group) slab
+    int64_t boff[4];                                                             // B block k: offset inside row r of h (< 0: x), or unused
+    bool bx[4], bvalid[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int fb = NB * nt + k;
+      bx[k] = fb >= HB;
+      const int col = bx[k] ? 32 * (fb - HB) + 4 * lch : 32 * fb + 4 * lch;
+      bvalid[k] = k < NB && (!bx[k] || col < a.IP);
+      boff[k] = col;
+    }
+    auto load_slab = [&]() {
+      const int s = (int)(ld_j % kStages);
+      if (ld_j < n_my) {
+        const int64_t slab = ld_t * a.G + ld_g;
+        const int64_t b = ld_g * 32 + lrow;
         const bool in = b < a.B;
-        const int64_t r = t * a.B + b;                 // row of the row-major streams
+        const int64_t r = ld_t * a.B + b;              // row of the row-major streams
         const uint32_t st = smem_u32(smem_raw + s * stage_bytes) + ldst;
         // RB8: 8-float block (256 mt + 32 k) / 8 + lch / 2 of sequence lrow, 16-byte half lch & 1
-        const float* g = a.dG + ((slab * (F4 >> 3) + 32 * mt + (lch >> 1)) * 256 + lrow * 8 + (lch & 1) * 4);
+        const float* g = a.dG + slab * slab_floats + g_off;
 #pragma unroll
         for (int k = 0; k < 8; ++k) cp_async16_zfill(st + k * kBlk, in ? g + 4 * k * 256 : a.dG, in);
+        const float* hrow = a.h + (r - a.B) * a.H;
+        const float* xrow = a.x + r * a.IP;
 #pragma unroll
-        for (int k = 0; k < NB; ++k) {
-          const int fb = NB * nt + k;
-          const float* src;
-          bool valid = in;
-          if (fb < HB) {
-            valid = valid && t > 0;
-            src = a.h + (r - a.B) * a.H + 32 * fb + 4 * lch;
-          } else {
-            const int col = 32 * (fb - HB) + 4 * lch;
-            valid = valid && col < a.IP;
-            src = a.x + r * a.IP + col;
+        for (int k = 0; k < 4; ++k) {
+          if (k < NB) {
+            const bool valid = in && bvalid[k] && (bx[k] || ld_t > 0);
+            cp_async16_zfill(st + (8 + k) * kBlk, valid ? (bx[k] ? xrow : hrow) + boff[k] : a.dG, valid);
           }
-          cp_async16_zfill(st + (8 + k) * kBlk, valid ? src : a.dG, valid);
         }
       }
-      cp_async_arrive(bar_full + s);     // also for j >= n_my: nobody waits for those phases
+      cp_async_arrive(bar_full + s);     // also for slabs past the end: nobody waits for those phases
+      ++ld_j;
+      ld_t += step_t; ld_g += step_g;
+      if (ld_g >= a.G) { ld_g -= a.G; ++ld_t; }
     };
-    load_slab(0);
-    load_slab(1);
+    load_slab();
+    load_slab();
     float4* lo_a4 = reinterpret_cast<float4*>(s_lo);
+    // float4 index (A part first) of the ones column among THIS thread's float4s of a stage, or -1: thread ct handles the
+    // B-part float4s eb = ct, ct + kConv, ...; float4 `pos` of row `row` of block `blk` holds features
+    // 8 ((pos >> 1) ^ (row & 3)) + 4 (pos & 1) .. + 3 of the block
+    int ones_e = -1;
+    for (int eb = ct; eb < NB * kBlk4; eb += kConv) {
+      const int blk = eb / kBlk4, w = eb - blk * kBlk4, row = w >> 3, pos = w & 7;
+      if (blk == ones_blk && (((pos >> 1) ^ (row & 3)) * 8 + (pos & 1) * 4) == (ones_col & ~3)) ones_e = kABytes / 16 + eb;
+    }
     for (int64_t i = 0; i < n_my; ++i) {
       const int s = (int)(i % kStages);
       float4* raw = reinterpret_cast<float4*>(smem_raw + s * stage_bytes);
@@ -196,14 +219,10 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_wgrad_rm_tc_kernel(Args a) {
       constexpr int kA4 = kABytes / 16;
       auto split4 = [&](int e) {                             // lo = v - trunc(v); the landed words are the hi operand
         float4 v = raw[e];
-        if (e >= kA4) {
-          const int eb = e - kA4, blk = eb / kBlk4, w = eb - blk * kBlk4, row = w >> 3, pos = w & 7;
-          // float4 `pos` of row `row` holds features 8 ((pos >> 1) ^ (row & 3)) + 4 (pos & 1) .. + 3 of the block
-          if (blk == ones_blk && (((pos >> 1) ^ (row & 3)) * 8 + (pos & 1) * 4) == (ones_col & ~3)) {
-            const int k = ones_col & 3;
-            if (k == 0) v.x = 1.f; else if (k == 1) v.y = 1.f; else if (k == 2) v.z = 1.f; else v.w = 1.f;
-            raw[e] = v;
-          }
+        if (e == ones_e) {                                   // the ones column of the bias gradient (decided once, below)
+          const int k = ones_col & 3;
+          if (k == 0) v.x = 1.f; else if (k == 1) v.y = 1.f; else if (k == 2) v.z = 1.f; else v.w = 1.f;
+          raw[e] = v;
         }
         const float4 hv = make_float4(__uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u),
                                       __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
@@ -224,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_wgrad_rm_tc_kernel(Args a) {
       mbar_arrive(bar_conv + 0);
       // ---- half 1: gate columns [128, 256)
       if (i > 0) mbar_wait(bar_lo_free + 1, (uint32_t)((i - 1) & 1));
-      load_slab(i + 2);      // its stage held slab i - 1, whose MMAs (hi operands) have just been seen to retire
+      load_slab();           // slab i + 2: its stage held slab i - 1, whose MMAs (hi operands) have just been seen to retire
 #pragma unroll 4
       for (int e = ct; e < 4 * kBlk4; e += kConv) split4(4 * kBlk4 + e);
       fence_async_smem();
