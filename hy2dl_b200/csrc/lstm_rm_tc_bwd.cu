@@ -340,13 +340,23 @@ bool lstm_rm_tc_bwd_supported(int64_t H) {
   return H == 128 || H == 256;
 }
 
+// the unit-split kernel for small batches (lstm_us_tc_bwd.cu)
+bool lstm_us_tc_bwd_supported(int64_t H);
+bool lstm_us_tc_bwd_preferred(int64_t B, int64_t H);
+int64_t lstm_us_tc_bwd_workspace(int64_t B, int64_t H);
+int lstm_us_tc_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const float* gates, const float* c_seq, const float* dh_seq,
+                   int64_t dh_t0, const float* dh_last, float* dG, void* ws, int64_t ws_bytes, int single, cudaStream_t s);
+
 // packed W_hh (hi | lo) + dc [B][H] + dh [2][B][H]
 int64_t lstm_rm_tc_bwd_workspace(int64_t B, int64_t H) {
-  return sizeof(float) * (8 * H * H + 3 * round_up(B, (int64_t)32) * H) + 256;
+  const int64_t own = sizeof(float) * (8 * H * H + 3 * round_up(B, (int64_t)32) * H) + 256;
+  return lstm_us_tc_bwd_preferred(B, H) ? std::max(own, lstm_us_tc_bwd_workspace(B, H)) : own;
 }
 
 int lstm_rm_tc_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const float* gates, const float* c_seq, const float* dh_seq,
                    int64_t dh_t0, const float* dh_last, float* dG, void* ws, int64_t ws_bytes, int single, cudaStream_t s) {
+  if (lstm_us_tc_bwd_preferred(B, H))
+    return lstm_us_tc_bwd(B, T, H, w_hh, gates, c_seq, dh_seq, dh_t0, dh_last, dG, ws, ws_bytes, single, s);
   const int64_t need = lstm_rm_tc_bwd_workspace(B, H);
   HY_REQUIRE(ws != nullptr && ws_bytes >= need, HY2DL_ERR_WORKSPACE, "hy2dl_lstm_bwd: workspace %lld < %lld bytes (H = %lld needs the "
              "packed W_hh and the dc / dh scratch)", (long long)ws_bytes, (long long)need, (long long)H);

@@ -417,16 +417,27 @@ bool lstm_rm_tc_fwd_supported(int64_t I, int64_t H) {
   return KX <= kMaxKX && rm_fwd_stages(KX, K) >= 3;
 }
 
+// the unit-split kernel for small batches (lstm_us_tc_fwd.cu)
+bool lstm_us_tc_fwd_supported(int64_t I, int64_t H);
+bool lstm_us_tc_fwd_preferred(int64_t B, int64_t I, int64_t H);
+int64_t lstm_us_tc_fwd_workspace(int64_t B, int64_t I, int64_t H);
+int lstm_us_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H, const float* w_ih, const float* w_hh,
+                   const float* b_ih, const float* b_hh, float* h_seq, float* c_seq, float* gates, float* h_last, void* ws,
+                   int64_t ws_bytes, int single, cudaStream_t s);
+
 // packed weights + (if no tape is requested) ping-pong buffers for h and c
 int64_t lstm_rm_tc_fwd_workspace(int64_t B, int64_t I, int64_t H) {
   int KX, K;
   rm_fwd_shape(I, H, KX, K);
-  return sizeof(float) * ((int64_t)(H / 32) * K * kChunkN * 2 + 4 * round_up(B, (int64_t)32) * H) + 256;   // weights + h_own + c ping-pong
+  const int64_t own = sizeof(float) * ((int64_t)(H / 32) * K * kChunkN * 2 + 4 * round_up(B, (int64_t)32) * H) + 256;   // weights + h_own + c ping-pong
+  return lstm_us_tc_fwd_supported(I, H) ? std::max(own, lstm_us_tc_fwd_workspace(B, I, H)) : own;
 }
 
 int lstm_rm_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H, const float* w_ih, const float* w_hh,
                    const float* b_ih, const float* b_hh, float* h_seq, float* c_seq, float* gates, float* h_last, void* ws,
                    int64_t ws_bytes, int single, cudaStream_t s) {
+  if (lstm_us_tc_fwd_preferred(B, I, H))
+    return lstm_us_tc_fwd(xT, B, T, I, IP, H, w_ih, w_hh, b_ih, b_hh, h_seq, c_seq, gates, h_last, ws, ws_bytes, single, s);
   const int64_t need = lstm_rm_tc_fwd_workspace(B, I, H);
   HY_REQUIRE(ws != nullptr && ws_bytes >= need, HY2DL_ERR_WORKSPACE, "hy2dl_lstm_fwd: workspace %lld < %lld bytes",
              (long long)ws_bytes, (long long)need);

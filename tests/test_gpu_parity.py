@@ -375,7 +375,11 @@ def test_train_steps_bit_reproducible(dev, precision, H):
                                                 # H = 128 / 256 tensor-core chain (streamed weights, blocked tapes): a single step, the
                                                 # widest input (ones column in its own K step), two tiles with a ragged second one
                                                 (1, 1, 3, 128, "fp32"), (130, 3, 64, 256, "fp32"), (33, 2, 8, 128, "fp32"),
-                                                (200, 120, 31, 256, "fp32")])
+                                                (200, 120, 31, 256, "fp32"),
+                                                # unit-split kernels (small batches, lstm_us_tc_*.cu): 11 tiles on 9 groups of 16
+                                                # CTAs (a group walks over two tiles, the last one ragged), 8-CTA groups with two
+                                                # x chunks, and the largest batch they take at H = 128 (72 tiles on 18 groups)
+                                                (1300, 6, 31, 256, "fp32"), (300, 9, 50, 128, "fp32"), (9216, 3, 12, 128, "fp32")])
 def test_lstm_vs_oracle(dev, B, T, I, H, precision):
     from hy2dl_b200.modelzoo import LSTM
     from hy2dl_b200.synthetic import lstm_weights
@@ -413,7 +417,8 @@ def test_lstm_real_shapes_vs_oracle(dev, B, T, I, H, wscale):
     gradient at rtol 1e-4 (tensor level) with the element-wise figures recorded (tests/_util.assert_close).
     Inputs are shaped like the reference's samples (dynamic forcings + static attributes constant in time).  Where the
     recurrence itself amplifies rounding (trained-like weights at H = 256) the bound is widened to 3 x the distance of
-    the fp32 oracle (the reference's arithmetic) from the fp64 one on the same inputs -- never below 1e-4."""
+    the fp32 oracle (the reference's arithmetic) from the fp64 one on the same inputs -- never below 1e-4 -- and the
+    element-wise allowance to 3 x the fp32 oracle's own share of elements outside the gate."""
     from _util import camels_like_inputs
     from hy2dl_b200.modelzoo import LSTM
     from hy2dl_b200.synthetic import lstm_weights
@@ -438,14 +443,19 @@ def test_lstm_real_shapes_vs_oracle(dev, B, T, I, H, wscale):
     ref, gref = oracle(torch.float64)
     rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
     rtol_h, rtol_g = 1e-4, 1e-4
+    frac = {}
     if wscale != 1.0:
+        from _util import gate_fraction
         r32, g32 = oracle(torch.float32)
         rtol_h = max(1e-4, 3 * rel(r32, ref))
         rtol_g = max(1e-4, 3 * max(rel(g32[k], gref[k]) for k in gref))
+        # the element-wise allowance is calibrated the same way: 3 x the share of the fp32 oracle's own elements outside
+        # the gate, never below the default 1e-3 (one of the 1024 bias gradients is outside for the fp32 oracle itself)
+        frac = {k: max(1e-3, 3 * gate_fraction(g32[k], gref[k], rtol_g, 1e-6)) for k in gref}
     assert_close(npy(out), ref, what="h_seq", rtol=rtol_h, atol=1e-6)
     assert_close(npy(hn[0]), ref[:, -1], what="h_n", rtol=rtol_h, atol=1e-6)
     for k, p in lstm.named_parameters():
-        assert_close(npy(p.grad), gref[k], what="grad " + k, rtol=rtol_g, atol=1e-6)
+        assert_close(npy(p.grad), gref[k], what="grad " + k, rtol=rtol_g, atol=1e-6, max_frac=frac.get(k))
 
 
 def test_hybrid_random_configurations(dev):
@@ -769,6 +779,34 @@ def test_trainer_native_path_matches_api_path(dev, precision):
     pred = model(x_lstm=ref["x_lstm"], x_conceptual=ref["x_conceptual"])
     l_api = nse_basin_averaged(y_sim=pred["y_hat"], y_obs=ref["y_obs"], per_basin_target_std=ref["basin_std"])
     assert_close(l_api.item(), losses[0][0], rtol=1e-6, what="API vs native loss")
+
+
+def test_unit_split_kernels_replay_in_a_cuda_graph(dev):
+    """The small-batch H = 128 / 256 kernels are cooperative launches (their CTAs wait for each other): they must be
+    capturable, since Trainer(use_graph=True) replays the whole step -- three graph-replayed updates equal three eager
+    ones bit for bit (the path has no atomics on floating-point data)."""
+    from hy2dl_b200.datasetzoo import ResidentDataset
+    from hy2dl_b200.modelzoo import CudaLSTM
+    from hy2dl_b200.synthetic import lstm_weights, make_basins
+    from hy2dl_b200.training import Trainer
+    data = make_basins("gb", n_basins=4, n_rows=120, seed=3)
+    L, H = 30, 128
+    ds = ResidentDataset(data.x_d, data.y_obs, L, 1, x_s=data.x_s, device=dev)
+    ds.calculate_basin_std(); ds.calculate_global_statistics(); ds.standardize_data(standardize_output=False)
+    hp = {"input_size_lstm": ds.input_size, "hidden_size": H, "no_of_layers": 1, "seq_length": L, "predict_last_n": 1,
+          "drop_out_rate": 0.0}
+    w = {k: torch.tensor(v) for k, v in lstm_weights(ds.input_size, H, 1, seed=4).items()}
+    ids = torch.randperm(len(ds), device=dev)[:40]
+    res = []
+    for graph in (False, True):
+        model = CudaLSTM(hp)
+        model.load_state_dict(w)
+        tr = Trainer(model.to(dev), ds, loss="nse", use_graph=graph)
+        losses = [tr.step(ids).item() for _ in range(3)]
+        res.append((losses, {k: v.detach().clone() for k, v in model.state_dict().items()}))
+    assert res[0][0] == res[1][0], f"graph replay losses {res[1][0]} vs eager {res[0][0]}"
+    for k in res[0][1]:
+        assert torch.equal(res[0][1][k], res[1][1][k]), k
 
 
 # ------------------------------------------------------------------------------------------------
