@@ -61,6 +61,11 @@ __global__ void us_pack_whh_kernel(const float* __restrict__ w_hh, int H, float 
   }
 }
 
+__device__ __forceinline__ uint32_t ld_relaxed_gpu_v(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ uint32_t ld_acquire_gpu_v(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -129,20 +134,26 @@ __global__ void __launch_bounds__(kThreadsV, 1) lstm_us_tc_bwd_kernel(UsBwdArgs 
           if (a.dh_last && st == 0) { const f8 e = ld256(a.dh_last + b * H + kUnitsV * s + 8 * hh); for (int k = 0; k < 8; ++k) dh.v[k] += e.v[k]; }
         }
         // ---- dh_rec(t): the S partials of the previous step, added in a fixed order
-        if (gs > 0) {
+        if (gs > 0) {                               // acquire polls by every thread: the fastest variant measured (lstm_us_tc_fwd.cu)
           const uint32_t target = (uint32_t)(gs * S);
           uint32_t spins = 0;
-          while ((int32_t)(ld_acquire_gpu_v(flag) - target) < 0) {
+          while ((int32_t)(ld_relaxed_gpu_v(flag) - target) < 0) {
             if (++spins > kSpinLimitV) __trap();
           }
+          (void)ld_acquire_gpu_v(flag);
         }
         if (st > 0) {
           const float* pp = a.px + ((((st - 1) & 1) * (int64_t)a.groups + group) * kRowsV + rloc) * S * H + kUnitsV * s + 8 * hh;
-          f8 acc = ld256_l2v(pp);
-          for (int j = 1; j < S; ++j) {
-            const f8 v = ld256_l2v(pp + (int64_t)j * H);
+          f8 acc = f8_zero();
+          for (int j0 = 0; j0 < S; j0 += 8) {     // 8 loads in flight (S is 8 or 16), then a fixed-order sum
+            f8 v[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc.v[k] += v.v[k];
+            for (int j = 0; j < 8; ++j) v[j] = ld256_l2v(pp + (int64_t)(j0 + j) * H);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) acc.v[k] += v[j].v[k];
+            }
           }
 #pragma unroll
           for (int k = 0; k < 8; ++k) dh.v[k] += acc.v[k];
@@ -204,9 +215,8 @@ __global__ void __launch_bounds__(kThreadsV, 1) lstm_us_tc_bwd_kernel(UsBwdArgs 
             st256(po + c0 + 8 * i, v);
           }
         }
-        __threadfence();
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (tid == 0) atomicAdd(flag, 1u);
+        if (tid == 0) { __threadfence(); atomicAdd(flag, 1u); }
       }
     }
   } else {

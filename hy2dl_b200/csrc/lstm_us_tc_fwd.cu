@@ -31,7 +31,13 @@ namespace {
 constexpr int kRowsU = 128;
 constexpr int kUnitsU = 16;                 // hidden units per CTA
 constexpr int kColsU = 64;                  // gate columns per CTA: column n = 4 uu + g
-constexpr int kChunkK = 32;                 // K columns per A chunk (4 K steps)
+// Ring geometry: 2 slots of 32 K columns.  4 slots of 16 columns (same bytes, chains still 4 K steps) measured SLOWER
+// (H = 128: 2.32 vs 2.13 ms; H = 256, I = 41: 4.20 vs 4.09): the per-slot hand-shake, not the pipeline depth, is what costs.
+constexpr int kChunkK = 32;                 // K columns per A chunk = ring slot (4 K steps)
+constexpr int kGroupK = 32;                 // K columns per accumulation chain (4 K steps) = one TMEM region
+constexpr int kCPR = kGroupK / kChunkK;     // chunks per region
+constexpr int kSlotsU = 2;                  // ring slots
+constexpr int kNV = kChunkK / 8;            // 256-bit loads per row and chunk
 constexpr int kThreadsU = 288;              // warps 0-3 own the rows (gates, state, tapes), 4-7 build A, warp 8 issues the MMAs
 constexpr int kHalfSlotU = kRowsU * kChunkK * 4;          // hi image of a chunk, 16 KB; lo follows
 constexpr int kSlotBytesU = 2 * kHalfSlotU;
@@ -76,6 +82,11 @@ __global__ void us_pack_w_kernel(const float* __restrict__ w_ih, const float* __
   }
 }
 
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -97,21 +108,21 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
   const int K = a.K, H = a.H, KX = a.KX, S = a.S;
   const int wbytes = K * kColsU * 4;                                 // one image (hi or lo) of the weight slice
   uint8_t* s_w = smem_raw;                                           // [hi | lo][K/4][64][4]
-  uint8_t* s_ring = s_w + 2 * (size_t)wbytes;                        // 2 slots of [hi | lo][8][128 rows][4]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + 2 * (size_t)kSlotBytesU);
-  uint64_t* bar_full = bars;            // [2] builders -> MMA
-  uint64_t* bar_free = bars + 2;        // [2] MMA commit -> builders
-  uint64_t* bar_reg = bars + 4;         // [8] MMA commit -> rows: chain region (7: correction region = whole step) complete
-  uint64_t* bar_rfree = bars + 12;      // [8] rows -> MMA: the region has been read
-  uint64_t* bar_w = bars + 20;          // weight slice has landed
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 21);
+  uint8_t* s_ring = s_w + 2 * (size_t)wbytes;                        // kSlotsU slots of [hi | lo][kChunkK / 4][128 rows][4]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + kSlotsU * (size_t)kSlotBytesU);
+  uint64_t* bar_full = bars;            // [4] builders -> MMA
+  uint64_t* bar_free = bars + 4;        // [4] MMA commit -> builders
+  uint64_t* bar_reg = bars + 8;         // [8] MMA commit -> rows: chain region (7: correction region = whole step) complete
+  uint64_t* bar_rfree = bars + 16;      // [8] rows -> MMA: the region has been read
+  uint64_t* bar_w = bars + 24;          // weight slice has landed
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 25);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int group = blockIdx.x / S, s = blockIdx.x % S;
   const int NXC = KX / kChunkK, NHC = H / kChunkK;
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_full + i, 128); mbar_init(bar_free + i, 1); }
-    for (int r = 0; r <= kRegU; ++r) { mbar_init(bar_reg + r, 1); mbar_init(bar_rfree + r, 128); }
+    for (int i = 0; i < kSlotsU; ++i) { mbar_init(bar_full + i, 4); mbar_init(bar_free + i, 1); }       // one arrival per warp
+    for (int r = 0; r <= kRegU; ++r) { mbar_init(bar_reg + r, 1); mbar_init(bar_rfree + r, 4); }
     mbar_init(bar_w, 1);
     mbar_fence_init();
   }
@@ -136,7 +147,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
       for (int u = 0; u < kUnitsU; ++u) c[u] = 0.f;
       for (int64_t t = 0; t < a.T; ++t) {
         // ---- add the chain regions as they complete (round to nearest)
-        const int nch = NXC + (t > 0 ? NHC : 0);
+        const int nch = (NXC + (t > 0 ? NHC : 0)) / kCPR;          // accumulation chains of the step
         float z[kColsU];
         for (int ch = 0; ch < nch + (a.single ? 0 : 1); ++ch) {
           const int r = ch < nch ? ch % kRegU : kRegU;             // after the chains: the correction region
@@ -148,7 +159,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
             uint32_t z0[32];
             tmem_ld32(lane_tm + kColsU * r + 32 * hp, z0);
             tmem_ld_wait();
-            if (hp == 1) { tc_fence_before(); mbar_arrive(bar_rfree + r); }
+            if (hp == 1) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar_rfree + r); }
             if (ch == 0) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) z[32 * hp + j] = __uint_as_float(z0[j]);
@@ -174,9 +185,8 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
         float* hxo = a.hx + ((t & 1) * (int64_t)a.tiles * kRowsU + brow) * H + kUnitsU * s;
         st256(hxo, hv[0]);
         st256(hxo + 8, hv[1]);
-        __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (tid == 0) atomicAdd(flag, 1u);
+        if (tid == 0) { __threadfence(); atomicAdd(flag, 1u); }
         // ---- tapes (nobody waits for them)
         if (live) {
           if (a.h_seq) { float* p = a.h_seq + (t * a.B + brow) * H + kUnitsU * s; stg256(p, hv[0]); stg256(p + 8, hv[1]); }
@@ -198,13 +208,13 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
     const int row = tid - 128;
     uint32_t nfill = 0;                                             // chunks built so far
     int64_t gs = 0;                                                 // step counter over all tiles of the group
-    auto fill = [&](const f8 (&v)[4]) {                             // 32 K columns of this row: split, store K-major
-      const uint32_t slot = nfill & 1, u = nfill >> 1;
+    auto fill = [&](const f8 (&v)[kNV]) {                           // kChunkK columns of this row: split, store K-major
+      const uint32_t slot = nfill & (kSlotsU - 1), u = nfill / kSlotsU;
       if (u > 0) { mbar_wait(bar_free + slot, (u - 1) & 1); tc_fence_after(); }
       float4* hi4 = reinterpret_cast<float4*>(s_ring + (size_t)slot * kSlotBytesU);
       float4* lo4 = hi4 + kHalfSlotU / 16;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int q = 0; q < kChunkK / 4; ++q) {
         const float* src = v[q >> 1].v + 4 * (q & 1);
         uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
         split_tf32(src[0], h0, l0); split_tf32(src[1], h1, l1); split_tf32(src[2], h2, l2); split_tf32(src[3], h3, l3);
@@ -212,7 +222,8 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
         lo4[q * kRowsU + row] = make_float4(__uint_as_float(l0), __uint_as_float(l1), __uint_as_float(l2), __uint_as_float(l3));
       }
       fence_async_smem();
-      mbar_arrive(bar_full + slot);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + slot);
       ++nfill;
     };
     for (int tile = group; tile < a.tiles; tile += a.groups) {
@@ -222,9 +233,9 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
         // ---- A chunks of x_t (no dependence on the other CTAs: built while the rows finish step t-1)
         const float* xr = a.x + (t * a.B + brow) * a.IP;
         for (int xc = 0; xc < NXC; ++xc) {
-          f8 v[4];
+          f8 v[kNV];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < kNV; ++i) {
             const int k0 = kChunkK * xc + 8 * i;
             v[i] = (live && k0 < a.IP) ? ldg256(xr + k0) : f8_zero();
             if ((a.I >> 3) == (k0 >> 3)) {                          // the ones column (bias) is input column I
@@ -236,23 +247,29 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
         }
         // ---- A chunks of h_{t-1}: wait until every CTA of the group has published its units
         if (t > 0) {
-          const uint32_t target = (uint32_t)(gs * S);
-          uint32_t spins = 0;
-          while ((int32_t)(ld_acquire_gpu(flag) - target) < 0) {
-            if (++spins > kSpinLimit) __trap();
+          // every builder polls with acquire loads.  Measured alternatives (B = 256, T = 365, forward / BPTT, H = 256 | 128):
+          // this 3.49 / 4.36 | 2.37 / 2.71 ms; relaxed polls + one fence per thread 3.58 / 4.50 | 2.53 / 2.90; one polling
+          // thread + CTA barrier, one cumulative fence on the writer's side (the grid-barrier pattern) - / 4.59 | 2.32 / 3.03.
+          {
+            const uint32_t target = (uint32_t)(gs * S);
+            uint32_t spins = 0;
+            while ((int32_t)(ld_relaxed_gpu(flag) - target) < 0) {
+              if (++spins > kSpinLimit) __trap();
+            }
+            (void)ld_acquire_gpu(flag);
           }
           const float* hp = a.hx + (((t - 1) & 1) * (int64_t)a.tiles * kRowsU + brow) * H;
-          f8 cur[4], nxt[4];                                        // loads run one chunk ahead of the split
+          f8 cur[kNV], nxt[kNV];                                    // loads run one chunk ahead of the split
 #pragma unroll
-          for (int i = 0; i < 4; ++i) cur[i] = ld256_l2(hp + 8 * i);
+          for (int i = 0; i < kNV; ++i) cur[i] = ld256_l2(hp + 8 * i);
           for (int hc = 0; hc < NHC; ++hc) {
             if (hc + 1 < NHC) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) nxt[i] = ld256_l2(hp + kChunkK * (hc + 1) + 8 * i);
+              for (int i = 0; i < kNV; ++i) nxt[i] = ld256_l2(hp + kChunkK * (hc + 1) + 8 * i);
             }
             fill(cur);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+            for (int i = 0; i < kNV; ++i) cur[i] = nxt[i];
           }
         }
       }
@@ -284,11 +301,11 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
           const int nch = NXC + (t > 0 ? NHC : 0);
           if (!a.single) claim(kRegU);
           for (int ch = 0; ch < nch; ++ch, ++nuse) {
-            const uint32_t slot = nuse & 1, u = nuse >> 1;
+            const uint32_t slot = nuse & (kSlotsU - 1), u = nuse / kSlotsU;
             mbar_wait(bar_full + slot, u & 1);
             tc_fence_after();
-            const int r = ch % kRegU;
-            claim(r);
+            const int r = (ch / kCPR) % kRegU, cr = ch % kCPR;      // region of this chain, chunk within the chain
+            if (cr == 0) claim(r);
             const uint32_t dreg = tmem + kColsU * r;
             const uint64_t ahi = ring0 + slot * kSlotStep, alo = ahi + kLoStep;
 #pragma unroll
@@ -298,10 +315,10 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
                 mma_tf32_ss(dcorr, alo + j * kAStep, whi0 + bo, idesc, (ch | j) != 0);
                 mma_tf32_ss(dcorr, ahi + j * kAStep, wlo0 + bo, idesc, 1);
               }
-              mma_tf32_ss(dreg, ahi + j * kAStep, whi0 + bo, idesc, j != 0);
+              mma_tf32_ss(dreg, ahi + j * kAStep, whi0 + bo, idesc, (cr | j) != 0);
             }
             mma_commit(bar_free + slot);
-            mma_commit(bar_reg + r);
+            if (cr == kCPR - 1) mma_commit(bar_reg + r);
           }
           if (!a.single) mma_commit(bar_reg + kRegU);
         }
@@ -314,7 +331,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
   if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
-int us_kx(int64_t I) { return (int)round_up(I + 1, kChunkK); }
+int us_kx(int64_t I) { return (int)round_up(I + 1, kGroupK); }
 }  // namespace
 
 // co-resident groups the device can hold
@@ -327,8 +344,8 @@ static int us_groups(int64_t B, int64_t H) {
 bool lstm_us_tc_fwd_supported(int64_t I, int64_t H) {
   if (!(H == 128 || H == 256)) return false;
   const int KX = us_kx(I);
-  if (KX > 2 * kChunkK) return false;
-  const int64_t smem = (int64_t)(KX + H) * kColsU * 8 + 2 * kSlotBytesU + 256 + 1024;
+  if (KX > 2 * kGroupK) return false;
+  const int64_t smem = (int64_t)(KX + H) * kColsU * 8 + kSlotsU * kSlotBytesU + 256 + 1024;
   return smem <= 232448 && sm_count() >= H / kUnitsU;
 }
 
@@ -377,7 +394,7 @@ int lstm_us_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
   a.h_seq = h_seq; a.c_seq = c_seq; a.gates = gates; a.h_last = h_last;
   a.B = B; a.T = T; a.H = (int)H; a.I = (int)I; a.IP = (int)IP;
   a.single = single;
-  const size_t smem = (size_t)a.K * kColsU * 8 + 2 * kSlotBytesU + 256 + 1024;
+  const size_t smem = (size_t)a.K * kColsU * 8 + kSlotsU * kSlotBytesU + 256 + 1024;
   cudaFuncSetAttribute(lstm_us_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(a.groups * a.S)); cfg.blockDim = dim3(kThreadsU); cfg.dynamicSmemBytes = smem; cfg.stream = s;
