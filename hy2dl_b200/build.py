@@ -19,7 +19,7 @@ OBJ = os.path.join(CSRC, "build")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("HY2DL_NVCC_EXTRA", "").split()      # e.g. -DHY2DL_US_STAMPS (timeline instrumentation of the unit-split kernels)
 # bucket / routing / loss kernels are latency- and HBM-bound: keep mul and add unfused so that the
 # step arithmetic rounds like the reference's separate ATen ops
 NO_FMAD = {"conceptual.cu", "routing.cu", "loss.cu"}

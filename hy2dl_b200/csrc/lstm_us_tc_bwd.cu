@@ -37,11 +37,12 @@ struct UsBwdArgs {
   const float* dh_seq;  // [T][B][H] row-major or null
   const float* dh_last; // [B][H] or null
   float* dG;            // RB8 tape, may alias gates
-  float* px;            // [2][groups][128 rows][S][H] partials of dh_rec
+  float* px;            // [2][groups][S][H/8][128 rows][8] partials of dh_rec
   uint32_t* flags;      // [groups], zero at launch
   int64_t B, T, dh_t0;
   int H, S, groups, tiles;
   int single;
+  long long* stamps;    // HY2DL_US_DBG bit 128: clock64 timeline of CTA 0, reverse steps 100-101
 };
 
 __global__ void us_pack_whh_kernel(const float* __restrict__ w_hh, int H, float comp, float* __restrict__ out) {
@@ -80,6 +81,11 @@ __device__ __forceinline__ f8 ld256_l2v(const float* p) {          // never an L
   return r;
 }
 
+#ifdef HY2DL_US_STAMPS    // timeline instrumentation, see lstm_us_tc_fwd.cu
+#define USB_STAMP(id) do { if (a.stamps && blockIdx.x == 0 && tid == 0 && st >= 100 && st < 102) a.stamps[(st - 100) * 16 + (id)] = clock64(); } while (0)
+#else
+#define USB_STAMP(id) do { } while (0)
+#endif
 __global__ void __launch_bounds__(kThreadsV, 1) lstm_us_tc_bwd_kernel(UsBwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* smem_raw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -89,15 +95,16 @@ __global__ void __launch_bounds__(kThreadsV, 1) lstm_us_tc_bwd_kernel(UsBwdArgs 
   uint8_t* s_a = s_w + 2 * (size_t)wbytes;                           // [hi | lo][16 k4][128 rows][4]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + 2 * (size_t)kAImgV);
   uint64_t* bar_a = bars;               // rows -> MMA: A image in place (and the accumulator of the previous step read)
-  uint64_t* bar_acc = bars + 1;         // MMA commit -> rows
-  uint64_t* bar_w = bars + 2;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* bar_acc = bars + 1;         // [2] MMA commit -> rows: column half hh of the accumulator is complete
+  uint64_t* bar_w = bars + 3;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int group = blockIdx.x / S, s = blockIdx.x % S;
   if (tid == 0) {
     mbar_init(bar_a, 256);
     mbar_init(bar_acc, 1);
+    mbar_init(bar_acc + 1, 1);
     mbar_init(bar_w, 1);
     mbar_fence_init();
   }
@@ -133,6 +140,7 @@ __global__ void __launch_bounds__(kThreadsV, 1) lstm_us_tc_bwd_kernel(UsBwdArgs 
           if (a.dh_seq && t >= a.dh_t0) dh = ld256(a.dh_seq + (t * a.B + b) * H + kUnitsV * s + 8 * hh);
           if (a.dh_last && st == 0) { const f8 e = ld256(a.dh_last + b * H + kUnitsV * s + 8 * hh); for (int k = 0; k < 8; ++k) dh.v[k] += e.v[k]; }
         }
+        USB_STAMP(0);
         // ---- dh_rec(t): the S partials of the previous step, added in a fixed order
         if (gs > 0) {                               // acquire polls by every thread: the fastest variant measured (lstm_us_tc_fwd.cu)
           const uint32_t target = (uint32_t)(gs * S);
@@ -142,13 +150,14 @@ __global__ void __launch_bounds__(kThreadsV, 1) lstm_us_tc_bwd_kernel(UsBwdArgs 
           }
           (void)ld_acquire_gpu_v(flag);
         }
+        USB_STAMP(1);
         if (st > 0) {
-          const float* pp = a.px + ((((st - 1) & 1) * (int64_t)a.groups + group) * kRowsV + rloc) * S * H + kUnitsV * s + 8 * hh;
+          const float* pp = a.px + (((((st - 1) & 1) * (int64_t)a.groups + group) * S * HB + ub) * kRowsV + rloc) * 8;   // partial j: + j * HB * 1024
           f8 acc = f8_zero();
           for (int j0 = 0; j0 < S; j0 += 8) {     // 8 loads in flight (S is 8 or 16), then a fixed-order sum
             f8 v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = ld256_l2v(pp + (int64_t)(j0 + j) * H);
+            for (int j = 0; j < 8; ++j) v[j] = ld256_l2v(pp + (int64_t)(j0 + j) * HB * (kRowsV * 8));
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
 #pragma unroll
@@ -158,6 +167,7 @@ __global__ void __launch_bounds__(kThreadsV, 1) lstm_us_tc_bwd_kernel(UsBwdArgs 
 #pragma unroll
           for (int k = 0; k < 8; ++k) dh.v[k] += acc.v[k];
         }
+        USB_STAMP(2);
         // ---- gate gradients of this thread's 8 units
         f8 di, df, dg, dO;
 #pragma unroll
@@ -179,6 +189,7 @@ __global__ void __launch_bounds__(kThreadsV, 1) lstm_us_tc_bwd_kernel(UsBwdArgs 
           if (tid == 0) atomicAdd(flag, 1u);
           continue;
         }
+        USB_STAMP(3);
         // ---- A image [128 x 64]: K index 16 g + 8 hh + k
         {
           float4* img_hi = reinterpret_cast<float4*>(s_a);
@@ -199,24 +210,38 @@ __global__ void __launch_bounds__(kThreadsV, 1) lstm_us_tc_bwd_kernel(UsBwdArgs 
         fence_async_smem();
         tc_fence_before();
         mbar_arrive(bar_a);
+        USB_STAMP(4);
         // ---- this CTA's partial of dh_rec(t-1): columns [hh H/2, (hh+1) H/2) of the accumulator -> exchange buffer
-        mbar_wait(bar_acc, (uint32_t)((gs - (tile - group) / a.groups) & 1));      // one MMA round per step but the last of a tile
+        mbar_wait(bar_acc + hh, (uint32_t)((gs - (tile - group) / a.groups) & 1));      // one MMA round per step but the last of a tile
         tc_fence_after();
-        float* po = a.px + ((((st & 1) * (int64_t)a.groups + group) * kRowsV + rloc) * S + s) * H + hh * HH;
-        for (int c0 = 0; c0 < HH; c0 += 32) {
-          uint32_t z[32];
+        USB_STAMP(5);
+        // exchange layout [slot][group][s][H/8 column blocks][128 rows][8]: a warp's 256-bit accesses cover 1 KB contiguous (row-major
+        // partials cost 4.1 us per step here and 1.9 us in the sum above: 32 lines per instruction)
+        float* po = a.px + (((((st & 1) * (int64_t)a.groups + group) * S + s) * HB + hh * (HB / 2)) * kRowsV + rloc) * 8;
+        for (int c0 = 0; c0 < HH; c0 += 64) {        // two 32-column pulls in flight
+          uint32_t z[32], y[32];
           tmem_ld32(lane_tm + hh * HH + c0, z);
+          tmem_ld32(lane_tm + hh * HH + c0 + 32, y);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             f8 v;
 #pragma unroll
             for (int k = 0; k < 8; ++k) v.v[k] = __uint_as_float(z[8 * i + k]);
-            st256(po + c0 + 8 * i, v);
+            st256(po + (c0 / 8 + i) * (kRowsV * 8), v);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            f8 v;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v.v[k] = __uint_as_float(y[8 * i + k]);
+            st256(po + (c0 / 8 + 4 + i) * (kRowsV * 8), v);
           }
         }
+        USB_STAMP(6);
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (tid == 0) { __threadfence(); atomicAdd(flag, 1u); }
+        USB_STAMP(7);
       }
     }
   } else {
@@ -228,7 +253,10 @@ __global__ void __launch_bounds__(kThreadsV, 1) lstm_us_tc_bwd_kernel(UsBwdArgs 
         for (int off = 0; off < 2 * wbytes; off += 16384) bulk_g2s(s_w + off, src + off, (uint32_t)min(16384, 2 * wbytes - off), bar_w);
         mbar_wait(bar_w, 0);
       }
-      const uint32_t idesc = idesc_tf32(kRowsV, H, 0, 0);
+      // the accumulator is computed in two column halves (N = H/2 each) with a commit in between: the row threads of
+      // half 0 pull and publish their columns while the tensor core still multiplies half 1 (the pull -- 128 KB through the
+      // 64 B/clk TMEM read port -- and the MMAs took 4.2 k + 3.3 k cycles one after the other, measured with HY2DL_US_STAMPS)
+      const uint32_t idesc = idesc_tf32(kRowsV, H / 2, 0, 0);
       const uint64_t whi0 = smem_desc(smem_u32(s_w), (uint32_t)H * 16, 128), wlo0 = smem_desc(smem_u32(s_w + wbytes), (uint32_t)H * 16, 128);
       const uint64_t ahi0 = smem_desc(smem_u32(s_a), kRowsV * 16, 128), alo0 = smem_desc(smem_u32(s_a + kAImgV), kRowsV * 16, 128);
       const uint64_t kBStep = (uint64_t)(2 * H * 16 / 16);
@@ -238,16 +266,20 @@ __global__ void __launch_bounds__(kThreadsV, 1) lstm_us_tc_bwd_kernel(UsBwdArgs 
         for (int64_t st = 0; st + 1 < a.T; ++st, ++n) {
           mbar_wait(bar_a, (uint32_t)(n & 1));
           tc_fence_after();
-          if (!a.single) {
+          for (int half = 0; half < 2; ++half) {
+            const uint32_t d = tmem + (uint32_t)(half * (H / 2));
+            const uint64_t bo = (uint64_t)(half * (H / 2));            // column n of B: n * 16 bytes
+            if (!a.single) {
 #pragma unroll
-            for (int j = 0; j < kKV / 8; ++j) {        // correction terms first, while the accumulator is small
-              mma_tf32_ss(tmem, alo0 + j * kAStep, whi0 + j * kBStep, idesc, j != 0);
-              mma_tf32_ss(tmem, ahi0 + j * kAStep, wlo0 + j * kBStep, idesc, 1);
+              for (int j = 0; j < kKV / 8; ++j) {        // correction terms first, while the accumulator is small
+                mma_tf32_ss(d, alo0 + j * kAStep, whi0 + bo + j * kBStep, idesc, j != 0);
+                mma_tf32_ss(d, ahi0 + j * kAStep, wlo0 + bo + j * kBStep, idesc, 1);
+              }
             }
-          }
 #pragma unroll
-          for (int j = 0; j < kKV / 8; ++j) mma_tf32_ss(tmem, ahi0 + j * kAStep, whi0 + j * kBStep, idesc, (a.single && j == 0) ? 0 : 1);
-          mma_commit(bar_acc);
+            for (int j = 0; j < kKV / 8; ++j) mma_tf32_ss(d, ahi0 + j * kAStep, whi0 + bo + j * kBStep, idesc, (a.single && j == 0) ? 0 : 1);
+            mma_commit(bar_acc + half);
+          }
         }
       }
     }
@@ -309,7 +341,16 @@ int lstm_us_tc_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const flo
   attr[0].id = cudaLaunchAttributeCooperative;       // all CTAs co-resident, or the launch fails: they wait for each other
   attr[0].val.cooperative = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  static const int dbg = [] { const char* e = getenv("HY2DL_US_DBG"); return e ? atoi(e) : 0; }();
+  if (dbg & 128) { cudaMalloc(&a.stamps, 32 * sizeof(long long)); cudaMemset(a.stamps, 0, 32 * sizeof(long long)); }
   cudaLaunchKernelEx(&cfg, lstm_us_tc_bwd_kernel, a);
+  if (a.stamps) {                                   // debugging only: timeline of CTA 0, thread 0, reverse steps 100-101
+    long long h[32];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, a.stamps, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(a.stamps);
+    for (int i = 0; i < 32; ++i) if (h[i]) fprintf(stderr, "USB_STAMP step %d id %2d  %8lld\n", 100 + i / 16, i % 16, h[i] - h[0]);
+  }
   HY_LAUNCH_CHECK();
   return HY2DL_OK;
 }

@@ -47,7 +47,7 @@ constexpr uint32_t kSpinLimit = 1u << 26;
 struct UsFwdArgs {
   const float* x;       // [T][B][IP]
   const float* wpk;     // [S][hi | lo][K/4][64][4]
-  float* hx;            // [2][tiles * 128][H] row-major exchange buffer
+  float* hx;            // [2][tiles][H/8][128][8] exchange buffer
   uint32_t* flags;      // [groups] arrival counters, zero at launch
   float* h_seq;         // [T][B][H] or null
   float* c_seq;         // RB8 tape or null
@@ -57,6 +57,7 @@ struct UsFwdArgs {
   int H, I, IP, KX, K;  // KX = x columns incl. the ones column, rounded up to 32; K = KX + H
   int S, groups, tiles;
   int single;           // HY2DL_PREC_TF32: hi*hi only
+  long long* stamps;    // -DHY2DL_US_STAMPS + HY2DL_US_DBG=128: clock64 timeline of CTA 0, steps 100-101
 };
 
 __global__ void us_pack_w_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, const float* __restrict__ b_ih,
@@ -102,6 +103,12 @@ __device__ __forceinline__ f8 ld256_l2(const float* p) {
   return r;
 }
 
+// Timeline instrumentation (compile with -DHY2DL_US_STAMPS, run with HY2DL_US_DBG=128): how DESIGN.md 3.8's per-step budget was measured.
+#ifdef HY2DL_US_STAMPS
+#define US_STAMP(id) do { if (a.stamps && blockIdx.x == 0 && t >= 100 && t < 102) a.stamps[(t - 100) * 64 + (id)] = clock64(); } while (0)
+#else
+#define US_STAMP(id) do { } while (0)
+#endif
 __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* smem_raw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -149,11 +156,13 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
         // ---- add the chain regions as they complete (round to nearest)
         const int nch = (NXC + (t > 0 ? NHC : 0)) / kCPR;          // accumulation chains of the step
         float z[kColsU];
+        if (tid == 0) US_STAMP(0);
         for (int ch = 0; ch < nch + (a.single ? 0 : 1); ++ch) {
           const int r = ch < nch ? ch % kRegU : kRegU;             // after the chains: the correction region
           mbar_wait(bar_reg + r, (regph >> r) & 1);
           regph ^= 1u << r;
           tc_fence_after();
+          if (tid == 0) US_STAMP(1 + ch);
 #pragma unroll
           for (int hp = 0; hp < 2; ++hp) {
             uint32_t z0[32];
@@ -181,12 +190,15 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
             hv[i].v[uu] = go[i].v[uu] * tanh_mufu(cv[i].v[uu]);
           }
         }
+        if (tid == 0) US_STAMP(12);
         // ---- publish h_t first: every row owner's stores are visible before the counter moves
-        float* hxo = a.hx + ((t & 1) * (int64_t)a.tiles * kRowsU + brow) * H + kUnitsU * s;
+        // exchange layout [slot][tile][H/8 unit blocks][128 rows][8]: a warp's 256-bit accesses cover 1 KB contiguous (with a
+        // row-major buffer every lane touched its own line: 32 lines per instruction, and the builders' fills ran ~1000 cycles)
+        float* hxo = a.hx + ((((t & 1) * (int64_t)a.tiles + tile) * (H / 8) + 2 * s) * kRowsU + row) * 8;
         st256(hxo, hv[0]);
-        st256(hxo + 8, hv[1]);
+        st256(hxo + kRowsU * 8, hv[1]);
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (tid == 0) { __threadfence(); atomicAdd(flag, 1u); }
+        if (tid == 0) { __threadfence(); atomicAdd(flag, 1u); US_STAMP(13); }
         // ---- tapes (nobody waits for them)
         if (live) {
           if (a.h_seq) { float* p = a.h_seq + (t * a.B + brow) * H + kUnitsU * s; stg256(p, hv[0]); stg256(p + 8, hv[1]); }
@@ -201,6 +213,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
           }
           if (a.h_last && t == a.T - 1) { float* p = a.h_last + brow * H + kUnitsU * s; stg256(p, hv[0]); stg256(p + 8, hv[1]); }
         }
+        if (tid == 0) US_STAMP(14);
       }
     }
   } else if (warp < 8) {
@@ -245,6 +258,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
           }
           fill(v);
         }
+        if (tid == 128) US_STAMP(16);
         // ---- A chunks of h_{t-1}: wait until every CTA of the group has published its units
         if (t > 0) {
           // every builder polls with acquire loads.  Measured alternatives (B = 256, T = 365, forward / BPTT, H = 256 | 128):
@@ -257,19 +271,23 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
               if (++spins > kSpinLimit) __trap();
             }
             (void)ld_acquire_gpu(flag);
+            if (tid == 128) US_STAMP(17);
           }
-          const float* hp = a.hx + (((t - 1) & 1) * (int64_t)a.tiles * kRowsU + brow) * H;
-          f8 cur[kNV], nxt[kNV];                                    // loads run one chunk ahead of the split
+          const float* hp = a.hx + ((((t - 1) & 1) * (int64_t)a.tiles + tile) * (H / 8) * kRowsU + row) * 8;      // unit block ub: + ub * 1024
+          // loads run TWO chunks ahead of the split: an L2 round trip (~0.7 us) is longer than a chunk's turn in the ring, with
+          // one chunk in flight the step was bound by it (0.8 us per chunk)
+          f8 p0[kNV], p1[kNV], p2[kNV];
 #pragma unroll
-          for (int i = 0; i < kNV; ++i) cur[i] = ld256_l2(hp + 8 * i);
+          for (int i = 0; i < kNV; ++i) { p0[i] = ld256_l2(hp + i * (kRowsU * 8)); p1[i] = ld256_l2(hp + (kNV + i) * (kRowsU * 8)); p2[i] = f8_zero(); }
           for (int hc = 0; hc < NHC; ++hc) {
-            if (hc + 1 < NHC) {
+            if (hc + 2 < NHC) {
 #pragma unroll
-              for (int i = 0; i < kNV; ++i) nxt[i] = ld256_l2(hp + kChunkK * (hc + 1) + 8 * i);
+              for (int i = 0; i < kNV; ++i) p2[i] = ld256_l2(hp + (kNV * (hc + 2) + i) * (kRowsU * 8));
             }
-            fill(cur);
+            fill(p0);
+            if (tid == 128) US_STAMP(18 + hc);
 #pragma unroll
-            for (int i = 0; i < kNV; ++i) cur[i] = nxt[i];
+            for (int i = 0; i < kNV; ++i) { p0[i] = p1[i]; p1[i] = p2[i]; }
           }
         }
       }
@@ -304,6 +322,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
             const uint32_t slot = nuse & (kSlotsU - 1), u = nuse / kSlotsU;
             mbar_wait(bar_full + slot, u & 1);
             tc_fence_after();
+            US_STAMP(32 + ch);
             const int r = (ch / kCPR) % kRegU, cr = ch % kCPR;      // region of this chain, chunk within the chain
             if (cr == 0) claim(r);
             const uint32_t dreg = tmem + kColsU * r;
@@ -321,6 +340,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
             if (cr == kCPR - 1) mma_commit(bar_reg + r);
           }
           if (!a.single) mma_commit(bar_reg + kRegU);
+          US_STAMP(44);
         }
       }
     }
@@ -394,6 +414,7 @@ int lstm_us_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
   a.h_seq = h_seq; a.c_seq = c_seq; a.gates = gates; a.h_last = h_last;
   a.B = B; a.T = T; a.H = (int)H; a.I = (int)I; a.IP = (int)IP;
   a.single = single;
+  static const int dbg = [] { const char* e = getenv("HY2DL_US_DBG"); return e ? atoi(e) : 0; }();
   const size_t smem = (size_t)a.K * kColsU * 8 + kSlotsU * kSlotBytesU + 256 + 1024;
   cudaFuncSetAttribute(lstm_us_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaLaunchConfig_t cfg = {};
@@ -402,7 +423,20 @@ int lstm_us_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
   attr[0].id = cudaLaunchAttributeCooperative;       // all CTAs co-resident, or the launch fails: they wait for each other
   attr[0].val.cooperative = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  if (dbg & 128) { cudaMalloc(&a.stamps, 128 * sizeof(long long)); cudaMemset(a.stamps, 0, 128 * sizeof(long long)); }
   cudaLaunchKernelEx(&cfg, lstm_us_tc_fwd_kernel, a);
+  if (a.stamps) {                                   // debugging only: print the timeline of CTA 0, steps 100-101
+    long long h[128];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, a.stamps, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(a.stamps);
+    const char* names[64] = {};
+    long long t0 = h[0];
+    for (int st = 0; st < 2; ++st)
+      for (int i = 0; i < 64; ++i)
+        if (h[st * 64 + i]) fprintf(stderr, "US_STAMP step %d id %2d  %8lld\n", 100 + st, i, h[st * 64 + i] - t0);
+    (void)names;
+  }
   HY_LAUNCH_CHECK();
   return HY2DL_OK;
 }

@@ -35,6 +35,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// Non-suspending poll (test_wait): for waits on the critical path of a latency-bound chain.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "SPIN_LOOP:\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra SPIN_DONE;\n\t"
+      "bra SPIN_LOOP;\n\t"
+      "SPIN_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+
 // Same for warps that are not on the critical path: back off between polls so that the spin does not
 // take issue slots from the warps sharing the scheduler.
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
