@@ -7,11 +7,12 @@
 // Here CTA s of a group of S = H / 16 owns hidden units [16 s, 16 s + 16) of the tile:
 //   * its 64 gate columns of [W_ih | b | W_hh] (hi + lo, K x 64 x 8 bytes = 152 KB at H = 256, I <= 31) are loaded ONCE and
 //     stay in shared memory for the whole kernel;
-//   * per step it multiplies the full A = [x_t | 1 | h_{t-1}] (128 x K, built hi + lo in shared memory in chunks of 32 K
-//     columns, a 2-slot ring) by its weight slice: M = 128, N = 64 MMAs, three terms (3xTF32) -- 1/16 of the tile's MMAs;
+//   * per step it multiplies the full A = [x_t | 1 | h_{t-1}] (128 x K, built in chunks of 32 K columns in a 4-slot ring: the
+//     hi image in TMEM, the lo image in shared memory) by its weight slice: M = 128, N = 64 MMAs, three terms (3xTF32) --
+//     1/16 of the tile's MMAs;
 //   * every chunk's 4 hi*hi MMAs form one chain into a 64-column TMEM region of its own (the tensor core's fp32
-//     accumulation truncates, see lstm_rm_tc_fwd.cu; the regions are added in registers, round to nearest; 7 regions are
-//     used in turn), the correction terms of the whole step go to an eighth; a region is pulled while the next chunks
+//     accumulation truncates, see lstm_rm_tc_fwd.cu; the regions are added in registers, round to nearest; 5 regions are
+//     used in turn), the correction terms of the whole step go to a sixth; a region is pulled while the next chunks
 //     are multiplied;
 //   * c stays in registers (a thread owns one sequence x 16 units for all T); h_t (16 units) goes to the row-major exchange
 //     buffer hx[t & 1] in L2 -- and to the tapes -- and a release / acquire counter per group tells the S CTAs that
@@ -31,17 +32,20 @@ namespace {
 constexpr int kRowsU = 128;
 constexpr int kUnitsU = 16;                 // hidden units per CTA
 constexpr int kColsU = 64;                  // gate columns per CTA: column n = 4 uu + g
-// Ring geometry: 2 slots of 32 K columns.  4 slots of 16 columns (same bytes, chains still 4 K steps) measured SLOWER
-// (H = 128: 2.32 vs 2.13 ms; H = 256, I = 41: 4.20 vs 4.09): the per-slot hand-shake, not the pipeline depth, is what costs.
+// Ring geometry: 4 slots of 32 K columns; a slot = the lo image in shared memory (16 KB) + the hi image in 32 TMEM columns
+// (TS-mode MMAs).  With both images in shared memory only 2 slots fit next to the weights, and the step was bound by the
+// slot cycle (MMAs -> commit -> builders wake -> fill -> issuer wakes: ~2000 cycles per 2 chunks, HY2DL_US_STAMPS);
+// 4 slots of 16 columns with both images in shared memory measured slower still (the hand-shakes, not the bytes, cost).
 constexpr int kChunkK = 32;                 // K columns per A chunk = ring slot (4 K steps)
 constexpr int kGroupK = 32;                 // K columns per accumulation chain (4 K steps) = one TMEM region
 constexpr int kCPR = kGroupK / kChunkK;     // chunks per region
-constexpr int kSlotsU = 2;                  // ring slots
+constexpr int kSlotsU = 4;                  // ring slots
 constexpr int kNV = kChunkK / 8;            // 256-bit loads per row and chunk
 constexpr int kThreadsU = 288;              // warps 0-3 own the rows (gates, state, tapes), 4-7 build A, warp 8 issues the MMAs
 constexpr int kHalfSlotU = kRowsU * kChunkK * 4;          // hi image of a chunk, 16 KB; lo follows
-constexpr int kSlotBytesU = 2 * kHalfSlotU;
-constexpr int kRegU = 7;                    // chain regions of 64 TMEM columns, used in turn by the chunks of a step; region 7: corrections
+constexpr int kSlotBytesU = kHalfSlotU;                   // shared-memory part of a slot: the lo image
+constexpr int kRegU = 5;                    // chain regions of 64 TMEM columns, used in turn by the chunks of a step; region 5: corrections
+constexpr uint32_t kColA = 64 * (kRegU + 1);      // TMEM columns [384, 512): hi images of the 4 ring slots
 constexpr uint32_t kSpinLimit = 1u << 26;
 
 struct UsFwdArgs {
@@ -115,7 +119,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
   const int K = a.K, H = a.H, KX = a.KX, S = a.S;
   const int wbytes = K * kColsU * 4;                                 // one image (hi or lo) of the weight slice
   uint8_t* s_w = smem_raw;                                           // [hi | lo][K/4][64][4]
-  uint8_t* s_ring = s_w + 2 * (size_t)wbytes;                        // kSlotsU slots of [hi | lo][kChunkK / 4][128 rows][4]
+  uint8_t* s_ring = s_w + 2 * (size_t)wbytes;                        // kSlotsU slots of the lo image [kChunkK / 4][128 rows][4]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + kSlotsU * (size_t)kSlotBytesU);
   uint64_t* bar_full = bars;            // [4] builders -> MMA
   uint64_t* bar_free = bars + 4;        // [4] MMA commit -> builders
@@ -221,20 +225,24 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
     const int row = tid - 128;
     uint32_t nfill = 0;                                             // chunks built so far
     int64_t gs = 0;                                                 // step counter over all tiles of the group
-    auto fill = [&](const f8 (&v)[kNV]) {                           // kChunkK columns of this row: split, store K-major
+    const uint32_t lane_tm_b = tmem + ((uint32_t)((warp & 3) * 32) << 16);     // builder warp w writes TMEM lanes 32 (w & 3) ..: its rows
+    auto fill = [&](const f8 (&v)[kNV]) {                           // kChunkK columns of this row: hi -> TMEM, lo -> shared memory (K-major)
       const uint32_t slot = nfill & (kSlotsU - 1), u = nfill / kSlotsU;
       if (u > 0) { mbar_wait(bar_free + slot, (u - 1) & 1); tc_fence_after(); }
-      float4* hi4 = reinterpret_cast<float4*>(s_ring + (size_t)slot * kSlotBytesU);
-      float4* lo4 = hi4 + kHalfSlotU / 16;
+      float4* lo4 = reinterpret_cast<float4*>(s_ring + (size_t)slot * kSlotBytesU);
+      const uint32_t ta = lane_tm_b + kColA + slot * kChunkK;
 #pragma unroll
-      for (int q = 0; q < kChunkK / 4; ++q) {
-        const float* src = v[q >> 1].v + 4 * (q & 1);
-        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-        split_tf32(src[0], h0, l0); split_tf32(src[1], h1, l1); split_tf32(src[2], h2, l2); split_tf32(src[3], h3, l3);
-        hi4[q * kRowsU + row] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(h2), __uint_as_float(h3));
-        lo4[q * kRowsU + row] = make_float4(__uint_as_float(l0), __uint_as_float(l1), __uint_as_float(l2), __uint_as_float(l3));
+      for (int i = 0; i < kNV; ++i) {
+        uint32_t hi8[8], lo8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_tf32(v[i].v[e], hi8[e], lo8[e]);
+        tmem_st8(ta + 8 * i, hi8);
+        lo4[(2 * i) * kRowsU + row] = make_float4(__uint_as_float(lo8[0]), __uint_as_float(lo8[1]), __uint_as_float(lo8[2]), __uint_as_float(lo8[3]));
+        lo4[(2 * i + 1) * kRowsU + row] = make_float4(__uint_as_float(lo8[4]), __uint_as_float(lo8[5]), __uint_as_float(lo8[6]), __uint_as_float(lo8[7]));
       }
+      tmem_st_wait();
       fence_async_smem();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full + slot);
       ++nfill;
@@ -305,7 +313,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
       const uint32_t idesc = idesc_tf32(kRowsU, kColsU, 0, 0);
       const uint64_t whi0 = smem_desc(smem_u32(s_w), kColsU * 16, 128), wlo0 = smem_desc(smem_u32(s_w + wbytes), kColsU * 16, 128);
       const uint64_t ring0 = smem_desc(smem_u32(s_ring), kRowsU * 16, 128);
-      constexpr uint64_t kBStep = 2 * kColsU * 16 / 16, kAStep = 2 * kRowsU * 16 / 16, kSlotStep = kSlotBytesU / 16, kLoStep = kHalfSlotU / 16;
+      constexpr uint64_t kBStep = 2 * kColsU * 16 / 16, kAStep = 2 * kRowsU * 16 / 16, kSlotStep = kSlotBytesU / 16;
       const uint32_t dcorr = tmem + kColsU * kRegU;
       uint32_t nuse = 0;
       uint32_t used = 0, freeph = 0;               // per region: written before / phase of bar_rfree
@@ -326,15 +334,16 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
             const int r = (ch / kCPR) % kRegU, cr = ch % kCPR;      // region of this chain, chunk within the chain
             if (cr == 0) claim(r);
             const uint32_t dreg = tmem + kColsU * r;
-            const uint64_t ahi = ring0 + slot * kSlotStep, alo = ahi + kLoStep;
+            const uint64_t alo = ring0 + slot * kSlotStep;
+            const uint32_t ahi = tmem + kColA + slot * kChunkK;        // hi image: TMEM columns, 8 per K step
 #pragma unroll
             for (int j = 0; j < kChunkK / 8; ++j) {
               const uint64_t bo = (uint64_t)(ch * (kChunkK / 8) + j) * kBStep;
               if (!a.single) {
                 mma_tf32_ss(dcorr, alo + j * kAStep, whi0 + bo, idesc, (ch | j) != 0);
-                mma_tf32_ss(dcorr, ahi + j * kAStep, wlo0 + bo, idesc, 1);
+                mma_tf32_ts(dcorr, ahi + 8 * j, wlo0 + bo, idesc, 1);
               }
-              mma_tf32_ss(dreg, ahi + j * kAStep, whi0 + bo, idesc, (cr | j) != 0);
+              mma_tf32_ts(dreg, ahi + 8 * j, whi0 + bo, idesc, (cr | j) != 0);
             }
             mma_commit(bar_free + slot);
             if (cr == kCPR - 1) mma_commit(bar_reg + r);
