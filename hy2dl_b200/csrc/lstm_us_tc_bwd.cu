@@ -300,7 +300,7 @@ bool lstm_us_tc_bwd_supported(int64_t H) {
   return (H == 128 || H == 256) && sm_count() >= H / kUnitsV;
 }
 
-// same rule as the forward kernel (lstm_us_tc_fwd_preferred); HY2DL_RM_US=0 / 1 forces
+// as lstm_us_tc_fwd_preferred: 2.9 ms per round against 25-29 ms (H = 256), 1.9 ms against 8-10 ms (H = 128); HY2DL_RM_US(_BWD)=0 / 1 forces
 bool lstm_us_tc_bwd_preferred(int64_t B, int64_t H) {
   if (!lstm_us_tc_bwd_supported(H)) return false;
   static const int force = [] { const char* e = getenv("HY2DL_RM_US_BWD"); if (!e) e = getenv("HY2DL_RM_US"); return e ? atoi(e) : -1; }();
@@ -308,7 +308,7 @@ bool lstm_us_tc_bwd_preferred(int64_t B, int64_t H) {
   if (force == 1) return true;
   const int64_t tiles = cdiv(B, (int64_t)kRowsV);
   const int64_t rounds = cdiv(tiles, (int64_t)usb_groups(B, H));
-  return rounds <= 4 && tiles <= sm_count() / 2;
+  return rounds <= (H == 256 ? 8 : 4);
 }
 
 int64_t lstm_us_tc_bwd_workspace(int64_t B, int64_t H) {

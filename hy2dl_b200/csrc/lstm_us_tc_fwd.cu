@@ -282,20 +282,21 @@ __global__ void __launch_bounds__(kThreadsU, 1) lstm_us_tc_fwd_kernel(UsFwdArgs 
             if (tid == 128) US_STAMP(17);
           }
           const float* hp = a.hx + ((((t - 1) & 1) * (int64_t)a.tiles + tile) * (H / 8) * kRowsU + row) * 8;      // unit block ub: + ub * 1024
-          // loads run TWO chunks ahead of the split: an L2 round trip (~0.7 us) is longer than a chunk's turn in the ring, with
-          // one chunk in flight the step was bound by it (0.8 us per chunk)
-          f8 p0[kNV], p1[kNV], p2[kNV];
+          // loads run one chunk ahead of the split (two ahead measured the same); two buffers used alternately, no register moves
+          f8 pa[kNV], pb[kNV];
 #pragma unroll
-          for (int i = 0; i < kNV; ++i) { p0[i] = ld256_l2(hp + i * (kRowsU * 8)); p1[i] = ld256_l2(hp + (kNV + i) * (kRowsU * 8)); p2[i] = f8_zero(); }
-          for (int hc = 0; hc < NHC; ++hc) {
+          for (int i = 0; i < kNV; ++i) pa[i] = ld256_l2(hp + i * (kRowsU * 8));
+          for (int hc = 0; hc < NHC; hc += 2) {                    // NHC = H / 32 is even
+#pragma unroll
+            for (int i = 0; i < kNV; ++i) pb[i] = ld256_l2(hp + (kNV * (hc + 1) + i) * (kRowsU * 8));
+            fill(pa);
+            if (tid == 128) US_STAMP(18 + hc);
             if (hc + 2 < NHC) {
 #pragma unroll
-              for (int i = 0; i < kNV; ++i) p2[i] = ld256_l2(hp + (kNV * (hc + 2) + i) * (kRowsU * 8));
+              for (int i = 0; i < kNV; ++i) pa[i] = ld256_l2(hp + (kNV * (hc + 2) + i) * (kRowsU * 8));
             }
-            fill(p0);
-            if (tid == 128) US_STAMP(18 + hc);
-#pragma unroll
-            for (int i = 0; i < kNV; ++i) { p0[i] = p1[i]; p1[i] = p2[i]; }
+            fill(pb);
+            if (tid == 128) US_STAMP(19 + hc);
           }
         }
       }
@@ -378,8 +379,9 @@ bool lstm_us_tc_fwd_supported(int64_t I, int64_t H) {
   return smem <= 232448 && sm_count() >= H / kUnitsU;
 }
 
-// Unit split pays while the tiles of a batch leave SMs idle in the one-CTA-per-tile kernel.  Per step a unit-split group
-// needs ~1/10 of the one-CTA chain, so with R rounds of groups it wins as long as R is small; HY2DL_RM_US=0 / 1 forces.
+// Unit split pays while rounds x (time of one round of groups) stays below the streamed kernel's time, which does not
+// depend on the batch up to a full wave.  Measured at T = 365: H = 256: 2.7 ms per round against 30-38 ms; H = 128: 1.8 ms against
+// 9.6-12 ms.  HY2DL_RM_US=0 / 1 forces.
 bool lstm_us_tc_fwd_preferred(int64_t B, int64_t I, int64_t H) {
   if (!lstm_us_tc_fwd_supported(I, H)) return false;
   static const int force = [] { const char* e = getenv("HY2DL_RM_US"); return e ? atoi(e) : -1; }();
@@ -387,7 +389,7 @@ bool lstm_us_tc_fwd_preferred(int64_t B, int64_t I, int64_t H) {
   if (force == 1) return true;
   const int64_t tiles = cdiv(B, (int64_t)kRowsU);
   const int64_t rounds = cdiv(tiles, (int64_t)us_groups(B, H));
-  return rounds <= 4 && tiles <= sm_count() / 2;
+  return rounds <= (H == 256 ? 10 : 5);
 }
 
 int64_t lstm_us_tc_fwd_workspace(int64_t B, int64_t I, int64_t H) {

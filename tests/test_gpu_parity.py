@@ -379,7 +379,7 @@ def test_train_steps_bit_reproducible(dev, precision, H):
                                                 # unit-split kernels (small batches, lstm_us_tc_*.cu): 11 tiles on 9 groups of 16
                                                 # CTAs (a group walks over two tiles, the last one ragged), 8-CTA groups with two
                                                 # x chunks, and the largest batch they take at H = 128 (72 tiles on 18 groups)
-                                                (1300, 6, 31, 256, "fp32"), (300, 9, 50, 128, "fp32"), (9216, 3, 12, 128, "fp32")])
+                                                (1300, 6, 31, 256, "fp32"), (300, 9, 50, 128, "fp32"), (9216, 3, 12, 128, "fp32"), (9300, 2, 31, 256, "fp32")])
 def test_lstm_vs_oracle(dev, B, T, I, H, precision):
     from hy2dl_b200.modelzoo import LSTM
     from hy2dl_b200.synthetic import lstm_weights
