@@ -43,6 +43,7 @@ struct Args {
   int64_t T, B, G;
   int H, I, IP, MT, NT, NB, parts;
   int single;         // HY2DL_PREC_TF32: hi*hi MMAs only
+  long long* stamps;  // -DHY2DL_US_STAMPS + HY2DL_US_DBG=128: clock64 timeline of CTA 0, slabs 100-101
 };
 
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
@@ -54,6 +55,11 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {   // arrives on
 }
 }  // namespace
 
+#ifdef HY2DL_US_STAMPS
+#define WG_STAMP(id) do { if (a.stamps && blockIdx.x == 0 && i >= 100 && i < 102) a.stamps[(i - 100) * 16 + (id)] = clock64(); } while (0)
+#else
+#define WG_STAMP(id) do { } while (0)
+#endif
 __global__ void __launch_bounds__(kThreads, 1) lstm_wgrad_rm_tc_kernel(Args a) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* smem_raw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -104,6 +110,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_wgrad_rm_tc_kernel(Args a) {
         for (int hf = 0; hf < 2; ++hf) {
           mbar_wait(bar_conv + hf, (uint32_t)(i & 1));
           tc_fence_after();
+          WG_STAMP(8 + 2 * hf);
           const uint32_t d = tmem + ND * hf;
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb) {
@@ -117,6 +124,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_wgrad_rm_tc_kernel(Args a) {
             mma_tf32_ss(d, a_hi, b_hi, idesc, !a.single || !(first && kb == 0));
           }
           mma_commit(bar_lo_free + hf);
+          WG_STAMP(9 + 2 * hf);
         }
       }
       mma_commit(bar_done);
@@ -217,37 +225,62 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_wgrad_rm_tc_kernel(Args a) {
       float4* raw = reinterpret_cast<float4*>(smem_raw + s * stage_bytes);
       float4* lo_b4 = reinterpret_cast<float4*>(s_lo + kABytes + (i & 1) * bbytes);
       constexpr int kA4 = kABytes / 16;
-      auto split4 = [&](int e) {                             // lo = v - trunc(v); the landed words are the hi operand
-        float4 v = raw[e];
-        if (e == ones_e) {                                   // the ones column of the bias gradient (decided once, below)
-          const int k = ones_col & 3;
-          if (k == 0) v.x = 1.f; else if (k == 1) v.y = 1.f; else if (k == 2) v.z = 1.f; else v.w = 1.f;
-          raw[e] = v;
-        }
+      // lo = v - trunc(v); the landed words are the hi operand.  Loads first, then arithmetic and stores: the shared-memory
+      // pipe is shared with the tensor core's operand reads, a dependent LDS -> STS chain per float4 cost ~230 cycles each
+      // (clock64 timeline: 1640 cycles for the 7 float4 of half 0).
+      auto lo_of = [&](const float4& v) {
         const float4 hv = make_float4(__uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u),
                                       __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u), __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
-        float4* lo = e < kA4 ? lo_a4 + e : lo_b4 + (e - kA4);
-        *lo = make_float4(v.x - hv.x, v.y - hv.y, v.z - hv.z, v.w - hv.w);
+        return make_float4(v.x - hv.x, v.y - hv.y, v.z - hv.z, v.w - hv.w);
       };
+      auto split_a = [&](int half) {                         // this thread's 4 float4 of gate-column half `half`
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = raw[half * 4 * kBlk4 + ct + k * kConv];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) lo_a4[half * 4 * kBlk4 + ct + k * kConv] = lo_of(v[k]);
+      };
+      auto split_b = [&]() {                                 // ... and its NB float4 of the B part (ones column patched)
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (k < NB) v[k] = raw[kA4 + ct + k * kConv];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < NB) {
+            const int e = kA4 + ct + k * kConv;
+            if (e == ones_e) {                               // the ones column of the bias gradient (decided once, above)
+              const int q = ones_col & 3;
+              if (q == 0) v[k].x = 1.f; else if (q == 1) v[k].y = 1.f; else if (q == 2) v[k].z = 1.f; else v[k].w = 1.f;
+              raw[e] = v[k];
+            }
+            lo_b4[ct + k * kConv] = lo_of(v[k]);
+          }
+        }
+      };
+      if (ct == 0) WG_STAMP(0);
       mbar_wait(bar_full + s, (uint32_t)((i / kStages) & 1));
+      if (ct == 0) WG_STAMP(1);
       // ---- half 0: the B operand (shared by both halves) and gate columns [0, 128)
       if (i > 0) mbar_wait(bar_lo_free + 0, (uint32_t)((i - 1) & 1));
       if (i > 0 && (i % kChain) == 0) {
         mbar_wait(bar_lo_free + 1, (uint32_t)((i - 1) & 1));
         drain();
       }
-      for (int e = ct; e < NB * kBlk4; e += kConv) split4(kA4 + e);
-#pragma unroll 4
-      for (int e = ct; e < 4 * kBlk4; e += kConv) split4(e);
+      if (ct == 0) WG_STAMP(2);
+      split_b();
+      split_a(0);
       fence_async_smem();
       mbar_arrive(bar_conv + 0);
+      if (ct == 0) WG_STAMP(3);
       // ---- half 1: gate columns [128, 256)
       if (i > 0) mbar_wait(bar_lo_free + 1, (uint32_t)((i - 1) & 1));
+      if (ct == 0) WG_STAMP(4);
       load_slab();           // slab i + 2: its stage held slab i - 1, whose MMAs (hi operands) have just been seen to retire
-#pragma unroll 4
-      for (int e = ct; e < 4 * kBlk4; e += kConv) split4(4 * kBlk4 + e);
+      if (ct == 0) WG_STAMP(5);
+      split_a(1);
       fence_async_smem();
       mbar_arrive(bar_conv + 1);
+      if (ct == 0) WG_STAMP(6);
     }
     mbar_wait(bar_done, 0);
     if (n_my > 0) drain();
@@ -315,7 +348,19 @@ int lstm_wgrad_rm_tc(const float* dG, const float* h_seq, const float* xT, int64
   const size_t bbytes = (size_t)a.NB * kBlk;
   const size_t smem = (size_t)kStages * (kABytes + bbytes) + kABytes + 2 * bbytes + 128 + 1024;
   cudaFuncSetAttribute(lstm_wgrad_rm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#ifdef HY2DL_US_STAMPS
+  cudaMalloc(&a.stamps, 32 * sizeof(long long)); cudaMemset(a.stamps, 0, 32 * sizeof(long long));
+#endif
   lstm_wgrad_rm_tc_kernel<<<a.MT * a.NT * a.parts, kThreads, smem, s>>>(a);
+#ifdef HY2DL_US_STAMPS
+  {
+    long long h[32];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, a.stamps, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(a.stamps);
+    for (int i = 0; i < 32; ++i) if (h[i]) fprintf(stderr, "WG_STAMP slab %d id %2d  %8lld\n", 100 + i / 16, i % 16, h[i] - h[0]);
+  }
+#endif
   const int64_t n_out = 4 * H * (H + I + 1);
   lstm_wgrad_rm_tc_finish_kernel<<<(unsigned)cdiv(n_out, (int64_t)256), 256, 0, s>>>(a.partial, a.parts, a.MT, a.NT, 32 * a.NB, (int)H, (int)I,
                                                                                  dw_ih, dw_hh, db);
