@@ -232,8 +232,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
       float4* lo_b4 = reinterpret_cast<float4*>(s_lo + kABytes + (i & 1) * kBBytes);
       constexpr int kA4 = kABytes / 16;
       // lo = x - trunc(x) of float4 `e` of the stage: A part -> lo_a4, B part -> lo_b4 (double buffered by slab)
-      auto split4 = [&](int e, bool one_w) {
-        float4 v = raw[e];
+      // (the loads of a half are issued first, the arithmetic and stores follow: the shared-memory pipe is shared with the tensor
+      // core's operand reads, and a dependent LDS -> STS chain per float4 cost ~230 cycles each in the H = 256 kernel's timeline)
+      auto split4v = [&](int e, float4 v, bool one_w) {
         if (one_w) v.w = 1.f;                      // x column 31 := 1 (bias gradient)
         float4* lo = e < kA4 ? lo_a4 + e : lo_b4 + (e - kA4);
         float4 hv, lv;
@@ -251,6 +252,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
         raw[e] = hv;
         *lo = lv;
       };
+      static_assert(kBlk4 == kWgConv, "one float4 per thread and block");
       mbar_wait(bar_full + s, (uint32_t)((i / kWgStages) & 1));
       // ---- half 0: dz, the B operand (shared by both halves) and gate columns [0, 128)
       if (i > 0) mbar_wait(bar_lo_free + 0, (uint32_t)((i - 1) & 1));    // MMAs of (slab i-1, half 0) and everything before retired
@@ -260,33 +262,46 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_tc_wgrad_kernel(TcWgradArg
         chain_flags(i - kChain, i - 1, m_any, h_any);
         drain(m_any, h_any);
       }
-      if (dzb) for (int e = ct; e < kBlk4; e += kWgConv) split4(e, false);                                  // dz(t-1)
-      if (main) {                                                                                          // x(t); row r's unit 3 sits at unit 3 ^ (r & 3)
-        for (int e = ct; e < kBlk4; e += kWgConv) split4(kA4 + 2 * kBlk4 + e, (e & 7) == 2 * (3 ^ ((e >> 3) & 3)) + 1);
-      } else {                                                                                             // slot t = T: no x, only the ones column
-        for (int e = ct; e < kBlk4; e += kWgConv) {
-          const bool one_w = (e & 7) == 2 * (3 ^ ((e >> 3) & 3)) + 1;
-          raw[kA4 + 2 * kBlk4 + e] = make_float4(0.f, 0.f, 0.f, one_w ? 1.f : 0.f);
-          lo_b4[2 * kBlk4 + e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-      if (t > 0) {
-        for (int e = ct; e < 2 * kBlk4; e += kWgConv) split4(kA4 + e, false);                               // h(t-1)
-      } else {                                                                                             // h(-1) = 0
+      {
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int e = ct; e < 2 * kBlk4; e += kWgConv) { raw[kA4 + e] = z; lo_b4[e] = z; }
-      }
-      if (main) {
-#pragma unroll 4
-        for (int e = ct; e < 4 * kBlk4; e += kWgConv) split4(kBlk4 + e, false);
+        const bool one_w = (ct & 7) == 2 * (3 ^ ((ct >> 3) & 3)) + 1;     // x column 31; row r's unit 3 sits at unit 3 ^ (r & 3)
+        float4 vd = z, vx = z, vh0 = z, vh1 = z, va[4];
+        if (dzb) vd = raw[ct];                                            // dz(t-1)
+        if (main) vx = raw[kA4 + 2 * kBlk4 + ct];                         // x(t)
+        if (t > 0) { vh0 = raw[kA4 + ct]; vh1 = raw[kA4 + kBlk4 + ct]; }  // h(t-1)
+        if (main) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) va[k] = raw[kBlk4 + ct + k * kWgConv];
+        }
+        if (dzb) split4v(ct, vd, false);
+        if (main) {
+          split4v(kA4 + 2 * kBlk4 + ct, vx, one_w);
+        } else {                                                          // slot t = T: no x, only the ones column
+          raw[kA4 + 2 * kBlk4 + ct] = make_float4(0.f, 0.f, 0.f, one_w ? 1.f : 0.f);
+          lo_b4[2 * kBlk4 + ct] = z;
+        }
+        if (t > 0) {
+          split4v(kA4 + ct, vh0, false);
+          split4v(kA4 + kBlk4 + ct, vh1, false);
+        } else {                                                          // h(-1) = 0
+          raw[kA4 + ct] = z; lo_b4[ct] = z;
+          raw[kA4 + kBlk4 + ct] = z; lo_b4[kBlk4 + ct] = z;
+        }
+        if (main) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) split4v(kBlk4 + ct + k * kWgConv, va[k], false);
+        }
       }
       fence_async_smem();
       mbar_arrive(bar_conv + 0);
       // ---- half 1: gate columns [128, 256)
       if (i > 0) mbar_wait(bar_lo_free + 1, (uint32_t)((i - 1) & 1));
       if (main) {
-#pragma unroll 4
-        for (int e = ct; e < 4 * kBlk4; e += kWgConv) split4(5 * kBlk4 + e, false);
+        float4 va[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) va[k] = raw[5 * kBlk4 + ct + k * kWgConv];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) split4v(5 * kBlk4 + ct + k * kWgConv, va[k], false);
       }
       fence_async_smem();
       mbar_arrive(bar_conv + 1);
