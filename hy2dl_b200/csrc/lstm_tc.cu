@@ -542,6 +542,7 @@ struct TcBwdArgs {
   int64_t B, T, G, dh_t0;
   int single;             // HY2DL_PREC_TF32: hi*hi MMAs only
   // fused head adjoint (has_head == 0: none): dh_ext(t) = dz_t * W_head with dz from dpar_sim / par_sim
+  long long* stamps;      // -DHY2DL_US_STAMPS: clock64 timeline of CTA 0, reverse steps 100-101
   int has_head;
   const float* wh_hi;     // [NH/4][64][4]
   const float* wh_lo;
@@ -576,6 +577,11 @@ __device__ __forceinline__ void bwd_load_chunk(const TcBwdArgs& a, int64_t t, in
   }
 }
 
+#ifdef HY2DL_US_STAMPS
+#define TB_STAMP(id) do { if (a.stamps && blockIdx.x == 0 && s >= 100 && s < 102) a.stamps[(s - 100) * 32 + (id)] = clock64(); } while (0)
+#else
+#define TB_STAMP(id) do { } while (0)
+#endif
 __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const bool head = a.has_head != 0;
@@ -660,6 +666,7 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
         tc_fence_after();
       }
       const bool have_prev = s > 0 || head;
+      if (tid == 0) TB_STAMP(0);
 #pragma unroll 1
       for (int k = 0; k < 4; ++k) {      // quarter k = 16 hidden units = 64 gate columns, lives in slot k & 1
         const int slot = k & 1;
@@ -667,6 +674,7 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
           mbar_wait(bar_free + slot, 0);
           tc_fence_after();
         }
+        if (tid == 0) TB_STAMP(1 + 4 * k);
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) { // blocks Q = 2k, 2k+1; this thread's 4 hidden units of each
           const int Q = 2 * k + kk;
@@ -717,10 +725,12 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
             tmem_st8(sbase + 8 * j, hi);
             tmem_st8(sbase + 64 + 8 * j, lo);
           }
+          if (tid == 0) TB_STAMP(2 + 4 * k + kk);
         }
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar_ready + slot);
+        if (tid == 0) TB_STAMP(4 + 4 * k);
       }
     }
   } else if (warp == kBwdRowWarps) {
@@ -763,6 +773,7 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
           const uint32_t d = tmem + kColDh0 + 128 * (uint32_t)(s & 1) + 64 * (uint32_t)(k >> 1);   // accumulator of quarters {0,1} / {2,3}
           mbar_wait(bar_ready + slot, (uint32_t)(k >> 1));
           tc_fence_after();
+          TB_STAMP(20 + k);
           if (k == 0 && has_dz) issue_dz(d);       // (the row threads have finished reading this buffer by now)
           const uint32_t abase = tmem + kColSlot0 + 128 * slot;
           const bool acc0 = k == 0 && has_dz;
@@ -782,6 +793,7 @@ __global__ void __launch_bounds__(kBwdThreadsHead, 1) lstm_tc_bwd_kernel(TcBwdAr
             mma_tf32_ts(d, abase + 8 * j, d_hi, idesc, !a.single || (((k & 1) | j) != 0) || acc0);
           }
           mma_commit(bar_free + slot);
+          TB_STAMP(24 + k);
         }
       }
     }
@@ -880,7 +892,19 @@ int lstm_tc_bwd(int64_t B, int64_t T, const float* w_hh, const float* gates, con
     threads = kBwdThreadsHead;
   }
   cudaFuncSetAttribute(lstm_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#ifdef HY2DL_US_STAMPS
+  cudaMalloc(&a.stamps, 64 * sizeof(long long)); cudaMemset(a.stamps, 0, 64 * sizeof(long long));
+#endif
   lstm_tc_bwd_kernel<<<(unsigned)cdiv(B, kRows), threads, smem, s>>>(a);
+#ifdef HY2DL_US_STAMPS
+  {
+    long long h[64];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, a.stamps, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(a.stamps);
+    for (int i = 0; i < 64; ++i) if (h[i]) fprintf(stderr, "TB_STAMP step %d id %2d  %8lld\n", 100 + i / 32, i % 32, h[i] - h[0]);
+  }
+#endif
   HY_LAUNCH_CHECK();
   return HY2DL_OK;
 }
