@@ -3,6 +3,7 @@ executed by the hy2dl_b200 recurrent kernels instead of cuDNN / oneDNN."""
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -38,9 +39,15 @@ class LSTM(nn.Module):
         if not (1 <= input_size <= 64):
             raise ValueError(f"hy2dl_b200.LSTM: input_size must be in [1, 64] (got {input_size})")
         self.kernel_hidden = 64 if hidden_size <= 64 else (128 if hidden_size <= 128 else 256)
+        # hidden_size <= 64 with 32 .. 64 inputs: the resident-weights kernels take input_size <= 31, and the CUDA-core
+        # kernels they used to fall back to are slower than the tensor-core chain run zero-padded to 128 units
+        # (I = 41, T = 365, forward + BPTT + weight gradients: 40.7 vs 33.7 ms at a batch of 18 944, 5.9 vs 4.1 ms at 256).
+        # HY2DL_FP32_TC=0 (CUDA-core kernels everywhere) keeps 64.
+        if self.kernel_hidden == 64 and input_size > 31 and precision != "tf32x3" and os.environ.get("HY2DL_FP32_TC") != "0":
+            self.kernel_hidden = 128
         # "auto": the fastest kernels that meet the fp32 tolerances (rtol 1e-4) for this shape -- the tcgen05 path with
-        # resident weights ("tf32x3": H = 64, input_size <= 31); otherwise "fp32", which is the streamed-weights tcgen05
-        # chain for H = 128 / 256 and the CUDA-core kernels for H = 64 with wider inputs.  "tf32" is the throughput mode
+        # resident weights ("tf32x3": H <= 64, input_size <= 31); otherwise "fp32", which is the tcgen05 chain of the
+        # H = 128 / 256 kernels (streamed weights, or unit split at small batches).  "tf32" is the throughput mode
         # (single-pass TF32 operands on the same tensor-core kernels; looser, stated tolerance -- never picked by "auto")
         if precision == "auto":
             precision = "tf32x3" if (self.kernel_hidden == 64 and input_size <= 31) else "fp32"
@@ -49,9 +56,9 @@ class LSTM(nn.Module):
         if precision == "tf32x3" and not (self.kernel_hidden == 64 and input_size <= 31):
             raise ValueError("hy2dl_b200.LSTM: precision 'tf32x3' (weights resident on chip) takes hidden_size <= 64 and "
                              f"input_size <= 31 (got {hidden_size}, {input_size}); use 'auto' or 'fp32'")
-        if precision == "tf32" and self.kernel_hidden == 64 and input_size > 31:
-            raise ValueError("hy2dl_b200.LSTM: precision 'tf32' (throughput mode) runs on the tensor-core kernels only: hidden_size <= 64 "
-                             f"with input_size <= 31, or hidden_size in (64, 256] (got {hidden_size}, {input_size})")
+        if precision == "tf32" and self.kernel_hidden == 64 and input_size > 31:       # only with HY2DL_FP32_TC=0
+            raise ValueError("hy2dl_b200.LSTM: precision 'tf32' (throughput mode) runs on the tensor-core kernels only "
+                             f"(got hidden_size {hidden_size}, input_size {input_size} with HY2DL_FP32_TC=0)")
         self.precision = precision
         H = hidden_size
         self.weight_ih_l0 = nn.Parameter(torch.empty(4 * H, input_size))

@@ -290,8 +290,12 @@ def test_zero_padded_kernel_weights_and_drop_in_checks():
         with pytest.raises(ValueError):
             LSTM(**bad)
     assert LSTM(25, 64, precision="tf32").layout == "ri32" and LSTM(31, 256, precision="tf32").layout == "rowmajor"
+    # hidden_size <= 64 with more than 31 inputs runs on the tensor-core chain zero-padded to 128 units (any precision but tf32x3)
+    wide = LSTM(41, 64)
+    assert wide.kernel_hidden == 128 and wide.precision == "fp32" and wide.layout == "rowmajor"
+    assert wide.kernel_weights()[1].shape == (512, 128) and LSTM(41, 64, precision="tf32").kernel_hidden == 128
     with pytest.raises(ValueError):
-        LSTM(41, 64, precision="tf32")
+        LSTM(41, 64, precision="tf32x3")
 
 
 REF_DATASETZOO = "/root/reference/Hy2DL/datasetzoo"
