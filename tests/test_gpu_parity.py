@@ -781,6 +781,60 @@ def test_trainer_native_path_matches_api_path(dev, precision):
     assert_close(l_api.item(), losses[0][0], rtol=1e-6, what="API vs native loss")
 
 
+@pytest.mark.parametrize("B,T,I,H", [(37, 5, 31, 256), (300, 4, 50, 128), (1300, 3, 31, 256), (129, 3, 7, 128),
+                                     (11700, 2, 31, 256)])      # the last one: the streamed-weights chain (92 tiles)
+def test_recurrent_kernels_stay_inside_their_buffers(dev, B, T, I, H):
+    """Memory safety of the H = 128 / 256 kernels through the C ABI (compute-sanitizer is not available on the GPU pool):
+    every buffer -- workspaces of exactly hy2dl_workspace_bytes, tapes of the documented sizes (RB8 tapes hold whole
+    groups of 32 sequences), inputs -- sits between guard zones filled with a pattern; after forward, BPTT and weight
+    gradients (ragged tiles, two x chunks, several tiles per group) the guards and the inputs are untouched."""
+    from hy2dl_b200 import _lib, ops
+    prec = ops.PRECISIONS["fp32"]
+    IP, Bp = (I + 7) // 8 * 8, (B + 31) // 32 * 32
+    GUARD = 4096                                                     # floats on either side
+    gen = torch.Generator(device=dev).manual_seed(B + T)
+
+    def guarded(n, fill=None):
+        buf = torch.full((n + 2 * GUARD,), 12345.0, device=dev)
+        core = buf[GUARD:GUARD + n]
+        if fill == "randn":
+            core.normal_(generator=gen)
+        return buf, core
+
+    k = 1 / float(np.sqrt(H))
+    bufs = {}
+    def mk(name, n, fill=None):
+        bufs[name], core = guarded(n, fill)
+        return core
+    x = mk("x", T * B * IP, "randn")
+    w_ih = mk("w_ih", 4 * H * I, "randn").mul_(k); w_hh = mk("w_hh", 4 * H * H, "randn").mul_(k)
+    b_ih = mk("b_ih", 4 * H, "randn").mul_(k); b_hh = mk("b_hh", 4 * H, "randn").mul_(k)
+    h = mk("h", T * B * H); c = mk("c", T * Bp * H); g = mk("g", T * Bp * 4 * H); hl = mk("hl", B * H)
+    dh = mk("dh", T * B * H, "randn")
+    dwi = mk("dwi", 4 * H * I); dwh = mk("dwh", 4 * H * H); db = mk("db", 4 * H)
+    ws = {}
+    for kind, name in ((_lib.WS_LSTM_FWD, "wsf"), (_lib.WS_LSTM_BWD, "wsb"), (_lib.WS_LSTM_WGRAD, "wsw")):
+        n = int(_lib.load().hy2dl_workspace_bytes(kind, B, T, I, H, prec))
+        assert n > 0
+        ws[name] = (mk(name, (n + 3) // 4), n)
+    inputs = {n: bufs[n].clone() for n in ("x", "w_ih", "w_hh", "b_ih", "b_hh", "dh")}
+    st = _lib.stream()
+    _lib.call("hy2dl_lstm_fwd", x.data_ptr(), B, T, I, IP, H, w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(),
+              h.data_ptr(), c.data_ptr(), g.data_ptr(), hl.data_ptr(), ws["wsf"][0].data_ptr(), ws["wsf"][1], prec, None, st)
+    _lib.call("hy2dl_lstm_bwd", B, T, H, w_hh.data_ptr(), g.data_ptr(), c.data_ptr(), dh.data_ptr(), T // 2, None, g.data_ptr(),
+              ws["wsb"][0].data_ptr(), ws["wsb"][1], prec, None, st)
+    _lib.call("hy2dl_lstm_wgrad", g.data_ptr(), h.data_ptr(), x.data_ptr(), B, T, I, IP, H, dwi.data_ptr(), dwh.data_ptr(), db.data_ptr(),
+              ws["wsw"][0].data_ptr(), ws["wsw"][1], prec, None, st)
+    torch.cuda.synchronize()
+    for name, buf in bufs.items():
+        assert bool((buf[:GUARD] == 12345.0).all()) and bool((buf[-GUARD:] == 12345.0).all()), f"guard zone of '{name}' was written"
+    for name, before in inputs.items():
+        assert torch.equal(bufs[name], before), f"input '{name}' was modified"
+    for name in ("h", "hl", "dwi", "dwh", "db"):
+        core = bufs[name][GUARD:-GUARD]
+        assert bool(torch.isfinite(core).all()) and not bool((core == 12345.0).any()), f"output '{name}' not fully written"
+
+
 def test_unit_split_kernels_replay_in_a_cuda_graph(dev):
     """The small-batch H = 128 / 256 kernels are cooperative launches (their CTAs wait for each other): they must be
     capturable, since Trainer(use_graph=True) replays the whole step -- three graph-replayed updates equal three eager
