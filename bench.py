@@ -114,7 +114,8 @@ def resolved_precision(cfg):
 
 
 PRECISION_TEXT = {"tf32x3": "fp32-class: tcgen05 kind::tf32, 3-term operand split, fp32 accumulate, weights resident on chip",
-                  "fp32": "fp32-class: H >= 128 tcgen05 kind::tf32 3-term split with streamed weights; H = 64 CUDA-core FMA",
+                  "fp32": "fp32-class: H >= 128 tcgen05 kind::tf32 3-term split (weights streamed from L2; unit-split kernels with resident weight "
+                          "slices at batches up to ~10 k); H = 64 CUDA-core FMA",
                   "tf32": "THROUGHPUT MODE, not the parity path: single-pass tcgen05 kind::tf32 (10-bit operands, fp32 accumulate), "
                           "stated tolerance 2e-3 (discharge) / 2e-2 (gradients)"}
 
