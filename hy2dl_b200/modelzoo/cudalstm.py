@@ -31,7 +31,7 @@ class CudaLSTM(nn.Module):
 
     def forward(self, x: torch.Tensor):
         """x: [batch_size, time_steps, input_size_lstm] on the GPU."""
-        return self.forward_native(ops.pack_x(x, self.lstm.layout), B=x.shape[0])
+        return self.forward_native(ops.pack_x(x, self.lstm.layout_for(x.shape[0])), B=x.shape[0])
 
     def forward_native(self, xT: torch.Tensor, B: int = None):
         """xT: [T, B, IP] (or RI32 with B given) as written by the GPU-resident sampler."""

@@ -73,7 +73,7 @@ class Hybrid(nn.Module):
         y_hat [B,T_sim,1], parameters / internal_states {name: [B,T_sim,m]}, final_states {name: [B,m]}."""
         if x_lstm.shape[:2] != x_conceptual.shape[:2]:
             raise ValueError("x_lstm and x_conceptual must share batch and time dimensions")
-        return self.forward_native(ops.pack_x(x_lstm, self.lstm.layout),
+        return self.forward_native(ops.pack_x(x_lstm, self.lstm.layout_for(x_lstm.shape[0])),
                                    ops.pack_forcing(self.conceptual_model._forcing(x_conceptual)))
 
     def forward_native(self, xT: torch.Tensor, forc: torch.Tensor):
@@ -88,13 +88,14 @@ class Hybrid(nn.Module):
         N, T_sim = B * m, T - warmup
 
         # LSTM over all T steps; only steps >= warmup receive gradient from the head
-        if self.lstm.layout == "ri32" and self.linear.out_features <= ops.FUSED_HEAD_MAX_COLUMNS:
+        if ops.is_ri32(xT) and self.linear.out_features <= ops.FUSED_HEAD_MAX_COLUMNS:
             # LSTM + head in one kernel: the hidden sequence is only written as the BPTT tape
             par_sim, par_warm = ops.lstm_head(xT, *self.lstm.kernel_weights(), self.lstm.pad_head(self.linear.weight),
                                               self.linear.bias, self.input_size_lstm, layout, self.lstm.precision)
         else:
             h_seq, _ = self.lstm.run_native(xT, dh_t0=warmup, want_seq=True, B=B)
-            par_sim, par_warm = ops.head_map(h_seq, self.lstm.pad_head(self.linear.weight), self.linear.bias, layout)
+            HK = h_seq.shape[-1] if not ops.is_ri32(h_seq) else None          # the family that ran (LSTM.layout_for)
+            par_sim, par_warm = ops.head_map(h_seq, self.lstm.pad_head(self.linear.weight, HK), self.linear.bias, layout)
 
         # warm-up: frozen parameters, no gradient (hybrid.py:99-102)
         with torch.no_grad():

@@ -49,7 +49,8 @@ class LSTM(nn.Module):
         # resident weights ("tf32x3": H <= 64, input_size <= 31); otherwise "fp32", which is the tcgen05 chain of the
         # H = 128 / 256 kernels (streamed weights, or unit split at small batches).  "tf32" is the throughput mode
         # (single-pass TF32 operands on the same tensor-core kernels; looser, stated tolerance -- never picked by "auto")
-        if precision == "auto":
+        auto = precision == "auto"
+        if auto:
             precision = "tf32x3" if (self.kernel_hidden == 64 and input_size <= 31) else "fp32"
         if precision not in ops.PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(ops.PRECISIONS)} or 'auto', got '{precision}'")
@@ -59,6 +60,13 @@ class LSTM(nn.Module):
         if precision == "tf32" and self.kernel_hidden == 64 and input_size > 31:       # only with HY2DL_FP32_TC=0
             raise ValueError("hy2dl_b200.LSTM: precision 'tf32' (throughput mode) runs on the tensor-core kernels only "
                              f"(got hidden_size {hidden_size}, input_size {input_size} with HY2DL_FP32_TC=0)")
+        # Small batches of a default ("auto") H <= 64 model run on the unit-split kernels zero-padded to 128 units: a 128-sequence
+        # tile of the resident-weights kernels occupies ONE SM whatever the batch (the reference's batch of 256 = 2 of 148 SMs),
+        # the unit-split kernels spread a tile over 8 SMs.  Forward + BPTT + weight gradients, T = 365, I = 25: 3.9 vs 5.5 ms at a
+        # batch of 256, 4.4 vs 5.7 at 1 024, 5.2 vs 5.8 at 2 304 (one round of 18 groups).  Chosen per call from the batch size
+        # (layout_for); both families meet the same fp32 tolerances.  HY2DL_SMALL_BATCH_US=0 switches it off.
+        self._small_family = (auto and precision == "tf32x3" and os.environ.get("HY2DL_SMALL_BATCH_US") != "0"
+                              and os.environ.get("HY2DL_FP32_TC") != "0" and os.environ.get("HY2DL_RM_US") != "0")
         self.precision = precision
         H = hidden_size
         self.weight_ih_l0 = nn.Parameter(torch.empty(4 * H, input_size))
@@ -75,11 +83,23 @@ class LSTM(nn.Module):
     def weights(self):
         return self.weight_ih_l0, self.weight_hh_l0, self.bias_ih_l0, self.bias_hh_l0
 
-    def kernel_weights(self):
-        """The four parameters at the kernels' hidden size HK = kernel_hidden: unit u of gate g sits at row
+    SMALL_BATCH_MAX = 2304      # one round of the 18 unit-split groups at 128 (padded) units
+
+    def family_for(self, B: int):
+        """(kernel hidden size, precision, layout) of the kernels a batch of B sequences runs on."""
+        if self._small_family and B <= self.SMALL_BATCH_MAX:
+            return 128, "fp32", "rowmajor"
+        return self.kernel_hidden, self.precision, self.layout
+
+    def layout_for(self, B: int) -> str:
+        """Layout the native input of a batch of B sequences must be packed in (the sampler / pack_x write it)."""
+        return self.family_for(B)[2]
+
+    def kernel_weights(self, HK: Optional[int] = None):
+        """The four parameters at the kernels' hidden size HK (default kernel_hidden): unit u of gate g sits at row
         g*HK + u, padded rows / columns are zero.  Differentiable torch indexing on the (small) weights, so the
         gradients of the padded tensors flow back to the real parameters."""
-        H, HK = self.hidden_size, self.kernel_hidden
+        H, HK = self.hidden_size, HK or self.kernel_hidden
         if H == HK:
             return self.weights()
         w_ih, w_hh, b_ih, b_hh = self.weights()
@@ -88,9 +108,9 @@ class LSTM(nn.Module):
         w_hh_p = torch.nn.functional.pad(pad_rows(w_hh), (0, HK - H))
         return w_ih_p, w_hh_p, pad_rows(b_ih.view(-1, 1)).view(-1), pad_rows(b_hh.view(-1, 1)).view(-1)
 
-    def pad_head(self, w_head: torch.Tensor) -> torch.Tensor:
+    def pad_head(self, w_head: torch.Tensor, HK: Optional[int] = None) -> torch.Tensor:
         """A Linear(H, C) weight [C, H] at the kernels' hidden size [C, HK] (zero columns for the padded units)."""
-        H, HK = self.hidden_size, self.kernel_hidden
+        H, HK = self.hidden_size, HK or self.kernel_hidden
         return w_head if H == HK else torch.nn.functional.pad(w_head, (0, HK - H))
 
     @property
@@ -100,8 +120,13 @@ class LSTM(nn.Module):
 
     def run_native(self, xT: torch.Tensor, dh_t0: int = 0, want_seq: bool = True, B: Optional[int] = None):
         """xT: native input ([T,B,IP], or RI32 for precision tf32x3 with B given) ->
-        (h_seq in the same layout or empty, h_last [B,H])."""
-        h_seq, h_last = ops.lstm(xT, *self.kernel_weights(), self.input_size, dh_t0, want_seq, self.precision, B)
+        (h_seq in the same layout or empty, h_last [B,HK]).  The layout of xT says which family runs (layout_for)."""
+        HK, precision = self.kernel_hidden, self.precision
+        if self.layout == "ri32" and not ops.is_ri32(xT):            # row-major input to a resident-weights model: small-batch family
+            if not self._small_family:
+                raise ValueError("hy2dl_b200.LSTM: this model reads RI32 input (precision tf32x3); got a row-major tensor")
+            HK, precision = 128, "fp32"
+        h_seq, h_last = ops.lstm(xT, *self.kernel_weights(HK), self.input_size, dh_t0, want_seq, precision, B)
         return h_seq, h_last
 
     def forward(self, x: torch.Tensor, hx: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
@@ -120,7 +145,7 @@ class LSTM(nn.Module):
                 raise NotImplementedError("hy2dl_b200.LSTM starts from h_0 = c_0 = 0 (as every reference model does); "
                                           "a non-zero initial state is not supported")
         B, H = x.shape[0], self.hidden_size
-        h_seq, h_last = self.run_native(ops.pack_x(x, self.layout), B=B)
+        h_seq, h_last = self.run_native(ops.pack_x(x, self.layout_for(B)), B=B)
         if ops.is_ri32(h_seq):
             h_seq = ops.from_ri32(h_seq, B)
         return h_seq[:, :, :H].permute(1, 0, 2), (h_last[:, :H].unsqueeze(0), None)

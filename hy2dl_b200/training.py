@@ -124,6 +124,7 @@ class Trainer:
         self._static_loss = None
 
     def _step_eager(self, ids: torch.Tensor) -> torch.Tensor:
+        self.dataset.layout = self.model.lstm.layout_for(int(ids.numel()))    # small batches of an H <= 64 model: other kernels, other layout
         batch = self.dataset.gather(ids)
         self.opt.zero_grad()
         loss = forward_loss(self.model, batch, self.loss_kind, self.group)

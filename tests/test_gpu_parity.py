@@ -739,7 +739,7 @@ def test_nse_device_edge_cases(dev):
         nse_device(torch.zeros(2, 5), torch.zeros(2, 5))
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "auto"])      # "auto" at this batch: the small-batch family (LSTM.layout_for)
 def test_trainer_native_path_matches_api_path(dev, precision):
     """Sampler -> native layouts -> Trainer.step equals the API path (pack_x from [B,T,I]) step."""
     from hy2dl_b200.datasetzoo import ResidentDataset
@@ -833,6 +833,37 @@ def test_recurrent_kernels_stay_inside_their_buffers(dev, B, T, I, H):
     for name in ("h", "hl", "dwi", "dwh", "db"):
         core = bufs[name][GUARD:-GUARD]
         assert bool(torch.isfinite(core).all()) and not bool((core == 12345.0).any()), f"output '{name}' not fully written"
+
+
+def test_small_batches_of_default_h64_models_take_the_unit_split_family(dev):
+    """A default ("auto") H <= 64 model runs small batches on the unit-split kernels zero-padded to 128 units and large ones
+    on the resident-weights kernels (LSTM.family_for): same model, same samples -- the two families agree with each other
+    and with the fp64 oracle within the fp32 tolerances, forward and gradients; an explicit precision pins the family."""
+    from hy2dl_b200.modelzoo import LSTM
+    from hy2dl_b200.synthetic import lstm_weights
+    from _util import camels_like_inputs
+    I, H, T = 25, 64, 60
+    lstm = LSTM(I, H).to(dev)
+    assert lstm.family_for(256) == (128, "fp32", "rowmajor") and lstm.family_for(4096) == (64, "tf32x3", "ri32")
+    assert LSTM(I, H, precision="tf32x3").family_for(256) == (64, "tf32x3", "ri32")
+    w = {k[5:]: torch.tensor(v) for k, v in lstm_weights(I, H, 1, seed=9).items() if k.startswith("lstm.")}
+    lstm.load_state_dict(w)
+    B_small, B_large = 96, LSTM.SMALL_BATCH_MAX + 64
+    x = camels_like_inputs(B_large, T, I, seed=5)
+    gh = np.random.default_rng(1).normal(0, 1, (B_large, T, H)).astype(np.float32)
+    res = {}
+    for name, B in (("small", B_small), ("large", B_large)):
+        lstm.zero_grad()
+        out, _ = lstm(cu(x[:B], dev))
+        (out * cu(gh[:B], dev)).sum().backward()
+        res[name] = (npy(out), {k: npy(p.grad).copy() for k, p in lstm.named_parameters()})
+    assert_close(res["small"][0], res["large"][0][:B_small], rtol=1e-4, atol=1e-6, what="h_seq: small-batch family vs resident-weights family")
+    wd = {k: tt(v.numpy(), torch.float64, True) for k, v in w.items()}
+    ref = O.lstm_cell_sequence(tt(x[:B_small], torch.float64), wd["weight_ih_l0"], wd["weight_hh_l0"], wd["bias_ih_l0"], wd["bias_hh_l0"])
+    (ref * tt(gh[:B_small], torch.float64)).sum().backward()
+    assert_close(res["small"][0], ref.detach().numpy(), rtol=1e-4, atol=1e-6, what="h_seq (small-batch family) vs fp64 oracle")
+    for k in wd:
+        assert_close(res["small"][1][k], wd[k].grad.numpy(), rtol=1e-4, atol=1e-6, what="grad " + k + " (small-batch family) vs fp64 oracle")
 
 
 def test_unit_split_kernels_replay_in_a_cuda_graph(dev):
