@@ -585,11 +585,38 @@ static bool rm_tc_chain(int64_t I, int64_t H) {
   return !off && tc::lstm_rm_tc_fwd_supported(I, H) && tc::lstm_rm_tc_bwd_supported(H) && tc::lstm_wgrad_rm_tc_supported(H);
 }
 
+// H = 64 at small batches: the unit-split forward / BPTT kernels (lstm_us_tc_*.cu, 4 CTAs per 128-sequence tile) and the
+// tensor-core weight-gradient GEMM, on RB8 tapes like the H = 128 / 256 chain -- instead of the CUDA-core kernels below,
+// whose tile of sequences sits on one SM for all T steps.  One round of 37 groups (4 736 sequences) takes 2.9 ms forward +
+// BPTT at T = 365 where the CUDA-core kernels need 5.7 ms and the resident-weights kernels (lstm_tc.cu) 5.5 ms.  The three
+// kernels share the tapes, so the rule depends only on what all three calls know: B and H.
+namespace tc {
+bool lstm_us_tc_fwd_preferred(int64_t B, int64_t I, int64_t H);
+bool lstm_us_tc_bwd_preferred(int64_t B, int64_t H);
+int64_t lstm_us_tc_fwd_workspace(int64_t B, int64_t I, int64_t H);
+int64_t lstm_us_tc_bwd_workspace(int64_t B, int64_t H);
+int lstm_us_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H, const float* w_ih, const float* w_hh,
+                   const float* b_ih, const float* b_hh, float* h_seq, float* c_seq, float* gates, float* h_last, void* ws,
+                   int64_t ws_bytes, int single, cudaStream_t s);
+int lstm_us_tc_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const float* gates, const float* c_seq, const float* dh_seq,
+                   int64_t dh_t0, const float* dh_last, float* dG, void* ws, int64_t ws_bytes, int single, cudaStream_t s);
+int64_t lstm_wgrad_rm_tc_workspace(int64_t H, int64_t I);
+int lstm_wgrad_rm_tc(const float* dG, const float* h_seq, const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H,
+                     float* dw_ih, float* dw_hh, float* db, void* ws, int64_t ws_bytes, int single, cudaStream_t s);
+}  // namespace tc
+static bool us64_chain(int64_t B, int64_t H) {
+  static const bool off = [] { const char* e = getenv("HY2DL_FP32_TC"); return e && e[0] == '0'; }();
+  return !off && H == 64 && tc::lstm_us_tc_fwd_preferred(B, 64, 64) && tc::lstm_us_tc_bwd_preferred(B, 64) &&
+         tc::lstm_wgrad_rm_tc_supported(64);
+}
+
 int lstm_fp32_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H, const float* w_ih,
                   const float* w_hh, const float* b_ih, const float* b_hh, float* h_seq, float* c_seq, float* gates,
                   float* h_last, void* ws, int64_t ws_bytes, int single, cudaStream_t s) {
   if (rm_tc_chain(I, H))
     return tc::lstm_rm_tc_fwd(xT, B, T, I, IP, H, w_ih, w_hh, b_ih, b_hh, h_seq, c_seq, gates, h_last, ws, ws_bytes, single, s);
+  if (us64_chain(B, H))
+    return tc::lstm_us_tc_fwd(xT, B, T, I, IP, H, w_ih, w_hh, b_ih, b_hh, h_seq, c_seq, gates, h_last, ws, ws_bytes, single, s);
   HY_REQUIRE(!single, HY2DL_ERR_SHAPE, "hy2dl_lstm_fwd: precision tf32 runs on the tensor-core kernels only (H = 64 with input_size <= 31, "
              "H = 128 / 256); got H=%lld I=%lld", (long long)H, (long long)I);
   const int64_t need = lstm_fp32_workspace(HY2DL_WS_LSTM_FWD, B, T, I, H);
@@ -619,6 +646,8 @@ int lstm_fp32_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const floa
                   cudaStream_t s) {
   if (rm_tc_chain(8, H))     // the chain's condition on the input size (I <= 64) holds for every accepted call
     return tc::lstm_rm_tc_bwd(B, T, H, w_hh, gates, c_seq, dh_seq, dh_t0, dh_last, dG, ws, ws_bytes, single, s);
+  if (us64_chain(B, H))
+    return tc::lstm_us_tc_bwd(B, T, H, w_hh, gates, c_seq, dh_seq, dh_t0, dh_last, dG, ws, ws_bytes, single, s);
   HY_REQUIRE(!single, HY2DL_ERR_SHAPE, "hy2dl_lstm_bwd: precision tf32 runs on the tensor-core kernels only (H=%lld)", (long long)H);
   LstmBwdArgs a{w_hh, gates, c_seq, dh_seq, dh_last, dG, B, T, dh_t0};
   const int spt = pick_spt(B);
@@ -637,7 +666,8 @@ int lstm_wgrad_rm_tc(const float* dG, const float* h_seq, const float* xT, int64
 
 int lstm_fp32_wgrad(const float* dG, const float* h_seq, const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
                     int64_t H, float* dw_ih, float* dw_hh, float* db, void* ws, int64_t ws_bytes, int single, cudaStream_t s) {
-  if (rm_tc_chain(I, H)) return tc::lstm_wgrad_rm_tc(dG, h_seq, xT, B, T, I, IP, H, dw_ih, dw_hh, db, ws, ws_bytes, single, s);
+  if (rm_tc_chain(I, H) || us64_chain(B, H))
+    return tc::lstm_wgrad_rm_tc(dG, h_seq, xT, B, T, I, IP, H, dw_ih, dw_hh, db, ws, ws_bytes, single, s);
   HY_REQUIRE(!single, HY2DL_ERR_SHAPE, "hy2dl_lstm_wgrad: precision tf32 runs on the tensor-core kernels only (H=%lld)", (long long)H);
   const int64_t need = lstm_fp32_workspace(HY2DL_WS_LSTM_WGRAD, B, T, I, H);
   HY_REQUIRE(ws != nullptr && ws_bytes >= need, HY2DL_ERR_WORKSPACE, "hy2dl_lstm_wgrad: workspace %lld < %lld bytes",
@@ -661,11 +691,12 @@ int64_t lstm_fp32_workspace(int kind, int64_t B, int64_t T, int64_t I, int64_t H
   const int64_t IP = round_up(I, 8);
   if (kind == HY2DL_WS_LSTM_FWD) {
     if (rm_tc_chain(I, H)) return tc::lstm_rm_tc_fwd_workspace(B, I, H);
+    if (us64_chain(B, H)) return tc::lstm_us_tc_fwd_workspace(B, I, H);
     return sizeof(float) * ((IP + H) * 4 * H + 4 * H);
   }
-  if (kind == HY2DL_WS_LSTM_BWD) return rm_tc_chain(I, H) ? tc::lstm_rm_tc_bwd_workspace(B, H) : 16;
+  if (kind == HY2DL_WS_LSTM_BWD) return rm_tc_chain(I, H) ? tc::lstm_rm_tc_bwd_workspace(B, H) : us64_chain(B, H) ? tc::lstm_us_tc_bwd_workspace(B, H) : 16;
   if (kind == HY2DL_WS_LSTM_WGRAD) {
-    if (rm_tc_chain(I, H)) return tc::lstm_wgrad_rm_tc_workspace(H, I);
+    if (rm_tc_chain(I, H) || us64_chain(B, H)) return tc::lstm_wgrad_rm_tc_workspace(H, I);
     const int M = (int)(4 * H), NP = (int)round_up(H + IP + 1, 128);
     return sizeof(float) * (int64_t)wgrad_splits(T * B, M, NP) * M * NP;
   }

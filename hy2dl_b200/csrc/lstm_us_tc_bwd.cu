@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kThreadsV, 1) lstm_us_tc_bwd_kernel(UsBwdArgs 
           for (int j0 = 0; j0 < S; j0 += 8) {     // 8 loads in flight (S is 8 or 16), then a fixed-order sum
             f8 v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = ld256_l2v(pp + (int64_t)(j0 + j) * HB * (kRowsV * 8));
+            for (int j = 0; j < 8; ++j) v[j] = (j0 + j < S) ? ld256_l2v(pp + (int64_t)(j0 + j) * HB * (kRowsV * 8)) : f8_zero();   // S = 4 at H = 64
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
 #pragma unroll
@@ -220,8 +220,9 @@ __global__ void __launch_bounds__(kThreadsV, 1) lstm_us_tc_bwd_kernel(UsBwdArgs 
         float* po = a.px + (((((st & 1) * (int64_t)a.groups + group) * S + s) * HB + hh * (HB / 2)) * kRowsV + rloc) * 8;
         for (int c0 = 0; c0 < HH; c0 += 64) {        // two 32-column pulls in flight
           uint32_t z[32], y[32];
+          const bool second = c0 + 32 < HH;          // H = 64: 32 columns per thread
           tmem_ld32(lane_tm + hh * HH + c0, z);
-          tmem_ld32(lane_tm + hh * HH + c0 + 32, y);
+          if (second) tmem_ld32(lane_tm + hh * HH + c0 + 32, y);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -230,6 +231,7 @@ __global__ void __launch_bounds__(kThreadsV, 1) lstm_us_tc_bwd_kernel(UsBwdArgs 
             for (int k = 0; k < 8; ++k) v.v[k] = __uint_as_float(z[8 * i + k]);
             st256(po + (c0 / 8 + i) * (kRowsV * 8), v);
           }
+          if (second)
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             f8 v;
@@ -297,7 +299,7 @@ static int usb_groups(int64_t B, int64_t H) {
 }
 
 bool lstm_us_tc_bwd_supported(int64_t H) {
-  return (H == 128 || H == 256) && sm_count() >= H / kUnitsV;
+  return (H == 64 || H == 128 || H == 256) && sm_count() >= H / kUnitsV;
 }
 
 // as lstm_us_tc_fwd_preferred: 2.9 ms per round against 25-29 ms (H = 256), 1.9 ms against 8-10 ms (H = 128); HY2DL_RM_US(_BWD)=0 / 1 forces
@@ -308,7 +310,7 @@ bool lstm_us_tc_bwd_preferred(int64_t B, int64_t H) {
   if (force == 1) return true;
   const int64_t tiles = cdiv(B, (int64_t)kRowsV);
   const int64_t rounds = cdiv(tiles, (int64_t)usb_groups(B, H));
-  return rounds <= (H == 256 ? 8 : 4);
+  return rounds <= (H == 256 ? 8 : H == 128 ? 4 : 1);
 }
 
 int64_t lstm_us_tc_bwd_workspace(int64_t B, int64_t H) {

@@ -372,10 +372,9 @@ static int us_groups(int64_t B, int64_t H) {
 }
 
 bool lstm_us_tc_fwd_supported(int64_t I, int64_t H) {
-  if (!(H == 128 || H == 256)) return false;
+  if (!(H == 64 || H == 128 || H == 256) || I < 1 || I > 64) return false;
   const int KX = us_kx(I);
-  if (KX > 2 * kGroupK) return false;
-  const int64_t smem = (int64_t)(KX + H) * kColsU * 8 + kSlotsU * kSlotBytesU + 256 + 1024;
+  const int64_t smem = (int64_t)(KX + H) * kColsU * 8 + kSlotsU * kSlotBytesU + 256 + 1024;     // H = 256: input_size <= 63
   return smem <= 232448 && sm_count() >= H / kUnitsU;
 }
 
@@ -389,7 +388,7 @@ bool lstm_us_tc_fwd_preferred(int64_t B, int64_t I, int64_t H) {
   if (force == 1) return true;
   const int64_t tiles = cdiv(B, (int64_t)kRowsU);
   const int64_t rounds = cdiv(tiles, (int64_t)us_groups(B, H));
-  return rounds <= (H == 256 ? 10 : 5);
+  return rounds <= (H == 256 ? 10 : H == 128 ? 5 : 1);      // H = 64: against the CUDA-core / resident-weights kernels (lstm_fp32.cu)
 }
 
 int64_t lstm_us_tc_fwd_workspace(int64_t B, int64_t I, int64_t H) {

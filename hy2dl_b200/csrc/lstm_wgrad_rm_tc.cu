@@ -327,7 +327,7 @@ static void rm_tc_shape(int64_t H, int64_t I, int& MT, int& NT, int& NB, int& pa
   parts = std::max(1, sm_count() / (MT * NT));
 }
 
-bool lstm_wgrad_rm_tc_supported(int64_t H) { return H == 128 || H == 256; }
+bool lstm_wgrad_rm_tc_supported(int64_t H) { return H == 64 || H == 128 || H == 256; }
 
 int64_t lstm_wgrad_rm_tc_workspace(int64_t H, int64_t I) {
   int MT, NT, NB, parts;

@@ -83,12 +83,12 @@ class LSTM(nn.Module):
     def weights(self):
         return self.weight_ih_l0, self.weight_hh_l0, self.bias_ih_l0, self.bias_hh_l0
 
-    SMALL_BATCH_MAX = 2304      # one round of the 18 unit-split groups at 128 (padded) units
+    SMALL_BATCH_MAX = 4736      # one round of the 37 unit-split groups of a 148-SM GPU at 64 units
 
     def family_for(self, B: int):
         """(kernel hidden size, precision, layout) of the kernels a batch of B sequences runs on."""
         if self._small_family and B <= self.SMALL_BATCH_MAX:
-            return 128, "fp32", "rowmajor"
+            return 64, "fp32", "rowmajor"
         return self.kernel_hidden, self.precision, self.layout
 
     def layout_for(self, B: int) -> str:
@@ -125,7 +125,7 @@ class LSTM(nn.Module):
         if self.layout == "ri32" and not ops.is_ri32(xT):            # row-major input to a resident-weights model: small-batch family
             if not self._small_family:
                 raise ValueError("hy2dl_b200.LSTM: this model reads RI32 input (precision tf32x3); got a row-major tensor")
-            HK, precision = 128, "fp32"
+            precision = "fp32"
         h_seq, h_last = ops.lstm(xT, *self.kernel_weights(HK), self.input_size, dh_t0, want_seq, precision, B)
         return h_seq, h_last
 

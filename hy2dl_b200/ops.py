@@ -150,7 +150,8 @@ class LstmFunction(torch.autograd.Function):
         h_last = torch.empty(B, H, dtype=torch.float32, device=dev)
         # c_seq and gates are tapes only the kernels read; the H = 128 / 256 tensor-core chain stores them blocked by
         # 32 sequences (include/hy2dl_b200.h, "RB8"), so they hold whole groups of rows
-        tape = seq if (ri or H < 128) else (lambda F: torch.empty(T, (B + 31) // 32 * 32, F, dtype=torch.float32, device=dev))
+        # (H = 64 at small batches as well: lstm_fp32.cu us64_chain; the CUDA-core kernels use the first T*B*F floats)
+        tape = seq if ri else (lambda F: torch.empty(T, (B + 31) // 32 * 32, F, dtype=torch.float32, device=dev))
         c_seq = tape(H) if need_grad else None
         gates = tape(4 * H) if need_grad else None
         ws = _ws(_lib.WS_LSTM_FWD, B, T, I, H, dev, precision)

@@ -54,9 +54,11 @@ extern "C" {
 typedef void* hy2dl_stream_t; /* cudaStream_t */
 
 /* precision of the recurrent / projection matmuls */
-#define HY2DL_PREC_FP32 0   /* fp32-class (parity path, rtol 1e-4).  H = 64: CUDA-core FMA kernels.  H = 128 / 256: tcgen05
-                             * kind::tf32 with the 3-term operand split and streamed weights (row-major streams, RB8 tapes);
-                             * HY2DL_FP32_TC=0 in the environment selects the CUDA-core kernels there as well */
+#define HY2DL_PREC_FP32 0   /* fp32-class (parity path, rtol 1e-4), row-major streams.  H = 128 / 256: tcgen05 kind::tf32 with the
+                             * 3-term operand split -- weights streamed from L2, or (batches up to ~10 k) the unit-split kernels
+                             * with resident weight slices; RB8 tapes.  H = 64: the unit-split kernels up to one round of groups
+                             * (4 736 sequences on 148 SMs; RB8 tapes), CUDA-core FMA kernels above (row-major tapes).
+                             * HY2DL_FP32_TC=0 in the environment selects the CUDA-core kernels everywhere */
 #define HY2DL_PREC_TF32X3 1 /* fp32-class: tcgen05 kind::tf32, 3-term split, weights resident on chip (H = 64, RI32 streams) */
 #define HY2DL_PREC_TF32 2   /* throughput mode: the same tensor-core kernels with the correction terms switched off (single-pass
                              * TF32 operands, 10-bit mantissa, fp32 accumulate).  NOT the parity path: measured against fp64,
@@ -147,9 +149,10 @@ typedef struct {
  * Weights come in PyTorch layout: w_ih [4H][I], w_hh [4H][H], b_ih [4H], b_hh [4H].
  * Tape outputs may be NULL (inference): c_seq, gates; h_seq may be NULL if only h_last is wanted.
  * c_seq, gates and dG are tapes that only hy2dl_lstm_bwd / hy2dl_lstm_wgrad read back: their layout is the forward
- * kernel's choice.  Row-major precisions, H = 64: [T][B][H] and [T][B][4][H].  Row-major precisions, H = 128 / 256
- * (tensor-core chain, unless HY2DL_FP32_TC=0): "RB8" = [T][ceil(B/32)][F/8][32 sequences][8 floats], F = H or 4H --
- * allocate T * ceil(B/32)*32 * F floats for them. */
+ * kernel's choice and the same for the three calls of one (B, T, H, precision).  Row-major precisions: ALWAYS allocate
+ * T * ceil(B/32)*32 * F floats for them (F = H or 4H): the tensor-core kernels (H = 128 / 256, and H = 64 at small batches,
+ * see HY2DL_PREC_FP32) store them as "RB8" = [T][ceil(B/32)][F/8][32 sequences][8 floats]; the CUDA-core kernels as
+ * [T][B][H] and [T][B][4][H] in the first T*B*F floats. */
 int hy2dl_lstm_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP, int64_t H,
                    const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
                    float* h_seq, float* c_seq, float* gates, float* h_last,

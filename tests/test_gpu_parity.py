@@ -379,7 +379,9 @@ def test_train_steps_bit_reproducible(dev, precision, H):
                                                 # unit-split kernels (small batches, lstm_us_tc_*.cu): 11 tiles on 9 groups of 16
                                                 # CTAs (a group walks over two tiles, the last one ragged), 8-CTA groups with two
                                                 # x chunks, and the largest batch they take at H = 128 (72 tiles on 18 groups)
-                                                (1300, 6, 31, 256, "fp32"), (300, 9, 50, 128, "fp32"), (9216, 3, 12, 128, "fp32"), (9300, 2, 31, 256, "fp32")])
+                                                (1300, 6, 31, 256, "fp32"), (300, 9, 50, 128, "fp32"), (9216, 3, 12, 128, "fp32"), (9300, 2, 31, 256, "fp32"),
+                                                # H = 64, fp32: unit split up to one round of 37 groups, the CUDA-core kernels above
+                                                (4736, 3, 25, 64, "fp32"), (4800, 3, 25, 64, "fp32")])
 def test_lstm_vs_oracle(dev, B, T, I, H, precision):
     from hy2dl_b200.modelzoo import LSTM
     from hy2dl_b200.synthetic import lstm_weights
@@ -782,7 +784,7 @@ def test_trainer_native_path_matches_api_path(dev, precision):
 
 
 @pytest.mark.parametrize("B,T,I,H", [(37, 5, 31, 256), (300, 4, 50, 128), (1300, 3, 31, 256), (129, 3, 7, 128),
-                                     (11700, 2, 31, 256)])      # the last one: the streamed-weights chain (92 tiles)
+                                     (11700, 2, 31, 256), (300, 4, 25, 64), (130, 3, 64, 64)])      # the streamed-weights chain (92 tiles); H = 64 unit split
 def test_recurrent_kernels_stay_inside_their_buffers(dev, B, T, I, H):
     """Memory safety of the H = 128 / 256 kernels through the C ABI (compute-sanitizer is not available on the GPU pool):
     every buffer -- workspaces of exactly hy2dl_workspace_bytes, tapes of the documented sizes (RB8 tapes hold whole
@@ -844,7 +846,7 @@ def test_small_batches_of_default_h64_models_take_the_unit_split_family(dev):
     from _util import camels_like_inputs
     I, H, T = 25, 64, 60
     lstm = LSTM(I, H).to(dev)
-    assert lstm.family_for(256) == (128, "fp32", "rowmajor") and lstm.family_for(4096) == (64, "tf32x3", "ri32")
+    assert lstm.family_for(256) == (64, "fp32", "rowmajor") and lstm.family_for(8192) == (64, "tf32x3", "ri32")
     assert LSTM(I, H, precision="tf32x3").family_for(256) == (64, "tf32x3", "ri32")
     w = {k[5:]: torch.tensor(v) for k, v in lstm_weights(I, H, 1, seed=9).items() if k.startswith("lstm.")}
     lstm.load_state_dict(w)

@@ -9,6 +9,14 @@ from _util import O, assert_close, tt
 pytestmark = pytest.mark.gpu
 
 
+def _unrb8(a, B):
+    """RB8 tape [T][ceil(B/32)][F/8][32 rows][8] (stored in a [T, Bp, F] buffer) -> row-major [T, B, F].  The fp32-class
+    kernels keep their internal tapes (c, gates / dG) in this layout: H = 128 / 256 always, H = 64 at the small batches that
+    run on the unit-split kernels (every batch of this file)."""
+    T, Bp, F = a.shape
+    return a.view(T, Bp // 32, F // 8, 32, 8).permute(0, 1, 3, 2, 4).reshape(T, Bp, F)[:, :B]
+
+
 def _run_fwd(dev, B, T, I, precision, seed=0, tape=True):
     from hy2dl_b200 import _lib, ops
     from hy2dl_b200.synthetic import lstm_weights
@@ -20,8 +28,8 @@ def _run_fwd(dev, B, T, I, precision, seed=0, tape=True):
     cu = lambda a: torch.tensor(a, device=dev)
     x_in = ops.pack_x(cu(x), "ri32" if ri else "rowmajor")
     G = (B + 31) // 32
-    Bp = G * 32 if precision == _lib.PREC_TF32X3 else B
-    h = torch.zeros(T, Bp, H, device=dev)
+    Bp = G * 32                                                     # tapes hold whole groups of 32 sequences
+    h = torch.zeros(T, Bp if ri else B, H, device=dev)
     c = torch.zeros(T, Bp, H, device=dev) if tape else None
     g = torch.zeros(T, Bp, 4 * H, device=dev) if tape else None
     hl = torch.zeros(B, H, device=dev)
@@ -37,6 +45,8 @@ def _run_fwd(dev, B, T, I, precision, seed=0, tape=True):
         if tape:
             c = unri(c, H)
             g = unri(g, 4 * H).reshape(T, B, H, 4).permute(0, 1, 3, 2).reshape(T, B, 4 * H)   # n = 4u+g -> g*H+u
+    elif tape:
+        c, g = _unrb8(c, B), _unrb8(g, B)
     wd64 = {k: tt(v, torch.float64) for k, v in w.items()}
     ref = O.lstm_cell_sequence(tt(x, torch.float64), wd64["lstm.weight_ih_l0"], wd64["lstm.weight_hh_l0"],
                                wd64["lstm.bias_ih_l0"], wd64["lstm.bias_hh_l0"]).numpy()   # [B,T,H]
@@ -76,10 +86,10 @@ def _bwd_both(dev, B, T, I, dh_t0, use_last, seed=3):
     out, wg = {}, {}
     for prec in (_lib.PREC_FP32, _lib.PREC_TF32X3):
         ri = prec == _lib.PREC_TF32X3
-        Bp = G * 32 if ri else B
+        Bp = G * 32
         IP = 32 if ri else (I + 7) // 8 * 8
         x_in = ops.pack_x(cu(x), "ri32" if ri else "rowmajor")
-        h = torch.zeros(T, Bp, H, device=dev); c = torch.zeros(T, Bp, H, device=dev)
+        h = torch.zeros(T, Bp if ri else B, H, device=dev); c = torch.zeros(T, Bp, H, device=dev)
         g = torch.zeros(T, Bp, 4 * H, device=dev); hl = torch.zeros(B, H, device=dev)
         ws = ops._ws(_lib.WS_LSTM_FWD, B, T, I, H, dev, prec)
         _lib.call("hy2dl_lstm_fwd", x_in.data_ptr(), B, T, I, IP, H, *[t.data_ptr() for t in wd], h.data_ptr(),
@@ -103,7 +113,7 @@ def _bwd_both(dev, B, T, I, dh_t0, use_last, seed=3):
             dG = ops.from_ri32(g.view(T, G, 4 * H // 32, 32, 32), B).reshape(T, B, H, 4).permute(0, 1, 3, 2).reshape(T, B, 4 * H)
             hh = ops.from_ri32(h.view(T, G, H // 32, 32, 32), B)
         else:
-            dG, hh = g, h
+            dG, hh = _unrb8(g, B), h
         out[prec] = (dG.cpu().double().numpy(), hh.cpu().double().numpy())
     # oracle gradients (fp64 autograd)
     wd64 = {k: tt(v, torch.float64, True) for k, v in w.items() if k.startswith("lstm.")}

@@ -21,7 +21,7 @@ w_ih = (torch.rand(4 * H, I, device=dev) * 2 - 1) * k; w_hh = (torch.rand(4 * H,
 b_ih = (torch.rand(4 * H, device=dev) * 2 - 1) * k; b_hh = (torch.rand(4 * H, device=dev) * 2 - 1) * k
 seq = (lambda F: torch.empty(T, G, F // 32, 32, 32, device=dev)) if ri else (lambda F: torch.empty(T, B, F, device=dev))
 x = seq(IP); x.normal_()
-tape = seq if (ri or H < 128) else (lambda F: torch.empty(T, G * 32, F, device=dev))     # RB8 tapes hold whole 32-row groups
+tape = seq if ri else (lambda F: torch.empty(T, G * 32, F, device=dev))     # RB8 tapes hold whole 32-row groups
 h, c, g = seq(H), tape(H), tape(4 * H)
 dh = seq(H); dh.normal_()
 hl = torch.empty(B, H, device=dev)
