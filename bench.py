@@ -493,7 +493,7 @@ def run_side_config(name, dev, rank, world, group, barrier, steps=3, warmup=3, b
     out = {"value": value, "unit": "sequences/s", "batch_per_gpu": batch, "ms_per_step": ms / steps, "steps": steps,
            "precision": resolved_precision(cfg), "workload": cfg["workload"], "roofline": rl,
            "algorithmic_bytes_per_sequence": algo_bytes(cfg)["total"], "algorithmic_flops_per_sequence": algo_flops(cfg)}
-    # the reference's own batch of 256 (latency-bound: 2 of 148 SMs have a tile)
+    # the reference's own batch of 256 (the unit-split kernels spread its 2 tiles over 8 - 32 SMs)
     ms2, _, _ = timed_steps(lambda: trainer.step(torch.randint(0, n_valid, (256,), device=dev, generator=gen)), 3, 3, None, barrier)
     out["reference_batch"] = {"batch_per_gpu": 256, "value": 256 * 3 / (ms2 * 1e-3), "ms_per_step": ms2 / 3}
     del trainer, model, ds
