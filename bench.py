@@ -494,9 +494,12 @@ def run_side_config(name, dev, rank, world, group, barrier, steps=3, warmup=3, b
            "precision": resolved_precision(cfg), "workload": cfg["workload"], "roofline": rl,
            "algorithmic_bytes_per_sequence": algo_bytes(cfg)["total"], "algorithmic_flops_per_sequence": algo_flops(cfg)}
     # the reference's own batch of 256 (the unit-split kernels spread its 2 tiles over 8 - 32 SMs)
-    ms2, _, _ = timed_steps(lambda: trainer.step(torch.randint(0, n_valid, (256,), device=dev, generator=gen)), 3, 3, None, barrier)
-    out["reference_batch"] = {"batch_per_gpu": 256, "value": 256 * 3 / (ms2 * 1e-3), "ms_per_step": ms2 / 3}
-    del trainer, model, ds
+    # (CUDA-graph replayed like the headline config's leg: at 3 - 8 ms per step the eager launches are a tenth of it)
+    from hy2dl_b200.training import Trainer
+    tr2 = Trainer(model, ds, loss=cfg["loss"], group=group, use_graph=True)
+    ms2, _, _ = timed_steps(lambda: tr2.step(torch.randint(0, n_valid, (256,), device=dev, generator=gen)), 10, 4, None, barrier)
+    out["reference_batch"] = {"batch_per_gpu": 256, "value": 256 * 10 / (ms2 * 1e-3), "ms_per_step": ms2 / 10, "cuda_graph": True}
+    del trainer, tr2, model, ds
     torch.cuda.empty_cache()
     return out
 
