@@ -343,9 +343,12 @@ int lstm_us_tc_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const flo
   attr[0].id = cudaLaunchAttributeCooperative;       // all CTAs co-resident, or the launch fails: they wait for each other
   attr[0].val.cooperative = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+#ifdef HY2DL_US_STAMPS
   static const int dbg = [] { const char* e = getenv("HY2DL_US_DBG"); return e ? atoi(e) : 0; }();
   if (dbg & 128) { cudaMalloc(&a.stamps, 32 * sizeof(long long)); cudaMemset(a.stamps, 0, 32 * sizeof(long long)); }
+#endif
   cudaLaunchKernelEx(&cfg, lstm_us_tc_bwd_kernel, a);
+#ifdef HY2DL_US_STAMPS
   if (a.stamps) {                                   // debugging only: timeline of CTA 0, thread 0, reverse steps 100-101
     long long h[32];
     cudaDeviceSynchronize();
@@ -353,6 +356,7 @@ int lstm_us_tc_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const flo
     cudaFree(a.stamps);
     for (int i = 0; i < 32; ++i) if (h[i]) fprintf(stderr, "USB_STAMP step %d id %2d  %8lld\n", 100 + i / 16, i % 16, h[i] - h[0]);
   }
+#endif
   HY_LAUNCH_CHECK();
   return HY2DL_OK;
 }

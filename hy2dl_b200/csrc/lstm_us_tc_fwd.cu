@@ -424,7 +424,6 @@ int lstm_us_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
   a.h_seq = h_seq; a.c_seq = c_seq; a.gates = gates; a.h_last = h_last;
   a.B = B; a.T = T; a.H = (int)H; a.I = (int)I; a.IP = (int)IP;
   a.single = single;
-  static const int dbg = [] { const char* e = getenv("HY2DL_US_DBG"); return e ? atoi(e) : 0; }();
   const size_t smem = (size_t)a.K * kColsU * 8 + kSlotsU * kSlotBytesU + 256 + 1024;
   cudaFuncSetAttribute(lstm_us_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaLaunchConfig_t cfg = {};
@@ -433,20 +432,22 @@ int lstm_us_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
   attr[0].id = cudaLaunchAttributeCooperative;       // all CTAs co-resident, or the launch fails: they wait for each other
   attr[0].val.cooperative = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+#ifdef HY2DL_US_STAMPS
+  static const int dbg = [] { const char* e = getenv("HY2DL_US_DBG"); return e ? atoi(e) : 0; }();
   if (dbg & 128) { cudaMalloc(&a.stamps, 128 * sizeof(long long)); cudaMemset(a.stamps, 0, 128 * sizeof(long long)); }
+#endif
   cudaLaunchKernelEx(&cfg, lstm_us_tc_fwd_kernel, a);
+#ifdef HY2DL_US_STAMPS
   if (a.stamps) {                                   // debugging only: print the timeline of CTA 0, steps 100-101
     long long h[128];
     cudaDeviceSynchronize();
     cudaMemcpy(h, a.stamps, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(a.stamps);
-    const char* names[64] = {};
-    long long t0 = h[0];
     for (int st = 0; st < 2; ++st)
       for (int i = 0; i < 64; ++i)
-        if (h[st * 64 + i]) fprintf(stderr, "US_STAMP step %d id %2d  %8lld\n", 100 + st, i, h[st * 64 + i] - t0);
-    (void)names;
+        if (h[st * 64 + i]) fprintf(stderr, "US_STAMP step %d id %2d  %8lld\n", 100 + st, i, h[st * 64 + i] - h[0]);
   }
+#endif
   HY_LAUNCH_CHECK();
   return HY2DL_OK;
 }
