@@ -89,7 +89,7 @@ class MFLSTM(nn.Module):
         xc = self.pack(x)
         B, T, _ = xc.shape
         t0 = T - self.predict_last_n
-        h_seq, _ = self.lstm.run_native(ops.pack_x(xc, self.lstm.layout), dh_t0=t0, want_seq=True, B=B)
+        h_seq, _ = self.lstm.run_native(ops.pack_x(xc, self.lstm.layout_for(B)), dh_t0=t0, want_seq=True, B=B)
         if ops.is_ri32(h_seq):
             h_seq = ops.from_ri32(h_seq, B)
         out = self.dropout(h_seq[t0:].permute(1, 0, 2))     # [B, n_last, H]

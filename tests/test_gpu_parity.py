@@ -689,7 +689,8 @@ def test_full_size_batch_properties(dev):
     assert_close(npy(y_full[pick]), ref["y_hat"].numpy(), what="subset vs fp64 oracle", **TOL)
 
 
-@pytest.mark.parametrize("B,H,precision,n_dyn,n_static", [(40, 64, "tf32x3", 3, 22), (9, 128, "fp32", 11, 27)])
+@pytest.mark.parametrize("B,H,precision,n_dyn,n_static", [(40, 64, "tf32x3", 3, 22), (9, 128, "fp32", 11, 27),
+                                                          (40, 64, "auto", 3, 22)])      # "auto" at this batch: the small-batch family
 def test_mflstm_vs_own_oracle(dev, B, H, precision, n_dyn, n_static):
     """Multi-frequency LSTM (365 daily + 336 hourly steps, last 24 hours predicted).  PARITY UNPINNED: no reference
     implementation exists in the snapshot; the check is against this project's own fp64 restatement of the
