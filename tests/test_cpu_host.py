@@ -290,6 +290,13 @@ def test_zero_padded_kernel_weights_and_drop_in_checks():
         with pytest.raises(ValueError):
             LSTM(**bad)
     assert LSTM(25, 64, precision="tf32").layout == "ri32" and LSTM(31, 256, precision="tf32").layout == "rowmajor"
+    # a default H <= 64 model picks the kernel family per call from the batch size; an explicit precision pins it
+    auto = LSTM(25, 64)
+    assert auto.family_for(256) == (64, "fp32", "rowmajor") and auto.layout_for(LSTM.SMALL_BATCH_MAX) == "rowmajor"
+    assert auto.family_for(LSTM.SMALL_BATCH_MAX + 1) == (64, "tf32x3", "ri32") and auto.layout == "ri32"
+    assert LSTM(25, 64, precision="tf32x3").family_for(256) == (64, "tf32x3", "ri32")
+    assert LSTM(25, 64, precision="fp32").family_for(256) == (64, "fp32", "rowmajor")
+    assert LSTM(31, 256).family_for(256) == (256, "fp32", "rowmajor")
     # hidden_size <= 64 with more than 31 inputs runs on the tensor-core chain zero-padded to 128 units (any precision but tf32x3)
     wide = LSTM(41, 64)
     assert wide.kernel_hidden == 128 and wide.precision == "fp32" and wide.layout == "rowmajor"
