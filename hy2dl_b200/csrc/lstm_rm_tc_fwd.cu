@@ -65,6 +65,7 @@ struct FwdArgs {
   int act_sep;          // experiment: one reciprocal per gate
   int splitj;           // K steps per split (a split's weight slices stay in the ring until its hi*hi MMAs are issued)
   int single;           // HY2DL_PREC_TF32: hi*hi MMAs only (one chain per chunk), only the hi half of the weights is streamed
+  long long* stamps;    // -DHY2DL_US_STAMPS: clock64 timeline of CTA 0, steps 100-101
   int dbg;              // timing experiments (HY2DL_RM_DBG): 1 no tape stores, 2 no correction MMAs, 4 no drains but the last, 8 no A rebuild
 };
 
@@ -105,6 +106,11 @@ __global__ void rm_tc_pack_w_kernel(const float* __restrict__ w_ih, const float*
 // the L2 -> shared-memory weight stream per sequence halves (it bounds the single-CTA kernel at a full wave: 148 CTAs x 2.4 MB
 // per step).  Row threads, tapes and the accumulator hand-shake are per CTA as before; completions are multicast to both CTAs,
 // the peer's arrivals reach the leader's mbarriers through the cluster's shared-memory window.
+#ifdef HY2DL_US_STAMPS
+#define RF_STAMP(id) do { if (a.stamps && blockIdx.x == 0 && t >= 100 && t < 102) a.stamps[(t - 100) * 64 + (id)] = clock64(); } while (0)
+#else
+#define RF_STAMP(id) do { } while (0)
+#endif
 template <bool PAIR>
 __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
@@ -179,6 +185,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
         mbar_wait(bar_step, (uint32_t)((t - 1) & 1));            // all MMAs of step t-1 retired
         tc_fence_after();
       }
+      if (tid == 0) RF_STAMP(0);
       if (hh == 0) {
         const float* xr = a.x + (t * a.B + b) * a.IP;
         for (int k0 = 0; k0 < KX; k0 += 4) {
@@ -195,16 +202,22 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
       }
       {
         const float* hp = (t > 0 && live && !(a.dbg & 8)) ? hown(t - 1) : nullptr;
+        // Eight 256-bit loads in flight, then their splits and stores.  The loads are volatile asm with a memory clobber (they
+        // must see this thread's own earlier stores), so the compiler keeps each behind the previous block's stores: one
+        // load -> split -> store per 8 units serialised 16 L2 / DRAM round trips, 22.9 k of the step's 163 k cycles (clock64
+        // timeline, -DHY2DL_US_STAMPS; 13.9 k batched); the scratch (39 MB at 18 944 sequences) does not survive 133 MB of tape
+        // stores in L2.  The kernel's time did not change (36.4 ms): at a full wave the step is bound elsewhere.
         if (!((a.dbg & 8) && t > 1))
-#pragma unroll 4
-        for (int c = 0; c < NC; ++c) {
+        for (int c0 = 0; c0 < NC; c0 += 4) {                      // NC = H / 32 = 4 or 8
+          f8 v[8];
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {                           // 8 units: one 256-bit load, one tcgen05.st, two lo chunks
-            const int u0 = 32 * c + 16 * hh + 8 * i;
-            const f8 v = hp ? ld256(hp + (4 * c + i) * 256) : f8_zero();    // own earlier stores: coherent loads
+          for (int k = 0; k < 8; ++k) v[k] = hp ? ld256(hp + (4 * (c0 + (k >> 1)) + (k & 1)) * 256) : f8_zero();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {                           // 8 units: one tcgen05.st, two lo chunks
+            const int u0 = 32 * (c0 + (k >> 1)) + 16 * hh + 8 * (k & 1);
             uint32_t hi8[8], lo8[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) split_tf32(v.v[e], hi8[e], lo8[e]);
+            for (int e = 0; e < 8; ++e) split_tf32(v[k].v[e], hi8[e], lo8[e]);
             tmem_st8(lane_tm + u0, hi8);
             alo4[((KX + u0) >> 2) * kRowsF + rloc] =
                 make_float4(__uint_as_float(lo8[0]), __uint_as_float(lo8[1]), __uint_as_float(lo8[2]), __uint_as_float(lo8[3]));
@@ -217,6 +230,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
       fence_async_smem();
       tc_fence_before();
       rows_arrive(bar_a);
+      if (tid == 0) RF_STAMP(1);
 
       // ---- epilogue of every chunk: 16 hidden units of this row
       const float* cprev = (t > 0 && live) ? cbuf(t - 1) : nullptr;
@@ -252,6 +266,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
             for (int j = 0; j < 32; ++j) { z[j] += __uint_as_float(z0[j]); z[32 + j] += __uint_as_float(z1[j]); }
           }
         }
+        if (tid == 0) RF_STAMP(2 + c);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {                             // 8 units per round: whole 32-byte sectors per access
           f8 hv, cv, gi, gf, gg, go;
@@ -278,6 +293,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
             if (hlast) stg256(hlast + o, hv);
           }
         }
+        if (tid == 0) RF_STAMP(12 + c);
       }
     }
   } else if (warp == 8) {
@@ -303,6 +319,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
         wait_rows(bar_a, (uint32_t)(t & 1));
         tc_fence_after();
         for (int c = 0; c < NC; ++c) {
+          RF_STAMP(24 + c);
           for (int Jb = 0; Jb < NJ; Jb += SJ, ++gsp) {
             const int n = min(SJ, NJ - Jb);
             const int r = (int)(gsp & 1);
@@ -354,6 +371,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) lstm_rm_tc_fwd_kernel(FwdArgs a)
           }
         }
         commit(bar_step);
+        RF_STAMP(40);
       }
     } else if (PAIR && rank == 1 && lane == 0) {
       // =========================== the peer's relay ============================================
@@ -501,7 +519,19 @@ int lstm_rm_tc_fwd(const float* xT, int64_t B, int64_t T, int64_t I, int64_t IP,
     cudaLaunchKernelEx(&cfg, lstm_rm_tc_fwd_kernel<true>, a);
   } else {
     cudaFuncSetAttribute(lstm_rm_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#ifdef HY2DL_US_STAMPS
+    cudaMalloc(&a.stamps, 128 * sizeof(long long)); cudaMemset(a.stamps, 0, 128 * sizeof(long long));
+#endif
     lstm_rm_tc_fwd_kernel<false><<<tiles, kThreadsF, smem, s>>>(a);
+#ifdef HY2DL_US_STAMPS
+    {
+      long long h[128];
+      cudaDeviceSynchronize();
+      cudaMemcpy(h, a.stamps, sizeof(h), cudaMemcpyDeviceToHost);
+      cudaFree(a.stamps);
+      for (int i = 0; i < 128; ++i) if (h[i]) fprintf(stderr, "RF_STAMP step %d id %2d  %8lld\n", 100 + i / 64, i % 64, h[i] - h[0]);
+    }
+#endif
   }
   HY_LAUNCH_CHECK();
   return HY2DL_OK;
