@@ -14,8 +14,8 @@ counts, name = {}, None
 for line in out.splitlines():
     m = re.match(r"\s*Function : (\S+)", line)
     if m:
-        name = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().split("(")[0]
-        name = re.sub(r"\(anonymous namespace\)::|hy2dl::", "", name)
+        name = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
+        name = re.sub(r"\(anonymous namespace\)::|hy2dl::", "", name).split("(")[0]
         counts[name] = dict.fromkeys(ops, 0)
         continue
     if name:
