@@ -1,4 +1,4 @@
-// Back-propagation through time for H = 128 / 256 at SMALL batches with the hidden units of a 128-sequence tile split
+// Back-propagation through time for H = 64 / 128 / 256 at SMALL batches with the hidden units of a 128-sequence tile split
 // over S = H / 16 co-resident CTAs; the counterpart of lstm_us_tc_fwd.cu (read its header first).
 //
 // CTA s owns hidden units [16 s, 16 s + 16) of the tile.  Per reverse step it

@@ -1,4 +1,4 @@
-// Recurrent LSTM forward for H = 128 / 256 at SMALL batches: the hidden units of one 128-sequence tile are split over
+// Recurrent LSTM forward for H = 64 / 128 / 256 at SMALL batches: the hidden units of one 128-sequence tile are split over
 // H / 16 co-resident CTAs ("unit split").
 //
 // lstm_rm_tc_fwd.cu gives one tile of 128 sequences to one CTA for all T steps.  A step then is a serial chain inside
